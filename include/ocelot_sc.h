@@ -1,0 +1,131 @@
+/*
+ * ocelot_sc.h -- C ABI of the B200-native 3D space-charge kick.
+ *
+ * This is the drop-in boundary for ONE hot path of Ocelot: SpaceCharge.apply()
+ * (reference: ocelot/cpbd/sc.py:208-251 and everything it calls).  The
+ * reference has no FFI for this path (it is numpy/scipy); these are the entry
+ * points a reference-side binding (ctypes) binds instead of
+ * calling sc.py's methods.  Plain pointers and sizes only.
+ *
+ * Conventions
+ *   - every function returning int returns 0 on success, non-zero on error;
+ *     ocl_sc_last_error(h) (or ocl_sc_last_error(NULL) for create failures)
+ *     returns a human-readable message.  There is NO CPU fallback.
+ *   - "d_" pointers are device pointers on the handle's device, "h_" pointers
+ *     are host pointers.  `stream` is a cudaStream_t passed as void* (NULL =
+ *     the legacy default stream).  Calls are asynchronous w.r.t. the host
+ *     unless stated; one handle = one device = one stream at a time; a handle
+ *     is not thread-safe, different handles are independent.
+ *   - particle layout = ParticleArray.rparticles (beam/particle.py:79-84):
+ *     6 rows [x, x', y, y', tau, delta], row r at d_r + r*ld, fp64; charges
+ *     q[n] fp64 (ParticleArray.q_array).
+ *   - mesh_draws: NULL, or two doubles {scale in [1,1.1), shift in [-0.5,0.5)}
+ *     = the two numpy draws of random_mesh mode (sc.py:175, :185), made by the
+ *     host so the numpy global RNG stream is consumed exactly as the reference
+ *     does.
+ */
+#ifndef OCELOT_SC_H
+#define OCELOT_SC_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ocl_sc ocl_sc_t;
+
+/* ABI version of this header (bumped on any signature change). */
+int ocl_sc_abi_version(void);
+
+/* Physical constants exactly as ocelot/common/globals.py:13-24 builds them:
+ * out = {m_e_eV, m_e_GeV, epsilon_0, pi, speed_of_light}.  Host only. */
+void ocl_sc_get_constants(double out[5]);
+
+/* Padded FFT length used for a mesh of n points along one axis
+ * (smallest power of two >= 2n-1; replaces the (2n-1) grid of sc.py:142). */
+int ocl_sc_fft_size(int n);
+
+/* Create / destroy a solver for mesh (nx,ny,nz) = SpaceCharge.nmesh_xyz
+ * (sc.py:95) on CUDA device `device`.  max_particles sizes the internal
+ * staging used by ocl_sc_kick_host only (0 = grow on demand). */
+int ocl_sc_create(int device, int nx, int ny, int nz, long long max_particles, ocl_sc_t** out);
+void ocl_sc_destroy(ocl_sc_t* h);
+const char* ocl_sc_last_error(const ocl_sc_t* h);
+
+/* One SpaceCharge.apply (sc.py:208-251) on device-resident particles, in
+ * place.  dz == 0 returns immediately (sc.py:210-212).  No host
+ * synchronisation; safe to capture in a CUDA graph. */
+int ocl_sc_kick_device(ocl_sc_t* h, double* d_r, long long ld, const double* d_q, long long n,
+                       double E_GeV, double dz, const double* mesh_draws, void* stream);
+
+/* Same, for host arrays (numpy rparticles / q_array): H2D, kick, D2H in place,
+ * synchronous.  This is the call a literal drop-in under track() makes. */
+int ocl_sc_kick_host(ocl_sc_t* h, double* h_r, long long ld, const double* h_q, long long n,
+                     double E_GeV, double dz, const double* mesh_draws);
+
+/* ---- staged form of the same kick, for particle-sharded multi-GPU runs ----
+ * Between stages the caller all-reduces the handle's small device buffers
+ * (ocl_sc_collective_buffer) across ranks; with one rank the five stages in
+ * order are exactly ocl_sc_kick_device.
+ *   stage_momentum : lab->Cartesian momenta (coord_transform.py:57-96), sums
+ *                    -> buffer MOMENTUM {sum px, sum py, sum pz, count}   [SUM]
+ *   stage_extent   : bunch frame (sc.py:224-239), rotate, gamma-stretch
+ *                    (sc.py:172), extents and charge centroid (sc.py:173,
+ *                    :181-182) -> buffer EXTENT_MAX {max xyz, -min xyz}   [MAX]
+ *                    and buffer EXTENT_SUM {sum q*x, q*y, q*z, sum q}     [SUM]
+ *   stage_deposit  : mesh geometry (sc.py:179-186), NGP deposit (sc.py:191-193)
+ *                    -> buffer RHO (nx*ny*nz doubles)                     [SUM]
+ *   stage_solve    : IGF + Hockney convolution (sc.py:109-168), staggered
+ *                    field (sc.py:195-200); local to each rank
+ *   stage_kick     : trilinear gather (sc.py:201-204), kick (sc.py:244-250),
+ *                    Cartesian->lab (coord_transform.py:16-54), in place
+ */
+enum {
+    OCL_SC_BUF_MOMENTUM = 0,   /* 4 doubles, reduce SUM */
+    OCL_SC_BUF_EXTENT_MAX = 1, /* 6 doubles, reduce MAX */
+    OCL_SC_BUF_EXTENT_SUM = 2, /* 4 doubles, reduce SUM */
+    OCL_SC_BUF_RHO = 3         /* nx*ny*nz doubles, reduce SUM */
+};
+int ocl_sc_collective_buffer(ocl_sc_t* h, int which, double** d_ptr, long long* count);
+
+int ocl_sc_stage_momentum(ocl_sc_t* h, const double* d_r, long long ld, long long n, double E_GeV, void* stream);
+int ocl_sc_stage_extent(ocl_sc_t* h, const double* d_r, long long ld, const double* d_q, long long n,
+                        double E_GeV, void* stream);
+int ocl_sc_stage_deposit(ocl_sc_t* h, const double* d_r, long long ld, const double* d_q, long long n,
+                         double E_GeV, const double* mesh_draws, void* stream);
+int ocl_sc_stage_solve(ocl_sc_t* h, const double* mesh_draws, void* stream);
+int ocl_sc_stage_kick(ocl_sc_t* h, double* d_r, long long ld, long long n, double E_GeV, double dz,
+                      const double* mesh_draws, void* stream);
+
+/* ---- stage taps (tests / diagnostics); each synchronises the stream last used ----
+ * geometry out[24] = {T row-major [9], pav, gamma0, beta0, steps[3], X_off[3],
+ *                     sum q, count, reserved[4]}  (sc.py:224-239, :179-185) */
+int ocl_sc_get_geometry(ocl_sc_t* h, double out[24]);
+int ocl_sc_get_rho(ocl_sc_t* h, double* h_out);          /* nx*ny*nz, C order, sc.py:193 */
+int ocl_sc_get_phi(ocl_sc_t* h, double* h_out);          /* nx*ny*nz, sc.py:167-168 */
+int ocl_sc_get_green(ocl_sc_t* h, double* h_out);        /* nx*ny*nz, sym_kernel sc.py:109-133 */
+/* rest-frame field at the particles WITHOUT kicking them: Exyz (n,3) row-major
+ * as SpaceCharge.el_field returns it (sc.py:201-205).  Runs all stages but the kick. */
+int ocl_sc_field_at_particles(ocl_sc_t* h, const double* d_r, long long ld, const double* d_q, long long n,
+                              double E_GeV, const double* mesh_draws, double* d_exyz, void* stream);
+
+/* Stand-alone stages for known-answer tests (device pointers). */
+int ocl_sc_mad_to_cartesian(ocl_sc_t* h, const double* d_r, long long ld, long long n, double E_GeV,
+                            double* d_xp, long long ld_xp, void* stream);   /* coord_transform.py:57-96 */
+int ocl_sc_cartesian_to_mad(ocl_sc_t* h, const double* d_xp, long long ld_xp, long long n, double E_GeV,
+                            double* d_r, long long ld, void* stream);       /* coord_transform.py:16-54 */
+/* potential(q, steps) of sc.py:135-168 for a host rho[nx*ny*nz] and steps[3]; result to h_phi. */
+int ocl_sc_potential_host(ocl_sc_t* h, const double* h_rho, const double steps[3], double* h_phi);
+
+/* Per-stage device timers.  enable=1 records CUDA events around each stage of
+ * every following kick; get returns the last kick's milliseconds:
+ * out[8] = {momentum, extent, deposit, green+fft, field, kick, total, reserved}. */
+int ocl_sc_enable_timers(ocl_sc_t* h, int enable);
+int ocl_sc_get_timers(ocl_sc_t* h, double out[8]);
+
+/* Number of kernel launches (own kernels + cuFFT execs) issued by the handle so far. */
+long long ocl_sc_launch_count(const ocl_sc_t* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OCELOT_SC_H */

@@ -1,0 +1,6 @@
+"""ocelot_b200 -- B200-native 3D space-charge kick behind Ocelot's PhysProc API."""
+from .physproc import PhysProc
+from .particles import ParticleArray, DeviceParticleArray
+from .sc import SpaceCharge, install
+
+__all__ = ["PhysProc", "ParticleArray", "DeviceParticleArray", "SpaceCharge", "install"]

@@ -1,0 +1,475 @@
+// sc_abi.cu -- handle management and the extern "C" entry points of include/ocelot_sc.h.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "../../include/ocelot_sc.h"
+#include "sc_kernels.h"
+
+using namespace ocl;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+enum TimerSlot { T_BEGIN = 0, T_MOM, T_EXT, T_DEP, T_SOLVE, T_FIELD, T_KICK, T_COUNT };
+
+}  // namespace
+
+struct ocl_sc {
+    int device = 0;
+    MeshDims md{};
+    ReduceState rs{};
+    // constants (ocelot/common/globals.py:13-24)
+    double m_e_eV = 0, m_e_GeV = 0;
+    // grids
+    double* rho = nullptr;    // n^3
+    double* gtab = nullptr;   // (n+1)^3 antiderivative table
+    double* k1 = nullptr;     // n^3 (tap only, lazily allocated)
+    double* real_buf = nullptr;               // M^3 real: K, then padded rho, then the convolution
+    cufftDoubleComplex* k_hat = nullptr;      // M*M*(M/2+1)
+    cufftDoubleComplex* rho_hat = nullptr;    // M*M*(M/2+1)
+    double* phi = nullptr;    // n^3
+    double* ex = nullptr;     // n^3 each
+    double* ey = nullptr;
+    double* ez = nullptr;
+    cufftHandle plan_fwd = 0, plan_inv = 0;
+    bool plans = false;
+    // host-mode staging
+    double* stage_r = nullptr;
+    double* stage_q = nullptr;
+    long long stage_cap = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t last_stream = nullptr;
+    // timers
+    bool timers = false;
+    cudaEvent_t ev[T_COUNT] = {};
+    bool ev_valid = false;
+    long long launches = 0;
+    std::string err;
+};
+
+namespace {
+
+int fail(ocl_sc* h, const char* what, const char* detail) {
+    std::string m = std::string(what) + ": " + detail;
+    if (h) h->err = m; else g_create_error = m;
+    return 1;
+}
+
+#define CU(h, call)                                                              \
+    do {                                                                         \
+        cudaError_t e_ = (call);                                                 \
+        if (e_ != cudaSuccess) return fail((h), #call, cudaGetErrorString(e_));  \
+    } while (0)
+
+#define FFT(h, call)                                                             \
+    do {                                                                         \
+        cufftResult r_ = (call);                                                 \
+        if (r_ != CUFFT_SUCCESS) {                                               \
+            char b_[64];                                                         \
+            snprintf(b_, sizeof b_, "cufft error %d", (int)r_);                  \
+            return fail((h), #call, b_);                                         \
+        }                                                                        \
+    } while (0)
+
+void constants(double& m_e_eV, double& m_e_GeV, double& eps0, double& pi, double& c) {
+    pi = 3.141592653589793;
+    c = 299792458.0;
+    const double q_e = 1.6021766208e-19, m_e_kg = 9.10938215e-31;
+    m_e_eV = m_e_kg * (c * c) / q_e;
+    m_e_GeV = m_e_eV / 1e+9;
+    const double mu0 = 4 * pi * 1e-7;
+    eps0 = 1 / mu0 / (c * c);
+}
+
+RefParams ref_params(const ocl_sc* h, double E_GeV) {
+    RefParams rp;
+    rp.m_e_eV = h->m_e_eV;
+    rp.m_e_eV2 = h->m_e_eV * h->m_e_eV;
+    rp.gamref = E_GeV / h->m_e_GeV;                                  // sc.py:214
+    rp.betaref = std::sqrt(1 - std::pow(rp.gamref, -2.0));           // sc.py:215-216
+    rp.gb_ref = rp.gamref * rp.betaref;
+    rp.pref = h->m_e_eV * std::sqrt(rp.gamref * rp.gamref - 1);      // coord_transform.py:19
+    return rp;
+}
+
+Draws draws_of(const double* mesh_draws) {
+    Draws d;
+    if (mesh_draws) { d.scale = mesh_draws[0]; d.shift = mesh_draws[1]; }
+    else { d.scale = 0.0; d.shift = 0.0; }
+    return d;
+}
+
+int check_launch(ocl_sc* h, const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(h, what, cudaGetErrorString(e));
+    return 0;
+}
+
+void mark(ocl_sc* h, int slot, cudaStream_t st) {
+    if (h->timers) { cudaEventRecord(h->ev[slot], st); if (slot == T_KICK) h->ev_valid = true; }
+}
+
+int set_device(ocl_sc* h) {
+    CU(h, cudaSetDevice(h->device));
+    return 0;
+}
+
+int ensure_plans(ocl_sc* h) {
+    if (h->plans) return 0;
+    FFT(h, cufftPlan3d(&h->plan_fwd, h->md.mx, h->md.my, h->md.mz, CUFFT_D2Z));
+    FFT(h, cufftPlan3d(&h->plan_inv, h->md.mx, h->md.my, h->md.mz, CUFFT_Z2D));
+    h->plans = true;
+    return 0;
+}
+
+// IGF -> K_hat, rho -> rho_hat, multiply, inverse: real_buf holds the convolution afterwards
+int convolve(ocl_sc* h, cudaStream_t st) {
+    if (ensure_plans(h)) return 1;
+    FFT(h, cufftSetStream(h->plan_fwd, st));
+    FFT(h, cufftSetStream(h->plan_inv, st));
+    launch_green_mirror(h->gtab, h->md, h->real_buf, st);
+    FFT(h, cufftExecD2Z(h->plan_fwd, h->real_buf, h->k_hat));
+    launch_pad_rho(h->rho, h->md, h->real_buf, st);
+    FFT(h, cufftExecD2Z(h->plan_fwd, h->real_buf, h->rho_hat));
+    launch_multiply(h->rho_hat, h->k_hat, h->md, st);
+    FFT(h, cufftExecZ2D(h->plan_inv, h->rho_hat, h->real_buf));
+    h->launches += 6;
+    return check_launch(h, "convolve");
+}
+
+}  // namespace
+
+extern "C" {
+
+int ocl_sc_abi_version(void) { return 1; }
+
+void ocl_sc_get_constants(double out[5]) {
+    constants(out[0], out[1], out[2], out[3], out[4]);
+}
+
+int ocl_sc_fft_size(int n) {
+    int m = 1;
+    while (m < 2 * n - 1) m *= 2;
+    return m;
+}
+
+const char* ocl_sc_last_error(const ocl_sc_t* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int ocl_sc_create(int device, int nx, int ny, int nz, long long max_particles, ocl_sc_t** out) {
+    if (!out) return fail(nullptr, "ocl_sc_create", "out is NULL");
+    *out = nullptr;
+    if (nx < 4 || ny < 4 || nz < 4) return fail(nullptr, "ocl_sc_create", "mesh needs at least 4 points per axis");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, "ocl_sc_create", "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(nullptr, "ocl_sc_create", "bad device index");
+    ocl_sc* h = new ocl_sc();
+    h->device = device;
+    double eps0, pi, c;
+    constants(h->m_e_eV, h->m_e_GeV, eps0, pi, c);
+    h->md.nx = nx; h->md.ny = ny; h->md.nz = nz;
+    h->md.mx = ocl_sc_fft_size(nx); h->md.my = ocl_sc_fft_size(ny); h->md.mz = ocl_sc_fft_size(nz);
+    const size_t n3 = (size_t)nx * ny * nz;
+    const size_t g3 = (size_t)(nx + 1) * (ny + 1) * (nz + 1);
+    const size_t m3 = (size_t)h->md.mx * h->md.my * h->md.mz;
+    const size_t c3 = (size_t)h->md.mx * h->md.my * (h->md.mz / 2 + 1);
+    h->rs.max_blocks = 148 * 4;
+#define TRY(call)                                                             \
+    do {                                                                      \
+        cudaError_t e2_ = (call);                                             \
+        if (e2_ != cudaSuccess) {                                             \
+            fail(nullptr, #call, cudaGetErrorString(e2_));                    \
+            ocl_sc_destroy(h);                                                \
+            return 1;                                                         \
+        }                                                                     \
+    } while (0)
+    TRY(cudaSetDevice(device));
+    TRY(cudaMalloc(&h->rs.part, sizeof(double) * 10 * h->rs.max_blocks));
+    TRY(cudaMalloc(&h->rs.ticket, sizeof(unsigned int) * 4));
+    TRY(cudaMemset(h->rs.ticket, 0, sizeof(unsigned int) * 4));
+    TRY(cudaMalloc(&h->rs.sums, sizeof(double) * 40));
+    TRY(cudaMemset(h->rs.sums, 0, sizeof(double) * 40));
+    h->rs.emax = h->rs.sums + 4;
+    h->rs.esum = h->rs.sums + 10;
+    h->rs.geom = h->rs.sums + 16;
+    TRY(cudaMalloc(&h->rho, sizeof(double) * n3));
+    TRY(cudaMalloc(&h->gtab, sizeof(double) * g3));
+    TRY(cudaMalloc(&h->real_buf, sizeof(double) * m3));
+    TRY(cudaMalloc(&h->k_hat, sizeof(cufftDoubleComplex) * c3));
+    TRY(cudaMalloc(&h->rho_hat, sizeof(cufftDoubleComplex) * c3));
+    TRY(cudaMalloc(&h->phi, sizeof(double) * n3));
+    TRY(cudaMalloc(&h->ex, sizeof(double) * n3 * 3));
+    h->ey = h->ex + n3;
+    h->ez = h->ey + n3;
+    TRY(cudaMemset(h->rho, 0, sizeof(double) * n3));
+    TRY(cudaMemset(h->phi, 0, sizeof(double) * n3));
+    TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < T_COUNT; ++i) TRY(cudaEventCreate(&h->ev[i]));
+    if (max_particles > 0) {
+        TRY(cudaMalloc(&h->stage_r, sizeof(double) * 6 * max_particles));
+        TRY(cudaMalloc(&h->stage_q, sizeof(double) * max_particles));
+        h->stage_cap = max_particles;
+    }
+#undef TRY
+    *out = h;
+    return 0;
+}
+
+void ocl_sc_destroy(ocl_sc_t* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->plans) { cufftDestroy(h->plan_fwd); cufftDestroy(h->plan_inv); }
+    cudaFree(h->rs.part); cudaFree(h->rs.ticket); cudaFree(h->rs.sums);
+    cudaFree(h->rho); cudaFree(h->gtab); cudaFree(h->k1); cudaFree(h->real_buf);
+    cudaFree(h->k_hat); cudaFree(h->rho_hat); cudaFree(h->phi); cudaFree(h->ex);
+    cudaFree(h->stage_r); cudaFree(h->stage_q);
+    for (int i = 0; i < T_COUNT; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+int ocl_sc_collective_buffer(ocl_sc_t* h, int which, double** d_ptr, long long* count) {
+    if (!h || !d_ptr || !count) return 1;
+    switch (which) {
+        case OCL_SC_BUF_MOMENTUM: *d_ptr = h->rs.sums; *count = 4; return 0;
+        case OCL_SC_BUF_EXTENT_MAX: *d_ptr = h->rs.emax; *count = 6; return 0;
+        case OCL_SC_BUF_EXTENT_SUM: *d_ptr = h->rs.esum; *count = 4; return 0;
+        case OCL_SC_BUF_RHO: *d_ptr = h->rho; *count = (long long)h->md.nx * h->md.ny * h->md.nz; return 0;
+    }
+    return fail(h, "ocl_sc_collective_buffer", "unknown buffer id");
+}
+
+// ---- stages ---------------------------------------------------------------
+int ocl_sc_stage_momentum(ocl_sc_t* h, const double* d_r, long long ld, long long n, double E_GeV, void* stream) {
+    if (!h) return 1;
+    if (n <= 0 || ld < n) return fail(h, "ocl_sc_stage_momentum", "need 0 < n <= ld");
+    if (set_device(h)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    h->last_stream = st;
+    mark(h, T_BEGIN, st);
+    launch_momentum(d_r, ld, n, ref_params(h, E_GeV), h->rs, st);
+    h->launches += 1;
+    mark(h, T_MOM, st);
+    return check_launch(h, "k_momentum");
+}
+
+int ocl_sc_stage_extent(ocl_sc_t* h, const double* d_r, long long ld, const double* d_q, long long n, double E_GeV,
+                        void* stream) {
+    if (!h) return 1;
+    if (set_device(h)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    h->last_stream = st;
+    launch_extent(d_r, ld, d_q, n, ref_params(h, E_GeV), h->rs, st);
+    h->launches += 1;
+    mark(h, T_EXT, st);
+    return check_launch(h, "k_extent");
+}
+
+int ocl_sc_stage_deposit(ocl_sc_t* h, const double* d_r, long long ld, const double* d_q, long long n, double E_GeV,
+                         const double* mesh_draws, void* stream) {
+    if (!h) return 1;
+    if (set_device(h)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    h->last_stream = st;
+    CU(h, cudaMemsetAsync(h->rho, 0, sizeof(double) * (size_t)h->md.nx * h->md.ny * h->md.nz, st));
+    launch_deposit(d_r, ld, d_q, n, ref_params(h, E_GeV), h->rs, h->md, draws_of(mesh_draws), h->rho, st);
+    h->launches += 2;
+    mark(h, T_DEP, st);
+    return check_launch(h, "k_deposit");
+}
+
+int ocl_sc_stage_solve(ocl_sc_t* h, const double* mesh_draws, void* stream) {
+    if (!h) return 1;
+    if (set_device(h)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    h->last_stream = st;
+    Draws dr = draws_of(mesh_draws);
+    launch_green_table(h->rs, h->md, dr, h->gtab, st);
+    h->launches += 1;
+    if (convolve(h, st)) return 1;
+    mark(h, T_SOLVE, st);
+    launch_crop_phi(h->real_buf, h->rs, h->md, dr, h->phi, st);
+    launch_field(h->phi, h->rs, h->md, dr, h->ex, h->ey, h->ez, st);
+    h->launches += 2;
+    mark(h, T_FIELD, st);
+    return check_launch(h, "stage_solve");
+}
+
+int ocl_sc_stage_kick(ocl_sc_t* h, double* d_r, long long ld, long long n, double E_GeV, double dz,
+                      const double* mesh_draws, void* stream) {
+    if (!h) return 1;
+    if (set_device(h)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    h->last_stream = st;
+    launch_gather_kick(d_r, ld, n, ref_params(h, E_GeV), h->rs, h->md, draws_of(mesh_draws), h->ex, h->ey, h->ez, dz,
+                       nullptr, 1, st);
+    h->launches += 1;
+    mark(h, T_KICK, st);
+    return check_launch(h, "k_gather_kick");
+}
+
+int ocl_sc_kick_device(ocl_sc_t* h, double* d_r, long long ld, const double* d_q, long long n, double E_GeV,
+                       double dz, const double* mesh_draws, void* stream) {
+    if (!h) return 1;
+    if (dz == 0.0) return 0;   // sc.py:210-212
+    if (!(E_GeV > 0.0)) return fail(h, "ocl_sc_kick_device", "beam energy must be positive");
+    if (ocl_sc_stage_momentum(h, d_r, ld, n, E_GeV, stream)) return 1;
+    if (ocl_sc_stage_extent(h, d_r, ld, d_q, n, E_GeV, stream)) return 1;
+    if (ocl_sc_stage_deposit(h, d_r, ld, d_q, n, E_GeV, mesh_draws, stream)) return 1;
+    if (ocl_sc_stage_solve(h, mesh_draws, stream)) return 1;
+    return ocl_sc_stage_kick(h, d_r, ld, n, E_GeV, dz, mesh_draws, stream);
+}
+
+static int ensure_stage(ocl_sc* h, long long n) {
+    if (n <= h->stage_cap) return 0;
+    cudaFree(h->stage_r); cudaFree(h->stage_q);
+    h->stage_r = h->stage_q = nullptr; h->stage_cap = 0;
+    long long cap = n + n / 8 + 1024;
+    cap = (cap + 31) / 32 * 32;
+    CU(h, cudaMalloc(&h->stage_r, sizeof(double) * 6 * cap));
+    CU(h, cudaMalloc(&h->stage_q, sizeof(double) * cap));
+    h->stage_cap = cap;
+    return 0;
+}
+
+int ocl_sc_kick_host(ocl_sc_t* h, double* h_r, long long ld, const double* h_q, long long n, double E_GeV, double dz,
+                     const double* mesh_draws) {
+    if (!h) return 1;
+    if (dz == 0.0) return 0;
+    if (n <= 0 || ld < n) return fail(h, "ocl_sc_kick_host", "need 0 < n <= ld");
+    if (set_device(h)) return 1;
+    if (ensure_stage(h, n)) return 1;
+    cudaStream_t st = h->own_stream;
+    const long long cap = h->stage_cap;
+    CU(h, cudaMemcpy2DAsync(h->stage_r, sizeof(double) * cap, h_r, sizeof(double) * ld, sizeof(double) * n, 6,
+                            cudaMemcpyHostToDevice, st));
+    CU(h, cudaMemcpyAsync(h->stage_q, h_q, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    if (ocl_sc_kick_device(h, h->stage_r, cap, h->stage_q, n, E_GeV, dz, mesh_draws, st)) return 1;
+    CU(h, cudaMemcpy2DAsync(h_r, sizeof(double) * ld, h->stage_r, sizeof(double) * cap, sizeof(double) * n, 6,
+                            cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    return 0;
+}
+
+// ---- taps -----------------------------------------------------------------
+static int sync_last(ocl_sc* h) {
+    if (set_device(h)) return 1;
+    CU(h, cudaStreamSynchronize(h->last_stream));
+    return 0;
+}
+
+int ocl_sc_get_geometry(ocl_sc_t* h, double out[24]) {
+    if (!h) return 1;
+    if (sync_last(h)) return 1;
+    CU(h, cudaMemcpy(out, h->rs.geom, sizeof(double) * 24, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int ocl_sc_get_rho(ocl_sc_t* h, double* h_out) {
+    if (!h) return 1;
+    if (sync_last(h)) return 1;
+    CU(h, cudaMemcpy(h_out, h->rho, sizeof(double) * (size_t)h->md.nx * h->md.ny * h->md.nz, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int ocl_sc_get_phi(ocl_sc_t* h, double* h_out) {
+    if (!h) return 1;
+    if (sync_last(h)) return 1;
+    CU(h, cudaMemcpy(h_out, h->phi, sizeof(double) * (size_t)h->md.nx * h->md.ny * h->md.nz, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int ocl_sc_get_green(ocl_sc_t* h, double* h_out) {
+    if (!h) return 1;
+    if (sync_last(h)) return 1;
+    const size_t n3 = (size_t)h->md.nx * h->md.ny * h->md.nz;
+    if (!h->k1) CU(h, cudaMalloc(&h->k1, sizeof(double) * n3));
+    launch_green_compact(h->gtab, h->md, h->k1, h->last_stream);
+    if (check_launch(h, "k_green_compact")) return 1;
+    CU(h, cudaStreamSynchronize(h->last_stream));
+    CU(h, cudaMemcpy(h_out, h->k1, sizeof(double) * n3, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int ocl_sc_field_at_particles(ocl_sc_t* h, const double* d_r, long long ld, const double* d_q, long long n,
+                              double E_GeV, const double* mesh_draws, double* d_exyz, void* stream) {
+    if (!h) return 1;
+    if (ocl_sc_stage_momentum(h, d_r, ld, n, E_GeV, stream)) return 1;
+    if (ocl_sc_stage_extent(h, d_r, ld, d_q, n, E_GeV, stream)) return 1;
+    if (ocl_sc_stage_deposit(h, d_r, ld, d_q, n, E_GeV, mesh_draws, stream)) return 1;
+    if (ocl_sc_stage_solve(h, mesh_draws, stream)) return 1;
+    launch_gather_kick(const_cast<double*>(d_r), ld, n, ref_params(h, E_GeV), h->rs, h->md, draws_of(mesh_draws),
+                       h->ex, h->ey, h->ez, 0.0, d_exyz, 0, (cudaStream_t)stream);
+    h->launches += 1;
+    return check_launch(h, "k_gather");
+}
+
+int ocl_sc_mad_to_cartesian(ocl_sc_t* h, const double* d_r, long long ld, long long n, double E_GeV, double* d_xp,
+                            long long ld_xp, void* stream) {
+    if (!h) return 1;
+    if (set_device(h)) return 1;
+    h->last_stream = (cudaStream_t)stream;
+    launch_mad_to_cart(d_r, ld, n, ref_params(h, E_GeV), d_xp, ld_xp, (cudaStream_t)stream);
+    h->launches += 1;
+    return check_launch(h, "k_mad_to_cart");
+}
+
+int ocl_sc_cartesian_to_mad(ocl_sc_t* h, const double* d_xp, long long ld_xp, long long n, double E_GeV, double* d_r,
+                            long long ld, void* stream) {
+    if (!h) return 1;
+    if (set_device(h)) return 1;
+    h->last_stream = (cudaStream_t)stream;
+    launch_cart_to_mad(d_xp, ld_xp, n, ref_params(h, E_GeV), d_r, ld, (cudaStream_t)stream);
+    h->launches += 1;
+    return check_launch(h, "k_cart_to_mad");
+}
+
+int ocl_sc_potential_host(ocl_sc_t* h, const double* h_rho, const double steps[3], double* h_phi) {
+    if (!h) return 1;
+    if (set_device(h)) return 1;
+    cudaStream_t st = h->own_stream;
+    h->last_stream = st;
+    const size_t n3 = (size_t)h->md.nx * h->md.ny * h->md.nz;
+    CU(h, cudaMemcpyAsync(h->rho, h_rho, sizeof(double) * n3, cudaMemcpyHostToDevice, st));
+    launch_green_table_steps(steps, h->md, h->gtab, st);
+    h->launches += 1;
+    if (convolve(h, st)) return 1;
+    launch_crop_phi_steps(h->real_buf, steps, h->md, h->phi, st);
+    h->launches += 1;
+    if (check_launch(h, "potential")) return 1;
+    CU(h, cudaMemcpyAsync(h_phi, h->phi, sizeof(double) * n3, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    return 0;
+}
+
+int ocl_sc_enable_timers(ocl_sc_t* h, int enable) {
+    if (!h) return 1;
+    h->timers = enable != 0;
+    h->ev_valid = false;
+    return 0;
+}
+
+int ocl_sc_get_timers(ocl_sc_t* h, double out[8]) {
+    if (!h) return 1;
+    for (int i = 0; i < 8; ++i) out[i] = 0.0;
+    if (!h->timers || !h->ev_valid) return fail(h, "ocl_sc_get_timers", "no timed kick recorded");
+    if (set_device(h)) return 1;
+    CU(h, cudaEventSynchronize(h->ev[T_KICK]));
+    float ms;
+    for (int s = T_MOM; s <= T_KICK; ++s) {
+        CU(h, cudaEventElapsedTime(&ms, h->ev[s - 1], h->ev[s]));
+        out[s - 1] = ms;
+    }
+    CU(h, cudaEventElapsedTime(&ms, h->ev[T_BEGIN], h->ev[T_KICK]));
+    out[6] = ms;
+    return 0;
+}
+
+long long ocl_sc_launch_count(const ocl_sc_t* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

@@ -1,0 +1,507 @@
+// sc_kernels.cu -- sm_100a kernels of the 3D space-charge kick.
+//
+// One SpaceCharge.apply (ocelot/cpbd/sc.py:208-251) is four sweeps over the
+// particles separated by the three global dependencies of the algorithm
+// (mean momentum -> frame; extents/centroid -> mesh; rho -> potential), plus
+// the grid work in between:
+//
+//   k_momentum     sweep 1  rows x',y',delta            -> sums[4]
+//   k_extent       sweep 2  6 rows + q                  -> emax[6], esum[4]
+//   k_deposit      sweep 3  6 rows + q                  -> rho (NGP, fp64 RED)
+//   k_green_table / k_green_mirror                      -> K on the padded grid
+//   cuFFT D2Z x2, k_multiply, cuFFT Z2D                 -> convolution
+//   k_crop_phi, k_field                                 -> phi, Ex/Ey/Ez
+//   k_gather_kick  sweep 4  6 rows in, 6 rows out       -> kicked particles
+//
+// No kernel needs a host round trip: the scalar state (frame, mesh) is
+// re-derived on the device by every block from the tiny reduced buffers, which
+// is also what lets a multi-GPU caller all-reduce those buffers in between.
+#include "sc_kernels.h"
+
+namespace ocl {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+int particle_grid(long long n, int max_blocks) {
+    long long b = (n + kThreads - 1) / kThreads;
+    if (b < 1) b = 1;
+    if (b > max_blocks) b = max_blocks;
+    return (int)b;
+}
+
+// ---------------------------------------------------------------------------
+// reductions: first NMAX slots reduce with max, the rest with +
+// ---------------------------------------------------------------------------
+template <int NV, int NMAX>
+__device__ __forceinline__ void block_reduce(double (&v)[NV], double* sh /* [NV*kWarps] */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        v[k] = (k < NMAX) ? warp_reduce(v[k], OpMax()) : warp_reduce(v[k], OpSum());
+        if (lane == 0) sh[k * kWarps + warp] = v[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double ident = (k < NMAX) ? -INFINITY : 0.0;
+            double x = (lane < kWarps) ? sh[k * kWarps + lane] : ident;
+            v[k] = (k < NMAX) ? warp_reduce(x, OpMax()) : warp_reduce(x, OpSum());
+        }
+    }
+    __syncthreads();
+}
+
+// every block stores its partial; the block that draws the last ticket folds
+// all partials in a fixed order and writes the result (deterministic for a
+// fixed grid).  Returns true in the finishing block (v valid in thread 0).
+template <int NV, int NMAX>
+__device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* part, unsigned int* ticket, double* sh) {
+    __shared__ bool last;
+    block_reduce<NV, NMAX>(v, sh);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) part[(size_t)blockIdx.x * NV + k] = v[k];
+        __threadfence();
+        unsigned int t = atomicAdd(ticket, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return false;
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = (k < NMAX) ? -INFINITY : 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += kThreads) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double x = __ldcg(part + (size_t)b * NV + k);
+            v[k] = (k < NMAX) ? fmax(v[k], x) : v[k] + x;
+        }
+    }
+    block_reduce<NV, NMAX>(v, sh);
+    if (threadIdx.x == 0) *ticket = 0;
+    return true;
+}
+
+// ---------------------------------------------------------------------------
+// sweep 1: mean momentum (sc.py:221,224)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_momentum(const double* __restrict__ r, long long ld, long long n,
+                                                      RefParams rp, ReduceState rs) {
+    __shared__ double sh[3 * kWarps];
+    double v[3] = {0.0, 0.0, 0.0};
+    const double* xs = r + ld;
+    const double* ys = r + 3 * ld;
+    const double* dl = r + 5 * ld;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+        double px, py, pz;
+        mad_to_cart_momentum(rp, xs[i], ys[i], dl[i], px, py, pz);
+        v[0] += px; v[1] += py; v[2] += pz;
+    }
+    if (grid_reduce<3, 0>(v, rs.part, rs.ticket + 0, sh) && threadIdx.x == 0) {
+        rs.sums[0] = v[0]; rs.sums[1] = v[1]; rs.sums[2] = v[2];
+        rs.sums[3] = (double)n;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// sweep 2: extents and charge centroid in the bunch frame (sc.py:172-173,181-182)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_extent(const double* __restrict__ r, long long ld,
+                                                    const double* __restrict__ q, long long n, RefParams rp,
+                                                    ReduceState rs) {
+    __shared__ double sh[10 * kWarps];
+    __shared__ Frame sf;
+    if (threadIdx.x == 0) derive_frame(rs.sums, rp.m_e_eV, sf);
+    __syncthreads();
+    const Frame f = sf;
+    double v[10] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, 0.0, 0.0, 0.0, 0.0};
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+        Cart c = mad_to_cart(rp, r[i], r[ld + i], r[2 * ld + i], r[3 * ld + i], r[4 * ld + i], r[5 * ld + i]);
+        double a, b, g;
+        rotate_stretch(f, c.x, c.y, c.z, a, b, g);
+        double qi = q[i];
+        v[0] = fmax(v[0], a); v[1] = fmax(v[1], b); v[2] = fmax(v[2], g);
+        v[3] = fmax(v[3], -a); v[4] = fmax(v[4], -b); v[5] = fmax(v[5], -g);
+        v[6] += qi * a; v[7] += qi * b; v[8] += qi * g; v[9] += qi;
+    }
+    if (grid_reduce<10, 6>(v, rs.part, rs.ticket + 1, sh) && threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) rs.emax[k] = v[k];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) rs.esum[k] = v[6 + k];
+    }
+}
+
+// ---------------------------------------------------------------------------
+// sweep 3: nearest-grid-point deposit (sc.py:186-193)
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) k_deposit(const double* __restrict__ r, long long ld,
+                                                     const double* __restrict__ q, long long n, RefParams rp,
+                                                     ReduceState rs, MeshDims md, Draws dr, double* __restrict__ rho) {
+    __shared__ Frame sf;
+    __shared__ Mesh sm;
+    if (threadIdx.x == 0) {
+        derive_frame(rs.sums, rp.m_e_eV, sf);
+        derive_mesh(rs.emax, rs.esum, md.nx, md.ny, md.nz, dr.scale, dr.shift, sm);
+        if (blockIdx.x == 0) {  // geometry tap
+            double* g = rs.geom;
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) g[i * 3 + j] = sf.T[i][j];
+            g[9] = sf.pav; g[10] = sf.gamma0; g[11] = sf.beta0;
+            for (int c = 0; c < 3; ++c) { g[12 + c] = sm.steps[c]; g[15 + c] = sm.xoff[c]; }
+            g[18] = sm.sumq; g[19] = rs.sums[3];
+        }
+    }
+    __syncthreads();
+    const Frame f = sf;
+    const Mesh m = sm;
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+        Cart c = mad_to_cart(rp, r[i], r[ld + i], r[2 * ld + i], r[3 * ld + i], r[4 * ld + i], r[5 * ld + i]);
+        double a, b, g, g0, g1, g2;
+        rotate_stretch(f, c.x, c.y, c.z, a, b, g);
+        to_grid(m, a, b, g, g0, g1, g2);
+        int i0 = (int)floor(g0) + 1, i1 = (int)floor(g1) + 1, i2 = (int)floor(g2) + 1;   // sc.py:191
+        if ((unsigned)i0 < (unsigned)md.nx && (unsigned)i1 < (unsigned)md.ny && (unsigned)i2 < (unsigned)md.nz)
+            atomicAdd(rho + ((size_t)i0 * md.ny + i1) * md.nz + i2, q[i]);               // sc.py:192-193
+    }
+}
+
+// ---------------------------------------------------------------------------
+// integrated Green's function (sc.py:109-133)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ double igf_antiderivative(double x, double y, double z) {
+    double rr = sqrt(x * x + y * y + z * z);
+    double g = -x * x * 0.5 * atan(y * z / (x * rr));
+    g = g + y * z * log(x + rr);
+    g = g - y * y * 0.5 * atan(z * x / (y * rr));
+    g = g + z * x * log(y + rr);
+    g = g - z * z * 0.5 * atan(x * y / (z * rr));
+    g = g + x * y * log(z + rr);
+    return g;
+}
+
+struct StepSrc {
+    int given;       // 1: use h[]; 0: derive from the reduced extents
+    double h[3];
+};
+
+__device__ __forceinline__ void resolve_steps(const StepSrc& src, const ReduceState& rs, const MeshDims& md,
+                                              const Draws& dr, double* h /* shared [3] */) {
+    if (threadIdx.x == 0) {
+        if (src.given) {
+            h[0] = src.h[0]; h[1] = src.h[1]; h[2] = src.h[2];
+        } else {
+            Mesh m;
+            derive_mesh(rs.emax, rs.esum, md.nx, md.ny, md.nz, dr.scale, dr.shift, m);
+            h[0] = m.steps[0]; h[1] = m.steps[1]; h[2] = m.steps[2];
+        }
+    }
+    __syncthreads();
+}
+
+// antiderivative on the (n+1)^3 half-offset points (sc.py:116-126)
+__global__ void __launch_bounds__(kThreads) k_green_table(StepSrc src, ReduceState rs, MeshDims md, Draws dr,
+                                                         double* __restrict__ gtab) {
+    __shared__ double h[3];
+    resolve_steps(src, rs, md, dr, h);
+    const int gx = md.nx + 1, gy = md.ny + 1, gz = md.nz + 1;
+    const long long total = (long long)gx * gy * gz;
+    for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total; t += (long long)gridDim.x * kThreads) {
+        int k = (int)(t % gz);
+        long long u = t / gz;
+        int j = (int)(u % gy);
+        int i = (int)(u / gy);
+        double x = h[0] * (double)i - h[0] / 2;
+        double y = h[1] * (double)j - h[1] / 2;
+        double z = h[2] * (double)k - h[2] / 2;
+        gtab[t] = igf_antiderivative(x, y, z);
+    }
+}
+
+// 8-corner difference (sc.py:128-131)
+__device__ __forceinline__ double green_entry(const double* __restrict__ G, int gy, int gz, int i, int j, int k) {
+    const size_t sx = (size_t)gy * gz, sy = gz;
+    const double* lo = G + (size_t)i * sx + (size_t)j * sy + k;
+    double v = __ldg(lo + sx + sy + 1) - __ldg(lo + sy + 1);
+    v = v - __ldg(lo + sx + 1);
+    v = v + __ldg(lo + 1);
+    v = v - __ldg(lo + sx + sy);
+    v = v + __ldg(lo + sy);
+    v = v + __ldg(lo + sx);
+    v = v - __ldg(lo);
+    return v;
+}
+
+// K on the padded periodic grid: K[d mod M] = K1[|d|], zero in the gap (sc.py:145-149)
+__global__ void __launch_bounds__(kThreads) k_green_mirror(const double* __restrict__ gtab, MeshDims md,
+                                                          double* __restrict__ kpad) {
+    const long long total = (long long)md.mx * md.my * md.mz;
+    const int gy = md.ny + 1, gz = md.nz + 1;
+    for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total; t += (long long)gridDim.x * kThreads) {
+        int c = (int)(t % md.mz);
+        long long u = t / md.mz;
+        int b = (int)(u % md.my);
+        int a = (int)(u / md.my);
+        int da = a < md.nx ? a : (a > md.mx - md.nx ? md.mx - a : -1);
+        int db = b < md.ny ? b : (b > md.my - md.ny ? md.my - b : -1);
+        int dc = c < md.nz ? c : (c > md.mz - md.nz ? md.mz - c : -1);
+        double v = 0.0;
+        if (da >= 0 && db >= 0 && dc >= 0) v = green_entry(gtab, gy, gz, da, db, dc);
+        kpad[t] = v;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_green_compact(const double* __restrict__ gtab, MeshDims md,
+                                                           double* __restrict__ k1) {
+    const long long total = (long long)md.nx * md.ny * md.nz;
+    for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total; t += (long long)gridDim.x * kThreads) {
+        int c = (int)(t % md.nz);
+        long long u = t / md.nz;
+        int b = (int)(u % md.ny);
+        int a = (int)(u / md.ny);
+        k1[t] = green_entry(gtab, md.ny + 1, md.nz + 1, a, b, c);
+    }
+}
+
+// zero-padded copy of rho (sc.py:142-143)
+__global__ void __launch_bounds__(kThreads) k_pad_rho(const double* __restrict__ rho, MeshDims md,
+                                                     double* __restrict__ pad) {
+    const long long total = (long long)md.mx * md.my * md.mz;
+    for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total; t += (long long)gridDim.x * kThreads) {
+        int c = (int)(t % md.mz);
+        long long u = t / md.mz;
+        int b = (int)(u % md.my);
+        int a = (int)(u / md.my);
+        double v = 0.0;
+        if (a < md.nx && b < md.ny && c < md.nz) v = __ldg(rho + ((size_t)a * md.ny + b) * md.nz + c);
+        pad[t] = v;
+    }
+}
+
+// rho_hat *= K_hat, then the inverse transform's 1/M^3 (sc.py:164)
+__global__ void __launch_bounds__(kThreads) k_multiply(cufftDoubleComplex* __restrict__ rho_hat,
+                                                      const cufftDoubleComplex* __restrict__ k_hat, long long total,
+                                                      double inv_m3) {
+    for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total; t += (long long)gridDim.x * kThreads) {
+        cufftDoubleComplex a = rho_hat[t], b = k_hat[t];
+        cufftDoubleComplex o;
+        o.x = (a.x * b.x - a.y * b.y) * inv_m3;
+        o.y = (a.x * b.y + a.y * b.x) * inv_m3;
+        rho_hat[t] = o;
+    }
+}
+
+// phi = conv[:n,:n,:n] / (4 pi eps0 hx hy hz)  (sc.py:167-168)
+__global__ void __launch_bounds__(kThreads) k_crop_phi(const double* __restrict__ conv, StepSrc src, ReduceState rs,
+                                                      MeshDims md, Draws dr, double four_pi_eps0,
+                                                      double* __restrict__ phi) {
+    __shared__ double h[3];
+    resolve_steps(src, rs, md, dr, h);
+    const double denom = four_pi_eps0 * h[0] * h[1] * h[2];
+    const long long total = (long long)md.nx * md.ny * md.nz;
+    for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total; t += (long long)gridDim.x * kThreads) {
+        int c = (int)(t % md.nz);
+        long long u = t / md.nz;
+        int b = (int)(u % md.ny);
+        int a = (int)(u / md.ny);
+        phi[t] = __ldg(conv + ((size_t)a * md.my + b) * md.mz + c) / denom;
+    }
+}
+
+// staggered backward differences, last plane zero (sc.py:195-200)
+__global__ void __launch_bounds__(kThreads) k_field(const double* __restrict__ phi, StepSrc src, ReduceState rs,
+                                                   MeshDims md, Draws dr, double* __restrict__ ex,
+                                                   double* __restrict__ ey, double* __restrict__ ez) {
+    __shared__ double h[3];
+    resolve_steps(src, rs, md, dr, h);
+    const long long total = (long long)md.nx * md.ny * md.nz;
+    const size_t sx = (size_t)md.ny * md.nz, sy = md.nz;
+    for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total; t += (long long)gridDim.x * kThreads) {
+        int c = (int)(t % md.nz);
+        long long u = t / md.nz;
+        int b = (int)(u % md.ny);
+        int a = (int)(u / md.ny);
+        double p = phi[t];
+        ex[t] = (a < md.nx - 1) ? (p - __ldg(phi + t + sx)) / h[0] : 0.0;
+        ey[t] = (b < md.ny - 1) ? (p - __ldg(phi + t + sy)) / h[1] : 0.0;
+        ez[t] = (c < md.nz - 1) ? (p - __ldg(phi + t + 1)) / h[2] : 0.0;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// sweep 4: gather, kick, back-transform (sc.py:201-204, :244-251)
+// ---------------------------------------------------------------------------
+template <bool KICK, bool TAP>
+__global__ void __launch_bounds__(kThreads) k_gather_kick(double* __restrict__ r, long long ld, long long n,
+                                                         RefParams rp, ReduceState rs, MeshDims md, Draws dr,
+                                                         const double* __restrict__ ex, const double* __restrict__ ey,
+                                                         const double* __restrict__ ez, double cdT,
+                                                         double* __restrict__ exyz_out) {
+    __shared__ Frame sf;
+    __shared__ Mesh sm;
+    if (threadIdx.x == 0) {
+        derive_frame(rs.sums, rp.m_e_eV, sf);
+        derive_mesh(rs.emax, rs.esum, md.nx, md.ny, md.nz, dr.scale, dr.shift, sm);
+    }
+    __syncthreads();
+    const Frame f = sf;
+    const Mesh m = sm;
+    const double kt = cdT * (1.0 - f.beta0 * f.beta0);   // sc.py:246-247
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+        Cart c = mad_to_cart(rp, r[i], r[ld + i], r[2 * ld + i], r[3 * ld + i], r[4 * ld + i], r[5 * ld + i]);
+        double a, b, g, g0, g1, g2;
+        rotate_stretch(f, c.x, c.y, c.z, a, b, g);
+        to_grid(m, a, b, g, g0, g1, g2);
+        double e0 = trilinear(ex, md.nx, md.ny, md.nz, g0, g1 + 0.5, g2 + 0.5) * f.gamma0;   // :202
+        double e1 = trilinear(ey, md.nx, md.ny, md.nz, g0 + 0.5, g1, g2 + 0.5) * f.gamma0;   // :203
+        double e2 = trilinear(ez, md.nx, md.ny, md.nz, g0 + 0.5, g1 + 0.5, g2);              // :204
+        if (TAP) {
+            exyz_out[3 * i + 0] = e0; exyz_out[3 * i + 1] = e1; exyz_out[3 * i + 2] = e2;
+        }
+        if (KICK) {
+            // momenta into the bunch frame (sc.py:234)
+            double p0 = c.px * f.T[0][0] + c.py * f.T[1][0] + c.pz * f.T[2][0];
+            double p1 = c.px * f.T[0][1] + c.py * f.T[1][1] + c.pz * f.T[2][1];
+            double p2 = c.px * f.T[0][2] + c.py * f.T[1][2] + c.pz * f.T[2][2];
+            p0 = p0 + kt * e0;                                                             // :246
+            p1 = p1 + kt * e1;                                                             // :247
+            p2 = p2 + cdT * e2;                                                            // :248
+            // back to the lab axes (sc.py:249-250)
+            c.px = p0 * f.T[0][0] + p1 * f.T[0][1] + p2 * f.T[0][2];
+            c.py = p0 * f.T[1][0] + p1 * f.T[1][1] + p2 * f.T[1][2];
+            c.pz = p0 * f.T[2][0] + p1 * f.T[2][1] + p2 * f.T[2][2];
+            double x, xs, y, ys, tau, delta;
+            cart_to_mad(rp, c, x, xs, y, ys, tau, delta);                                  // :251
+            r[i] = x; r[ld + i] = xs; r[2 * ld + i] = y; r[3 * ld + i] = ys; r[4 * ld + i] = tau;
+            r[5 * ld + i] = delta;
+        }
+    }
+}
+
+// stand-alone transforms (known-answer tests)
+__global__ void __launch_bounds__(kThreads) k_mad_to_cart(const double* __restrict__ r, long long ld, long long n,
+                                                         RefParams rp, double* __restrict__ xp, long long lx) {
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+        Cart c = mad_to_cart(rp, r[i], r[ld + i], r[2 * ld + i], r[3 * ld + i], r[4 * ld + i], r[5 * ld + i]);
+        xp[i] = c.x; xp[lx + i] = c.y; xp[2 * lx + i] = c.z;
+        xp[3 * lx + i] = c.px; xp[4 * lx + i] = c.py; xp[5 * lx + i] = c.pz;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) k_cart_to_mad(const double* __restrict__ xp, long long lx, long long n,
+                                                         RefParams rp, double* __restrict__ r, long long ld) {
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
+        Cart c;
+        c.x = xp[i]; c.y = xp[lx + i]; c.z = xp[2 * lx + i];
+        c.px = xp[3 * lx + i]; c.py = xp[4 * lx + i]; c.pz = xp[5 * lx + i];
+        double x, xs, y, ys, tau, delta;
+        cart_to_mad(rp, c, x, xs, y, ys, tau, delta);
+        r[i] = x; r[ld + i] = xs; r[2 * ld + i] = y; r[3 * ld + i] = ys; r[4 * ld + i] = tau; r[5 * ld + i] = delta;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// launch wrappers
+// ---------------------------------------------------------------------------
+static inline int grid_for(long long total, int cap) {
+    long long b = (total + kThreads - 1) / kThreads;
+    if (b < 1) b = 1;
+    if (b > cap) b = cap;
+    return (int)b;
+}
+constexpr int kSweepCap = 148 * 8;    // grid-stride particle sweeps without reduction
+constexpr int kGridCap = 148 * 16;    // grid kernels
+
+void launch_momentum(const double* r, long long ld, long long n, RefParams rp, ReduceState rs, cudaStream_t st) {
+    k_momentum<<<particle_grid(n, rs.max_blocks), kThreads, 0, st>>>(r, ld, n, rp, rs);
+}
+void launch_extent(const double* r, long long ld, const double* q, long long n, RefParams rp, ReduceState rs,
+                   cudaStream_t st) {
+    k_extent<<<particle_grid(n, rs.max_blocks), kThreads, 0, st>>>(r, ld, q, n, rp, rs);
+}
+void launch_deposit(const double* r, long long ld, const double* q, long long n, RefParams rp, ReduceState rs,
+                    MeshDims md, Draws dr, double* rho, cudaStream_t st) {
+    k_deposit<<<grid_for(n, kSweepCap), kThreads, 0, st>>>(r, ld, q, n, rp, rs, md, dr, rho);
+}
+void launch_green_table(ReduceState rs, MeshDims md, Draws dr, double* gtab, cudaStream_t st) {
+    StepSrc src;
+    src.given = 0; src.h[0] = src.h[1] = src.h[2] = 0.0;
+    long long total = (long long)(md.nx + 1) * (md.ny + 1) * (md.nz + 1);
+    k_green_table<<<grid_for(total, kGridCap), kThreads, 0, st>>>(src, rs, md, dr, gtab);
+}
+void launch_green_table_steps(const double steps[3], MeshDims md, double* gtab, cudaStream_t st) {
+    StepSrc src;
+    src.given = 1; src.h[0] = steps[0]; src.h[1] = steps[1]; src.h[2] = steps[2];
+    ReduceState rs = {};
+    Draws dr = {0.0, 0.0};
+    long long total = (long long)(md.nx + 1) * (md.ny + 1) * (md.nz + 1);
+    k_green_table<<<grid_for(total, kGridCap), kThreads, 0, st>>>(src, rs, md, dr, gtab);
+}
+void launch_green_mirror(const double* gtab, MeshDims md, double* kpad, cudaStream_t st) {
+    long long total = (long long)md.mx * md.my * md.mz;
+    k_green_mirror<<<grid_for(total, kGridCap), kThreads, 0, st>>>(gtab, md, kpad);
+}
+void launch_green_compact(const double* gtab, MeshDims md, double* k1, cudaStream_t st) {
+    long long total = (long long)md.nx * md.ny * md.nz;
+    k_green_compact<<<grid_for(total, kGridCap), kThreads, 0, st>>>(gtab, md, k1);
+}
+void launch_pad_rho(const double* rho, MeshDims md, double* pad, cudaStream_t st) {
+    long long total = (long long)md.mx * md.my * md.mz;
+    k_pad_rho<<<grid_for(total, kGridCap), kThreads, 0, st>>>(rho, md, pad);
+}
+void launch_multiply(cufftDoubleComplex* rho_hat, const cufftDoubleComplex* k_hat, MeshDims md, cudaStream_t st) {
+    long long total = (long long)md.mx * md.my * (md.mz / 2 + 1);
+    double inv = 1.0 / ((double)md.mx * (double)md.my * (double)md.mz);
+    k_multiply<<<grid_for(total, kGridCap), kThreads, 0, st>>>(rho_hat, k_hat, total, inv);
+}
+static double four_pi_eps0() {
+    const double pi = 3.141592653589793, c = 299792458.0;   // ocelot/common/globals.py:13-24
+    const double mu0 = 4 * pi * 1e-7;
+    const double eps0 = 1 / mu0 / (c * c);
+    return 4 * pi * eps0;
+}
+void launch_crop_phi(const double* conv, ReduceState rs, MeshDims md, Draws dr, double* phi, cudaStream_t st) {
+    StepSrc src;
+    src.given = 0; src.h[0] = src.h[1] = src.h[2] = 0.0;
+    long long total = (long long)md.nx * md.ny * md.nz;
+    k_crop_phi<<<grid_for(total, kGridCap), kThreads, 0, st>>>(conv, src, rs, md, dr, four_pi_eps0(), phi);
+}
+void launch_crop_phi_steps(const double* conv, const double steps[3], MeshDims md, double* phi, cudaStream_t st) {
+    StepSrc src;
+    src.given = 1; src.h[0] = steps[0]; src.h[1] = steps[1]; src.h[2] = steps[2];
+    ReduceState rs = {};
+    Draws dr = {0.0, 0.0};
+    long long total = (long long)md.nx * md.ny * md.nz;
+    k_crop_phi<<<grid_for(total, kGridCap), kThreads, 0, st>>>(conv, src, rs, md, dr, four_pi_eps0(), phi);
+}
+void launch_field(const double* phi, ReduceState rs, MeshDims md, Draws dr, double* ex, double* ey, double* ez,
+                  cudaStream_t st) {
+    StepSrc src;
+    src.given = 0; src.h[0] = src.h[1] = src.h[2] = 0.0;
+    long long total = (long long)md.nx * md.ny * md.nz;
+    k_field<<<grid_for(total, kGridCap), kThreads, 0, st>>>(phi, src, rs, md, dr, ex, ey, ez);
+}
+void launch_gather_kick(double* r, long long ld, long long n, RefParams rp, ReduceState rs, MeshDims md, Draws dr,
+                        const double* ex, const double* ey, const double* ez, double dz, double* exyz_out,
+                        int do_kick, cudaStream_t st) {
+    const double cdT = dz / rp.betaref;   // sc.py:244
+    int grid = grid_for(n, kSweepCap);
+    if (do_kick && exyz_out)
+        k_gather_kick<true, true><<<grid, kThreads, 0, st>>>(r, ld, n, rp, rs, md, dr, ex, ey, ez, cdT, exyz_out);
+    else if (do_kick)
+        k_gather_kick<true, false><<<grid, kThreads, 0, st>>>(r, ld, n, rp, rs, md, dr, ex, ey, ez, cdT, nullptr);
+    else
+        k_gather_kick<false, true><<<grid, kThreads, 0, st>>>(r, ld, n, rp, rs, md, dr, ex, ey, ez, cdT, exyz_out);
+}
+void launch_mad_to_cart(const double* r, long long ld, long long n, RefParams rp, double* xp, long long ld_xp,
+                        cudaStream_t st) {
+    k_mad_to_cart<<<grid_for(n, kSweepCap), kThreads, 0, st>>>(r, ld, n, rp, xp, ld_xp);
+}
+void launch_cart_to_mad(const double* xp, long long ld_xp, long long n, RefParams rp, double* r, long long ld,
+                        cudaStream_t st) {
+    k_cart_to_mad<<<grid_for(n, kSweepCap), kThreads, 0, st>>>(xp, ld_xp, n, rp, r, ld);
+}
+
+}  // namespace ocl

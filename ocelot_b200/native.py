@@ -1,0 +1,289 @@
+"""ctypes binding of the C-ABI library (include/ocelot_sc.h).
+
+The library is the product: there is no Python or CPU fallback.  If
+``libocelot_sc.so`` is absent it is built once with nvcc; if that is impossible,
+or if no CUDA device is present when a solver is created, a ``RuntimeError`` is
+raised.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libocelot_sc.so")
+HEADER = os.path.join(os.path.dirname(_HERE), "include", "ocelot_sc.h")
+
+BUF_MOMENTUM, BUF_EXTENT_MAX, BUF_EXTENT_SUM, BUF_RHO = 0, 1, 2, 3
+
+_lib = None
+
+_dp = C.POINTER(C.c_double)
+_vp = C.c_void_p
+_ll = C.c_longlong
+
+_SIGNATURES = {
+    "ocl_sc_abi_version": (C.c_int, []),
+    "ocl_sc_get_constants": (None, [_dp]),
+    "ocl_sc_fft_size": (C.c_int, [C.c_int]),
+    "ocl_sc_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _ll, C.POINTER(_vp)]),
+    "ocl_sc_destroy": (None, [_vp]),
+    "ocl_sc_last_error": (C.c_char_p, [_vp]),
+    "ocl_sc_kick_device": (C.c_int, [_vp, _vp, _ll, _vp, _ll, C.c_double, C.c_double, _dp, _vp]),
+    "ocl_sc_kick_host": (C.c_int, [_vp, _vp, _ll, _vp, _ll, C.c_double, C.c_double, _dp]),
+    "ocl_sc_collective_buffer": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_ll)]),
+    "ocl_sc_stage_momentum": (C.c_int, [_vp, _vp, _ll, _ll, C.c_double, _vp]),
+    "ocl_sc_stage_extent": (C.c_int, [_vp, _vp, _ll, _vp, _ll, C.c_double, _vp]),
+    "ocl_sc_stage_deposit": (C.c_int, [_vp, _vp, _ll, _vp, _ll, C.c_double, _dp, _vp]),
+    "ocl_sc_stage_solve": (C.c_int, [_vp, _dp, _vp]),
+    "ocl_sc_stage_kick": (C.c_int, [_vp, _vp, _ll, _ll, C.c_double, C.c_double, _dp, _vp]),
+    "ocl_sc_get_geometry": (C.c_int, [_vp, _dp]),
+    "ocl_sc_get_rho": (C.c_int, [_vp, _vp]),
+    "ocl_sc_get_phi": (C.c_int, [_vp, _vp]),
+    "ocl_sc_get_green": (C.c_int, [_vp, _vp]),
+    "ocl_sc_field_at_particles": (C.c_int, [_vp, _vp, _ll, _vp, _ll, C.c_double, _dp, _vp, _vp]),
+    "ocl_sc_mad_to_cartesian": (C.c_int, [_vp, _vp, _ll, _ll, C.c_double, _vp, _ll, _vp]),
+    "ocl_sc_cartesian_to_mad": (C.c_int, [_vp, _vp, _ll, _ll, C.c_double, _vp, _ll, _vp]),
+    "ocl_sc_potential_host": (C.c_int, [_vp, _vp, _dp, _vp]),
+    "ocl_sc_enable_timers": (C.c_int, [_vp, C.c_int]),
+    "ocl_sc_get_timers": (C.c_int, [_vp, _dp]),
+    "ocl_sc_launch_count": (_ll, [_vp]),
+}
+
+
+def declared_symbols() -> list[str]:
+    """Names of the functions include/ocelot_sc.h declares."""
+    with open(HEADER) as f:
+        text = f.read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ocl_sc_[a-z_0-9]+)\s*\(", text)))
+
+
+def load():
+    """Load (building if needed) the native library; raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        try:
+            _build.build()
+        except Exception as exc:  # noqa: BLE001
+            raise RuntimeError(
+                f"ocelot_b200: native library {LIB_PATH} is missing and could not be built ({exc}). "
+                "There is no CPU fallback for the space-charge kick.") from exc
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def constants() -> dict:
+    out = (C.c_double * 5)()
+    load().ocl_sc_get_constants(out)
+    return dict(m_e_eV=out[0], m_e_GeV=out[1], epsilon_0=out[2], pi=out[3], speed_of_light=out[4])
+
+
+def fft_size(n: int) -> int:
+    return int(load().ocl_sc_fft_size(int(n)))
+
+
+def _draws(mesh_draws):
+    if mesh_draws is None:
+        return None
+    arr = (C.c_double * 2)(float(mesh_draws[0]), float(mesh_draws[1]))
+    return arr
+
+
+def _stream_ptr(stream):
+    if stream is None:
+        import torch
+        return torch.cuda.current_stream().cuda_stream
+    if hasattr(stream, "cuda_stream"):
+        return stream.cuda_stream
+    return int(stream)
+
+
+class Solver:
+    """One native solver handle = one device + one mesh size."""
+
+    def __init__(self, device: int, nmesh_xyz, max_particles: int = 0):
+        self._lib = load()
+        self.device = int(device)
+        self.nmesh = tuple(int(v) for v in nmesh_xyz)
+        if len(self.nmesh) != 3:
+            raise ValueError("nmesh_xyz must have three entries")
+        h = _vp()
+        rc = self._lib.ocl_sc_create(self.device, *self.nmesh, int(max_particles), C.byref(h))
+        if rc != 0:
+            raise RuntimeError("ocl_sc_create failed: " + self._lib.ocl_sc_last_error(None).decode())
+        self._h = h
+
+    # -- lifetime -----------------------------------------------------------
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.ocl_sc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed: " + self._lib.ocl_sc_last_error(self._h).decode())
+
+    # -- kicks --------------------------------------------------------------
+    @staticmethod
+    def _dev_rows(r, q=None):
+        """(ptr, ld, n) of a torch CUDA fp64 tensor of shape (6, n) with contiguous rows."""
+        import torch
+        if not (isinstance(r, torch.Tensor) and r.is_cuda and r.dtype == torch.float64 and r.dim() == 2
+                and r.shape[0] == 6 and r.stride(1) == 1):
+            raise TypeError("rparticles must be a CUDA float64 tensor of shape (6, n) with unit column stride")
+        n = r.shape[1]
+        if q is not None:
+            if not (q.is_cuda and q.dtype == torch.float64 and q.dim() == 1 and q.shape[0] == n and q.stride(0) == 1):
+                raise TypeError("q_array must be a contiguous CUDA float64 tensor of length n")
+        return r.data_ptr(), (r.stride(0) if n > 0 else 0), n
+
+    def kick_device(self, r, q, E_GeV, dz, mesh_draws=None, stream=None):
+        ptr, ld, n = self._dev_rows(r, q)
+        self._check(self._lib.ocl_sc_kick_device(self._h, ptr, ld, q.data_ptr(), n, float(E_GeV), float(dz),
+                                                 _draws(mesh_draws), _stream_ptr(stream)), "ocl_sc_kick_device")
+
+    def kick_host(self, r: np.ndarray, q: np.ndarray, E_GeV, dz, mesh_draws=None):
+        if not (isinstance(r, np.ndarray) and r.dtype == np.float64 and r.ndim == 2 and r.shape[0] == 6
+                and r.strides[1] == 8 and r.flags.writeable):
+            raise TypeError("rparticles must be a writable float64 array of shape (6, n) with contiguous rows")
+        n = r.shape[1]
+        q = np.ascontiguousarray(q, dtype=np.float64)
+        if q.shape != (n,):
+            raise ValueError("q_array must have one charge per particle")
+        ld = r.strides[0] // 8 if n > 0 else 0
+        self._check(self._lib.ocl_sc_kick_host(self._h, r.ctypes.data, ld, q.ctypes.data, n, float(E_GeV), float(dz),
+                                               _draws(mesh_draws)), "ocl_sc_kick_host")
+
+    # -- stages (sharded operation) ----------------------------------------
+    def collective_buffer(self, which: int):
+        """torch view (no copy) of one of the handle's small reduction buffers."""
+        import torch
+        ptr, cnt = _vp(), _ll()
+        self._check(self._lib.ocl_sc_collective_buffer(self._h, which, C.byref(ptr), C.byref(cnt)),
+                    "ocl_sc_collective_buffer")
+        return _wrap_device_doubles(ptr.value, cnt.value, self.device)
+
+    def stage_momentum(self, r, E_GeV, stream=None):
+        ptr, ld, n = self._dev_rows(r)
+        self._check(self._lib.ocl_sc_stage_momentum(self._h, ptr, ld, n, float(E_GeV), _stream_ptr(stream)),
+                    "ocl_sc_stage_momentum")
+
+    def stage_extent(self, r, q, E_GeV, stream=None):
+        ptr, ld, n = self._dev_rows(r, q)
+        self._check(self._lib.ocl_sc_stage_extent(self._h, ptr, ld, q.data_ptr(), n, float(E_GeV),
+                                                  _stream_ptr(stream)), "ocl_sc_stage_extent")
+
+    def stage_deposit(self, r, q, E_GeV, mesh_draws=None, stream=None):
+        ptr, ld, n = self._dev_rows(r, q)
+        self._check(self._lib.ocl_sc_stage_deposit(self._h, ptr, ld, q.data_ptr(), n, float(E_GeV),
+                                                   _draws(mesh_draws), _stream_ptr(stream)), "ocl_sc_stage_deposit")
+
+    def stage_solve(self, mesh_draws=None, stream=None):
+        self._check(self._lib.ocl_sc_stage_solve(self._h, _draws(mesh_draws), _stream_ptr(stream)),
+                    "ocl_sc_stage_solve")
+
+    def stage_kick(self, r, E_GeV, dz, mesh_draws=None, stream=None):
+        ptr, ld, n = self._dev_rows(r)
+        self._check(self._lib.ocl_sc_stage_kick(self._h, ptr, ld, n, float(E_GeV), float(dz), _draws(mesh_draws),
+                                                _stream_ptr(stream)), "ocl_sc_stage_kick")
+
+    # -- taps -----------------------------------------------------------------
+    def geometry(self) -> dict:
+        out = (C.c_double * 24)()
+        self._check(self._lib.ocl_sc_get_geometry(self._h, out), "ocl_sc_get_geometry")
+        a = np.array(out[:])
+        return dict(T=a[:9].reshape(3, 3), pav=a[9], gamma0=a[10], beta0=a[11], steps=a[12:15], X_off=a[15:18],
+                    sum_q=a[18], count=a[19])
+
+    def _grid(self, fn, what):
+        out = np.empty(self.nmesh, dtype=np.float64)
+        self._check(fn(self._h, out.ctypes.data), what)
+        return out
+
+    def rho(self):
+        return self._grid(self._lib.ocl_sc_get_rho, "ocl_sc_get_rho")
+
+    def phi(self):
+        return self._grid(self._lib.ocl_sc_get_phi, "ocl_sc_get_phi")
+
+    def green(self):
+        return self._grid(self._lib.ocl_sc_get_green, "ocl_sc_get_green")
+
+    def field_at_particles(self, r, q, E_GeV, mesh_draws=None, stream=None):
+        import torch
+        ptr, ld, n = self._dev_rows(r, q)
+        out = torch.empty((n, 3), dtype=torch.float64, device=r.device)
+        self._check(self._lib.ocl_sc_field_at_particles(self._h, ptr, ld, q.data_ptr(), n, float(E_GeV),
+                                                        _draws(mesh_draws), out.data_ptr(), _stream_ptr(stream)),
+                    "ocl_sc_field_at_particles")
+        return out
+
+    def mad_to_cartesian(self, r, E_GeV, stream=None):
+        import torch
+        ptr, ld, n = self._dev_rows(r)
+        xp = torch.empty((6, n), dtype=torch.float64, device=r.device)
+        self._check(self._lib.ocl_sc_mad_to_cartesian(self._h, ptr, ld, n, float(E_GeV), xp.data_ptr(), n,
+                                                      _stream_ptr(stream)), "ocl_sc_mad_to_cartesian")
+        return xp
+
+    def cartesian_to_mad(self, xp, E_GeV, stream=None):
+        import torch
+        ptr, ld, n = self._dev_rows(xp)
+        r = torch.empty((6, n), dtype=torch.float64, device=xp.device)
+        self._check(self._lib.ocl_sc_cartesian_to_mad(self._h, ptr, ld, n, float(E_GeV), r.data_ptr(), n,
+                                                      _stream_ptr(stream)), "ocl_sc_cartesian_to_mad")
+        return r
+
+    def potential_host(self, rho: np.ndarray, steps) -> np.ndarray:
+        rho = np.ascontiguousarray(rho, dtype=np.float64)
+        if rho.shape != self.nmesh:
+            raise ValueError(f"rho must have shape {self.nmesh}")
+        st = (C.c_double * 3)(*[float(s) for s in steps])
+        out = np.empty(self.nmesh, dtype=np.float64)
+        self._check(self._lib.ocl_sc_potential_host(self._h, rho.ctypes.data, st, out.ctypes.data),
+                    "ocl_sc_potential_host")
+        return out
+
+    # -- timers ---------------------------------------------------------------
+    def enable_timers(self, on=True):
+        self._check(self._lib.ocl_sc_enable_timers(self._h, 1 if on else 0), "ocl_sc_enable_timers")
+
+    def timers(self) -> dict:
+        out = (C.c_double * 8)()
+        self._check(self._lib.ocl_sc_get_timers(self._h, out), "ocl_sc_get_timers")
+        keys = ("momentum", "extent", "deposit", "solve", "field", "kick", "total")
+        return {k: out[i] for i, k in enumerate(keys)}
+
+    def launch_count(self) -> int:
+        return int(self._lib.ocl_sc_launch_count(self._h))
+
+
+def _wrap_device_doubles(ptr: int, count: int, device: int):
+    """Zero-copy torch tensor over ``count`` doubles at device address ``ptr``."""
+    import torch
+
+    class _Span:
+        pass
+
+    span = _Span()
+    span.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8", "data": (int(ptr), False),
+                                     "version": 2}
+    return torch.as_tensor(span, device=torch.device("cuda", device))

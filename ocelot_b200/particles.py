@@ -1,0 +1,105 @@
+"""Particle containers.
+
+``ParticleArray`` mirrors the data contract of the reference's
+``ocelot.cpbd.beam.particle.ParticleArray`` (particle.py:79-84): ``rparticles``
+(6, n) fp64 C-order = rows [x, x', y, y', tau, delta], ``q_array`` (n,), ``E``
+[GeV], ``s`` [m].  It exists so the package runs where Ocelot is not installed;
+``SpaceCharge.apply`` accepts the reference's own class just the same (duck
+typing on those four attributes).
+
+``DeviceParticleArray`` keeps ``rparticles`` and ``q_array`` resident in HBM as
+torch CUDA tensors between kicks (rows padded to a 128-byte multiple so every
+row start is aligned for vector loads).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+class ParticleArray:
+    """Host container, same fields as particle.py:79-84."""
+
+    def __init__(self, n=0):
+        self.rparticles = np.zeros((6, n))
+        self.q_array = np.zeros(n)
+        self.s = 0.0
+        self.E = 0.0
+
+    @property
+    def n(self):
+        return self.rparticles.shape[1]
+
+    def size(self):
+        return self.rparticles.shape[1]
+
+    def x(self):
+        return self.rparticles[0]
+
+    def px(self):
+        return self.rparticles[1]
+
+    def y(self):
+        return self.rparticles[2]
+
+    def py(self):
+        return self.rparticles[3]
+
+    def tau(self):
+        return self.rparticles[4]
+
+    def p(self):
+        return self.rparticles[5]
+
+
+class DeviceParticleArray:
+    """Device-resident particles: ``rparticles`` is a (6, n) view into a
+    (6, ld) CUDA fp64 buffer, ``q_array`` a (n,) CUDA fp64 tensor."""
+
+    ALIGN = 16  # doubles (128 bytes)
+
+    def __init__(self, n=0, device=None):
+        import torch
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        ld = max(self.ALIGN, (int(n) + self.ALIGN - 1) // self.ALIGN * self.ALIGN)
+        self._buf = torch.zeros((6, ld), dtype=torch.float64, device=self.device)
+        self._q = torch.zeros(ld, dtype=torch.float64, device=self.device)
+        self._n = int(n)
+        self.s = 0.0
+        self.E = 0.0
+
+    @property
+    def n(self):
+        return self._n
+
+    def size(self):
+        return self._n
+
+    @property
+    def rparticles(self):
+        return self._buf[:, :self._n]
+
+    @property
+    def q_array(self):
+        return self._q[:self._n]
+
+    @classmethod
+    def from_host(cls, p_array, device=None):
+        """Copy any object with rparticles/q_array/E/s (e.g. Ocelot's ParticleArray) to the device."""
+        import torch
+        r = np.ascontiguousarray(p_array.rparticles, dtype=np.float64)
+        out = cls(r.shape[1], device=device)
+        out.rparticles.copy_(torch.from_numpy(r))
+        out.q_array.copy_(torch.from_numpy(np.ascontiguousarray(p_array.q_array, dtype=np.float64)))
+        out.E = float(p_array.E)
+        out.s = float(getattr(p_array, "s", 0.0))
+        return out
+
+    def to_host(self, p_array=None):
+        """Copy back into ``p_array`` (in place) or into a new ParticleArray."""
+        if p_array is None:
+            p_array = ParticleArray(self._n)
+        p_array.rparticles[:] = self.rparticles.cpu().numpy()
+        p_array.q_array[:] = self.q_array.cpu().numpy()
+        p_array.E = self.E
+        p_array.s = self.s
+        return p_array

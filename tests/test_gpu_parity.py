@@ -1,0 +1,314 @@
+"""Parity of the CUDA path (through the C ABI) with the reference.
+
+Three kinds of evidence:
+  * golden vectors produced by the unmodified reference (tests/golden/*.npz),
+  * the CPU oracle on the same seeded inputs at sizes it finishes in seconds,
+  * size-independent properties at BASELINE config-2 size (1M particles, 63^3).
+
+Tolerance model: the field at the particles is compared
+per component relative to max|E| (<= 1e-10, the north-star "per-particle kick"
+bound); post-kick coordinates per row relative to the row rms (<= 1e-10);
+cell indices / rho must agree exactly up to fp64 summation order; geometry
+scalars to 1e-14 relative.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import sc_oracle as orc  # noqa: E402  (checker only)
+
+
+@pytest.fixture(scope="module")
+def native():
+    if not torch.cuda.is_available():
+        pytest.fail("gpu-marked test running without a CUDA device")
+    from ocelot_b200 import native as nat
+    nat.load()
+    return nat
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def rel_to_max(a, b):
+    return float(np.max(np.abs(a - b)) / np.max(np.abs(b)))
+
+
+def row_err(r, ref):
+    return max(float(np.max(np.abs(r[k] - ref[k])) / np.std(ref[k])) for k in range(6))
+
+
+def field_err(E, ref):
+    return max(rel_to_max(E[:, c], ref[:, c]) for c in range(3))
+
+
+# ---------------------------------------------------------------------------
+# stage-level known answers
+# ---------------------------------------------------------------------------
+def test_constants_match_reference_bits(native):
+    from ocelot_b200 import constants as c
+    k = native.constants()
+    assert k["m_e_eV"] == orc.M_E_EV == c.m_e_eV
+    assert k["epsilon_0"] == orc.EPS_0 == c.epsilon_0
+
+
+def test_mad_transforms(native, golden):
+    g = golden("kat_small.npz")
+    s = native.Solver(0, g["nmesh"])
+    xp = s.mad_to_cartesian(dev(g["r_in"]), float(g["E"])).cpu().numpy()
+    for k in range(6):
+        assert np.max(np.abs(xp[k] - g["xp"][k])) <= 4e-16 * np.max(np.abs(g["xp"][k])), k
+    # the only non-IEEE step is gamma**-2 (libm pow in numpy): most entries are bit-identical
+    assert np.mean(xp == g["xp"]) > 0.9
+    back = s.cartesian_to_mad(dev(g["xp"]), float(g["E"])).cpu().numpy()
+    for k in range(6):
+        assert np.max(np.abs(back[k] - g["mad_roundtrip"][k])) <= 1e-15 * np.max(np.abs(g["mad_roundtrip"][k])) + 1e-22, k
+
+
+def test_green_and_potential_kat(native, golden):
+    g = golden("kat_poisson.npz")
+    s = native.Solver(0, g["rho"].shape)
+    phi = s.potential_host(g["rho"], g["steps"])
+    assert rel_to_max(phi, g["phi"]) < 1e-12
+    K1 = s.green()
+    # K entries carry the reference's own 1e-9..1e-7 cancellation noise; compare to max|K|
+    assert rel_to_max(K1, g["K1"]) < 1e-10
+    # linearity of the solve
+    phi2 = s.potential_host(3.0 * g["rho"], g["steps"])
+    assert rel_to_max(phi2, 3.0 * phi) < 1e-14
+
+
+@pytest.mark.parametrize("name", ["kat_small.npz", "kat_c1_31.npz"])
+def test_stage_taps_vs_reference(native, golden, name):
+    g = golden(name)
+    s = native.Solver(0, g["nmesh"])
+    r, q = dev(g["r_in"]), dev(g["q"])
+    E = s.field_at_particles(r, q, float(g["E"])).cpu().numpy()
+    geo = s.geometry()
+    assert np.max(np.abs(geo["steps"] / g["steps"] - 1)) < 1e-14
+    assert abs(geo["gamma0"] / float(g["gamma0"]) - 1) < 1e-14
+    rho = s.rho()
+    # identical cell for every particle: any flip would change rho by a whole charge
+    assert np.max(np.abs(rho - g["rho"])) < 1e-3 * np.min(g["q"])
+    assert rel_to_max(rho, g["rho"]) < 1e-13
+    assert abs(rho.sum() / g["q"].sum() - 1) < 1e-13
+    assert rel_to_max(s.phi(), g["phi"]) < 1e-11
+    assert field_err(E, g["Exyz"]) < 1e-10
+    # the tap must not modify the particles
+    assert np.array_equal(r.cpu().numpy(), g["r_in"])
+
+
+@pytest.mark.parametrize("name", ["kat_small.npz", "kat_c1_31.npz"])
+def test_kick_vs_reference(native, golden, name):
+    g = golden(name)
+    s = native.Solver(0, g["nmesh"])
+    r, q = dev(g["r_in"]), dev(g["q"])
+    s.kick_device(r, q, float(g["E"]), float(g["dz"]))
+    assert row_err(r.cpu().numpy(), g["r_out"]) < 1e-10
+
+
+def test_random_mesh_vs_reference(native, golden):
+    g = golden("kat_randmesh.npz")
+    s = native.Solver(0, g["nmesh"])
+    r, q = dev(g["r_in"]), dev(g["q"])
+    E = s.field_at_particles(r, q, float(g["E"]), mesh_draws=g["draws"]).cpu().numpy()
+    assert np.max(np.abs(s.geometry()["steps"] / g["steps"] - 1)) < 1e-14
+    assert np.max(np.abs(s.rho() - g["rho"])) < 1e-3 * np.min(g["q"])
+    assert field_err(E, g["Exyz"]) < 1e-10
+    s.kick_device(r, q, float(g["E"]), float(g["dz"]), mesh_draws=g["draws"])
+    assert row_err(r.cpu().numpy(), g["r_out"]) < 1e-10
+
+
+@pytest.mark.parametrize("which", ["first", "last"])
+def test_injector_kicks_from_reference_golden_path(native, golden, which):
+    """Kicks 1 and 193 of the reference's own golden test (space_charge_test.py:51-66)."""
+    g = golden("kat_injector_63.npz")
+    s = native.Solver(0, g["nmesh"])
+    r, q = dev(g[f"r_in_{which}"]), dev(g["q"])
+    s.kick_device(r, q, float(g[f"E_{which}"]), float(g[f"dz_{which}"]))
+    assert row_err(r.cpu().numpy(), g[f"r_out_{which}"]) < 1e-10
+
+
+# ---------------------------------------------------------------------------
+# boundary behaviour
+# ---------------------------------------------------------------------------
+def test_zero_step_and_padding_and_host_mode(native, golden):
+    g = golden("kat_small.npz")
+    n = g["r_in"].shape[1]
+    s = native.Solver(0, g["nmesh"])
+    r, q = dev(g["r_in"]), dev(g["q"])
+    s.kick_device(r, q, float(g["E"]), 0.0)
+    assert np.array_equal(r.cpu().numpy(), g["r_in"])
+    # rows embedded in a wider buffer (ld > n), sentinel beyond n untouched
+    wide = torch.full((6, n + 37), 7.0, dtype=torch.float64, device="cuda")
+    wide[:, :n] = dev(g["r_in"])
+    s.kick_device(wide[:, :n], q, float(g["E"]), float(g["dz"]))
+    assert torch.all(wide[:, n:] == 7.0)
+    ref = dev(g["r_in"])
+    s.kick_device(ref, q, float(g["E"]), float(g["dz"]))
+    assert torch.equal(wide[:, :n], ref)
+    # host arrays in place, same bits as the device path
+    rh = g["r_in"].copy()
+    s.kick_host(rh, g["q"], float(g["E"]), float(g["dz"]))
+    assert np.array_equal(rh, ref.cpu().numpy())
+
+
+def test_space_charge_class_host_and_device(native, golden):
+    import copy
+    from ocelot_b200 import SpaceCharge, ParticleArray, DeviceParticleArray
+    g = golden("kat_c1_31.npz")
+    sc = SpaceCharge(step=1, nmesh_xyz=[31, 31, 31], bogus_kwarg=3)
+    sc.prepare(None)
+    p = ParticleArray(g["r_in"].shape[1])
+    p.rparticles[:] = g["r_in"]
+    p.q_array[:] = g["q"]
+    p.E = float(g["E"])
+    buf = p.rparticles
+    sc.apply(p, float(g["dz"]))
+    assert p.rparticles is buf                       # in place, same array object
+    assert row_err(p.rparticles, g["r_out"]) < 1e-10
+    sc2 = copy.deepcopy(sc)                          # Navigator deep-copies processes (navi.py:189)
+    p2 = ParticleArray(g["r_in"].shape[1])
+    p2.rparticles[:] = g["r_in"]
+    p2.q_array[:] = g["q"]
+    p2.E = float(g["E"])
+    d = DeviceParticleArray.from_host(p2)
+    sc2.apply(d, float(g["dz"]))
+    assert np.array_equal(d.to_host().rparticles, p.rparticles)
+    sc2.apply(d, 0)                                  # kick-type call
+    assert np.array_equal(d.to_host().rparticles, p.rparticles)
+
+
+# ---------------------------------------------------------------------------
+# oracle at larger sizes + properties at BASELINE config-2 size
+# ---------------------------------------------------------------------------
+def _bunch(n, seed, energy=0.13, charge=250e-12):
+    np.random.seed(seed)
+    return orc.gaussian_bunch(n, energy=energy, charge=charge)
+
+
+def test_config2_vs_oracle_and_properties(native):
+    n, nmesh = 1_000_000, (63, 63, 63)
+    r0, q0, E = _bunch(n, 5)
+    s = native.Solver(0, nmesh)
+    r, q = dev(r0), dev(q0)
+    Exyz = s.field_at_particles(r, q, E)
+    rho = s.rho()
+    assert abs(rho.sum() / q0.sum() - 1) < 1e-12                      # charge conservation
+    assert rho[0].sum() == 0 and rho[-1].sum() == 0 and rho[:, 0].sum() == 0 and rho[:, :, -1].sum() == 0
+
+    # oracle (padded real FFT, threaded) on identical input
+    taps = {}
+    r_ref = r0.copy()
+    orc.sc_kick(r_ref, q0, E, 0.1, nmesh, fft="padded", workers=8, taps=taps)
+    assert np.max(np.abs(rho - taps["rho"])) < 1e-3 * q0[0]            # identical cell for every particle
+    assert field_err(Exyz.cpu().numpy(), taps["Exyz"]) < 1e-10
+    s.kick_device(r, q, E, 0.1)
+    got = r.cpu().numpy()
+    assert row_err(got, r_ref) < 1e-10
+
+    # linearity in charge: doubling q doubles E (same geometry)
+    E2 = s.field_at_particles(dev(r0), dev(2.0 * q0), E)
+    assert float((E2 - 2.0 * Exyz).abs().max() / Exyz.abs().max()) < 1e-12
+
+    # permutation invariance: particle order only changes summation order
+    perm = np.random.RandomState(0).permutation(n)
+    Ep = s.field_at_particles(dev(r0[:, perm]), dev(q0[perm]), E)
+    assert float((Ep - Exyz[torch.from_numpy(perm).cuda()]).abs().max() / Exyz.abs().max()) < 1e-11
+
+    # repeatability: same input, same bits for the reductions' fixed launch shape (rho uses atomics)
+    r_again = dev(r0)
+    s.kick_device(r_again, q, E, 0.1)
+    assert row_err(r_again.cpu().numpy(), got) < 1e-12
+
+
+def test_mesh_127_vs_oracle(native):
+    n, nmesh = 400_000, (127, 127, 127)
+    r0, q0, E = _bunch(n, 9)
+    s = native.Solver(0, nmesh)
+    r, q = dev(r0), dev(q0)
+    taps = {}
+    r_ref = r0.copy()
+    orc.sc_kick(r_ref, q0, E, 0.1, nmesh, fft="padded", workers=8, taps=taps)
+    Exyz = s.field_at_particles(r, q, E).cpu().numpy()
+    assert np.max(np.abs(s.rho() - taps["rho"])) < 1e-3 * q0[0]
+    assert field_err(Exyz, taps["Exyz"]) < 1e-10
+    s.kick_device(r, q, E, 0.1)
+    assert row_err(r.cpu().numpy(), r_ref) < 1e-10
+
+
+def test_ragged_and_tiny_inputs(native):
+    # non-cubic mesh, non-uniform charges, few particles, low energy
+    rng = np.random.RandomState(3)
+    for n, nmesh, E in ((5, (5, 4, 6), 0.005), (1000, (9, 17, 33), 0.05), (257, (33, 8, 8), 1.0)):
+        r0 = np.zeros((6, n))
+        r0[0], r0[2], r0[4] = rng.randn(n) * 1e-4, rng.randn(n) * 2e-4, rng.randn(n) * 5e-4
+        r0[1], r0[3], r0[5] = rng.randn(n) * 1e-5, rng.randn(n) * 1e-5, rng.randn(n) * 1e-3
+        q0 = (0.2 + rng.rand(n)) * 1e-12
+        s = native.Solver(0, nmesh)
+        r_ref = r0.copy()
+        taps = {}
+        orc.sc_kick(r_ref, q0, E, 0.02, nmesh, fft="padded", taps=taps)
+        r = dev(r0)
+        Exyz = s.field_at_particles(r, dev(q0), E).cpu().numpy()
+        assert np.max(np.abs(s.rho() - taps["rho"])) < 1e-3 * q0.min()
+        assert field_err(Exyz, taps["Exyz"]) < 1e-10
+        s.kick_device(r, dev(q0), E, 0.02)
+        assert row_err(r.cpu().numpy(), r_ref) < 1e-10
+
+
+def test_staged_equals_fused(native, golden):
+    g = golden("kat_c1_31.npz")
+    s = native.Solver(0, g["nmesh"])
+    q = dev(g["q"])
+    a, b = dev(g["r_in"]), dev(g["r_in"])
+    E, dz = float(g["E"]), float(g["dz"])
+    s.kick_device(a, q, E, dz)
+    s.stage_momentum(b, E)
+    s.stage_extent(b, q, E)
+    s.stage_deposit(b, q, E)
+    s.stage_solve()
+    s.stage_kick(b, E, dz)
+    assert row_err(b.cpu().numpy(), a.cpu().numpy()) < 1e-12
+    assert s.collective_buffer(native.BUF_MOMENTUM)[3].item() == g["r_in"].shape[1]
+    assert abs(s.collective_buffer(native.BUF_RHO).sum().item() / g["q"].sum() - 1) < 1e-13
+
+
+# ---------------------------------------------------------------------------
+# moment-level parity after tracking (north-star: within 1e-9)
+# ---------------------------------------------------------------------------
+def test_track_config1_moments(native, golden):
+    """BASELINE config 1: 200k Gaussian particles, 31^3, 10 m FODO, kick every
+    0.1 m (100 kicks), replayed with the transfer matrices the reference used."""
+    g = golden("track_c1.npz")
+    keys = [str(k) for k in g["moment_keys"]]
+    np.random.seed(int(g["seed"]))
+    r0, q0, E = orc.gaussian_bunch(int(g["n"]), energy=float(g["E"]), charge=float(g["charge"]))
+    assert np.array_equal(r0[:, :64], g["r0_head"])
+    s = native.Solver(0, g["nmesh"])
+    r, q = dev(r0), dev(q0)
+    R, B = dev(g["R"]), dev(g["B"])
+    map_step = g["map_step"]
+    worst = 0.0
+    for step, dz in enumerate(g["kick_dz"]):
+        for m in np.nonzero(map_step == step)[0]:
+            r.copy_(R[m] @ r + B[m].reshape(6, 1))      # first-order map (transfer_map.py:51-52); library GEMM, not the hot path
+        s.kick_device(r, q, E, float(dz))
+        if step % 10 == 9 or step == len(g["kick_dz"]) - 1:
+            got = orc.beam_moments(r.cpu().numpy())
+            ref = dict(zip(keys, g["moments"][step + 1]))
+            sig = {"x": ref["xx"], "px": ref["pxpx"], "y": ref["yy"], "py": ref["pypy"], "tau": ref["tautau"],
+                   "p": ref["pp"]}
+            for k in keys:
+                e = abs(got[k] - ref[k]) / (np.sqrt(sig[k]) if k in sig else abs(ref[k]))
+                worst = max(worst, e)
+    assert worst < 1e-9, worst
+    stride = int(g["sample_stride"])
+    final = r.cpu().numpy()[:, ::stride]
+    for row in range(6):
+        ref = g["r_final_sample"][row]
+        assert np.max(np.abs(final[row] - ref)) / np.std(ref) < 1e-10
