@@ -15,7 +15,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libocelot_sc.so")
-SOURCES = ["sc_kernels.cu", "sc_abi.cu"]
+SOURCES = ["sc_kernels.cu", "sc_fft.cu", "sc_abi.cu"]
 HEADERS = ["sc_device.cuh", "sc_kernels.h", os.path.join("..", "..", "include", "ocelot_sc.h")]
 
 
@@ -35,8 +35,9 @@ def command(verbose: bool = False) -> list[str]:
     cmd = [nvcc, "-O3", "-std=c++17",
            "-gencode", "arch=compute_100a,code=sm_100a",
            "-lineinfo",
-           # parity: no fused multiply-add contraction, IEEE division / square root
-           "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
+           # IEEE division / square root everywhere; FMA contraction is allowed except where the
+           # source uses explicit __dmul_rn/__dadd_rn (Green's function, see sc_kernels.cu)
+           "-prec-div=true", "-prec-sqrt=true",
            "-Xcompiler", "-fPIC", "-shared",
            "-o", LIB]
     if verbose:

@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <vector>
 
 #include "../../include/ocelot_sc.h"
 #include "sc_kernels.h"
@@ -28,13 +29,17 @@ struct ocl_sc {
     double* rho = nullptr;    // n^3
     double* gtab = nullptr;   // (n+1)^3 antiderivative table
     double* k1 = nullptr;     // n^3 (tap only, lazily allocated)
+    // solver 0 (default): hand-written pruned/symmetric Hockney convolution (sc_fft.cu)
+    // solver 1: cuFFT D2Z/Z2D on the full padded box (cross-check; also used when M > 1024)
+    int solver = 0;
+    FftWork fw{};
+    double2* tw[3] = {nullptr, nullptr, nullptr};
+    double* h3 = nullptr;                     // mesh steps of the current kick
     double* real_buf = nullptr;               // M^3 real: K, then padded rho, then the convolution
     cufftDoubleComplex* k_hat = nullptr;      // M*M*(M/2+1)
     cufftDoubleComplex* rho_hat = nullptr;    // M*M*(M/2+1)
     double* phi = nullptr;    // n^3
-    double* ex = nullptr;     // n^3 each
-    double* ey = nullptr;
-    double* ez = nullptr;
+    EQuad* equad = nullptr;   // 3*n^3 quads: the field table the gather reads
     cufftHandle plan_fwd = 0, plan_inv = 0;
     bool plans = false;
     // host-mode staging
@@ -88,11 +93,14 @@ void constants(double& m_e_eV, double& m_e_GeV, double& eps0, double& pi, double
 RefParams ref_params(const ocl_sc* h, double E_GeV) {
     RefParams rp;
     rp.m_e_eV = h->m_e_eV;
-    rp.m_e_eV2 = h->m_e_eV * h->m_e_eV;
+    rp.inv_m2 = 1.0 / (h->m_e_eV * h->m_e_eV);
     rp.gamref = E_GeV / h->m_e_GeV;                                  // sc.py:214
     rp.betaref = std::sqrt(1 - std::pow(rp.gamref, -2.0));           // sc.py:215-216
+    rp.inv_betaref = 1.0 / rp.betaref;
     rp.gb_ref = rp.gamref * rp.betaref;
-    rp.pref = h->m_e_eV * std::sqrt(rp.gamref * rp.gamref - 1);      // coord_transform.py:19
+    rp.inv_gb2 = 1.0 / (rp.gb_ref * rp.gb_ref);
+    rp.pc = rp.gb_ref * h->m_e_eV;
+    rp.inv_pref = 1.0 / (h->m_e_eV * std::sqrt(rp.gamref * rp.gamref - 1));   // coord_transform.py:19
     return rp;
 }
 
@@ -120,10 +128,41 @@ int set_device(ocl_sc* h) {
 
 int ensure_plans(ocl_sc* h) {
     if (h->plans) return 0;
+    const size_t m3 = (size_t)h->md.mx * h->md.my * h->md.mz;
+    const size_t c3 = (size_t)h->md.mx * h->md.my * (h->md.mz / 2 + 1);
+    CU(h, cudaMalloc(&h->real_buf, sizeof(double) * m3));
+    CU(h, cudaMalloc(&h->k_hat, sizeof(cufftDoubleComplex) * c3));
+    CU(h, cudaMalloc(&h->rho_hat, sizeof(cufftDoubleComplex) * c3));
     FFT(h, cufftPlan3d(&h->plan_fwd, h->md.mx, h->md.my, h->md.mz, CUFFT_D2Z));
     FFT(h, cufftPlan3d(&h->plan_inv, h->md.mx, h->md.my, h->md.mz, CUFFT_Z2D));
     h->plans = true;
     return 0;
+}
+
+// exp(-2 pi i m / M), m = 0..M-1, rounded from long double
+int make_twiddles(ocl_sc* h, int M, double2** out) {
+    std::vector<double2> t((size_t)M);
+    const long double two_pi = 6.283185307179586476925286766559L;
+    for (int m = 0; m < M; ++m) {
+        long double a = two_pi * (long double)m / (long double)M;
+        t[m].x = (double)cosl(a);
+        t[m].y = (double)(-sinl(a));
+    }
+    // exact values on the axes
+    t[0] = make_double2(1.0, 0.0);
+    if (M % 2 == 0) t[M / 2] = make_double2(-1.0, 0.0);
+    if (M % 4 == 0) { t[M / 4] = make_double2(0.0, -1.0); t[3 * M / 4] = make_double2(0.0, 1.0); }
+    CU(h, cudaMalloc(out, sizeof(double2) * M));
+    CU(h, cudaMemcpy(*out, t.data(), sizeof(double2) * M, cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// hand-written path: K_hat (3 real-even passes), rho passes with the multiply fused in x; writes phi
+int solve_fused(ocl_sc* h, cudaStream_t st) {
+    launch_khat(h->gtab, h->md, h->fw, st);
+    launch_convolve(h->rho, h->md, h->fw, h->h3, four_pi_eps0_value(), h->phi, st);
+    h->launches += 8;
+    return check_launch(h, "solve_fused");
 }
 
 // IGF -> K_hat, rho -> rho_hat, multiply, inverse: real_buf holds the convolution afterwards
@@ -137,7 +176,7 @@ int convolve(ocl_sc* h, cudaStream_t st) {
     FFT(h, cufftExecD2Z(h->plan_fwd, h->real_buf, h->rho_hat));
     launch_multiply(h->rho_hat, h->k_hat, h->md, st);
     FFT(h, cufftExecZ2D(h->plan_inv, h->rho_hat, h->real_buf));
-    h->launches += 6;
+    h->launches += 7;
     return check_launch(h, "convolve");
 }
 
@@ -199,13 +238,28 @@ int ocl_sc_create(int device, int nx, int ny, int nz, long long max_particles, o
     h->rs.geom = h->rs.sums + 16;
     TRY(cudaMalloc(&h->rho, sizeof(double) * n3));
     TRY(cudaMalloc(&h->gtab, sizeof(double) * g3));
-    TRY(cudaMalloc(&h->real_buf, sizeof(double) * m3));
-    TRY(cudaMalloc(&h->k_hat, sizeof(cufftDoubleComplex) * c3));
-    TRY(cudaMalloc(&h->rho_hat, sizeof(cufftDoubleComplex) * c3));
+    (void)m3; (void)c3;
+    {
+        const char* env = getenv("OCL_SC_SOLVER");
+        h->solver = (env && strcmp(env, "cufft") == 0) ? 1 : 0;
+        if (h->md.mx > fft_max_length() || h->md.my > fft_max_length() || h->md.mz > fft_max_length()) h->solver = 1;
+    }
+    TRY(cudaMalloc(&h->h3, sizeof(double) * 4));
+    if (h->solver == 0) {
+        const size_t hx1 = h->md.mx / 2 + 1, hy1 = h->md.my / 2 + 1, hz1 = h->md.mz / 2 + 1;
+        fft_init_kernels();
+        const int ms[3] = {h->md.mx, h->md.my, h->md.mz};
+        for (int a = 0; a < 3; ++a)
+            if (make_twiddles(nullptr, ms[a], &h->tw[a])) { ocl_sc_destroy(h); return 1; }
+        h->fw.tw_x = h->tw[0]; h->fw.tw_y = h->tw[1]; h->fw.tw_z = h->tw[2];
+        TRY(cudaMalloc(&h->fw.P, sizeof(double) * nx * ny * hz1));
+        TRY(cudaMalloc(&h->fw.Q, sizeof(double) * nx * hy1 * hz1));
+        TRY(cudaMalloc(&h->fw.khat, sizeof(double) * hx1 * hy1 * hz1));
+        TRY(cudaMalloc(&h->fw.A, sizeof(double2) * nx * ny * hz1));
+        TRY(cudaMalloc(&h->fw.B, sizeof(double2) * nx * h->md.my * hz1));
+    }
     TRY(cudaMalloc(&h->phi, sizeof(double) * n3));
-    TRY(cudaMalloc(&h->ex, sizeof(double) * n3 * 3));
-    h->ey = h->ex + n3;
-    h->ez = h->ey + n3;
+    TRY(cudaMalloc(&h->equad, sizeof(EQuad) * n3 * 3));
     TRY(cudaMemset(h->rho, 0, sizeof(double) * n3));
     TRY(cudaMemset(h->phi, 0, sizeof(double) * n3));
     TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
@@ -226,7 +280,9 @@ void ocl_sc_destroy(ocl_sc_t* h) {
     if (h->plans) { cufftDestroy(h->plan_fwd); cufftDestroy(h->plan_inv); }
     cudaFree(h->rs.part); cudaFree(h->rs.ticket); cudaFree(h->rs.sums);
     cudaFree(h->rho); cudaFree(h->gtab); cudaFree(h->k1); cudaFree(h->real_buf);
-    cudaFree(h->k_hat); cudaFree(h->rho_hat); cudaFree(h->phi); cudaFree(h->ex);
+    cudaFree(h->k_hat); cudaFree(h->rho_hat); cudaFree(h->phi); cudaFree(h->equad);
+    cudaFree(h->fw.P); cudaFree(h->fw.Q); cudaFree(h->fw.khat); cudaFree(h->fw.A); cudaFree(h->fw.B);
+    cudaFree(h->tw[0]); cudaFree(h->tw[1]); cudaFree(h->tw[2]); cudaFree(h->h3);
     cudaFree(h->stage_r); cudaFree(h->stage_q);
     for (int i = 0; i < T_COUNT; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -289,13 +345,19 @@ int ocl_sc_stage_solve(ocl_sc_t* h, const double* mesh_draws, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     h->last_stream = st;
     Draws dr = draws_of(mesh_draws);
-    launch_green_table(h->rs, h->md, dr, h->gtab, st);
+    launch_green_table(h->rs, h->md, dr, h->gtab, h->h3, st);
     h->launches += 1;
-    if (convolve(h, st)) return 1;
-    mark(h, T_SOLVE, st);
-    launch_crop_phi(h->real_buf, h->rs, h->md, dr, h->phi, st);
-    launch_field(h->phi, h->rs, h->md, dr, h->ex, h->ey, h->ez, st);
-    h->launches += 2;
+    if (h->solver == 0) {
+        if (solve_fused(h, st)) return 1;
+        mark(h, T_SOLVE, st);
+    } else {
+        if (convolve(h, st)) return 1;
+        mark(h, T_SOLVE, st);
+        launch_crop_phi(h->real_buf, h->rs, h->md, dr, h->phi, st);
+        h->launches += 1;
+    }
+    launch_field(h->phi, h->rs, h->md, dr, h->equad, st);
+    h->launches += 1;
     mark(h, T_FIELD, st);
     return check_launch(h, "stage_solve");
 }
@@ -306,8 +368,7 @@ int ocl_sc_stage_kick(ocl_sc_t* h, double* d_r, long long ld, long long n, doubl
     if (set_device(h)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     h->last_stream = st;
-    launch_gather_kick(d_r, ld, n, ref_params(h, E_GeV), h->rs, h->md, draws_of(mesh_draws), h->ex, h->ey, h->ez, dz,
-                       nullptr, 1, st);
+    launch_gather_kick(d_r, ld, n, ref_params(h, E_GeV), h->rs, h->md, draws_of(mesh_draws), h->equad, dz, nullptr, 1, st);
     h->launches += 1;
     mark(h, T_KICK, st);
     return check_launch(h, "k_gather_kick");
@@ -404,7 +465,7 @@ int ocl_sc_field_at_particles(ocl_sc_t* h, const double* d_r, long long ld, cons
     if (ocl_sc_stage_deposit(h, d_r, ld, d_q, n, E_GeV, mesh_draws, stream)) return 1;
     if (ocl_sc_stage_solve(h, mesh_draws, stream)) return 1;
     launch_gather_kick(const_cast<double*>(d_r), ld, n, ref_params(h, E_GeV), h->rs, h->md, draws_of(mesh_draws),
-                       h->ex, h->ey, h->ez, 0.0, d_exyz, 0, (cudaStream_t)stream);
+                       h->equad, 0.0, d_exyz, 0, (cudaStream_t)stream);
     h->launches += 1;
     return check_launch(h, "k_gather");
 }
@@ -436,11 +497,15 @@ int ocl_sc_potential_host(ocl_sc_t* h, const double* h_rho, const double steps[3
     h->last_stream = st;
     const size_t n3 = (size_t)h->md.nx * h->md.ny * h->md.nz;
     CU(h, cudaMemcpyAsync(h->rho, h_rho, sizeof(double) * n3, cudaMemcpyHostToDevice, st));
-    launch_green_table_steps(steps, h->md, h->gtab, st);
+    launch_green_table_steps(steps, h->md, h->gtab, h->h3, st);
     h->launches += 1;
-    if (convolve(h, st)) return 1;
-    launch_crop_phi_steps(h->real_buf, steps, h->md, h->phi, st);
-    h->launches += 1;
+    if (h->solver == 0) {
+        if (solve_fused(h, st)) return 1;
+    } else {
+        if (convolve(h, st)) return 1;
+        launch_crop_phi_steps(h->real_buf, steps, h->md, h->phi, st);
+        h->launches += 1;
+    }
     if (check_launch(h, "potential")) return 1;
     CU(h, cudaMemcpyAsync(h_phi, h->phi, sizeof(double) * n3, cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));

@@ -1,11 +1,13 @@
 // sc_device.cuh -- per-particle and per-kick device math shared by all kernels.
 //
-// Everything here restates, operation by operation, the arithmetic of the
-// reference (ocelot/cpbd/sc.py, ocelot/cpbd/coord_transform.py).  The library
-// is compiled with -fmad=false so that +,-,*,/ and sqrt round exactly like the
-// numpy expressions they follow; the only places that cannot be bit-identical
-// are sums over particles (order), libm calls (pow/atan/log) and BLAS-backed
-// 3x3 products.
+// Everything here restates the arithmetic of the reference (ocelot/cpbd/sc.py,
+// ocelot/cpbd/coord_transform.py).  Where rounding is amplified downstream --
+// the mesh geometry (cell assignment) and the integrated Green's function
+// (8-corner cancellation) -- the reference's operation order is kept exactly,
+// with explicit round-to-nearest intrinsics so the compiler cannot contract
+// them into FMAs.  The per-particle MAD<->Cartesian transforms are reduced
+// algebraically (derivations at the functions); they agree with the reference
+// to a few ulp, far inside the 1e-10 parity bound, at a fifth of the fp64 work.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -17,9 +19,12 @@ struct RefParams {
     double gamref;     // E / m_e_GeV
     double betaref;    // sqrt(1 - gamref^-2)
     double gb_ref;     // gamref * betaref
-    double pref;       // m_e_eV * sqrt(gamref^2 - 1)
+    double inv_gb2;    // 1 / gb_ref^2
+    double pc;         // gb_ref * m_e_eV : momentum per unit slope (= pref up to rounding)
+    double inv_pref;   // 1 / (m_e_eV * sqrt(gamref^2 - 1))      coord_transform.py:19
     double m_e_eV;
-    double m_e_eV2;    // m_e_eV ** 2
+    double inv_m2;     // 1 / m_e_eV^2
+    double inv_betaref;
 };
 
 // bunch frame (sc.py:224-239); T columns are t1, t2, t3
@@ -40,58 +45,48 @@ struct Cart {
     double x, y, z, px, py, pz;
 };
 
-// ---- coord_transform.py:57-96 (numpy branch) ---------------------------------
-__device__ __forceinline__ void mad_momentum(const RefParams& rp, double xs, double ys, double delta,
-                                             double& u0, double& u1, double& u2, double& gam, double& bet) {
+// ---- coord_transform.py:57-96, algebraically reduced ---------------------------
+// The reference builds gamma, beta, pz/p_ref, normalises the direction u and
+// multiplies back (:68-95).  In exact arithmetic |u_unnormalised| * pz/p_ref ==
+// gamma*beta/(gamref*betaref) =: ratio, so
+//     u = (x', y', pz_rel) / ratio,   u*beta = (x', y', pz_rel) * gb_ref/gamma,
+//     p = u*gamma*beta*m_e = (x', y', pz_rel) * gb_ref*m_e,
+//     pz_rel^2 = (gamma^2 - 1)/gb_ref^2 - x'^2 - y'^2.
+// Same values to a few ulp, with 1 division + 1 square root instead of 10.
+__device__ __forceinline__ double mad_pz_rel(const RefParams& rp, double xs, double ys, double delta, double& gam) {
     gam = (rp.betaref * delta + 1.0) * rp.gamref;                 // :68
-    bet = sqrt(1.0 - 1.0 / (gam * gam));                          // :69  (gamma ** -2)
-    double ratio = (gam * bet) / rp.gb_ref;
-    double pz_rel = sqrt(ratio * ratio - xs * xs - ys * ys);      // :70
-    double a = xs / pz_rel, b = ys / pz_rel;                      // :72
-    double nrm = sqrt(a * a + b * b + 1.0);                       // :74 (2-norm along axis 1)
-    u0 = a / nrm;                                                 // :77
-    u1 = b / nrm;
-    u2 = 1.0 / nrm;
-}
-
-__device__ __forceinline__ void mad_to_cart_momentum(const RefParams& rp, double xs, double ys, double delta,
-                                                     double& px, double& py, double& pz) {
-    double u0, u1, u2, gam, bet;
-    mad_momentum(rp, xs, ys, delta, u0, u1, u2, gam, bet);
-    px = u0 * gam * bet * rp.m_e_eV;                              // :93
-    py = u1 * gam * bet * rp.m_e_eV;                              // :94
-    pz = u2 * gam * bet * rp.m_e_eV;                              // :95
+    return sqrt((gam * gam - 1.0) * rp.inv_gb2 - xs * xs - ys * ys);   // :69-70
 }
 
 __device__ __forceinline__ Cart mad_to_cart(const RefParams& rp, double x, double xs, double y, double ys,
                                             double tau, double delta) {
-    double u0, u1, u2, gam, bet;
-    mad_momentum(rp, xs, ys, delta, u0, u1, u2, gam, bet);
+    double gam;
+    double pzr = mad_pz_rel(rp, xs, ys, delta, gam);
+    double kt = (rp.gb_ref / gam) * tau;                          // beta/ratio * tau
     Cart c;
-    c.x = x - u0 * bet * tau;                                     // :90
-    c.y = y - u1 * bet * tau;                                     // :91
-    c.z = -u2 * bet * tau;                                        // :92
-    c.px = u0 * gam * bet * rp.m_e_eV;
-    c.py = u1 * gam * bet * rp.m_e_eV;
-    c.pz = u2 * gam * bet * rp.m_e_eV;
+    c.x = x - xs * kt;                                            // :90
+    c.y = y - ys * kt;                                            // :91
+    c.z = -pzr * kt;                                              // :92
+    c.px = xs * rp.pc;                                            // :93
+    c.py = ys * rp.pc;                                            // :94
+    c.pz = pzr * rp.pc;                                           // :95
     return c;
 }
 
-// ---- coord_transform.py:16-54 (numpy branch) ---------------------------------
+// ---- coord_transform.py:16-54, algebraically reduced ---------------------------
+// With p0 = |p| = gamma*beta*m_e:  beta*u = p/(gamma*m_e), so
+//     cdt = -z/(beta*u2) = -z*gamma*m_e/pz,   x + beta*u0*cdt = x - z*px/pz.
 __device__ __forceinline__ void cart_to_mad(const RefParams& rp, const Cart& c, double& x, double& xs, double& y,
                                             double& ys, double& tau, double& delta) {
-    double s = c.px * c.px + c.py * c.py + c.pz * c.pz;           // sum(u*u, 1)
-    double gam = sqrt(1.0 + s / rp.m_e_eV2);                      // :27
-    double bet = sqrt(1.0 - 1.0 / (gam * gam));                   // :28
-    double p0 = sqrt(s);                                          // :31
-    double u0 = c.px / p0, u1 = c.py / p0, u2 = c.pz / p0;        // :34
-    double cdt = -c.z / (bet * u2);                               // :47
-    x = c.x + bet * u0 * cdt;                                     // :48
-    y = c.y + bet * u1 * cdt;                                     // :49
-    delta = (gam / rp.gamref - 1.0) / rp.betaref;                 // :50
-    tau = cdt;                                                    // :51
-    xs = c.px / rp.pref;                                          // :52
-    ys = c.py / rp.pref;                                          // :53
+    double s = c.px * c.px + c.py * c.py + c.pz * c.pz;
+    double gam = sqrt(1.0 + s * rp.inv_m2);                       // :27
+    double zp = c.z / c.pz;
+    tau = -zp * (gam * rp.m_e_eV);                                // :47, :51
+    x = c.x - zp * c.px;                                          // :48
+    y = c.y - zp * c.py;                                          // :49
+    delta = (gam / rp.gamref - 1.0) * rp.inv_betaref;             // :50
+    xs = c.px * rp.inv_pref;                                      // :52
+    ys = c.py * rp.inv_pref;                                      // :53
 }
 
 // ---- sc.py:224-239 -----------------------------------------------------------
@@ -156,11 +151,18 @@ __device__ __forceinline__ void to_grid(const Mesh& m, double a, double b, doubl
     g2 = c / m.steps[2] - m.xoff[2];
 }
 
+// Field table entry: the four (y,z) neighbours of one component at one cell,
+// {E[i][j][k], E[i][j][k+1], E[i][j+1][k], E[i][j+1][k+1]} (indices clamped at
+// the upper edge).  32 bytes = one L2 sector = one 256-bit load.
+struct __align__(32) EQuad {
+    double v00, v01, v10, v11;
+};
+
 // order-1 interpolation with zero outside [0, n-1] (scipy.ndimage.map_coordinates
 // order=1, mode='constant', cval=0 as used at sc.py:202-204): each corner value
 // is multiplied by its x, y, z weights in that order; corners accumulate with z
-// fastest.
-__device__ __forceinline__ double trilinear(const double* __restrict__ F, int nx, int ny, int nz, double c0,
+// fastest.  Two 256-bit loads fetch the eight corners.
+__device__ __forceinline__ double trilinear(const EQuad* __restrict__ F, int nx, int ny, int nz, double c0,
                                             double c1, double c2) {
     if (!(c0 >= 0.0 && c0 <= (double)(nx - 1) && c1 >= 0.0 && c1 <= (double)(ny - 1) && c2 >= 0.0 &&
           c2 <= (double)(nz - 1)))
@@ -168,18 +170,19 @@ __device__ __forceinline__ double trilinear(const double* __restrict__ F, int nx
     double f0 = floor(c0), f1 = floor(c1), f2 = floor(c2);
     int i0 = (int)f0, i1 = (int)f1, i2 = (int)f2;
     double t0 = c0 - f0, t1 = c1 - f1, t2 = c2 - f2;
-    int j0 = min(i0 + 1, nx - 1), j1 = min(i1 + 1, ny - 1), j2 = min(i2 + 1, nz - 1);
-    double w0[2] = {1.0 - t0, t0}, w1[2] = {1.0 - t1, t1}, w2[2] = {1.0 - t2, t2};
-    int a[2] = {i0, j0}, b[2] = {i1, j1}, c[2] = {i2, j2};
-    double acc = 0.0;
-#pragma unroll
-    for (int p = 0; p < 2; ++p)
-#pragma unroll
-        for (int q = 0; q < 2; ++q) {
-            const double* row = F + ((size_t)a[p] * ny + b[q]) * nz;
-#pragma unroll
-            for (int s = 0; s < 2; ++s) acc = acc + __ldg(row + c[s]) * w0[p] * w1[q] * w2[s];
-        }
+    int j0 = min(i0 + 1, nx - 1);
+    const size_t row = (size_t)i1 * nz + i2, plane = (size_t)ny * nz;
+    const EQuad A = F[(size_t)i0 * plane + row];
+    const EQuad B = F[(size_t)j0 * plane + row];
+    const double a0 = 1.0 - t0, b0 = 1.0 - t1, d0 = 1.0 - t2;
+    double acc = A.v00 * a0 * b0 * d0;
+    acc = acc + A.v01 * a0 * b0 * t2;
+    acc = acc + A.v10 * a0 * t1 * d0;
+    acc = acc + A.v11 * a0 * t1 * t2;
+    acc = acc + B.v00 * t0 * b0 * d0;
+    acc = acc + B.v01 * t0 * b0 * t2;
+    acc = acc + B.v10 * t0 * t1 * d0;
+    acc = acc + B.v11 * t0 * t1 * t2;
     return acc;
 }
 

@@ -24,7 +24,7 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 
 int particle_grid(long long n, int max_blocks) {
-    long long b = (n + kThreads - 1) / kThreads;
+    long long b = (n + 4 * kThreads - 1) / (4 * kThreads);   // sweeps handle 4 particles per thread per trip
     if (b < 1) b = 1;
     if (b > max_blocks) b = max_blocks;
     return (int)b;
@@ -94,13 +94,28 @@ __global__ void __launch_bounds__(kThreads) k_momentum(const double* __restrict_
     const double* xs = r + ld;
     const double* ys = r + 3 * ld;
     const double* dl = r + 5 * ld;
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
-        double px, py, pz;
-        mad_to_cart_momentum(rp, xs[i], ys[i], dl[i], px, py, pz);
-        v[0] += px; v[1] += py; v[2] += pz;
+    // U particles per thread per trip: all loads are issued before any arithmetic
+    constexpr int U = 4;
+    for (long long i0 = (long long)blockIdx.x * (kThreads * U) + threadIdx.x; i0 < n;
+         i0 += (long long)gridDim.x * (kThreads * U)) {
+        double a[U], b[U], d[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * kThreads;
+            const bool ok = i < n;
+            a[u] = ok ? xs[i] : 0.0; b[u] = ok ? ys[i] : 0.0; d[u] = ok ? dl[i] : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i0 + u * kThreads < n) {
+                double gam;
+                double pzr = mad_pz_rel(rp, a[u], b[u], d[u], gam);
+                v[0] += a[u]; v[1] += b[u]; v[2] += pzr;   // p = (x', y', pz_rel) * pc: scaled once at the end
+            }
+        }
     }
     if (grid_reduce<3, 0>(v, rs.part, rs.ticket + 0, sh) && threadIdx.x == 0) {
-        rs.sums[0] = v[0]; rs.sums[1] = v[1]; rs.sums[2] = v[2];
+        rs.sums[0] = v[0] * rp.pc; rs.sums[1] = v[1] * rp.pc; rs.sums[2] = v[2] * rp.pc;
         rs.sums[3] = (double)n;
     }
 }
@@ -117,14 +132,31 @@ __global__ void __launch_bounds__(kThreads) k_extent(const double* __restrict__ 
     __syncthreads();
     const Frame f = sf;
     double v[10] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, 0.0, 0.0, 0.0, 0.0};
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
-        Cart c = mad_to_cart(rp, r[i], r[ld + i], r[2 * ld + i], r[3 * ld + i], r[4 * ld + i], r[5 * ld + i]);
-        double a, b, g;
-        rotate_stretch(f, c.x, c.y, c.z, a, b, g);
-        double qi = q[i];
-        v[0] = fmax(v[0], a); v[1] = fmax(v[1], b); v[2] = fmax(v[2], g);
-        v[3] = fmax(v[3], -a); v[4] = fmax(v[4], -b); v[5] = fmax(v[5], -g);
-        v[6] += qi * a; v[7] += qi * b; v[8] += qi * g; v[9] += qi;
+    constexpr int U = 4;
+    for (long long i0 = (long long)blockIdx.x * (kThreads * U) + threadIdx.x; i0 < n;
+         i0 += (long long)gridDim.x * (kThreads * U)) {
+        double w[U][7];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * kThreads;
+            if (i < n) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) w[u][k] = r[k * ld + i];
+                w[u][6] = q[i];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i0 + u * kThreads < n) {
+                Cart c = mad_to_cart(rp, w[u][0], w[u][1], w[u][2], w[u][3], w[u][4], w[u][5]);
+                double a, b, g;
+                rotate_stretch(f, c.x, c.y, c.z, a, b, g);
+                const double qi = w[u][6];
+                v[0] = fmax(v[0], a); v[1] = fmax(v[1], b); v[2] = fmax(v[2], g);
+                v[3] = fmax(v[3], -a); v[4] = fmax(v[4], -b); v[5] = fmax(v[5], -g);
+                v[6] += qi * a; v[7] += qi * b; v[8] += qi * g; v[9] += qi;
+            }
+        }
     }
     if (grid_reduce<10, 6>(v, rs.part, rs.ticket + 1, sh) && threadIdx.x == 0) {
 #pragma unroll
@@ -157,28 +189,50 @@ __global__ void __launch_bounds__(kThreads) k_deposit(const double* __restrict__
     __syncthreads();
     const Frame f = sf;
     const Mesh m = sm;
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
-        Cart c = mad_to_cart(rp, r[i], r[ld + i], r[2 * ld + i], r[3 * ld + i], r[4 * ld + i], r[5 * ld + i]);
-        double a, b, g, g0, g1, g2;
-        rotate_stretch(f, c.x, c.y, c.z, a, b, g);
-        to_grid(m, a, b, g, g0, g1, g2);
-        int i0 = (int)floor(g0) + 1, i1 = (int)floor(g1) + 1, i2 = (int)floor(g2) + 1;   // sc.py:191
-        if ((unsigned)i0 < (unsigned)md.nx && (unsigned)i1 < (unsigned)md.ny && (unsigned)i2 < (unsigned)md.nz)
-            atomicAdd(rho + ((size_t)i0 * md.ny + i1) * md.nz + i2, q[i]);               // sc.py:192-193
+    constexpr int U = 4;
+    for (long long i0 = (long long)blockIdx.x * (kThreads * U) + threadIdx.x; i0 < n;
+         i0 += (long long)gridDim.x * (kThreads * U)) {
+        double w[U][7];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * kThreads;
+            if (i < n) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) w[u][k] = r[k * ld + i];
+                w[u][6] = q[i];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (i0 + u * kThreads < n) {
+                Cart c = mad_to_cart(rp, w[u][0], w[u][1], w[u][2], w[u][3], w[u][4], w[u][5]);
+                double a, b, g, g0, g1, g2;
+                rotate_stretch(f, c.x, c.y, c.z, a, b, g);
+                to_grid(m, a, b, g, g0, g1, g2);
+                int c0 = (int)floor(g0) + 1, c1 = (int)floor(g1) + 1, c2 = (int)floor(g2) + 1;   // sc.py:191
+                if ((unsigned)c0 < (unsigned)md.nx && (unsigned)c1 < (unsigned)md.ny && (unsigned)c2 < (unsigned)md.nz)
+                    atomicAdd(rho + ((size_t)c0 * md.ny + c1) * md.nz + c2, w[u][6]);            // sc.py:192-193
+            }
+        }
     }
 }
 
 // ---------------------------------------------------------------------------
 // integrated Green's function (sc.py:109-133)
 // ---------------------------------------------------------------------------
+// every product and sum is an explicitly rounded operation, in the order of
+// sc.py:124-126, so the compiler cannot contract them: the 8-corner difference
+// below amplifies any rounding difference by up to (r/h)^3.
 __device__ __forceinline__ double igf_antiderivative(double x, double y, double z) {
-    double rr = sqrt(x * x + y * y + z * z);
-    double g = -x * x * 0.5 * atan(y * z / (x * rr));
-    g = g + y * z * log(x + rr);
-    g = g - y * y * 0.5 * atan(z * x / (y * rr));
-    g = g + z * x * log(y + rr);
-    g = g - z * z * 0.5 * atan(x * y / (z * rr));
-    g = g + x * y * log(z + rr);
+    const double xx = __dmul_rn(x, x), yy = __dmul_rn(y, y), zz = __dmul_rn(z, z);
+    const double rr = sqrt(__dadd_rn(__dadd_rn(xx, yy), zz));
+    const double yz = __dmul_rn(y, z), zx = __dmul_rn(z, x), xy = __dmul_rn(x, y);
+    double g = __dmul_rn(__dmul_rn(-xx, 0.5), atan(yz / __dmul_rn(x, rr)));
+    g = __dadd_rn(g, __dmul_rn(yz, log(__dadd_rn(x, rr))));
+    g = __dsub_rn(g, __dmul_rn(__dmul_rn(yy, 0.5), atan(zx / __dmul_rn(y, rr))));
+    g = __dadd_rn(g, __dmul_rn(zx, log(__dadd_rn(y, rr))));
+    g = __dsub_rn(g, __dmul_rn(__dmul_rn(zz, 0.5), atan(xy / __dmul_rn(z, rr))));
+    g = __dadd_rn(g, __dmul_rn(xy, log(__dadd_rn(z, rr))));
     return g;
 }
 
@@ -203,9 +257,10 @@ __device__ __forceinline__ void resolve_steps(const StepSrc& src, const ReduceSt
 
 // antiderivative on the (n+1)^3 half-offset points (sc.py:116-126)
 __global__ void __launch_bounds__(kThreads) k_green_table(StepSrc src, ReduceState rs, MeshDims md, Draws dr,
-                                                         double* __restrict__ gtab) {
+                                                         double* __restrict__ gtab, double* __restrict__ h3) {
     __shared__ double h[3];
     resolve_steps(src, rs, md, dr, h);
+    if (blockIdx.x == 0 && threadIdx.x == 0) { h3[0] = h[0]; h3[1] = h[1]; h3[2] = h[2]; }   // for the solver
     const int gx = md.nx + 1, gy = md.ny + 1, gz = md.nz + 1;
     const long long total = (long long)gx * gy * gz;
     for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total; t += (long long)gridDim.x * kThreads) {
@@ -213,9 +268,9 @@ __global__ void __launch_bounds__(kThreads) k_green_table(StepSrc src, ReduceSta
         long long u = t / gz;
         int j = (int)(u % gy);
         int i = (int)(u / gy);
-        double x = h[0] * (double)i - h[0] / 2;
-        double y = h[1] * (double)j - h[1] / 2;
-        double z = h[2] * (double)k - h[2] / 2;
+        double x = __dsub_rn(__dmul_rn(h[0], (double)i), h[0] / 2);
+        double y = __dsub_rn(__dmul_rn(h[1], (double)j), h[1] / 2);
+        double z = __dsub_rn(__dmul_rn(h[2], (double)k), h[2] / 2);
         gtab[t] = igf_antiderivative(x, y, z);
     }
 }
@@ -234,22 +289,27 @@ __device__ __forceinline__ double green_entry(const double* __restrict__ G, int 
     return v;
 }
 
-// K on the padded periodic grid: K[d mod M] = K1[|d|], zero in the gap (sc.py:145-149)
+// K on the padded periodic grid: K[d mod M] = K1[|d|] (sc.py:145-149).  One
+// thread per K1 entry writes its (up to 8) mirror images; the gap planes
+// n <= d <= M-n were zeroed by a memset.
 __global__ void __launch_bounds__(kThreads) k_green_mirror(const double* __restrict__ gtab, MeshDims md,
                                                           double* __restrict__ kpad) {
-    const long long total = (long long)md.mx * md.my * md.mz;
+    const long long total = (long long)md.nx * md.ny * md.nz;
     const int gy = md.ny + 1, gz = md.nz + 1;
     for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total; t += (long long)gridDim.x * kThreads) {
-        int c = (int)(t % md.mz);
-        long long u = t / md.mz;
-        int b = (int)(u % md.my);
-        int a = (int)(u / md.my);
-        int da = a < md.nx ? a : (a > md.mx - md.nx ? md.mx - a : -1);
-        int db = b < md.ny ? b : (b > md.my - md.ny ? md.my - b : -1);
-        int dc = c < md.nz ? c : (c > md.mz - md.nz ? md.mz - c : -1);
-        double v = 0.0;
-        if (da >= 0 && db >= 0 && dc >= 0) v = green_entry(gtab, gy, gz, da, db, dc);
-        kpad[t] = v;
+        int c = (int)(t % md.nz);
+        long long u = t / md.nz;
+        int b = (int)(u % md.ny);
+        int a = (int)(u / md.ny);
+        const double v = green_entry(gtab, gy, gz, a, b, c);
+        const int na = a ? 2 : 1, nb = b ? 2 : 1, nc = c ? 2 : 1;
+        for (int ia = 0; ia < na; ++ia) {
+            const size_t pa = (size_t)(ia ? md.mx - a : a) * md.my;
+            for (int ib = 0; ib < nb; ++ib) {
+                const size_t pb = (pa + (ib ? md.my - b : b)) * md.mz;
+                for (int ic = 0; ic < nc; ++ic) kpad[pb + (ic ? md.mz - c : c)] = v;
+            }
+        }
     }
 }
 
@@ -310,23 +370,38 @@ __global__ void __launch_bounds__(kThreads) k_crop_phi(const double* __restrict_
     }
 }
 
-// staggered backward differences, last plane zero (sc.py:195-200)
+// staggered backward differences, last plane zero (sc.py:195-200), stored as
+// the quad table the gather reads: equad[comp][i][j][k] = E_comp at
+// (i,j,k), (i,j,k+1), (i,j+1,k), (i,j+1,k+1) with the upper indices clamped.
+__device__ __forceinline__ double field_value(const double* __restrict__ phi, const MeshDims& md, const double* h,
+                                              int comp, int i, int j, int k) {
+    const size_t sy = md.nz, sx = (size_t)md.ny * md.nz;
+    const size_t t = (size_t)i * sx + (size_t)j * sy + k;
+    if (comp == 0) return (i < md.nx - 1) ? (__ldg(phi + t) - __ldg(phi + t + sx)) / h[0] : 0.0;
+    if (comp == 1) return (j < md.ny - 1) ? (__ldg(phi + t) - __ldg(phi + t + sy)) / h[1] : 0.0;
+    return (k < md.nz - 1) ? (__ldg(phi + t) - __ldg(phi + t + 1)) / h[2] : 0.0;
+}
+
 __global__ void __launch_bounds__(kThreads) k_field(const double* __restrict__ phi, StepSrc src, ReduceState rs,
-                                                   MeshDims md, Draws dr, double* __restrict__ ex,
-                                                   double* __restrict__ ey, double* __restrict__ ez) {
+                                                   MeshDims md, Draws dr, EQuad* __restrict__ equad) {
     __shared__ double h[3];
     resolve_steps(src, rs, md, dr, h);
-    const long long total = (long long)md.nx * md.ny * md.nz;
-    const size_t sx = (size_t)md.ny * md.nz, sy = md.nz;
+    const long long cells = (long long)md.nx * md.ny * md.nz;
+    const long long total = 3 * cells;
     for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total; t += (long long)gridDim.x * kThreads) {
-        int c = (int)(t % md.nz);
-        long long u = t / md.nz;
-        int b = (int)(u % md.ny);
-        int a = (int)(u / md.ny);
-        double p = phi[t];
-        ex[t] = (a < md.nx - 1) ? (p - __ldg(phi + t + sx)) / h[0] : 0.0;
-        ey[t] = (b < md.ny - 1) ? (p - __ldg(phi + t + sy)) / h[1] : 0.0;
-        ez[t] = (c < md.nz - 1) ? (p - __ldg(phi + t + 1)) / h[2] : 0.0;
+        int comp = (int)(t / cells);
+        long long w = t - comp * cells;
+        int k = (int)(w % md.nz);
+        long long u = w / md.nz;
+        int j = (int)(u % md.ny);
+        int i = (int)(u / md.ny);
+        int j1 = min(j + 1, md.ny - 1), k1 = min(k + 1, md.nz - 1);
+        EQuad e;
+        e.v00 = field_value(phi, md, h, comp, i, j, k);
+        e.v01 = field_value(phi, md, h, comp, i, j, k1);
+        e.v10 = field_value(phi, md, h, comp, i, j1, k);
+        e.v11 = field_value(phi, md, h, comp, i, j1, k1);
+        equad[t] = e;
     }
 }
 
@@ -336,8 +411,7 @@ __global__ void __launch_bounds__(kThreads) k_field(const double* __restrict__ p
 template <bool KICK, bool TAP>
 __global__ void __launch_bounds__(kThreads) k_gather_kick(double* __restrict__ r, long long ld, long long n,
                                                          RefParams rp, ReduceState rs, MeshDims md, Draws dr,
-                                                         const double* __restrict__ ex, const double* __restrict__ ey,
-                                                         const double* __restrict__ ez, double cdT,
+                                                         const EQuad* __restrict__ equad, double cdT,
                                                          double* __restrict__ exyz_out) {
     __shared__ Frame sf;
     __shared__ Mesh sm;
@@ -349,33 +423,53 @@ __global__ void __launch_bounds__(kThreads) k_gather_kick(double* __restrict__ r
     const Frame f = sf;
     const Mesh m = sm;
     const double kt = cdT * (1.0 - f.beta0 * f.beta0);   // sc.py:246-247
-    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n; i += (long long)gridDim.x * kThreads) {
-        Cart c = mad_to_cart(rp, r[i], r[ld + i], r[2 * ld + i], r[3 * ld + i], r[4 * ld + i], r[5 * ld + i]);
-        double a, b, g, g0, g1, g2;
-        rotate_stretch(f, c.x, c.y, c.z, a, b, g);
-        to_grid(m, a, b, g, g0, g1, g2);
-        double e0 = trilinear(ex, md.nx, md.ny, md.nz, g0, g1 + 0.5, g2 + 0.5) * f.gamma0;   // :202
-        double e1 = trilinear(ey, md.nx, md.ny, md.nz, g0 + 0.5, g1, g2 + 0.5) * f.gamma0;   // :203
-        double e2 = trilinear(ez, md.nx, md.ny, md.nz, g0 + 0.5, g1 + 0.5, g2);              // :204
-        if (TAP) {
-            exyz_out[3 * i + 0] = e0; exyz_out[3 * i + 1] = e1; exyz_out[3 * i + 2] = e2;
+    const size_t cells = (size_t)md.nx * md.ny * md.nz;
+    const EQuad* __restrict__ ex = equad;
+    const EQuad* __restrict__ ey = equad + cells;
+    const EQuad* __restrict__ ez = equad + 2 * cells;
+    constexpr int U = 2;
+    for (long long i0 = (long long)blockIdx.x * (kThreads * U) + threadIdx.x; i0 < n;
+         i0 += (long long)gridDim.x * (kThreads * U)) {
+        double w[U][6];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * kThreads;
+            if (i < n) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) w[u][k] = r[k * ld + i];
+            }
         }
-        if (KICK) {
-            // momenta into the bunch frame (sc.py:234)
-            double p0 = c.px * f.T[0][0] + c.py * f.T[1][0] + c.pz * f.T[2][0];
-            double p1 = c.px * f.T[0][1] + c.py * f.T[1][1] + c.pz * f.T[2][1];
-            double p2 = c.px * f.T[0][2] + c.py * f.T[1][2] + c.pz * f.T[2][2];
-            p0 = p0 + kt * e0;                                                             // :246
-            p1 = p1 + kt * e1;                                                             // :247
-            p2 = p2 + cdT * e2;                                                            // :248
-            // back to the lab axes (sc.py:249-250)
-            c.px = p0 * f.T[0][0] + p1 * f.T[0][1] + p2 * f.T[0][2];
-            c.py = p0 * f.T[1][0] + p1 * f.T[1][1] + p2 * f.T[1][2];
-            c.pz = p0 * f.T[2][0] + p1 * f.T[2][1] + p2 * f.T[2][2];
-            double x, xs, y, ys, tau, delta;
-            cart_to_mad(rp, c, x, xs, y, ys, tau, delta);                                  // :251
-            r[i] = x; r[ld + i] = xs; r[2 * ld + i] = y; r[3 * ld + i] = ys; r[4 * ld + i] = tau;
-            r[5 * ld + i] = delta;
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long i = i0 + u * kThreads;
+            if (i >= n) continue;
+            Cart c = mad_to_cart(rp, w[u][0], w[u][1], w[u][2], w[u][3], w[u][4], w[u][5]);
+            double a, b, g, g0, g1, g2;
+            rotate_stretch(f, c.x, c.y, c.z, a, b, g);
+            to_grid(m, a, b, g, g0, g1, g2);
+            double e0 = trilinear(ex, md.nx, md.ny, md.nz, g0, g1 + 0.5, g2 + 0.5) * f.gamma0;   // :202
+            double e1 = trilinear(ey, md.nx, md.ny, md.nz, g0 + 0.5, g1, g2 + 0.5) * f.gamma0;   // :203
+            double e2 = trilinear(ez, md.nx, md.ny, md.nz, g0 + 0.5, g1 + 0.5, g2);              // :204
+            if (TAP) {
+                exyz_out[3 * i + 0] = e0; exyz_out[3 * i + 1] = e1; exyz_out[3 * i + 2] = e2;
+            }
+            if (KICK) {
+                // momenta into the bunch frame (sc.py:234)
+                double p0 = c.px * f.T[0][0] + c.py * f.T[1][0] + c.pz * f.T[2][0];
+                double p1 = c.px * f.T[0][1] + c.py * f.T[1][1] + c.pz * f.T[2][1];
+                double p2 = c.px * f.T[0][2] + c.py * f.T[1][2] + c.pz * f.T[2][2];
+                p0 = p0 + kt * e0;                                                             // :246
+                p1 = p1 + kt * e1;                                                             // :247
+                p2 = p2 + cdT * e2;                                                            // :248
+                // back to the lab axes (sc.py:249-250)
+                c.px = p0 * f.T[0][0] + p1 * f.T[0][1] + p2 * f.T[0][2];
+                c.py = p0 * f.T[1][0] + p1 * f.T[1][1] + p2 * f.T[1][2];
+                c.pz = p0 * f.T[2][0] + p1 * f.T[2][1] + p2 * f.T[2][2];
+                double x, xs, y, ys, tau, delta;
+                cart_to_mad(rp, c, x, xs, y, ys, tau, delta);                                  // :251
+                r[i] = x; r[ld + i] = xs; r[2 * ld + i] = y; r[3 * ld + i] = ys; r[4 * ld + i] = tau;
+                r[5 * ld + i] = delta;
+            }
         }
     }
 }
@@ -423,24 +517,25 @@ void launch_extent(const double* r, long long ld, const double* q, long long n, 
 }
 void launch_deposit(const double* r, long long ld, const double* q, long long n, RefParams rp, ReduceState rs,
                     MeshDims md, Draws dr, double* rho, cudaStream_t st) {
-    k_deposit<<<grid_for(n, kSweepCap), kThreads, 0, st>>>(r, ld, q, n, rp, rs, md, dr, rho);
+    k_deposit<<<grid_for((n + 3) / 4, kSweepCap), kThreads, 0, st>>>(r, ld, q, n, rp, rs, md, dr, rho);
 }
-void launch_green_table(ReduceState rs, MeshDims md, Draws dr, double* gtab, cudaStream_t st) {
+void launch_green_table(ReduceState rs, MeshDims md, Draws dr, double* gtab, double* h3, cudaStream_t st) {
     StepSrc src;
     src.given = 0; src.h[0] = src.h[1] = src.h[2] = 0.0;
     long long total = (long long)(md.nx + 1) * (md.ny + 1) * (md.nz + 1);
-    k_green_table<<<grid_for(total, kGridCap), kThreads, 0, st>>>(src, rs, md, dr, gtab);
+    k_green_table<<<grid_for(total, kGridCap), kThreads, 0, st>>>(src, rs, md, dr, gtab, h3);
 }
-void launch_green_table_steps(const double steps[3], MeshDims md, double* gtab, cudaStream_t st) {
+void launch_green_table_steps(const double steps[3], MeshDims md, double* gtab, double* h3, cudaStream_t st) {
     StepSrc src;
     src.given = 1; src.h[0] = steps[0]; src.h[1] = steps[1]; src.h[2] = steps[2];
     ReduceState rs = {};
     Draws dr = {0.0, 0.0};
     long long total = (long long)(md.nx + 1) * (md.ny + 1) * (md.nz + 1);
-    k_green_table<<<grid_for(total, kGridCap), kThreads, 0, st>>>(src, rs, md, dr, gtab);
+    k_green_table<<<grid_for(total, kGridCap), kThreads, 0, st>>>(src, rs, md, dr, gtab, h3);
 }
 void launch_green_mirror(const double* gtab, MeshDims md, double* kpad, cudaStream_t st) {
-    long long total = (long long)md.mx * md.my * md.mz;
+    cudaMemsetAsync(kpad, 0, sizeof(double) * (size_t)md.mx * md.my * md.mz, st);
+    long long total = (long long)md.nx * md.ny * md.nz;
     k_green_mirror<<<grid_for(total, kGridCap), kThreads, 0, st>>>(gtab, md, kpad);
 }
 void launch_green_compact(const double* gtab, MeshDims md, double* k1, cudaStream_t st) {
@@ -456,7 +551,9 @@ void launch_multiply(cufftDoubleComplex* rho_hat, const cufftDoubleComplex* k_ha
     double inv = 1.0 / ((double)md.mx * (double)md.my * (double)md.mz);
     k_multiply<<<grid_for(total, kGridCap), kThreads, 0, st>>>(rho_hat, k_hat, total, inv);
 }
-static double four_pi_eps0() {
+double four_pi_eps0_value();
+static double four_pi_eps0() { return four_pi_eps0_value(); }
+double four_pi_eps0_value() {
     const double pi = 3.141592653589793, c = 299792458.0;   // ocelot/common/globals.py:13-24
     const double mu0 = 4 * pi * 1e-7;
     const double eps0 = 1 / mu0 / (c * c);
@@ -476,24 +573,22 @@ void launch_crop_phi_steps(const double* conv, const double steps[3], MeshDims m
     long long total = (long long)md.nx * md.ny * md.nz;
     k_crop_phi<<<grid_for(total, kGridCap), kThreads, 0, st>>>(conv, src, rs, md, dr, four_pi_eps0(), phi);
 }
-void launch_field(const double* phi, ReduceState rs, MeshDims md, Draws dr, double* ex, double* ey, double* ez,
-                  cudaStream_t st) {
+void launch_field(const double* phi, ReduceState rs, MeshDims md, Draws dr, EQuad* equad, cudaStream_t st) {
     StepSrc src;
     src.given = 0; src.h[0] = src.h[1] = src.h[2] = 0.0;
-    long long total = (long long)md.nx * md.ny * md.nz;
-    k_field<<<grid_for(total, kGridCap), kThreads, 0, st>>>(phi, src, rs, md, dr, ex, ey, ez);
+    long long total = 3LL * md.nx * md.ny * md.nz;
+    k_field<<<grid_for(total, kGridCap), kThreads, 0, st>>>(phi, src, rs, md, dr, equad);
 }
 void launch_gather_kick(double* r, long long ld, long long n, RefParams rp, ReduceState rs, MeshDims md, Draws dr,
-                        const double* ex, const double* ey, const double* ez, double dz, double* exyz_out,
-                        int do_kick, cudaStream_t st) {
+                        const EQuad* equad, double dz, double* exyz_out, int do_kick, cudaStream_t st) {
     const double cdT = dz / rp.betaref;   // sc.py:244
-    int grid = grid_for(n, kSweepCap);
+    int grid = grid_for((n + 1) / 2, kSweepCap);
     if (do_kick && exyz_out)
-        k_gather_kick<true, true><<<grid, kThreads, 0, st>>>(r, ld, n, rp, rs, md, dr, ex, ey, ez, cdT, exyz_out);
+        k_gather_kick<true, true><<<grid, kThreads, 0, st>>>(r, ld, n, rp, rs, md, dr, equad, cdT, exyz_out);
     else if (do_kick)
-        k_gather_kick<true, false><<<grid, kThreads, 0, st>>>(r, ld, n, rp, rs, md, dr, ex, ey, ez, cdT, nullptr);
+        k_gather_kick<true, false><<<grid, kThreads, 0, st>>>(r, ld, n, rp, rs, md, dr, equad, cdT, nullptr);
     else
-        k_gather_kick<false, true><<<grid, kThreads, 0, st>>>(r, ld, n, rp, rs, md, dr, ex, ey, ez, cdT, exyz_out);
+        k_gather_kick<false, true><<<grid, kThreads, 0, st>>>(r, ld, n, rp, rs, md, dr, equad, cdT, exyz_out);
 }
 void launch_mad_to_cart(const double* r, long long ld, long long n, RefParams rp, double* xp, long long ld_xp,
                         cudaStream_t st) {

@@ -34,23 +34,39 @@ void launch_extent(const double* r, long long ld, const double* q, long long n, 
                    cudaStream_t st);
 void launch_deposit(const double* r, long long ld, const double* q, long long n, RefParams rp, ReduceState rs,
                     MeshDims md, Draws dr, double* rho, cudaStream_t st);
-void launch_green_table(ReduceState rs, MeshDims md, Draws dr, double* gtab, cudaStream_t st);
+void launch_green_table(ReduceState rs, MeshDims md, Draws dr, double* gtab, double* h3, cudaStream_t st);
 void launch_green_mirror(const double* gtab, MeshDims md, double* kpad, cudaStream_t st);
 void launch_green_compact(const double* gtab, MeshDims md, double* k1, cudaStream_t st);
 void launch_pad_rho(const double* rho, MeshDims md, double* pad, cudaStream_t st);
 void launch_multiply(cufftDoubleComplex* rho_hat, const cufftDoubleComplex* k_hat, MeshDims md, cudaStream_t st);
 void launch_crop_phi(const double* conv, ReduceState rs, MeshDims md, Draws dr, double* phi, cudaStream_t st);
-void launch_field(const double* phi, ReduceState rs, MeshDims md, Draws dr, double* ex, double* ey, double* ez,
-                  cudaStream_t st);
+void launch_field(const double* phi, ReduceState rs, MeshDims md, Draws dr, EQuad* equad, cudaStream_t st);
 void launch_gather_kick(double* r, long long ld, long long n, RefParams rp, ReduceState rs, MeshDims md, Draws dr,
-                        const double* ex, const double* ey, const double* ez, double dz, double* exyz_out,
-                        int do_kick, cudaStream_t st);
+                        const EQuad* equad, double dz, double* exyz_out, int do_kick, cudaStream_t st);
 void launch_mad_to_cart(const double* r, long long ld, long long n, RefParams rp, double* xp, long long ld_xp,
                         cudaStream_t st);
 void launch_cart_to_mad(const double* xp, long long ld_xp, long long n, RefParams rp, double* r, long long ld,
                         cudaStream_t st);
+// ---- hand-written Hockney convolution (sc_fft.cu) ----
+struct FftWork {
+    const double2* tw_x;   // exp(-2 pi i m / M) tables, one per axis
+    const double2* tw_y;
+    const double2* tw_z;
+    double* P;             // [nx][ny][Mz/2+1]            K_hat after pass z
+    double* Q;             // [nx][My/2+1][Mz/2+1]        K_hat after pass y
+    double* khat;          // [Mx/2+1][My/2+1][Mz/2+1]    real, even
+    double2* A;            // [nx][ny][Mz/2+1]            rho after pass z / before inverse z
+    double2* B;            // [nx][My][Mz/2+1]            rho after pass y; pass x in place
+};
+void fft_init_kernels();
+int fft_max_length();
+void launch_khat(const double* gtab, MeshDims md, FftWork w, cudaStream_t st);
+void launch_convolve(const double* rho, MeshDims md, FftWork w, const double* h3, double four_pi_eps0, double* phi,
+                     cudaStream_t st);
+double four_pi_eps0_value();
+
 // potential KAT helpers: steps given explicitly instead of derived from particles
-void launch_green_table_steps(const double steps[3], MeshDims md, double* gtab, cudaStream_t st);
+void launch_green_table_steps(const double steps[3], MeshDims md, double* gtab, double* h3, cudaStream_t st);
 void launch_crop_phi_steps(const double* conv, const double steps[3], MeshDims md, double* phi, cudaStream_t st);
 
 }  // namespace ocl

@@ -1,0 +1,147 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol the header
+declares; the host-side mirror behaves like the reference's plugin (API,
+side effects, copy semantics); the product never routes through the oracle."""
+import copy
+import os
+import pickle
+import re
+import sys
+
+import numpy as np
+import pytest
+
+from ocelot_b200 import SpaceCharge, PhysProc, ParticleArray, native, constants
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = native.load()
+    declared = native.declared_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert set(declared) == set(native._SIGNATURES)
+    assert lib.ocl_sc_abi_version() == 1
+
+
+def test_constants_and_fft_size_without_gpu():
+    k = native.constants()                           # ocelot/common/globals.py:13-24
+    assert k["m_e_eV"] == constants.m_e_eV == 9.10938215e-31 * 299792458.0 ** 2 / 1.6021766208e-19
+    assert k["m_e_GeV"] == constants.m_e_GeV
+    assert k["epsilon_0"] == constants.epsilon_0
+    assert [native.fft_size(n) for n in (4, 31, 63, 64, 65, 127, 255)] == [8, 64, 128, 128, 256, 256, 512]
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(RuntimeError, match="no CUDA device|no CPU fallback"):
+        native.Solver(0, (31, 31, 31))
+    sc = SpaceCharge()
+    p = ParticleArray(10)
+    p.E = 0.1
+    with pytest.raises(RuntimeError):
+        sc.apply(p, 0.1)
+    sc.apply(p, 0)                                   # zstep == 0 returns before touching anything (sc.py:210-212)
+
+
+def test_product_does_not_import_oracle_or_reference():
+    pkg = os.path.join(ROOT, "ocelot_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, re.M), f
+                assert "/root/reference" not in text, f
+
+
+def test_plugin_api_matches_reference_class():
+    sc = SpaceCharge(step=5, nmesh_xyz=[31, 31, 31], random_mesh=True, ste=1)   # unknown kwargs ignored (sc.py:92-102)
+    assert isinstance(sc, PhysProc)
+    assert sc.step == 5 and sc.nmesh_xyz == [31, 31, 31] and sc.random_mesh is True
+    assert sc.low_order_kick is True and sc.random_seed == 10 and sc.debug is False
+    for attr in ("start_elem", "end_elem", "indx0", "indx1", "s_start", "s_stop", "z0", "energy"):
+        assert hasattr(sc, attr)
+    assert repr(sc) == "<SpaceCharge: step=5, nmesh_xyz=[31, 31, 31], random_mesh=True>"   # sc.py:253-258
+    d = SpaceCharge()
+    assert d.step == 1 and d.nmesh_xyz == [63, 63, 63] and d.random_mesh is False
+    sc.finalize()
+    # prepare reseeds the GLOBAL numpy RNG (sc.py:104-107)
+    sc.prepare(None)
+    a = np.random.uniform()
+    np.random.seed(10)
+    assert a == np.random.uniform()
+    sc.random_seed = None
+    np.random.seed(123)
+    x = np.random.uniform()
+    np.random.seed(123)
+    sc.prepare(None)
+    assert x == np.random.uniform()
+
+
+def test_deepcopy_and_pickle_drop_native_handles():
+    sc = SpaceCharge(step=2, nmesh_xyz=[15, 15, 15])
+    sc._solvers = {("fake",): object()}
+    sc.counter = 2                                   # injected by Navigator (navi.py:81)
+    c = copy.deepcopy(sc)
+    assert c._solvers == {} and c.step == 2 and c.nmesh_xyz == [15, 15, 15] and c.counter == 2
+    assert c.nmesh_xyz is not sc.nmesh_xyz
+    sc._solvers = {}
+    r = pickle.loads(pickle.dumps(sc))
+    assert r._solvers == {} and r.step == 2
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/ocelot"), reason="reference checkout not present")
+def test_drop_in_under_reference_navigator_and_track(monkeypatch):
+    """Unmodified Navigator/track() drive the class (navi.py:63-98, track.py:470-477);
+    the native engine is replaced by an oracle-backed double because this box has no GPU."""
+    sys.path.insert(0, "/root/reference")
+    import logging
+    logging.disable(logging.WARNING)
+    from ocelot import MagneticLattice, Navigator, Drift, Quadrupole, Marker, track
+    from ocelot.cpbd.beam import ParticleArray as RefParticleArray
+    from ocelot.cpbd.sc import SpaceCharge as RefSpaceCharge
+    from oracle import sc_oracle as orc
+
+    calls = []
+
+    class OracleSolver:                                # stands in for native.Solver in this CPU-only test
+        def __init__(self, device, nmesh):
+            self.nmesh = nmesh
+
+        def kick_host(self, r, q, E, dz, draws):
+            calls.append(dz)
+            kw = {} if draws is None else dict(mesh_scale=draws[0], mesh_shift=draws[1])
+            orc.sc_kick(r, q, E, dz, self.nmesh, **kw)
+
+    monkeypatch.setattr(SpaceCharge, "_host_device", lambda self: 0)
+    monkeypatch.setattr(native, "Solver", OracleSolver)
+
+    def build(sc_cls):
+        m1, m2 = Marker(), Marker()
+        cell = (m1, Drift(l=0.25), Quadrupole(l=0.2, k1=2.0), Drift(l=0.25), Quadrupole(l=0.2, k1=-2.0), Drift(l=0.1), m2)
+        lat = MagneticLattice(cell)
+        navi = Navigator(lat)
+        navi.unit_step = 0.1
+        sc = sc_cls()
+        sc.step = 2
+        sc.nmesh_xyz = [15, 15, 15]
+        navi.add_physics_proc(sc, m1, m2)
+        np.random.seed(5)
+        p = RefParticleArray(n=3000)
+        p.rparticles[:] = orc.gaussian_bunch(3000, energy=0.02, charge=2e-10)[0]
+        p.q_array[:] = 2e-10 / 3000
+        p.E = 0.02
+        return lat, navi, p
+
+    lat, navi, p = build(SpaceCharge)
+    track(lat, p, navi, print_progress=False)
+    lat2, navi2, p2 = build(RefSpaceCharge)
+    track(lat2, p2, navi2, print_progress=False)
+    assert len(calls) >= 4
+    assert np.array_equal(p.rparticles, p2.rparticles)   # same arithmetic, same bits
+    # reset_position deep-copies the process table and calls prepare again (navi.py:142-156)
+    navi.reset_position()
+    assert navi.process_table.proc_list[0]._solvers == {}

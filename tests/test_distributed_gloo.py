@@ -1,0 +1,146 @@
+"""world_size-2 gloo test of the particle-sharded kick (CPU only).
+
+The sharding / collective logic of ocelot_b200.distributed is exercised with a
+stage engine backed by the oracle (test infrastructure standing in for the
+CUDA stages): two ranks, each holding half of the bunch, must reproduce the
+single-process oracle kick."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import sc_oracle as orc
+from ocelot_b200.distributed import shard_bounds, sharded_kick
+
+
+class OracleStageEngine:
+    """The five stages restated on the CPU from oracle functions, with the same
+    reduction buffers as the native handle (include/ocelot_sc.h)."""
+
+    def __init__(self, nmesh):
+        self.nmesh = np.array(nmesh)
+        self.buffers = {"momentum": torch.zeros(4, dtype=torch.float64),
+                        "extent_max": torch.zeros(6, dtype=torch.float64),
+                        "extent_sum": torch.zeros(4, dtype=torch.float64),
+                        "rho": torch.zeros(int(np.prod(nmesh)), dtype=torch.float64)}
+
+    def momentum(self, r, q, E):
+        self.gamref = E / orc.M_E_GEV
+        self.xp = orc.mad_to_cartesian(r.numpy(), self.gamref)
+        self.buffers["momentum"][:3] = torch.from_numpy(self.xp[3:6].sum(axis=1))
+        self.buffers["momentum"][3] = r.shape[1]
+
+    def _frame(self):
+        s = self.buffers["momentum"].numpy()
+        mean = s[:3] / s[3]
+        # bunch_frame takes the momenta; feed it the global mean as a single "particle"
+        return orc.bunch_frame(mean.reshape(3, 1))
+
+    def extent(self, r, q, E):
+        self.T, self.pav, self.gamma0, self.beta0 = self._frame()
+        X = np.dot(self.xp[0:3].T, self.T)
+        X[:, 2] *= self.gamma0
+        self.X = X
+        qn = q.numpy()
+        self.buffers["extent_max"][:3] = torch.from_numpy(X.max(axis=0))
+        self.buffers["extent_max"][3:] = torch.from_numpy(-X.min(axis=0))
+        self.buffers["extent_sum"][:3] = torch.from_numpy(qn @ X)
+        self.buffers["extent_sum"][3] = qn.sum()
+
+    def _mesh(self, draws):
+        em, es = self.buffers["extent_max"].numpy(), self.buffers["extent_sum"].numpy()
+        extent = em[:3] + em[3:]
+        if draws is not None:
+            extent = extent * draws[0]
+        steps = extent / (self.nmesh - 3)
+        xmid = (es[:3] / steps) / es[3]
+        xoff = np.floor(-em[3:] / steps - xmid) + xmid
+        if draws is not None:
+            xoff = xoff + draws[1]
+        return steps, xoff
+
+    def deposit(self, r, q, E, draws):
+        self.steps, self.xoff = self._mesh(draws)
+        self.Xg = self.X / self.steps - self.xoff
+        idx = orc.cell_index(self.Xg, self.nmesh)
+        self.buffers["rho"][:] = torch.from_numpy(orc.deposit_ngp(idx, q.numpy(), self.nmesh).ravel())
+
+    def solve(self, draws):
+        rho = self.buffers["rho"].numpy().reshape(tuple(self.nmesh))
+        phi = orc.poisson_potential(rho, self.steps, fft="padded")
+        self.E3 = orc.staggered_field(phi, self.steps)
+
+    def kick(self, r, E, dz, draws):
+        Xg, g0 = self.Xg, self.gamma0
+        Ex = orc.trilinear(self.E3[0], Xg[:, 0], Xg[:, 1] + 0.5, Xg[:, 2] + 0.5) * g0
+        Ey = orc.trilinear(self.E3[1], Xg[:, 0] + 0.5, Xg[:, 1], Xg[:, 2] + 0.5) * g0
+        Ez = orc.trilinear(self.E3[2], Xg[:, 0] + 0.5, Xg[:, 1] + 0.5, Xg[:, 2])
+        xp = self.xp
+        betref = np.sqrt(1 - self.gamref ** -2)
+        cdT = dz / betref
+        p = np.dot(xp[3:6].T, self.T).T
+        p[0] += cdT * (1 - self.beta0 * self.beta0) * Ex
+        p[1] += cdT * (1 - self.beta0 * self.beta0) * Ey
+        p[2] += cdT * Ez
+        xp[3:6] = np.dot(p.T, self.T.T).T
+        orc.cartesian_to_mad(xp, r.numpy(), self.gamref)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, n, nmesh, draws, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        np.random.seed(3)
+        r0, q0, E = orc.gaussian_bunch(n, energy=0.05, charge=1e-10)
+        q0 = q0 * (0.5 + np.random.rand(n))
+        lo, hi = shard_bounds(n, world, rank)
+        r = torch.from_numpy(r0[:, lo:hi].copy())
+        q = torch.from_numpy(q0[lo:hi].copy())
+        sharded_kick(OracleStageEngine(nmesh), r, q, E, 0.07, draws)
+        out[rank] = (lo, hi, r.numpy().copy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("draws", [None, (1.05, 0.3)])
+def test_two_rank_sharded_kick_matches_single_process(draws):
+    n, nmesh, world = 6001, (15, 13, 17), 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_worker, args=(world, port, n, nmesh, draws, out), nprocs=world, join=True)
+        parts = [out[k] for k in range(world)]
+    np.random.seed(3)
+    r0, q0, E = orc.gaussian_bunch(n, energy=0.05, charge=1e-10)
+    q0 = q0 * (0.5 + np.random.rand(n))
+    ref = r0.copy()
+    kw = {} if draws is None else dict(mesh_scale=draws[0], mesh_shift=draws[1])
+    orc.sc_kick(ref, q0, E, 0.07, nmesh, fft="padded", **kw)
+    got = np.empty_like(ref)
+    covered = 0
+    for lo, hi, rr in parts:
+        got[:, lo:hi] = rr
+        covered += hi - lo
+    assert covered == n
+    for row in range(6):
+        assert np.max(np.abs(got[row] - ref[row])) / np.std(ref[row]) < 1e-10
+
+
+def test_shard_bounds_cover_everything():
+    for n in (0, 1, 7, 1000, 1001):
+        for w in (1, 2, 3, 8):
+            spans = [shard_bounds(n, w, r) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
