@@ -47,6 +47,9 @@ struct ocl_sc {
     double* stage_q = nullptr;
     long long stage_cap = 0;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t side_stream = nullptr;       // K_hat chain runs here, concurrent with the deposit
+    cudaEvent_t ev_fork = nullptr, ev_khat = nullptr;
+    bool khat_pending = false;
     cudaStream_t last_stream = nullptr;
     // timers
     bool timers = false;
@@ -97,6 +100,7 @@ RefParams ref_params(const ocl_sc* h, double E_GeV) {
     rp.gamref = E_GeV / h->m_e_GeV;                                  // sc.py:214
     rp.betaref = std::sqrt(1 - std::pow(rp.gamref, -2.0));           // sc.py:215-216
     rp.inv_betaref = 1.0 / rp.betaref;
+    rp.inv_gamref = 1.0 / rp.gamref;
     rp.gb_ref = rp.gamref * rp.betaref;
     rp.inv_gb2 = 1.0 / (rp.gb_ref * rp.gb_ref);
     rp.pc = rp.gb_ref * h->m_e_eV;
@@ -157,12 +161,30 @@ int make_twiddles(ocl_sc* h, int M, double2** out) {
     return 0;
 }
 
-// hand-written path: K_hat (3 real-even passes), rho passes with the multiply fused in x; writes phi
+// hand-written path: K_hat (3 real-even passes), rho passes with the multiply fused in x; writes phi.
+// If the K_hat chain was forked onto the side stream (khat_pending), join it before the x pass.
 int solve_fused(ocl_sc* h, cudaStream_t st) {
-    launch_khat(h->gtab, h->md, h->fw, st);
-    launch_convolve(h->rho, h->md, h->fw, h->h3, four_pi_eps0_value(), h->phi, st);
+    if (!h->khat_pending) launch_khat(h->gtab, h->md, h->fw, st);
+    launch_convolve_pre(h->rho, h->md, h->fw, st);
+    if (h->khat_pending) {
+        CU(h, cudaStreamWaitEvent(st, h->ev_khat, 0));
+        h->khat_pending = false;
+    }
+    launch_convolve_post(h->md, h->fw, h->h3, four_pi_eps0_value(), h->phi, st);
     h->launches += 8;
     return check_launch(h, "solve_fused");
+}
+
+// Green's function table + K_hat on the side stream, ordered after everything already in st
+int fork_khat(ocl_sc* h, Draws dr, cudaStream_t st) {
+    CU(h, cudaEventRecord(h->ev_fork, st));
+    CU(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
+    launch_green_table(h->rs, h->md, dr, h->gtab, h->h3, h->side_stream);
+    launch_khat(h->gtab, h->md, h->fw, h->side_stream);
+    CU(h, cudaEventRecord(h->ev_khat, h->side_stream));
+    h->khat_pending = true;
+    h->launches += 1;
+    return check_launch(h, "fork_khat");
 }
 
 // IGF -> K_hat, rho -> rho_hat, multiply, inverse: real_buf holds the convolution afterwards
@@ -263,6 +285,9 @@ int ocl_sc_create(int device, int nx, int ny, int nz, long long max_particles, o
     TRY(cudaMemset(h->rho, 0, sizeof(double) * n3));
     TRY(cudaMemset(h->phi, 0, sizeof(double) * n3));
     TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    TRY(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
+    TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    TRY(cudaEventCreateWithFlags(&h->ev_khat, cudaEventDisableTiming));
     for (int i = 0; i < T_COUNT; ++i) TRY(cudaEventCreate(&h->ev[i]));
     if (max_particles > 0) {
         TRY(cudaMalloc(&h->stage_r, sizeof(double) * 6 * max_particles));
@@ -286,6 +311,9 @@ void ocl_sc_destroy(ocl_sc_t* h) {
     cudaFree(h->stage_r); cudaFree(h->stage_q);
     for (int i = 0; i < T_COUNT; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->side_stream) cudaStreamDestroy(h->side_stream);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_khat) cudaEventDestroy(h->ev_khat);
     delete h;
 }
 
@@ -304,6 +332,7 @@ int ocl_sc_collective_buffer(ocl_sc_t* h, int which, double** d_ptr, long long* 
 int ocl_sc_stage_momentum(ocl_sc_t* h, const double* d_r, long long ld, long long n, double E_GeV, void* stream) {
     if (!h) return 1;
     if (n <= 0 || ld < n) return fail(h, "ocl_sc_stage_momentum", "need 0 < n <= ld");
+    if (n >= 2147483647LL - 2 * 148 * 4 * 256) return fail(h, "ocl_sc_stage_momentum", "more than 2^31 particles per GPU");
     if (set_device(h)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     h->last_stream = st;
@@ -332,6 +361,9 @@ int ocl_sc_stage_deposit(ocl_sc_t* h, const double* d_r, long long ld, const dou
     if (set_device(h)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     h->last_stream = st;
+    // the mesh steps are final once the extents are reduced: start the Green's-function / K_hat
+    // chain now, concurrently with the deposit and the first two rho passes
+    if (h->solver == 0 && fork_khat(h, draws_of(mesh_draws), st)) return 1;
     CU(h, cudaMemsetAsync(h->rho, 0, sizeof(double) * (size_t)h->md.nx * h->md.ny * h->md.nz, st));
     launch_deposit(d_r, ld, d_q, n, ref_params(h, E_GeV), h->rs, h->md, draws_of(mesh_draws), h->rho, st);
     h->launches += 2;
@@ -345,8 +377,10 @@ int ocl_sc_stage_solve(ocl_sc_t* h, const double* mesh_draws, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     h->last_stream = st;
     Draws dr = draws_of(mesh_draws);
-    launch_green_table(h->rs, h->md, dr, h->gtab, h->h3, st);
-    h->launches += 1;
+    if (!h->khat_pending) {
+        launch_green_table(h->rs, h->md, dr, h->gtab, h->h3, st);
+        h->launches += 1;
+    }
     if (h->solver == 0) {
         if (solve_fused(h, st)) return 1;
         mark(h, T_SOLVE, st);

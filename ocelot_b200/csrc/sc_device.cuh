@@ -25,6 +25,7 @@ struct RefParams {
     double m_e_eV;
     double inv_m2;     // 1 / m_e_eV^2
     double inv_betaref;
+    double inv_gamref;
 };
 
 // bunch frame (sc.py:224-239); T columns are t1, t2, t3
@@ -36,6 +37,7 @@ struct Frame {
 // mesh geometry (sc.py:173-186)
 struct Mesh {
     double steps[3];
+    double inv_steps[3];   // 1/steps (IEEE), so the per-particle X/steps is one multiply
     double xoff[3];
     double sumq;
     int n[3];
@@ -44,6 +46,33 @@ struct Mesh {
 struct Cart {
     double x, y, z, px, py, pz;
 };
+
+// Branch-free fp64 reciprocal and square root for normal, positive-range operands
+// (every use below is on gamma, momenta or mesh steps): hardware seed (MUFU.RCP64H /
+// MUFU.RSQ64H, ~2^-20) plus Newton / Goldschmidt steps in FMA arithmetic.  Results
+// are within 1 ulp of the IEEE value; the IEEE library routines cost ~4x the
+// instructions because of their special-case paths.
+__device__ __forceinline__ double fast_rcp(double a) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(a));
+    double e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-a, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-a, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ double fast_sqrt(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double g = a * y, h = 0.5 * y;
+    double r = fma(-h, g, 0.5);
+    g = fma(g, r, g); h = fma(h, r, h);
+    r = fma(-h, g, 0.5);
+    g = fma(g, r, g); h = fma(h, r, h);
+    const double d = fma(-g, g, a);      // residual correction: result within 1 ulp
+    return fma(d, h, g);
+}
 
 // ---- coord_transform.py:57-96, algebraically reduced ---------------------------
 // The reference builds gamma, beta, pz/p_ref, normalises the direction u and
@@ -55,14 +84,14 @@ struct Cart {
 // Same values to a few ulp, with 1 division + 1 square root instead of 10.
 __device__ __forceinline__ double mad_pz_rel(const RefParams& rp, double xs, double ys, double delta, double& gam) {
     gam = (rp.betaref * delta + 1.0) * rp.gamref;                 // :68
-    return sqrt((gam * gam - 1.0) * rp.inv_gb2 - xs * xs - ys * ys);   // :69-70
+    return fast_sqrt((gam * gam - 1.0) * rp.inv_gb2 - xs * xs - ys * ys);   // :69-70
 }
 
 __device__ __forceinline__ Cart mad_to_cart(const RefParams& rp, double x, double xs, double y, double ys,
                                             double tau, double delta) {
     double gam;
     double pzr = mad_pz_rel(rp, xs, ys, delta, gam);
-    double kt = (rp.gb_ref / gam) * tau;                          // beta/ratio * tau
+    double kt = (rp.gb_ref * fast_rcp(gam)) * tau;                // beta/ratio * tau
     Cart c;
     c.x = x - xs * kt;                                            // :90
     c.y = y - ys * kt;                                            // :91
@@ -79,12 +108,12 @@ __device__ __forceinline__ Cart mad_to_cart(const RefParams& rp, double x, doubl
 __device__ __forceinline__ void cart_to_mad(const RefParams& rp, const Cart& c, double& x, double& xs, double& y,
                                             double& ys, double& tau, double& delta) {
     double s = c.px * c.px + c.py * c.py + c.pz * c.pz;
-    double gam = sqrt(1.0 + s * rp.inv_m2);                       // :27
-    double zp = c.z / c.pz;
+    double gam = fast_sqrt(1.0 + s * rp.inv_m2);                  // :27
+    double zp = c.z * fast_rcp(c.pz);
     tau = -zp * (gam * rp.m_e_eV);                                // :47, :51
     x = c.x - zp * c.px;                                          // :48
     y = c.y - zp * c.py;                                          // :49
-    delta = (gam / rp.gamref - 1.0) * rp.inv_betaref;             // :50
+    delta = (gam * rp.inv_gamref - 1.0) * rp.inv_betaref;         // :50
     xs = c.px * rp.inv_pref;                                      // :52
     ys = c.py * rp.inv_pref;                                      // :53
 }
@@ -130,6 +159,7 @@ __device__ __forceinline__ void derive_mesh(const double* emax, const double* es
         double off = floor(xmin - xmid) + xmid;                        // :183
         if (scale > 0.0) off = off + shift;                            // :185
         m.steps[c] = h;
+        m.inv_steps[c] = 1.0 / h;
         m.xoff[c] = off;
     }
 }
@@ -146,9 +176,9 @@ __device__ __forceinline__ void rotate_stretch(const Frame& f, double x, double 
 // position in cell units relative to the mesh origin (sc.py:180, :186)
 __device__ __forceinline__ void to_grid(const Mesh& m, double a, double b, double c, double& g0, double& g1,
                                         double& g2) {
-    g0 = a / m.steps[0] - m.xoff[0];
-    g1 = b / m.steps[1] - m.xoff[1];
-    g2 = c / m.steps[2] - m.xoff[2];
+    g0 = __dsub_rn(__dmul_rn(a, m.inv_steps[0]), m.xoff[0]);   // two roundings, like X/steps - X_off
+    g1 = __dsub_rn(__dmul_rn(b, m.inv_steps[1]), m.xoff[1]);
+    g2 = __dsub_rn(__dmul_rn(c, m.inv_steps[2]), m.xoff[2]);
 }
 
 // Field table entry: the four (y,z) neighbours of one component at one cell,
@@ -184,6 +214,66 @@ __device__ __forceinline__ double trilinear(const EQuad* __restrict__ F, int nx,
     acc = acc + B.v10 * t0 * t1 * d0;
     acc = acc + B.v11 * t0 * t1 * t2;
     return acc;
+}
+
+// ---- asynchronous row pipeline -------------------------------------------------
+// Every particle sweep streams NR rows (6 coordinate rows and/or q) exactly once.
+// Each thread prefetches its own next D-1 trips into shared memory with
+// cp.async (LDGSTS) while it does the fp64 math of the current one: the bytes in
+// flight live in shared memory instead of registers, so the kernels keep 4
+// blocks/SM resident and neither the HBM latency nor the long fp64 div/sqrt
+// dependency chains are exposed.  A thread only ever reads the slots it filled
+// itself, so no block barrier is needed.
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+constexpr int kSweepThreads = 256;
+
+// body(i, v) is called once per particle i with v[k] = base[k][i].  n < 2^31.
+template <int NR, int D, typename F>
+__device__ __forceinline__ void pipelined_sweep(const double* const (&base)[NR], int n, double* sm, F&& body) {
+    const int stride = (int)gridDim.x * kSweepThreads;
+    int i = (int)blockIdx.x * kSweepThreads + (int)threadIdx.x;
+    int ip = i;
+    double* slot = sm + threadIdx.x;
+#pragma unroll
+    for (int d = 0; d < D - 1; ++d) {
+        if (ip < n) {
+#pragma unroll
+            for (int k = 0; k < NR; ++k) cp_async8(slot + (d * NR + k) * kSweepThreads, base[k] + ip);
+        }
+        cp_async_commit();
+        ip += stride;
+    }
+    while (i < n) {
+#pragma unroll
+        for (int st = 0; st < D; ++st) {           // static stage index: all shared-memory offsets are immediates
+            if (i < n) {
+                constexpr int dummy = 0; (void)dummy;
+                const int sp = (st + D - 1) % D;
+                if (ip < n) {
+#pragma unroll
+                    for (int k = 0; k < NR; ++k) cp_async8(slot + (sp * NR + k) * kSweepThreads, base[k] + ip);
+                }
+                cp_async_commit();
+                ip += stride;
+                cp_async_wait<D - 1>();
+                double v[NR];
+#pragma unroll
+                for (int k = 0; k < NR; ++k) v[k] = slot[(st * NR + k) * kSweepThreads];
+                body(i, v);
+                i += stride;
+            }
+        }
+    }
+    cp_async_wait<0>();
 }
 
 // ---- block reductions (fixed order => deterministic for a fixed launch shape) ----

@@ -18,33 +18,27 @@
 //   * the 1/(Mx My Mz) of the inverse transform and the 1/(4 pi eps0 hx hy hz) of
 //     sc.py:167 are applied in the last store.
 //
-// All 1-D transforms are Stockham radix-4/2 FFTs in shared memory (fp64,
-// natural order in and out), LB lines per 256-thread block.
+// All 1-D transforms are Stockham FFTs in shared memory (fp64, natural order in
+// and out) with radix-16/8/4/2 butterflies held in registers; the transform
+// length is a template parameter, so every stride is an immediate.
 #include "sc_kernels.h"
 
 namespace ocl {
 
-constexpr int kFftThreads = 256;
+constexpr int kFftThreads = 128;
 
 // Shared-memory layout: complex point o of line l lives at x[o * NLP + l] with
-// NLP = NL + 1.  Lines run across lanes, so every butterfly stage reads and writes
-// whole rows (NL consecutive double2) whatever its stride -- no bank conflicts --
-// and the odd pitch keeps the transposed accesses of the z passes (lanes along
-// o) conflict-free per quarter-warp as well.
-struct FftGeom {
-    int M;     // transform length (power of two, 8..512)
-    int NL;    // lines resident per block
-    int NLP;   // row pitch (NL + 1)
+// NLP = NL + 1.  Lines run across lanes, so every butterfly stage reads and
+// writes whole rows (NL consecutive double2) whatever its stride -- no bank
+// conflicts -- and the odd pitch keeps the transposed accesses of the z passes
+// (lanes along o) conflict-free per quarter-warp as well.
+template <int M>
+struct Geom {
+    static constexpr int NL = (M >= 256) ? 8 : ((2048 / M) > 32 ? 32 : (2048 / M));   // lines per block
+    static constexpr int NLP = NL + 1;
+    static constexpr int ELEMS = M * NLP;
+    static constexpr size_t SMEM = sizeof(double2) * (2 * (size_t)ELEMS);
 };
-__host__ __device__ inline FftGeom fft_geom(int M) {
-    FftGeom g;
-    g.M = M;
-    g.NL = (M >= 256) ? 8 : 2048 / M;
-    if (g.NL > 64) g.NL = 64;
-    g.NLP = g.NL + 1;
-    return g;
-}
-__host__ __device__ inline size_t fft_buf_elems(const FftGeom& g) { return (size_t)g.M * g.NLP; }
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
     return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -56,6 +50,12 @@ template <bool INV>
 __device__ __forceinline__ double2 rot90(double2 d) {
     return INV ? make_double2(-d.y, d.x) : make_double2(d.y, -d.x);
 }
+// multiply by the constant forward twiddle (cr, -si) (inverse: its conjugate)
+template <bool INV>
+__device__ __forceinline__ double2 mulw(double2 v, double cr, double si) {
+    return INV ? make_double2(v.x * cr - v.y * si, v.y * cr + v.x * si)
+               : make_double2(v.x * cr + v.y * si, v.y * cr - v.x * si);
+}
 
 template <bool INV>
 __device__ __forceinline__ void dft4(double2& v0, double2& v1, double2& v2, double2& v3) {
@@ -63,96 +63,118 @@ __device__ __forceinline__ void dft4(double2& v0, double2& v1, double2& v2, doub
     v0 = cadd(a0, a2); v1 = cadd(a1, a3); v2 = csub(a0, a2); v3 = csub(a1, a3);
 }
 
-template <bool INV>
-__device__ __forceinline__ void dft8(double2 (&v)[8]) {
-    // decimation in time: evens and odds through dft4, then the w8^k twiddles
-    dft4<INV>(v[0], v[2], v[4], v[6]);
-    dft4<INV>(v[1], v[3], v[5], v[7]);
-    const double h = 0.70710678118654752440;
-    // w8^1 = (1 -+ i)/sqrt2, w8^2 = -+i, w8^3 = (-1 -+ i)/sqrt2   (upper sign: forward)
-    double2 o1 = INV ? make_double2(h * (v[3].x - v[3].y), h * (v[3].x + v[3].y))
-                     : make_double2(h * (v[3].x + v[3].y), h * (v[3].y - v[3].x));
-    double2 o2 = rot90<INV>(v[5]);
-    double2 o3 = INV ? make_double2(-h * (v[7].x + v[7].y), h * (v[7].x - v[7].y))
-                     : make_double2(h * (v[7].y - v[7].x), -h * (v[7].x + v[7].y));
-    double2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6], o0 = v[1];
-    v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
-    v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
-    v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
-    v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+constexpr double kH = 0.70710678118654752440;    // cos(pi/4)
+constexpr double kC1 = 0.92387953251128673848;   // cos(pi/8)
+constexpr double kS1 = 0.38268343236508978178;   // sin(pi/8)
+
+// natural-order DFTs of register arrays: v[m] <- sum_r v[r] W_R^{r m}
+template <bool INV, int R>
+__device__ __forceinline__ void dft(double2 (&v)[R]) {
+    static_assert(R == 2 || R == 4 || R == 8 || R == 16, "radix");
+    if constexpr (R == 2) {
+        double2 a = v[0], b = v[1];
+        v[0] = cadd(a, b); v[1] = csub(a, b);
+    } else if constexpr (R == 4) {
+        dft4<INV>(v[0], v[1], v[2], v[3]);
+    } else if constexpr (R == 8) {
+        dft4<INV>(v[0], v[2], v[4], v[6]);          // evens -> v[0,2,4,6] = E[0..3]
+        dft4<INV>(v[1], v[3], v[5], v[7]);          // odds  -> v[1,3,5,7] = O[0..3]
+        double2 o0 = v[1], o1 = mulw<INV>(v[3], kH, kH), o2 = rot90<INV>(v[5]), o3 = mulw<INV>(v[7], -kH, kH);
+        double2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+        v[0] = cadd(e0, o0); v[4] = csub(e0, o0);
+        v[1] = cadd(e1, o1); v[5] = csub(e1, o1);
+        v[2] = cadd(e2, o2); v[6] = csub(e2, o2);
+        v[3] = cadd(e3, o3); v[7] = csub(e3, o3);
+    } else {   // R == 16: input r = 4 n1 + a, output m = b + 4 c
+#pragma unroll
+        for (int a = 0; a < 4; ++a) dft4<INV>(v[a], v[a + 4], v[a + 8], v[a + 12]);   // u_a[b] at v[a + 4 b]
+        // t_a[b] = u_a[b] W16^{a b}
+        v[1 + 4] = mulw<INV>(v[1 + 4], kC1, kS1);       // a=1,b=1: W^1
+        v[1 + 8] = mulw<INV>(v[1 + 8], kH, kH);         // a=1,b=2: W^2
+        v[1 + 12] = mulw<INV>(v[1 + 12], kS1, kC1);     // a=1,b=3: W^3
+        v[2 + 4] = mulw<INV>(v[2 + 4], kH, kH);         // a=2,b=1: W^2
+        v[2 + 8] = rot90<INV>(v[2 + 8]);                // a=2,b=2: W^4
+        v[2 + 12] = mulw<INV>(v[2 + 12], -kH, kH);      // a=2,b=3: W^6
+        v[3 + 4] = mulw<INV>(v[3 + 4], kS1, kC1);       // a=3,b=1: W^3
+        v[3 + 8] = mulw<INV>(v[3 + 8], -kH, kH);        // a=3,b=2: W^6
+        v[3 + 12] = mulw<INV>(v[3 + 12], -kC1, -kS1);   // a=3,b=3: W^9
+        // X[b + 4 c] = sum_a t_a[b] W4^{a c}: dft4 over a for each b, result c lands at position a
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dft4<INV>(v[4 * b], v[4 * b + 1], v[4 * b + 2], v[4 * b + 3]);
+        // now v[4 b + c] = X[b + 4 c]: transpose the 4x4 index
+        double2 t;
+#define OCL_SWAP(i, j) t = v[i]; v[i] = v[j]; v[j] = t;
+        OCL_SWAP(1, 4) OCL_SWAP(2, 8) OCL_SWAP(3, 12) OCL_SWAP(6, 9) OCL_SWAP(7, 13) OCL_SWAP(11, 14)
+#undef OCL_SWAP
+    }
 }
 
+template <int M>
 struct FftSmem {
     double2* a;
     double2* b;
-    double2* tw;
+    const double2* tw;
 };
 
-__device__ __forceinline__ FftSmem fft_smem(const FftGeom& g, const double2* __restrict__ tw_g) {
+template <int M>
+__device__ __forceinline__ FftSmem<M> fft_smem(const double2* __restrict__ tw_g) {
     extern __shared__ __align__(16) unsigned char raw[];
-    FftSmem s;
+    FftSmem<M> s;
     s.a = reinterpret_cast<double2*>(raw);
-    s.b = s.a + fft_buf_elems(g);
-    s.tw = s.b + fft_buf_elems(g);
-    for (int t = threadIdx.x; t < g.M; t += kFftThreads) s.tw[t] = tw_g[t];
+    s.b = s.a + Geom<M>::ELEMS;
+    s.tw = tw_g;          // 16*M bytes, read through L1 with __ldg: keeps three blocks resident per SM
     return s;
 }
 
+__host__ __device__ constexpr int radix_for(int rem) { return (rem % 16 == 0) ? 16 : (rem % 8 == 0) ? 8 : (rem % 4 == 0) ? 4 : 2; }
+
 // One Stockham stage of radix R on all NL lines: work item t -> (butterfly j, line l), l fastest.
-template <bool INV, int R>
+template <bool INV, int M, int Ns, int R>
 __device__ __forceinline__ void fft_stage(const double2* __restrict__ x, double2* __restrict__ y,
-                                          const double2* __restrict__ tw, const FftGeom& g, int Ns) {
-    const int nb = g.M / R;
-    const int step = g.M / (Ns * R);
-    const int total = nb * g.NL;
+                                          const double2* __restrict__ tw) {
+    constexpr int NL = Geom<M>::NL, NLP = Geom<M>::NLP;
+    constexpr int nb = M / R;
+    constexpr int step = M / (Ns * R);
+    constexpr int total = nb * NL;
     for (int t = threadIdx.x; t < total; t += kFftThreads) {
-        const int j = t / g.NL, l = t - j * g.NL;
+        const int j = t / NL, l = t % NL;       // NL is a power of two: shift / mask
         const int k = j & (Ns - 1);
         double2 v[R];
+        const double2* src = x + j * NLP + l;
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[r] = x[(j + r * nb) * g.NLP + l];
-        if (k) {
+        for (int r = 0; r < R; ++r) v[r] = src[r * nb * NLP];
+        if (Ns > 1) {
 #pragma unroll
             for (int r = 1; r < R; ++r) {
-                double2 w = tw[r * k * step];
+                double2 w = __ldg(tw + r * k * step);
                 if (INV) w.y = -w.y;
                 v[r] = cmul(v[r], w);
             }
         }
-        if (R == 8) {
-            double2 u[8];
+        dft<INV, R>(v);
+        double2* dst = y + ((j - k) * R + k) * NLP + l;
 #pragma unroll
-            for (int r = 0; r < 8; ++r) u[r] = v[r % R];
-            dft8<INV>(u);
-#pragma unroll
-            for (int r = 0; r < 8; ++r) v[r % R] = u[r];
-        } else if (R == 4) {
-            dft4<INV>(v[0], v[1 % R], v[2 % R], v[3 % R]);
-        } else {
-            double2 a = v[0], b = v[1 % R];
-            v[0] = cadd(a, b); v[1 % R] = csub(a, b);
-        }
-        double2* dst = y + ((j - k) * R + k) * g.NLP + l;
-#pragma unroll
-        for (int r = 0; r < R; ++r) dst[r * Ns * g.NLP] = v[r];
+        for (int r = 0; r < R; ++r) dst[r * Ns * NLP] = v[r];
+    }
+}
+
+template <bool INV, int M, int Ns>
+__device__ __forceinline__ void fft_stages(double2*& x, double2*& y, const double2* tw) {
+    if constexpr (Ns < M) {
+        constexpr int R = radix_for(M / Ns);
+        fft_stage<INV, M, Ns, R>(x, y, tw);
+        __syncthreads();
+        double2* tmp = x; x = y; y = tmp;
+        fft_stages<INV, M, Ns * R>(x, y, tw);
     }
 }
 
 // All NL lines of length M in x.  Returns the buffer holding the result (natural order).
 // tw[m] = exp(-2 pi i m / M); the inverse transform conjugates it (unnormalised).
-template <bool INV>
-__device__ double2* block_fft(double2* x, double2* y, const double2* tw, const FftGeom& g) {
+template <bool INV, int M>
+__device__ __forceinline__ double2* block_fft(double2* x, double2* y, const double2* tw) {
     __syncthreads();
-    for (int Ns = 1; Ns < g.M;) {
-        const int rem = g.M / Ns;
-        int R;
-        if ((rem & 7) == 0) { fft_stage<INV, 8>(x, y, tw, g, Ns); R = 8; }
-        else if ((rem & 3) == 0) { fft_stage<INV, 4>(x, y, tw, g, Ns); R = 4; }
-        else { fft_stage<INV, 2>(x, y, tw, g, Ns); R = 2; }
-        __syncthreads();
-        double2* tmp = x; x = y; y = tmp;
-        Ns *= R;
-    }
+    fft_stages<INV, M, 1>(x, y, tw);
     return x;
 }
 
@@ -174,30 +196,31 @@ __device__ __forceinline__ double green_entry_dev(const double* __restrict__ G, 
 // table, sc.py:128-131), even-extended to Mz, two lines per complex FFT.
 // out P[a][b][kz], kz <= Mz/2 (real).
 // ---------------------------------------------------------------------------
+template <int M>
 __global__ void __launch_bounds__(kFftThreads) k_khat_z(const double* __restrict__ gtab, MeshDims md,
                                                        const double2* __restrict__ tw_g, double* __restrict__ P) {
-    const FftGeom g = fft_geom(md.mz);
-    const int M = g.M, n = md.nz, H = M / 2;
-    FftSmem s = fft_smem(g, tw_g);
+    constexpr int NL = Geom<M>::NL, NLP = Geom<M>::NLP, H = M / 2;
+    const int n = md.nz;
+    FftSmem<M> s = fft_smem<M>(tw_g);
     const int nlines = md.nx * md.ny;
-    const int line0 = blockIdx.x * (2 * g.NL);            // 2 real lines per complex line
-    for (int t = threadIdx.x; t < M * g.NLP; t += kFftThreads) s.a[t] = make_double2(0.0, 0.0);
+    const int line0 = blockIdx.x * (2 * NL);              // 2 real lines per complex line
+    for (int t = threadIdx.x; t < M * NLP; t += kFftThreads) s.a[t] = make_double2(0.0, 0.0);
     __syncthreads();
-    for (int t = threadIdx.x; t < g.NL * n; t += kFftThreads) {
+    for (int t = threadIdx.x; t < NL * n; t += kFftThreads) {
         const int p = t / n, c = t - p * n;               // c fastest: contiguous table reads
         const int l1 = line0 + 2 * p, l2 = l1 + 1;
         if (l1 >= nlines) continue;
         double e1 = green_entry_dev(gtab, md.ny + 1, md.nz + 1, l1 / md.ny, l1 % md.ny, c);
         double e2 = (l2 < nlines) ? green_entry_dev(gtab, md.ny + 1, md.nz + 1, l2 / md.ny, l2 % md.ny, c) : 0.0;
-        s.a[c * g.NLP + p] = make_double2(e1, e2);
-        if (c) s.a[(M - c) * g.NLP + p] = make_double2(e1, e2);
+        s.a[c * NLP + p] = make_double2(e1, e2);
+        if (c) s.a[(M - c) * NLP + p] = make_double2(e1, e2);
     }
-    double2* X = block_fft<false>(s.a, s.b, s.tw, g);
-    for (int t = threadIdx.x; t < g.NL * (H + 1); t += kFftThreads) {
+    double2* X = block_fft<false, M>(s.a, s.b, s.tw);
+    for (int t = threadIdx.x; t < NL * (H + 1); t += kFftThreads) {
         const int p = t / (H + 1), kz = t - p * (H + 1);
         const int l1 = line0 + 2 * p, l2 = l1 + 1;
         if (l1 >= nlines) continue;
-        const double2 v = X[kz * g.NLP + p];
+        const double2 v = X[kz * NLP + p];
         P[(size_t)l1 * (H + 1) + kz] = v.x;
         if (l2 < nlines) P[(size_t)l2 * (H + 1) + kz] = v.y;
     }
@@ -208,36 +231,52 @@ __global__ void __launch_bounds__(kFftThreads) k_khat_z(const double* __restrict
 // in[batch][n][inner] -> out[batch][M/2+1][inner]; two adjacent inner indices
 // per complex FFT.
 // ---------------------------------------------------------------------------
+template <int M>
 __global__ void __launch_bounds__(kFftThreads) k_real_even_outer(const double* __restrict__ in,
-                                                                double* __restrict__ out, int n, int M, int inner,
+                                                                double* __restrict__ out, int n, int inner,
                                                                 const double2* __restrict__ tw_g) {
-    const FftGeom g = fft_geom(M);
-    const int H = M / 2;
-    FftSmem s = fft_smem(g, tw_g);
+    constexpr int NL = Geom<M>::NL, NLP = Geom<M>::NLP, H = M / 2;
+    FftSmem<M> s = fft_smem<M>(tw_g);
     const int pairs_total = (inner + 1) / 2;
-    const int blocks_per_batch = (pairs_total + g.NL - 1) / g.NL;
+    const int blocks_per_batch = (pairs_total + NL - 1) / NL;
     const int batch = blockIdx.x / blocks_per_batch;
-    const int pair0 = (blockIdx.x - batch * blocks_per_batch) * g.NL;
-    const int pairs = min(g.NL, pairs_total - pair0);
+    const int pair0 = (blockIdx.x - batch * blocks_per_batch) * NL;
+    const int pairs = min(NL, pairs_total - pair0);
     const double* src = in + (size_t)batch * n * inner;
     double* dst = out + (size_t)batch * (H + 1) * inner;
-    for (int t = threadIdx.x; t < M * g.NLP; t += kFftThreads) s.a[t] = make_double2(0.0, 0.0);
+    for (int t = threadIdx.x; t < M * NLP; t += kFftThreads) s.a[t] = make_double2(0.0, 0.0);
     __syncthreads();
-    for (int t = threadIdx.x; t < g.NL * n; t += kFftThreads) {
-        const int o = t / g.NL, p = t - o * g.NL;         // p fastest: adjacent inner indices
-        if (p >= pairs) continue;
+    {   // p fastest: adjacent inner indices; U independent load pairs in flight per thread
+        constexpr int U = 4;
+        const int p = threadIdx.x % NL, o0 = threadIdx.x / NL;
+        constexpr int OSTEP = kFftThreads / NL;
         const int f = 2 * (pair0 + p);
-        const double e1 = __ldg(src + (size_t)o * inner + f);
-        const double e2 = (f + 1 < inner) ? __ldg(src + (size_t)o * inner + f + 1) : 0.0;
-        s.a[o * g.NLP + p] = make_double2(e1, e2);
-        if (o) s.a[(M - o) * g.NLP + p] = make_double2(e1, e2);
+        const bool live = p < pairs, two = f + 1 < inner;
+        for (int ob = o0; ob < n; ob += U * OSTEP) {
+            double e1[U], e2[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int o = ob + u * OSTEP;
+                const bool ok = live && o < n;
+                e1[u] = ok ? __ldg(src + (size_t)o * inner + f) : 0.0;
+                e2[u] = (ok && two) ? __ldg(src + (size_t)o * inner + f + 1) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int o = ob + u * OSTEP;
+                if (live && o < n) {
+                    s.a[o * NLP + p] = make_double2(e1[u], e2[u]);
+                    if (o) s.a[(M - o) * NLP + p] = make_double2(e1[u], e2[u]);
+                }
+            }
+        }
     }
-    double2* X = block_fft<false>(s.a, s.b, s.tw, g);
-    for (int t = threadIdx.x; t < g.NL * (H + 1); t += kFftThreads) {
-        const int ko = t / g.NL, p = t - ko * g.NL;
+    double2* X = block_fft<false, M>(s.a, s.b, s.tw);
+    for (int t = threadIdx.x; t < NL * (H + 1); t += kFftThreads) {
+        const int ko = t / NL, p = t % NL;
         if (p >= pairs) continue;
         const int f = 2 * (pair0 + p);
-        const double2 v = X[ko * g.NLP + p];
+        const double2 v = X[ko * NLP + p];
         dst[(size_t)ko * inner + f] = v.x;
         if (f + 1 < inner) dst[(size_t)ko * inner + f + 1] = v.y;
     }
@@ -247,30 +286,40 @@ __global__ void __launch_bounds__(kFftThreads) k_real_even_outer(const double* _
 // rho, pass z: real lines rho[l][k<nz] zero-padded to Mz, two per complex FFT,
 // separated by Hermitian symmetry.  out A[l][kz], kz <= Mz/2 (complex).
 // ---------------------------------------------------------------------------
+template <int M>
 __global__ void __launch_bounds__(kFftThreads) k_rho_z(const double* __restrict__ rho, MeshDims md,
                                                       const double2* __restrict__ tw_g, double2* __restrict__ A) {
-    const FftGeom g = fft_geom(md.mz);
-    const int M = g.M, n = md.nz, H = M / 2;
-    FftSmem s = fft_smem(g, tw_g);
+    constexpr int NL = Geom<M>::NL, NLP = Geom<M>::NLP, H = M / 2;
+    const int n = md.nz;
+    FftSmem<M> s = fft_smem<M>(tw_g);
     const int nlines = md.nx * md.ny;
-    const int line0 = blockIdx.x * (2 * g.NL);
-    for (int t = threadIdx.x; t < g.NL * M; t += kFftThreads) {
-        const int p = t / M, k = t - p * M;               // k fastest: contiguous reads of rho
-        const int l1 = line0 + 2 * p, l2 = l1 + 1;
-        double a = 0.0, b = 0.0;
-        if (k < n && l1 < nlines) {
-            a = __ldg(rho + (size_t)l1 * n + k);
-            if (l2 < nlines) b = __ldg(rho + (size_t)l2 * n + k);
+    const int line0 = blockIdx.x * (2 * NL);
+    {   // k fastest: contiguous reads of rho; U independent loads in flight per thread
+        constexpr int PER = NL * M / kFftThreads, U = PER < 8 ? PER : 8;
+        for (int c = 0; c < PER; c += U) {
+            double a[U], b[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int t = threadIdx.x + (c + u) * kFftThreads;
+                const int p = t / M, k = t % M;
+                const int l1 = line0 + 2 * p, l2 = l1 + 1;
+                a[u] = (k < n && l1 < nlines) ? __ldg(rho + (size_t)l1 * n + k) : 0.0;
+                b[u] = (k < n && l2 < nlines) ? __ldg(rho + (size_t)l2 * n + k) : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int t = threadIdx.x + (c + u) * kFftThreads;
+                s.a[(t % M) * NLP + t / M] = make_double2(a[u], b[u]);
+            }
         }
-        s.a[k * g.NLP + p] = make_double2(a, b);
     }
-    double2* Z = block_fft<false>(s.a, s.b, s.tw, g);
-    for (int t = threadIdx.x; t < g.NL * (H + 1); t += kFftThreads) {
+    double2* Z = block_fft<false, M>(s.a, s.b, s.tw);
+    for (int t = threadIdx.x; t < NL * (H + 1); t += kFftThreads) {
         const int p = t / (H + 1), kz = t - p * (H + 1);
         const int l1 = line0 + 2 * p, l2 = l1 + 1;
         if (l1 >= nlines) continue;
-        const double2 z = Z[kz * g.NLP + p];
-        const double2 w = Z[((M - kz) & (M - 1)) * g.NLP + p];   // Z[M-k], Z[M] == Z[0]
+        const double2 z = Z[kz * NLP + p];
+        const double2 w = Z[((M - kz) & (M - 1)) * NLP + p];   // Z[M-k], Z[M] == Z[0]
         // F1 = (Z[k] + conj(Z[M-k]))/2 ; F2 = (Z[k] - conj(Z[M-k]))/(2i)
         A[(size_t)l1 * (H + 1) + kz] = make_double2(0.5 * (z.x + w.x), 0.5 * (z.y - w.y));
         if (l2 < nlines) A[(size_t)l2 * (H + 1) + kz] = make_double2(0.5 * (z.y + w.y), 0.5 * (w.x - z.x));
@@ -285,44 +334,70 @@ __global__ void __launch_bounds__(kFftThreads) k_rho_z(const double* __restrict_
 //   MODE 2: forward, multiply by the real even K_hat, inverse  (pass x, in place)
 // For MODE 2 inner = My*(Mz/2+1) and khat is [Mx/2+1][My/2+1][Mz/2+1].
 // ---------------------------------------------------------------------------
-template <int MODE>
+template <int M, int MODE>
 __global__ void __launch_bounds__(kFftThreads) k_cplx_outer(const double2* in, double2* out,   // may alias (MODE 2)
-                                                           int n_in, int n_out, int M, int inner,
+                                                           int n_in, int n_out, int inner,
                                                            const double2* __restrict__ tw_g,
                                                            const double* __restrict__ khat, MeshDims md) {
-    const FftGeom g = fft_geom(M);
-    FftSmem s = fft_smem(g, tw_g);
-    const int blocks_per_batch = (inner + g.NL - 1) / g.NL;
+    constexpr int NL = Geom<M>::NL, NLP = Geom<M>::NLP;
+    FftSmem<M> s = fft_smem<M>(tw_g);
+    const int blocks_per_batch = (inner + NL - 1) / NL;
     const int batch = blockIdx.x / blocks_per_batch;
-    const int f0 = (blockIdx.x - batch * blocks_per_batch) * g.NL;
-    const int nl = min(g.NL, inner - f0);
-    const double2* src = in + (size_t)batch * n_in * inner;
-    double2* dst = out + (size_t)batch * n_out * inner;
-    for (int t = threadIdx.x; t < g.NL * M; t += kFftThreads) {
-        const int o = t / g.NL, l = t - o * g.NL;          // l fastest: adjacent inner indices
-        double2 v = make_double2(0.0, 0.0);
-        if (o < n_in && l < nl) v = src[(size_t)o * inner + f0 + l];
-        s.a[o * g.NLP + l] = v;
+    const int f0 = (blockIdx.x - batch * blocks_per_batch) * NL;
+    const int nl = min(NL, inner - f0);
+    const double2* src = in + (size_t)batch * n_in * inner + f0;
+    double2* dst = out + (size_t)batch * n_out * inner + f0;
+    {   // global -> shared, U independent 16-byte loads in flight per thread
+        constexpr int PER = NL * M / kFftThreads, U = PER < 8 ? PER : 8;
+        static_assert(PER % U == 0, "load batching");
+        const int l = threadIdx.x % NL, o0 = threadIdx.x / NL;          // l fastest: adjacent inner indices
+        constexpr int OSTEP = kFftThreads / NL;
+        const double2* col = src + l;
+        for (int c = 0; c < PER; c += U) {
+            double2 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int o = o0 + (c + u) * OSTEP;
+                v[u] = (o < n_in && l < nl) ? col[(size_t)o * inner] : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) s.a[(o0 + (c + u) * OSTEP) * NLP + l] = v[u];
+        }
     }
-    double2* X = (MODE == 1) ? block_fft<true>(s.a, s.b, s.tw, g) : block_fft<false>(s.a, s.b, s.tw, g);
+    double2* X = (MODE == 1) ? block_fft<true, M>(s.a, s.b, s.tw) : block_fft<false, M>(s.a, s.b, s.tw);
     if (MODE == 2) {
         const int hz1 = md.mz / 2 + 1, hy1 = md.my / 2 + 1;
-        for (int t = threadIdx.x; t < g.NL * M; t += kFftThreads) {
-            const int kx = t / g.NL, l = t - kx * g.NL;
-            if (l >= nl) continue;
+        // each thread owns one line l for the multiply: its (ky, kz) is computed once
+        const int l = threadIdx.x % NL;
+        if (l < nl) {
             const int f = f0 + l;
             const int ky = f / hz1, kz = f - ky * hz1;
-            const int sx = min(kx, M - kx), sy = min(ky, md.my - ky);
-            const double gk = __ldg(khat + ((size_t)sx * hy1 + sy) * hz1 + kz);
-            double2 v = X[kx * g.NLP + l];
-            X[kx * g.NLP + l] = make_double2(v.x * gk, v.y * gk);
+            const int sy = min(ky, md.my - ky);
+            const double* kcol = khat + (size_t)sy * hz1 + kz;
+            const size_t kplane = (size_t)hy1 * hz1;
+            constexpr int KSTEP = kFftThreads / NL, KPER = M / KSTEP, KU = KPER < 8 ? KPER : 8;
+            const int kx0 = threadIdx.x / NL;
+            for (int c = 0; c < KPER; c += KU) {
+                double gk[KU];
+#pragma unroll
+                for (int u = 0; u < KU; ++u) {
+                    const int kx = kx0 + (c + u) * KSTEP;
+                    gk[u] = __ldg(kcol + (size_t)min(kx, M - kx) * kplane);
+                }
+#pragma unroll
+                for (int u = 0; u < KU; ++u) {
+                    const int kx = kx0 + (c + u) * KSTEP;
+                    double2 v = X[kx * NLP + l];
+                    X[kx * NLP + l] = make_double2(v.x * gk[u], v.y * gk[u]);
+                }
+            }
         }
         double2* Y = (X == s.a) ? s.b : s.a;
-        X = block_fft<true>(X, Y, s.tw, g);
+        X = block_fft<true, M>(X, Y, s.tw);
     }
-    for (int t = threadIdx.x; t < g.NL * n_out; t += kFftThreads) {
-        const int o = t / g.NL, l = t - o * g.NL;
-        if (l < nl) dst[(size_t)o * inner + f0 + l] = X[o * g.NLP + l];
+    for (int t = threadIdx.x; t < NL * n_out; t += kFftThreads) {
+        const int o = t / NL, l = t % NL;
+        if (l < nl) dst[(size_t)o * inner + l] = X[o * NLP + l];
     }
 }
 
@@ -330,55 +405,81 @@ __global__ void __launch_bounds__(kFftThreads) k_cplx_outer(const double2* in, d
 // inverse pass z: Hermitian lines D[l][kz<=Mz/2] -> real, two per complex FFT;
 // phi[l][k<nz] = value / (Mx My Mz) / (4 pi eps0 hx hy hz)   (sc.py:164,167)
 // ---------------------------------------------------------------------------
+template <int M>
 __global__ void __launch_bounds__(kFftThreads) k_inv_z(const double2* __restrict__ D, MeshDims md,
                                                       const double2* __restrict__ tw_g, const double* __restrict__ hsrc,
                                                       double four_pi_eps0, double* __restrict__ phi) {
-    const FftGeom g = fft_geom(md.mz);
-    const int M = g.M, n = md.nz, H = M / 2;
-    FftSmem s = fft_smem(g, tw_g);
+    constexpr int NL = Geom<M>::NL, NLP = Geom<M>::NLP, H = M / 2;
+    const int n = md.nz;
+    FftSmem<M> s = fft_smem<M>(tw_g);
     const int nlines = md.nx * md.ny;
-    const int line0 = blockIdx.x * (2 * g.NL);
-    for (int t = threadIdx.x; t < g.NL * (H + 1); t += kFftThreads) {
-        const int p = t / (H + 1), k = t - p * (H + 1);   // k fastest: contiguous reads of D
-        const int l1 = line0 + 2 * p, l2 = l1 + 1;
-        double2 d1 = make_double2(0.0, 0.0), d2 = make_double2(0.0, 0.0);
-        if (l1 < nlines) d1 = D[(size_t)l1 * (H + 1) + k];
-        if (l2 < nlines) d2 = D[(size_t)l2 * (H + 1) + k];
-        s.a[k * g.NLP + p] = make_double2(d1.x - d2.y, d1.y + d2.x);                    // d1 + i d2
-        if (k > 0 && k < H)                                                             // Hermitian extension
-            s.a[(M - k) * g.NLP + p] = make_double2(d1.x + d2.y, -d1.y + d2.x);         // conj(d1) + i conj(d2)
+    const int line0 = blockIdx.x * (2 * NL);
+    {   // k fastest: contiguous reads of D; U independent load pairs in flight per thread
+        constexpr int TOTAL = NL * (H + 1), U = 4;
+        for (int t0 = threadIdx.x; t0 < TOTAL; t0 += U * kFftThreads) {
+            double2 d1[U], d2[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int t = t0 + u * kFftThreads;
+                const int p = t / (H + 1), k = t - p * (H + 1);
+                const int l1 = line0 + 2 * p, l2 = l1 + 1;
+                d1[u] = (t < TOTAL && l1 < nlines) ? D[(size_t)l1 * (H + 1) + k] : make_double2(0.0, 0.0);
+                d2[u] = (t < TOTAL && l2 < nlines) ? D[(size_t)l2 * (H + 1) + k] : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const int t = t0 + u * kFftThreads;
+                if (t >= TOTAL) continue;
+                const int p = t / (H + 1), k = t - p * (H + 1);
+                s.a[k * NLP + p] = make_double2(d1[u].x - d2[u].y, d1[u].y + d2[u].x);          // d1 + i d2
+                if (k > 0 && k < H)                                                             // Hermitian extension
+                    s.a[(M - k) * NLP + p] = make_double2(d1[u].x + d2[u].y, -d1[u].y + d2[u].x);   // conj(d1) + i conj(d2)
+            }
+        }
     }
-    double2* X = block_fft<true>(s.a, s.b, s.tw, g);
+    double2* X = block_fft<true, M>(s.a, s.b, s.tw);
     const double inv_m3 = 1.0 / ((double)md.mx * (double)md.my * (double)md.mz);
     const double denom = four_pi_eps0 * hsrc[0] * hsrc[1] * hsrc[2];
-    for (int t = threadIdx.x; t < g.NL * n; t += kFftThreads) {
+    for (int t = threadIdx.x; t < NL * n; t += kFftThreads) {
         const int p = t / n, k = t - p * n;
         const int l1 = line0 + 2 * p, l2 = l1 + 1;
         if (l1 >= nlines) continue;
-        const double2 v = X[k * g.NLP + p];
+        const double2 v = X[k * NLP + p];
         phi[(size_t)l1 * n + k] = (v.x * inv_m3) / denom;
         if (l2 < nlines) phi[(size_t)l2 * n + k] = (v.y * inv_m3) / denom;
     }
 }
 
-static size_t fft_smem_bytes(int M) {
-    const FftGeom g = fft_geom(M);
-    return sizeof(double2) * (2 * fft_buf_elems(g) + (size_t)M);
-}
+// ---------------------------------------------------------------------------
+// host side: dispatch on the transform length
+// ---------------------------------------------------------------------------
+#define OCL_FFT_DISPATCH(M_, ...)                                  \
+    switch (M_) {                                                  \
+        case 8: { constexpr int MM = 8; __VA_ARGS__ } break;       \
+        case 16: { constexpr int MM = 16; __VA_ARGS__ } break;     \
+        case 32: { constexpr int MM = 32; __VA_ARGS__ } break;     \
+        case 64: { constexpr int MM = 64; __VA_ARGS__ } break;     \
+        case 128: { constexpr int MM = 128; __VA_ARGS__ } break;   \
+        case 256: { constexpr int MM = 256; __VA_ARGS__ } break;   \
+        case 512: { constexpr int MM = 512; __VA_ARGS__ } break;   \
+        default: break;                                            \
+    }
 
-template <typename K>
-static void opt_in(K kernel) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fft_smem_bytes(512));
+template <int M>
+static void opt_in_all() {
+    const int bytes = (int)Geom<M>::SMEM;
+    cudaFuncSetAttribute(k_khat_z<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_real_even_outer<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_rho_z<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_cplx_outer<M, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_cplx_outer<M, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_cplx_outer<M, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    cudaFuncSetAttribute(k_inv_z<M>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 void fft_init_kernels() {
-    opt_in(k_khat_z);
-    opt_in(k_real_even_outer);
-    opt_in(k_rho_z);
-    opt_in(k_cplx_outer<0>);
-    opt_in(k_cplx_outer<1>);
-    opt_in(k_cplx_outer<2>);
-    opt_in(k_inv_z);
+    opt_in_all<8>(); opt_in_all<16>(); opt_in_all<32>(); opt_in_all<64>();
+    opt_in_all<128>(); opt_in_all<256>(); opt_in_all<512>();
 }
 
 int fft_max_length() { return 512; }
@@ -386,52 +487,63 @@ int fft_max_length() { return 512; }
 // K_hat from the antiderivative table: three real-even passes
 void launch_khat(const double* gtab, MeshDims md, FftWork w, cudaStream_t st) {
     const int hz1 = md.mz / 2 + 1, hy1 = md.my / 2 + 1;
-    {   // z: P[nx][ny][hz1]
-        const int lb = 2 * fft_geom(md.mz).NL;
+    OCL_FFT_DISPATCH(md.mz,   // z: P[nx][ny][hz1]
+        const int lb = 2 * Geom<MM>::NL;
         const int blocks = (md.nx * md.ny + lb - 1) / lb;
-        k_khat_z<<<blocks, kFftThreads, fft_smem_bytes(md.mz), st>>>(gtab, md, w.tw_z, w.P);
-    }
-    {   // y: per a, in [ny][hz1] -> Q[a][hy1][hz1]
-        const int pb = fft_geom(md.my).NL;
+        k_khat_z<MM><<<blocks, kFftThreads, Geom<MM>::SMEM, st>>>(gtab, md, w.tw_z, w.P);
+    )
+    OCL_FFT_DISPATCH(md.my,   // y: per a, in [ny][hz1] -> Q[a][hy1][hz1]
+        const int pb = Geom<MM>::NL;
         const int blocks_per_batch = ((hz1 + 1) / 2 + pb - 1) / pb;
-        k_real_even_outer<<<blocks_per_batch * md.nx, kFftThreads, fft_smem_bytes(md.my), st>>>(w.P, w.Q, md.ny, md.my,
-                                                                                              hz1, w.tw_y);
-    }
-    {   // x: in [nx][hy1*hz1] -> khat[hx1][hy1*hz1]
+        k_real_even_outer<MM><<<blocks_per_batch * md.nx, kFftThreads, Geom<MM>::SMEM, st>>>(w.P, w.Q, md.ny, hz1,
+                                                                                           w.tw_y);
+    )
+    OCL_FFT_DISPATCH(md.mx,   // x: in [nx][hy1*hz1] -> khat[hx1][hy1*hz1]
         const int inner = hy1 * hz1;
-        const int pb = fft_geom(md.mx).NL;
+        const int pb = Geom<MM>::NL;
         const int blocks = ((inner + 1) / 2 + pb - 1) / pb;
-        k_real_even_outer<<<blocks, kFftThreads, fft_smem_bytes(md.mx), st>>>(w.Q, w.khat, md.nx, md.mx, inner, w.tw_x);
-    }
+        k_real_even_outer<MM><<<blocks, kFftThreads, Geom<MM>::SMEM, st>>>(w.Q, w.khat, md.nx, inner, w.tw_x);
+    )
 }
 
-// phi = (rho (*) K) / (4 pi eps0 hx hy hz) on [0,n)^3
-void launch_convolve(const double* rho, MeshDims md, FftWork w, const double* h3, double four_pi_eps0, double* phi,
-                     cudaStream_t st) {
+// phi = (rho (*) K) / (4 pi eps0 hx hy hz) on [0,n)^3, in two halves: the forward z and y
+// passes of rho do not need K_hat, so the caller can overlap them with the K_hat chain.
+void launch_convolve_pre(const double* rho, MeshDims md, FftWork w, cudaStream_t st) {
     const int hz1 = md.mz / 2 + 1;
-    const int lbz = 2 * fft_geom(md.mz).NL;
-    const int zblocks = (md.nx * md.ny + lbz - 1) / lbz;
-    k_rho_z<<<zblocks, kFftThreads, fft_smem_bytes(md.mz), st>>>(rho, md, w.tw_z, w.A);
-    {   // y forward: per i, [ny][hz1] -> [My][hz1]
-        const int lb = fft_geom(md.my).NL;
+    OCL_FFT_DISPATCH(md.mz,
+        const int lbz = 2 * Geom<MM>::NL;
+        const int zblocks = (md.nx * md.ny + lbz - 1) / lbz;
+        k_rho_z<MM><<<zblocks, kFftThreads, Geom<MM>::SMEM, st>>>(rho, md, w.tw_z, w.A);
+    )
+    OCL_FFT_DISPATCH(md.my,   // y forward: per i, [ny][hz1] -> [My][hz1]
+        const int lb = Geom<MM>::NL;
         const int bpb = (hz1 + lb - 1) / lb;
-        k_cplx_outer<0><<<bpb * md.nx, kFftThreads, fft_smem_bytes(md.my), st>>>(w.A, w.B, md.ny, md.my, md.my, hz1,
-                                                                                w.tw_y, nullptr, md);
-    }
-    {   // x: forward, * K_hat, inverse, keep i < nx (in place)
+        k_cplx_outer<MM, 0><<<bpb * md.nx, kFftThreads, Geom<MM>::SMEM, st>>>(w.A, w.B, md.ny, md.my, hz1, w.tw_y,
+                                                                             nullptr, md);
+    )
+}
+
+void launch_convolve_post(MeshDims md, FftWork w, const double* h3, double four_pi_eps0, double* phi,
+                          cudaStream_t st) {
+    const int hz1 = md.mz / 2 + 1;
+    OCL_FFT_DISPATCH(md.mx,   // x: forward, * K_hat, inverse, keep i < nx (in place)
         const int inner = md.my * hz1;
-        const int lb = fft_geom(md.mx).NL;
+        const int lb = Geom<MM>::NL;
         const int blocks = (inner + lb - 1) / lb;
-        k_cplx_outer<2><<<blocks, kFftThreads, fft_smem_bytes(md.mx), st>>>(w.B, w.B, md.nx, md.nx, md.mx, inner,
-                                                                           w.tw_x, w.khat, md);
-    }
-    {   // y inverse: per i, [My][hz1] -> [ny][hz1]
-        const int lb = fft_geom(md.my).NL;
+        k_cplx_outer<MM, 2><<<blocks, kFftThreads, Geom<MM>::SMEM, st>>>(w.B, w.B, md.nx, md.nx, inner, w.tw_x, w.khat,
+                                                                        md);
+    )
+    OCL_FFT_DISPATCH(md.my,   // y inverse: per i, [My][hz1] -> [ny][hz1]
+        const int lb = Geom<MM>::NL;
         const int bpb = (hz1 + lb - 1) / lb;
-        k_cplx_outer<1><<<bpb * md.nx, kFftThreads, fft_smem_bytes(md.my), st>>>(w.B, w.A, md.my, md.ny, md.my, hz1,
-                                                                                w.tw_y, nullptr, md);
-    }
-    k_inv_z<<<zblocks, kFftThreads, fft_smem_bytes(md.mz), st>>>(w.A, md, w.tw_z, h3, four_pi_eps0, phi);
+        k_cplx_outer<MM, 1><<<bpb * md.nx, kFftThreads, Geom<MM>::SMEM, st>>>(w.B, w.A, md.my, md.ny, hz1, w.tw_y,
+                                                                             nullptr, md);
+    )
+    OCL_FFT_DISPATCH(md.mz,
+        const int lbz = 2 * Geom<MM>::NL;
+        const int zblocks = (md.nx * md.ny + lbz - 1) / lbz;
+        k_inv_z<MM><<<zblocks, kFftThreads, Geom<MM>::SMEM, st>>>(w.A, md, w.tw_z, h3, four_pi_eps0, phi);
+    )
 }
 
 }  // namespace ocl

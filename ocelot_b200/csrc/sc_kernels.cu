@@ -24,7 +24,7 @@ constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
 
 int particle_grid(long long n, int max_blocks) {
-    long long b = (n + 4 * kThreads - 1) / (4 * kThreads);   // sweeps handle 4 particles per thread per trip
+    long long b = (n + kThreads - 1) / kThreads;
     if (b < 1) b = 1;
     if (b > max_blocks) b = max_blocks;
     return (int)b;
@@ -84,36 +84,22 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* part, unsig
     return true;
 }
 
+constexpr int kPipeDepth = 3;
+
 // ---------------------------------------------------------------------------
 // sweep 1: mean momentum (sc.py:221,224)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_momentum(const double* __restrict__ r, long long ld, long long n,
-                                                      RefParams rp, ReduceState rs) {
+__global__ void __launch_bounds__(kThreads, 4) k_momentum(const double* __restrict__ r, long long ld, long long n,
+                                                         RefParams rp, ReduceState rs) {
     __shared__ double sh[3 * kWarps];
+    __shared__ double pipe[kPipeDepth * 3 * kThreads];
     double v[3] = {0.0, 0.0, 0.0};
-    const double* xs = r + ld;
-    const double* ys = r + 3 * ld;
-    const double* dl = r + 5 * ld;
-    // U particles per thread per trip: all loads are issued before any arithmetic
-    constexpr int U = 4;
-    for (long long i0 = (long long)blockIdx.x * (kThreads * U) + threadIdx.x; i0 < n;
-         i0 += (long long)gridDim.x * (kThreads * U)) {
-        double a[U], b[U], d[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long i = i0 + u * kThreads;
-            const bool ok = i < n;
-            a[u] = ok ? xs[i] : 0.0; b[u] = ok ? ys[i] : 0.0; d[u] = ok ? dl[i] : 0.0;
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (i0 + u * kThreads < n) {
-                double gam;
-                double pzr = mad_pz_rel(rp, a[u], b[u], d[u], gam);
-                v[0] += a[u]; v[1] += b[u]; v[2] += pzr;   // p = (x', y', pz_rel) * pc: scaled once at the end
-            }
-        }
-    }
+    const double* const base[3] = {r + ld, r + 3 * ld, r + 5 * ld};
+    pipelined_sweep<3, kPipeDepth>(base, (int)n, pipe, [&](int, const double (&w)[3]) {
+        double gam;
+        const double pzr = mad_pz_rel(rp, w[0], w[1], w[2], gam);
+        v[0] += w[0]; v[1] += w[1]; v[2] += pzr;       // p = (x', y', pz_rel) * pc: scaled once at the end
+    });
     if (grid_reduce<3, 0>(v, rs.part, rs.ticket + 0, sh) && threadIdx.x == 0) {
         rs.sums[0] = v[0] * rp.pc; rs.sums[1] = v[1] * rp.pc; rs.sums[2] = v[2] * rp.pc;
         rs.sums[3] = (double)n;
@@ -123,41 +109,26 @@ __global__ void __launch_bounds__(kThreads) k_momentum(const double* __restrict_
 // ---------------------------------------------------------------------------
 // sweep 2: extents and charge centroid in the bunch frame (sc.py:172-173,181-182)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_extent(const double* __restrict__ r, long long ld,
-                                                    const double* __restrict__ q, long long n, RefParams rp,
-                                                    ReduceState rs) {
+__global__ void __launch_bounds__(kThreads, 3) k_extent(const double* __restrict__ r, long long ld,
+                                                       const double* __restrict__ q, long long n, RefParams rp,
+                                                       ReduceState rs) {
     __shared__ double sh[10 * kWarps];
+    __shared__ double pipe[kPipeDepth * 7 * kThreads];
     __shared__ Frame sf;
     if (threadIdx.x == 0) derive_frame(rs.sums, rp.m_e_eV, sf);
     __syncthreads();
     const Frame f = sf;
     double v[10] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, 0.0, 0.0, 0.0, 0.0};
-    constexpr int U = 4;
-    for (long long i0 = (long long)blockIdx.x * (kThreads * U) + threadIdx.x; i0 < n;
-         i0 += (long long)gridDim.x * (kThreads * U)) {
-        double w[U][7];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long i = i0 + u * kThreads;
-            if (i < n) {
-#pragma unroll
-                for (int k = 0; k < 6; ++k) w[u][k] = r[k * ld + i];
-                w[u][6] = q[i];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (i0 + u * kThreads < n) {
-                Cart c = mad_to_cart(rp, w[u][0], w[u][1], w[u][2], w[u][3], w[u][4], w[u][5]);
-                double a, b, g;
-                rotate_stretch(f, c.x, c.y, c.z, a, b, g);
-                const double qi = w[u][6];
-                v[0] = fmax(v[0], a); v[1] = fmax(v[1], b); v[2] = fmax(v[2], g);
-                v[3] = fmax(v[3], -a); v[4] = fmax(v[4], -b); v[5] = fmax(v[5], -g);
-                v[6] += qi * a; v[7] += qi * b; v[8] += qi * g; v[9] += qi;
-            }
-        }
-    }
+    const double* const base[7] = {r, r + ld, r + 2 * ld, r + 3 * ld, r + 4 * ld, r + 5 * ld, q};
+    pipelined_sweep<7, kPipeDepth>(base, (int)n, pipe, [&](int, const double (&w)[7]) {
+        const Cart c = mad_to_cart(rp, w[0], w[1], w[2], w[3], w[4], w[5]);
+        double a, b, g;
+        rotate_stretch(f, c.x, c.y, c.z, a, b, g);
+        const double qi = w[6];
+        v[0] = fmax(v[0], a); v[1] = fmax(v[1], b); v[2] = fmax(v[2], g);
+        v[3] = fmax(v[3], -a); v[4] = fmax(v[4], -b); v[5] = fmax(v[5], -g);
+        v[6] += qi * a; v[7] += qi * b; v[8] += qi * g; v[9] += qi;
+    });
     if (grid_reduce<10, 6>(v, rs.part, rs.ticket + 1, sh) && threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) rs.emax[k] = v[k];
@@ -169,9 +140,11 @@ __global__ void __launch_bounds__(kThreads) k_extent(const double* __restrict__ 
 // ---------------------------------------------------------------------------
 // sweep 3: nearest-grid-point deposit (sc.py:186-193)
 // ---------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) k_deposit(const double* __restrict__ r, long long ld,
-                                                     const double* __restrict__ q, long long n, RefParams rp,
-                                                     ReduceState rs, MeshDims md, Draws dr, double* __restrict__ rho) {
+__global__ void __launch_bounds__(kThreads, 3) k_deposit(const double* __restrict__ r, long long ld,
+                                                        const double* __restrict__ q, long long n, RefParams rp,
+                                                        ReduceState rs, MeshDims md, Draws dr,
+                                                        double* __restrict__ rho) {
+    __shared__ double pipe[kPipeDepth * 7 * kThreads];
     __shared__ Frame sf;
     __shared__ Mesh sm;
     if (threadIdx.x == 0) {
@@ -189,32 +162,16 @@ __global__ void __launch_bounds__(kThreads) k_deposit(const double* __restrict__
     __syncthreads();
     const Frame f = sf;
     const Mesh m = sm;
-    constexpr int U = 4;
-    for (long long i0 = (long long)blockIdx.x * (kThreads * U) + threadIdx.x; i0 < n;
-         i0 += (long long)gridDim.x * (kThreads * U)) {
-        double w[U][7];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long i = i0 + u * kThreads;
-            if (i < n) {
-#pragma unroll
-                for (int k = 0; k < 6; ++k) w[u][k] = r[k * ld + i];
-                w[u][6] = q[i];
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            if (i0 + u * kThreads < n) {
-                Cart c = mad_to_cart(rp, w[u][0], w[u][1], w[u][2], w[u][3], w[u][4], w[u][5]);
-                double a, b, g, g0, g1, g2;
-                rotate_stretch(f, c.x, c.y, c.z, a, b, g);
-                to_grid(m, a, b, g, g0, g1, g2);
-                int c0 = (int)floor(g0) + 1, c1 = (int)floor(g1) + 1, c2 = (int)floor(g2) + 1;   // sc.py:191
-                if ((unsigned)c0 < (unsigned)md.nx && (unsigned)c1 < (unsigned)md.ny && (unsigned)c2 < (unsigned)md.nz)
-                    atomicAdd(rho + ((size_t)c0 * md.ny + c1) * md.nz + c2, w[u][6]);            // sc.py:192-193
-            }
-        }
-    }
+    const double* const base[7] = {r, r + ld, r + 2 * ld, r + 3 * ld, r + 4 * ld, r + 5 * ld, q};
+    pipelined_sweep<7, kPipeDepth>(base, (int)n, pipe, [&](int, const double (&w)[7]) {
+        const Cart c = mad_to_cart(rp, w[0], w[1], w[2], w[3], w[4], w[5]);
+        double a, b, g, g0, g1, g2;
+        rotate_stretch(f, c.x, c.y, c.z, a, b, g);
+        to_grid(m, a, b, g, g0, g1, g2);
+        const int c0 = (int)floor(g0) + 1, c1 = (int)floor(g1) + 1, c2 = (int)floor(g2) + 1;   // sc.py:191
+        if ((unsigned)c0 < (unsigned)md.nx && (unsigned)c1 < (unsigned)md.ny && (unsigned)c2 < (unsigned)md.nz)
+            atomicAdd(rho + ((size_t)c0 * md.ny + c1) * md.nz + c2, w[6]);                     // sc.py:192-193
+    });
 }
 
 // ---------------------------------------------------------------------------
@@ -373,46 +330,46 @@ __global__ void __launch_bounds__(kThreads) k_crop_phi(const double* __restrict_
 // staggered backward differences, last plane zero (sc.py:195-200), stored as
 // the quad table the gather reads: equad[comp][i][j][k] = E_comp at
 // (i,j,k), (i,j,k+1), (i,j+1,k), (i,j+1,k+1) with the upper indices clamped.
-__device__ __forceinline__ double field_value(const double* __restrict__ phi, const MeshDims& md, const double* h,
+__device__ __forceinline__ double field_value(const double* __restrict__ phi, const MeshDims& md, const double* ih,
                                               int comp, int i, int j, int k) {
     const size_t sy = md.nz, sx = (size_t)md.ny * md.nz;
     const size_t t = (size_t)i * sx + (size_t)j * sy + k;
-    if (comp == 0) return (i < md.nx - 1) ? (__ldg(phi + t) - __ldg(phi + t + sx)) / h[0] : 0.0;
-    if (comp == 1) return (j < md.ny - 1) ? (__ldg(phi + t) - __ldg(phi + t + sy)) / h[1] : 0.0;
-    return (k < md.nz - 1) ? (__ldg(phi + t) - __ldg(phi + t + 1)) / h[2] : 0.0;
+    // (phi - phi_next) * (1/h): within one ulp of the reference's (phi - phi_next)/h
+    if (comp == 0) return (i < md.nx - 1) ? (__ldg(phi + t) - __ldg(phi + t + sx)) * ih[0] : 0.0;
+    if (comp == 1) return (j < md.ny - 1) ? (__ldg(phi + t) - __ldg(phi + t + sy)) * ih[1] : 0.0;
+    return (k < md.nz - 1) ? (__ldg(phi + t) - __ldg(phi + t + 1)) * ih[2] : 0.0;
 }
 
+// grid = (ceil(nz*ny / threads), nx, 3): no integer division by runtime strides per thread
 __global__ void __launch_bounds__(kThreads) k_field(const double* __restrict__ phi, StepSrc src, ReduceState rs,
                                                    MeshDims md, Draws dr, EQuad* __restrict__ equad) {
     __shared__ double h[3];
+    __shared__ double ih[3];
     resolve_steps(src, rs, md, dr, h);
-    const long long cells = (long long)md.nx * md.ny * md.nz;
-    const long long total = 3 * cells;
-    for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total; t += (long long)gridDim.x * kThreads) {
-        int comp = (int)(t / cells);
-        long long w = t - comp * cells;
-        int k = (int)(w % md.nz);
-        long long u = w / md.nz;
-        int j = (int)(u % md.ny);
-        int i = (int)(u / md.ny);
-        int j1 = min(j + 1, md.ny - 1), k1 = min(k + 1, md.nz - 1);
-        EQuad e;
-        e.v00 = field_value(phi, md, h, comp, i, j, k);
-        e.v01 = field_value(phi, md, h, comp, i, j, k1);
-        e.v10 = field_value(phi, md, h, comp, i, j1, k);
-        e.v11 = field_value(phi, md, h, comp, i, j1, k1);
-        equad[t] = e;
-    }
+    if (threadIdx.x < 3) ih[threadIdx.x] = 1.0 / h[threadIdx.x];
+    __syncthreads();
+    const int comp = blockIdx.z, i = blockIdx.y;
+    const int jk = blockIdx.x * kThreads + threadIdx.x;
+    if (jk >= md.ny * md.nz) return;
+    const int j = jk / md.nz, k = jk - j * md.nz;
+    const int j1 = min(j + 1, md.ny - 1), k1 = min(k + 1, md.nz - 1);
+    EQuad e;
+    e.v00 = field_value(phi, md, ih, comp, i, j, k);
+    e.v01 = field_value(phi, md, ih, comp, i, j, k1);
+    e.v10 = field_value(phi, md, ih, comp, i, j1, k);
+    e.v11 = field_value(phi, md, ih, comp, i, j1, k1);
+    equad[((size_t)comp * md.nx + i) * md.ny * md.nz + jk] = e;
 }
 
 // ---------------------------------------------------------------------------
 // sweep 4: gather, kick, back-transform (sc.py:201-204, :244-251)
 // ---------------------------------------------------------------------------
 template <bool KICK, bool TAP>
-__global__ void __launch_bounds__(kThreads) k_gather_kick(double* __restrict__ r, long long ld, long long n,
-                                                         RefParams rp, ReduceState rs, MeshDims md, Draws dr,
-                                                         const EQuad* __restrict__ equad, double cdT,
-                                                         double* __restrict__ exyz_out) {
+__global__ void __launch_bounds__(kThreads, 2) k_gather_kick(double* __restrict__ r, long long ld, long long n,
+                                                            RefParams rp, ReduceState rs, MeshDims md, Draws dr,
+                                                            const EQuad* __restrict__ equad, double cdT,
+                                                            double* __restrict__ exyz_out) {
+    __shared__ double pipe[kPipeDepth * 6 * kThreads];
     __shared__ Frame sf;
     __shared__ Mesh sm;
     if (threadIdx.x == 0) {
@@ -427,51 +384,36 @@ __global__ void __launch_bounds__(kThreads) k_gather_kick(double* __restrict__ r
     const EQuad* __restrict__ ex = equad;
     const EQuad* __restrict__ ey = equad + cells;
     const EQuad* __restrict__ ez = equad + 2 * cells;
-    constexpr int U = 2;
-    for (long long i0 = (long long)blockIdx.x * (kThreads * U) + threadIdx.x; i0 < n;
-         i0 += (long long)gridDim.x * (kThreads * U)) {
-        double w[U][6];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long i = i0 + u * kThreads;
-            if (i < n) {
-#pragma unroll
-                for (int k = 0; k < 6; ++k) w[u][k] = r[k * ld + i];
-            }
+    const double* const base[6] = {r, r + ld, r + 2 * ld, r + 3 * ld, r + 4 * ld, r + 5 * ld};
+    pipelined_sweep<6, kPipeDepth>(base, (int)n, pipe, [&](int i, const double (&w)[6]) {
+        Cart c = mad_to_cart(rp, w[0], w[1], w[2], w[3], w[4], w[5]);
+        double a, b, g, g0, g1, g2;
+        rotate_stretch(f, c.x, c.y, c.z, a, b, g);
+        to_grid(m, a, b, g, g0, g1, g2);
+        const double e0 = trilinear(ex, md.nx, md.ny, md.nz, g0, g1 + 0.5, g2 + 0.5) * f.gamma0;   // :202
+        const double e1 = trilinear(ey, md.nx, md.ny, md.nz, g0 + 0.5, g1, g2 + 0.5) * f.gamma0;   // :203
+        const double e2 = trilinear(ez, md.nx, md.ny, md.nz, g0 + 0.5, g1 + 0.5, g2);              // :204
+        if (TAP) {
+            exyz_out[3 * (size_t)i + 0] = e0; exyz_out[3 * (size_t)i + 1] = e1; exyz_out[3 * (size_t)i + 2] = e2;
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long i = i0 + u * kThreads;
-            if (i >= n) continue;
-            Cart c = mad_to_cart(rp, w[u][0], w[u][1], w[u][2], w[u][3], w[u][4], w[u][5]);
-            double a, b, g, g0, g1, g2;
-            rotate_stretch(f, c.x, c.y, c.z, a, b, g);
-            to_grid(m, a, b, g, g0, g1, g2);
-            double e0 = trilinear(ex, md.nx, md.ny, md.nz, g0, g1 + 0.5, g2 + 0.5) * f.gamma0;   // :202
-            double e1 = trilinear(ey, md.nx, md.ny, md.nz, g0 + 0.5, g1, g2 + 0.5) * f.gamma0;   // :203
-            double e2 = trilinear(ez, md.nx, md.ny, md.nz, g0 + 0.5, g1 + 0.5, g2);              // :204
-            if (TAP) {
-                exyz_out[3 * i + 0] = e0; exyz_out[3 * i + 1] = e1; exyz_out[3 * i + 2] = e2;
-            }
-            if (KICK) {
-                // momenta into the bunch frame (sc.py:234)
-                double p0 = c.px * f.T[0][0] + c.py * f.T[1][0] + c.pz * f.T[2][0];
-                double p1 = c.px * f.T[0][1] + c.py * f.T[1][1] + c.pz * f.T[2][1];
-                double p2 = c.px * f.T[0][2] + c.py * f.T[1][2] + c.pz * f.T[2][2];
-                p0 = p0 + kt * e0;                                                             // :246
-                p1 = p1 + kt * e1;                                                             // :247
-                p2 = p2 + cdT * e2;                                                            // :248
-                // back to the lab axes (sc.py:249-250)
-                c.px = p0 * f.T[0][0] + p1 * f.T[0][1] + p2 * f.T[0][2];
-                c.py = p0 * f.T[1][0] + p1 * f.T[1][1] + p2 * f.T[1][2];
-                c.pz = p0 * f.T[2][0] + p1 * f.T[2][1] + p2 * f.T[2][2];
-                double x, xs, y, ys, tau, delta;
-                cart_to_mad(rp, c, x, xs, y, ys, tau, delta);                                  // :251
-                r[i] = x; r[ld + i] = xs; r[2 * ld + i] = y; r[3 * ld + i] = ys; r[4 * ld + i] = tau;
-                r[5 * ld + i] = delta;
-            }
+        if (KICK) {
+            // momenta into the bunch frame (sc.py:234)
+            double p0 = c.px * f.T[0][0] + c.py * f.T[1][0] + c.pz * f.T[2][0];
+            double p1 = c.px * f.T[0][1] + c.py * f.T[1][1] + c.pz * f.T[2][1];
+            double p2 = c.px * f.T[0][2] + c.py * f.T[1][2] + c.pz * f.T[2][2];
+            p0 = p0 + kt * e0;                                                             // :246
+            p1 = p1 + kt * e1;                                                             // :247
+            p2 = p2 + cdT * e2;                                                            // :248
+            // back to the lab axes (sc.py:249-250)
+            c.px = p0 * f.T[0][0] + p1 * f.T[0][1] + p2 * f.T[0][2];
+            c.py = p0 * f.T[1][0] + p1 * f.T[1][1] + p2 * f.T[1][2];
+            c.pz = p0 * f.T[2][0] + p1 * f.T[2][1] + p2 * f.T[2][2];
+            double x, xs, y, ys, tau, delta;
+            cart_to_mad(rp, c, x, xs, y, ys, tau, delta);                                  // :251
+            r[i] = x; r[ld + i] = xs; r[2 * ld + i] = y; r[3 * ld + i] = ys; r[4 * ld + i] = tau;
+            r[5 * ld + i] = delta;
         }
-    }
+    });
 }
 
 // stand-alone transforms (known-answer tests)
@@ -505,7 +447,8 @@ static inline int grid_for(long long total, int cap) {
     if (b > cap) b = cap;
     return (int)b;
 }
-constexpr int kSweepCap = 148 * 8;    // grid-stride particle sweeps without reduction
+constexpr int kSweepCap = 148 * 4;    // persistent grid-stride sweeps: 4 resident blocks per SM
+constexpr int kGatherCap = 148 * 2;   // gather/kick: 2 resident blocks per SM
 constexpr int kGridCap = 148 * 16;    // grid kernels
 
 void launch_momentum(const double* r, long long ld, long long n, RefParams rp, ReduceState rs, cudaStream_t st) {
@@ -513,11 +456,11 @@ void launch_momentum(const double* r, long long ld, long long n, RefParams rp, R
 }
 void launch_extent(const double* r, long long ld, const double* q, long long n, RefParams rp, ReduceState rs,
                    cudaStream_t st) {
-    k_extent<<<particle_grid(n, rs.max_blocks), kThreads, 0, st>>>(r, ld, q, n, rp, rs);
+    k_extent<<<particle_grid(n, 148 * 3), kThreads, 0, st>>>(r, ld, q, n, rp, rs);
 }
 void launch_deposit(const double* r, long long ld, const double* q, long long n, RefParams rp, ReduceState rs,
                     MeshDims md, Draws dr, double* rho, cudaStream_t st) {
-    k_deposit<<<grid_for((n + 3) / 4, kSweepCap), kThreads, 0, st>>>(r, ld, q, n, rp, rs, md, dr, rho);
+    k_deposit<<<grid_for(n, 148 * 3), kThreads, 0, st>>>(r, ld, q, n, rp, rs, md, dr, rho);
 }
 void launch_green_table(ReduceState rs, MeshDims md, Draws dr, double* gtab, double* h3, cudaStream_t st) {
     StepSrc src;
@@ -576,13 +519,13 @@ void launch_crop_phi_steps(const double* conv, const double steps[3], MeshDims m
 void launch_field(const double* phi, ReduceState rs, MeshDims md, Draws dr, EQuad* equad, cudaStream_t st) {
     StepSrc src;
     src.given = 0; src.h[0] = src.h[1] = src.h[2] = 0.0;
-    long long total = 3LL * md.nx * md.ny * md.nz;
-    k_field<<<grid_for(total, kGridCap), kThreads, 0, st>>>(phi, src, rs, md, dr, equad);
+    dim3 grid((md.ny * md.nz + kThreads - 1) / kThreads, md.nx, 3);
+    k_field<<<grid, kThreads, 0, st>>>(phi, src, rs, md, dr, equad);
 }
 void launch_gather_kick(double* r, long long ld, long long n, RefParams rp, ReduceState rs, MeshDims md, Draws dr,
                         const EQuad* equad, double dz, double* exyz_out, int do_kick, cudaStream_t st) {
     const double cdT = dz / rp.betaref;   // sc.py:244
-    int grid = grid_for((n + 1) / 2, kSweepCap);
+    int grid = grid_for(n, kGatherCap);
     if (do_kick && exyz_out)
         k_gather_kick<true, true><<<grid, kThreads, 0, st>>>(r, ld, n, rp, rs, md, dr, equad, cdT, exyz_out);
     else if (do_kick)

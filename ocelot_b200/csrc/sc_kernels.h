@@ -61,8 +61,9 @@ struct FftWork {
 void fft_init_kernels();
 int fft_max_length();
 void launch_khat(const double* gtab, MeshDims md, FftWork w, cudaStream_t st);
-void launch_convolve(const double* rho, MeshDims md, FftWork w, const double* h3, double four_pi_eps0, double* phi,
-                     cudaStream_t st);
+void launch_convolve_pre(const double* rho, MeshDims md, FftWork w, cudaStream_t st);
+void launch_convolve_post(MeshDims md, FftWork w, const double* h3, double four_pi_eps0, double* phi,
+                          cudaStream_t st);
 double four_pi_eps0_value();
 
 // potential KAT helpers: steps given explicitly instead of derived from particles
