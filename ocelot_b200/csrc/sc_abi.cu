@@ -51,6 +51,16 @@ struct ocl_sc {
     cudaEvent_t ev_fork = nullptr, ev_khat = nullptr;
     bool khat_pending = false;
     cudaStream_t last_stream = nullptr;
+    // whole-kick CUDA graph (single-GPU ocl_sc_kick_device): captured once per (r, ld, q, n),
+    // per kick only the parameter node (E, dz, mesh draws) is refreshed
+    KickParams* kp_dev = nullptr;
+    bool use_graph = true;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    cudaGraphNode_t param_node = nullptr;
+    const void* g_r = nullptr; const void* g_q = nullptr; long long g_ld = 0, g_n = 0;
+    long long graph_launches_per_kick = 0;
+    const KickParams* cur_pp = nullptr;       // non-null while stages are being captured
     // timers
     bool timers = false;
     cudaEvent_t ev[T_COUNT] = {};
@@ -115,6 +125,22 @@ Draws draws_of(const double* mesh_draws) {
     return d;
 }
 
+KickParams kick_params(const ocl_sc* h, double E_GeV, double dz, const double* mesh_draws) {
+    KickParams k;
+    k.rp = ref_params(h, E_GeV);
+    k.dr = draws_of(mesh_draws);
+    k.cdT = dz / k.rp.betaref;                                       // sc.py:244
+    return k;
+}
+
+// by value for direct launches, through the device block while a graph is captured / replayed
+KP kp_of(const ocl_sc* h, double E_GeV, double dz, const double* mesh_draws) {
+    KP k;
+    k.v = kick_params(h, E_GeV, dz, mesh_draws);
+    k.p = h->cur_pp;
+    return k;
+}
+
 int check_launch(ocl_sc* h, const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return fail(h, what, cudaGetErrorString(e));
@@ -176,10 +202,10 @@ int solve_fused(ocl_sc* h, cudaStream_t st) {
 }
 
 // Green's function table + K_hat on the side stream, ordered after everything already in st
-int fork_khat(ocl_sc* h, Draws dr, cudaStream_t st) {
+int fork_khat(ocl_sc* h, KP kp, cudaStream_t st) {
     CU(h, cudaEventRecord(h->ev_fork, st));
     CU(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
-    launch_green_table(h->rs, h->md, dr, h->gtab, h->h3, h->side_stream);
+    launch_green_table(h->rs, h->md, kp, h->gtab, h->h3, h->side_stream);
     launch_khat(h->gtab, h->md, h->fw, h->side_stream);
     CU(h, cudaEventRecord(h->ev_khat, h->side_stream));
     h->khat_pending = true;
@@ -205,6 +231,8 @@ int convolve(ocl_sc* h, cudaStream_t st) {
 }  // namespace
 
 extern "C" {
+
+static void drop_graph(ocl_sc* h);
 
 int ocl_sc_abi_version(void) { return 1; }
 
@@ -267,6 +295,11 @@ int ocl_sc_create(int device, int nx, int ny, int nz, long long max_particles, o
         if (h->md.mx > fft_max_length() || h->md.my > fft_max_length() || h->md.mz > fft_max_length()) h->solver = 1;
     }
     TRY(cudaMalloc(&h->h3, sizeof(double) * 4));
+    TRY(cudaMalloc(&h->kp_dev, sizeof(KickParams)));
+    {
+        const char* env = getenv("OCL_SC_GRAPH");
+        h->use_graph = !(env && strcmp(env, "0") == 0);
+    }
     if (h->solver == 0) {
         const size_t hx1 = h->md.mx / 2 + 1, hy1 = h->md.my / 2 + 1, hz1 = h->md.mz / 2 + 1;
         fft_init_kernels();
@@ -302,6 +335,8 @@ int ocl_sc_create(int device, int nx, int ny, int nz, long long max_particles, o
 void ocl_sc_destroy(ocl_sc_t* h) {
     if (!h) return;
     cudaSetDevice(h->device);
+    drop_graph(h);
+    cudaFree(h->kp_dev);
     if (h->plans) { cufftDestroy(h->plan_fwd); cufftDestroy(h->plan_inv); }
     cudaFree(h->rs.part); cudaFree(h->rs.ticket); cudaFree(h->rs.sums);
     cudaFree(h->rho); cudaFree(h->gtab); cudaFree(h->k1); cudaFree(h->real_buf);
@@ -337,7 +372,7 @@ int ocl_sc_stage_momentum(ocl_sc_t* h, const double* d_r, long long ld, long lon
     cudaStream_t st = (cudaStream_t)stream;
     h->last_stream = st;
     mark(h, T_BEGIN, st);
-    launch_momentum(d_r, ld, n, ref_params(h, E_GeV), h->rs, st);
+    launch_momentum(d_r, ld, n, kp_of(h, E_GeV, 0.0, nullptr), h->rs, st);
     h->launches += 1;
     mark(h, T_MOM, st);
     return check_launch(h, "k_momentum");
@@ -349,7 +384,7 @@ int ocl_sc_stage_extent(ocl_sc_t* h, const double* d_r, long long ld, const doub
     if (set_device(h)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     h->last_stream = st;
-    launch_extent(d_r, ld, d_q, n, ref_params(h, E_GeV), h->rs, st);
+    launch_extent(d_r, ld, d_q, n, kp_of(h, E_GeV, 0.0, nullptr), h->rs, st);
     h->launches += 1;
     mark(h, T_EXT, st);
     return check_launch(h, "k_extent");
@@ -363,9 +398,9 @@ int ocl_sc_stage_deposit(ocl_sc_t* h, const double* d_r, long long ld, const dou
     h->last_stream = st;
     // the mesh steps are final once the extents are reduced: start the Green's-function / K_hat
     // chain now, concurrently with the deposit and the first two rho passes
-    if (h->solver == 0 && fork_khat(h, draws_of(mesh_draws), st)) return 1;
+    if (h->solver == 0 && fork_khat(h, kp_of(h, E_GeV, 0.0, mesh_draws), st)) return 1;
     CU(h, cudaMemsetAsync(h->rho, 0, sizeof(double) * (size_t)h->md.nx * h->md.ny * h->md.nz, st));
-    launch_deposit(d_r, ld, d_q, n, ref_params(h, E_GeV), h->rs, h->md, draws_of(mesh_draws), h->rho, st);
+    launch_deposit(d_r, ld, d_q, n, kp_of(h, E_GeV, 0.0, mesh_draws), h->rs, h->md, h->rho, st);
     h->launches += 2;
     mark(h, T_DEP, st);
     return check_launch(h, "k_deposit");
@@ -376,7 +411,7 @@ int ocl_sc_stage_solve(ocl_sc_t* h, const double* mesh_draws, void* stream) {
     if (set_device(h)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     h->last_stream = st;
-    Draws dr = draws_of(mesh_draws);
+    KP dr = kp_of(h, 1.0, 0.0, mesh_draws);   // only the mesh draws are used by the solve
     if (!h->khat_pending) {
         launch_green_table(h->rs, h->md, dr, h->gtab, h->h3, st);
         h->launches += 1;
@@ -402,10 +437,65 @@ int ocl_sc_stage_kick(ocl_sc_t* h, double* d_r, long long ld, long long n, doubl
     if (set_device(h)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     h->last_stream = st;
-    launch_gather_kick(d_r, ld, n, ref_params(h, E_GeV), h->rs, h->md, draws_of(mesh_draws), h->equad, dz, nullptr, 1, st);
+    launch_gather_kick(d_r, ld, n, kp_of(h, E_GeV, dz, mesh_draws), h->rs, h->md, h->equad, nullptr, 1, st);
     h->launches += 1;
     mark(h, T_KICK, st);
     return check_launch(h, "k_gather_kick");
+}
+
+static int run_stages(ocl_sc_t* h, double* d_r, long long ld, const double* d_q, long long n, double E_GeV,
+                      double dz, const double* mesh_draws, void* stream) {
+    if (ocl_sc_stage_momentum(h, d_r, ld, n, E_GeV, stream)) return 1;
+    if (ocl_sc_stage_extent(h, d_r, ld, d_q, n, E_GeV, stream)) return 1;
+    if (ocl_sc_stage_deposit(h, d_r, ld, d_q, n, E_GeV, mesh_draws, stream)) return 1;
+    if (ocl_sc_stage_solve(h, mesh_draws, stream)) return 1;
+    return ocl_sc_stage_kick(h, d_r, ld, n, E_GeV, dz, mesh_draws, stream);
+}
+
+static void drop_graph(ocl_sc* h) {
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    if (h->graph) cudaGraphDestroy(h->graph);
+    h->graph_exec = nullptr; h->graph = nullptr; h->param_node = nullptr;
+}
+
+// Capture the whole kick (parameter node + ~19 kernels + the side-stream fork/join) once.
+static int capture_kick(ocl_sc* h, double* d_r, long long ld, const double* d_q, long long n, double E_GeV,
+                        double dz, const double* mesh_draws) {
+    drop_graph(h);
+    cudaStream_t cs = h->own_stream;
+    CU(h, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    launch_set_params(kick_params(h, E_GeV, dz, mesh_draws), h->kp_dev, cs);
+    h->cur_pp = h->kp_dev;
+    const long long before = h->launches;
+    int rc = run_stages(h, d_r, ld, d_q, n, E_GeV, dz, mesh_draws, cs);
+    h->cur_pp = nullptr;
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(cs, &g);
+    h->graph_launches_per_kick = h->launches - before + 1;
+    h->launches = before;
+    if (rc || e != cudaSuccess || !g) {
+        if (g) cudaGraphDestroy(g);
+        h->khat_pending = false;
+        return rc ? rc : fail(h, "cudaStreamEndCapture", cudaGetErrorString(e));
+    }
+    h->graph = g;
+    CU(h, cudaGraphInstantiate(&h->graph_exec, g, 0));
+    size_t nn = 0;
+    CU(h, cudaGraphGetNodes(g, nullptr, &nn));
+    std::vector<cudaGraphNode_t> nodes(nn);
+    CU(h, cudaGraphGetNodes(g, nodes.data(), &nn));
+    for (size_t i = 0; i < nn; ++i) {
+        cudaGraphNodeType t;
+        if (cudaGraphNodeGetType(nodes[i], &t) != cudaSuccess || t != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp;
+        if (cudaGraphKernelNodeGetParams(nodes[i], &kp) == cudaSuccess && kp.func == set_params_kernel()) {
+            h->param_node = nodes[i];
+            break;
+        }
+    }
+    if (!h->param_node) { drop_graph(h); return fail(h, "capture_kick", "parameter node not found"); }
+    h->g_r = d_r; h->g_q = d_q; h->g_ld = ld; h->g_n = n;
+    return 0;
 }
 
 int ocl_sc_kick_device(ocl_sc_t* h, double* d_r, long long ld, const double* d_q, long long n, double E_GeV,
@@ -413,11 +503,32 @@ int ocl_sc_kick_device(ocl_sc_t* h, double* d_r, long long ld, const double* d_q
     if (!h) return 1;
     if (dz == 0.0) return 0;   // sc.py:210-212
     if (!(E_GeV > 0.0)) return fail(h, "ocl_sc_kick_device", "beam energy must be positive");
-    if (ocl_sc_stage_momentum(h, d_r, ld, n, E_GeV, stream)) return 1;
-    if (ocl_sc_stage_extent(h, d_r, ld, d_q, n, E_GeV, stream)) return 1;
-    if (ocl_sc_stage_deposit(h, d_r, ld, d_q, n, E_GeV, mesh_draws, stream)) return 1;
-    if (ocl_sc_stage_solve(h, mesh_draws, stream)) return 1;
-    return ocl_sc_stage_kick(h, d_r, ld, n, E_GeV, dz, mesh_draws, stream);
+    if (n <= 0 || ld < n) return fail(h, "ocl_sc_kick_device", "need 0 < n <= ld");
+    cudaStream_t st = (cudaStream_t)stream;
+    bool graph_ok = h->use_graph && h->solver == 0 && !h->timers;
+    if (graph_ok) {
+        if (set_device(h)) return 1;
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+            cudaGetLastError();
+            graph_ok = false;       // the caller is capturing us into a graph of its own
+        }
+    }
+    if (!graph_ok) return run_stages(h, d_r, ld, d_q, n, E_GeV, dz, mesh_draws, stream);
+    if (!h->graph_exec || h->g_r != d_r || h->g_q != d_q || h->g_ld != ld || h->g_n != n) {
+        if (capture_kick(h, d_r, ld, d_q, n, E_GeV, dz, mesh_draws)) return 1;
+    }
+    KickParams kp = kick_params(h, E_GeV, dz, mesh_draws);
+    void* args[2] = {&kp, &h->kp_dev};
+    cudaKernelNodeParams np = {};
+    np.func = const_cast<void*>(set_params_kernel());
+    np.gridDim = dim3(1); np.blockDim = dim3(32); np.sharedMemBytes = 0;
+    np.kernelParams = args; np.extra = nullptr;
+    CU(h, cudaGraphExecKernelNodeSetParams(h->graph_exec, h->param_node, &np));
+    CU(h, cudaGraphLaunch(h->graph_exec, st));
+    h->launches += h->graph_launches_per_kick;
+    h->last_stream = st;
+    return 0;
 }
 
 static int ensure_stage(ocl_sc* h, long long n) {
@@ -498,8 +609,8 @@ int ocl_sc_field_at_particles(ocl_sc_t* h, const double* d_r, long long ld, cons
     if (ocl_sc_stage_extent(h, d_r, ld, d_q, n, E_GeV, stream)) return 1;
     if (ocl_sc_stage_deposit(h, d_r, ld, d_q, n, E_GeV, mesh_draws, stream)) return 1;
     if (ocl_sc_stage_solve(h, mesh_draws, stream)) return 1;
-    launch_gather_kick(const_cast<double*>(d_r), ld, n, ref_params(h, E_GeV), h->rs, h->md, draws_of(mesh_draws),
-                       h->equad, 0.0, d_exyz, 0, (cudaStream_t)stream);
+    launch_gather_kick(const_cast<double*>(d_r), ld, n, kp_of(h, E_GeV, 0.0, mesh_draws), h->rs, h->md, h->equad,
+                       d_exyz, 0, (cudaStream_t)stream);
     h->launches += 1;
     return check_launch(h, "k_gather");
 }

@@ -28,6 +28,25 @@ struct RefParams {
     double inv_gamref;
 };
 
+// per-kick scalars.  Kernels receive them either by value (direct launches) or through a
+// device-resident copy (CUDA-graph launches, where one parameter node is refreshed per kick).
+struct Draws {
+    double scale;  // <= 0: random_mesh off   (sc.py:175)
+    double shift;  //                          (sc.py:185)
+};
+struct KickParams {
+    RefParams rp;
+    Draws dr;
+    double cdT;    // dz / betaref             (sc.py:244)
+};
+struct KP {
+    KickParams v;
+    const KickParams* p;   // nullptr: use v
+};
+__device__ __forceinline__ RefParams kp_ref(const KP& k) { return k.p ? k.p->rp : k.v.rp; }
+__device__ __forceinline__ Draws kp_draws(const KP& k) { return k.p ? k.p->dr : k.v.dr; }
+__device__ __forceinline__ double kp_cdT(const KP& k) { return k.p ? k.p->cdT : k.v.cdT; }
+
 // bunch frame (sc.py:224-239); T columns are t1, t2, t3
 struct Frame {
     double T[3][3];

@@ -90,7 +90,8 @@ constexpr int kPipeDepth = 3;
 // sweep 1: mean momentum (sc.py:221,224)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 4) k_momentum(const double* __restrict__ r, long long ld, long long n,
-                                                         RefParams rp, ReduceState rs) {
+                                                         KP kp, ReduceState rs) {
+    const RefParams rp = kp_ref(kp);
     __shared__ double sh[3 * kWarps];
     __shared__ double pipe[kPipeDepth * 3 * kThreads];
     double v[3] = {0.0, 0.0, 0.0};
@@ -110,8 +111,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_momentum(const double* __restri
 // sweep 2: extents and charge centroid in the bunch frame (sc.py:172-173,181-182)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 3) k_extent(const double* __restrict__ r, long long ld,
-                                                       const double* __restrict__ q, long long n, RefParams rp,
+                                                       const double* __restrict__ q, long long n, KP kp,
                                                        ReduceState rs) {
+    const RefParams rp = kp_ref(kp);
     __shared__ double sh[10 * kWarps];
     __shared__ double pipe[kPipeDepth * 7 * kThreads];
     __shared__ Frame sf;
@@ -141,9 +143,10 @@ __global__ void __launch_bounds__(kThreads, 3) k_extent(const double* __restrict
 // sweep 3: nearest-grid-point deposit (sc.py:186-193)
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 3) k_deposit(const double* __restrict__ r, long long ld,
-                                                        const double* __restrict__ q, long long n, RefParams rp,
-                                                        ReduceState rs, MeshDims md, Draws dr,
-                                                        double* __restrict__ rho) {
+                                                        const double* __restrict__ q, long long n, KP kp,
+                                                        ReduceState rs, MeshDims md, double* __restrict__ rho) {
+    const RefParams rp = kp_ref(kp);
+    const Draws dr = kp_draws(kp);
     __shared__ double pipe[kPipeDepth * 7 * kThreads];
     __shared__ Frame sf;
     __shared__ Mesh sm;
@@ -213,8 +216,9 @@ __device__ __forceinline__ void resolve_steps(const StepSrc& src, const ReduceSt
 }
 
 // antiderivative on the (n+1)^3 half-offset points (sc.py:116-126)
-__global__ void __launch_bounds__(kThreads) k_green_table(StepSrc src, ReduceState rs, MeshDims md, Draws dr,
+__global__ void __launch_bounds__(kThreads) k_green_table(StepSrc src, ReduceState rs, MeshDims md, KP kp,
                                                          double* __restrict__ gtab, double* __restrict__ h3) {
+    const Draws dr = kp_draws(kp);
     __shared__ double h[3];
     resolve_steps(src, rs, md, dr, h);
     if (blockIdx.x == 0 && threadIdx.x == 0) { h3[0] = h[0]; h3[1] = h[1]; h3[2] = h[2]; }   // for the solver
@@ -312,8 +316,9 @@ __global__ void __launch_bounds__(kThreads) k_multiply(cufftDoubleComplex* __res
 
 // phi = conv[:n,:n,:n] / (4 pi eps0 hx hy hz)  (sc.py:167-168)
 __global__ void __launch_bounds__(kThreads) k_crop_phi(const double* __restrict__ conv, StepSrc src, ReduceState rs,
-                                                      MeshDims md, Draws dr, double four_pi_eps0,
+                                                      MeshDims md, KP kp, double four_pi_eps0,
                                                       double* __restrict__ phi) {
+    const Draws dr = kp_draws(kp);
     __shared__ double h[3];
     resolve_steps(src, rs, md, dr, h);
     const double denom = four_pi_eps0 * h[0] * h[1] * h[2];
@@ -342,7 +347,8 @@ __device__ __forceinline__ double field_value(const double* __restrict__ phi, co
 
 // grid = (ceil(nz*ny / threads), nx, 3): no integer division by runtime strides per thread
 __global__ void __launch_bounds__(kThreads) k_field(const double* __restrict__ phi, StepSrc src, ReduceState rs,
-                                                   MeshDims md, Draws dr, EQuad* __restrict__ equad) {
+                                                   MeshDims md, KP kp, EQuad* __restrict__ equad) {
+    const Draws dr = kp_draws(kp);
     __shared__ double h[3];
     __shared__ double ih[3];
     resolve_steps(src, rs, md, dr, h);
@@ -366,9 +372,12 @@ __global__ void __launch_bounds__(kThreads) k_field(const double* __restrict__ p
 // ---------------------------------------------------------------------------
 template <bool KICK, bool TAP>
 __global__ void __launch_bounds__(kThreads, 2) k_gather_kick(double* __restrict__ r, long long ld, long long n,
-                                                            RefParams rp, ReduceState rs, MeshDims md, Draws dr,
-                                                            const EQuad* __restrict__ equad, double cdT,
+                                                            KP kp, ReduceState rs, MeshDims md,
+                                                            const EQuad* __restrict__ equad,
                                                             double* __restrict__ exyz_out) {
+    const RefParams rp = kp_ref(kp);
+    const Draws dr = kp_draws(kp);
+    const double cdT = kp_cdT(kp);
     __shared__ double pipe[kPipeDepth * 6 * kThreads];
     __shared__ Frame sf;
     __shared__ Mesh sm;
@@ -451,30 +460,36 @@ constexpr int kSweepCap = 148 * 4;    // persistent grid-stride sweeps: 4 reside
 constexpr int kGatherCap = 148 * 2;   // gather/kick: 2 resident blocks per SM
 constexpr int kGridCap = 148 * 16;    // grid kernels
 
-void launch_momentum(const double* r, long long ld, long long n, RefParams rp, ReduceState rs, cudaStream_t st) {
-    k_momentum<<<particle_grid(n, rs.max_blocks), kThreads, 0, st>>>(r, ld, n, rp, rs);
+__global__ void k_set_params(KickParams v, KickParams* dst) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) *dst = v;
 }
-void launch_extent(const double* r, long long ld, const double* q, long long n, RefParams rp, ReduceState rs,
+void launch_set_params(KickParams v, KickParams* dst, cudaStream_t st) { k_set_params<<<1, 32, 0, st>>>(v, dst); }
+const void* set_params_kernel() { return (const void*)k_set_params; }
+
+void launch_momentum(const double* r, long long ld, long long n, KP kp, ReduceState rs, cudaStream_t st) {
+    k_momentum<<<particle_grid(n, rs.max_blocks), kThreads, 0, st>>>(r, ld, n, kp, rs);
+}
+void launch_extent(const double* r, long long ld, const double* q, long long n, KP kp, ReduceState rs,
                    cudaStream_t st) {
-    k_extent<<<particle_grid(n, 148 * 3), kThreads, 0, st>>>(r, ld, q, n, rp, rs);
+    k_extent<<<particle_grid(n, 148 * 3), kThreads, 0, st>>>(r, ld, q, n, kp, rs);
 }
-void launch_deposit(const double* r, long long ld, const double* q, long long n, RefParams rp, ReduceState rs,
-                    MeshDims md, Draws dr, double* rho, cudaStream_t st) {
-    k_deposit<<<grid_for(n, 148 * 3), kThreads, 0, st>>>(r, ld, q, n, rp, rs, md, dr, rho);
+void launch_deposit(const double* r, long long ld, const double* q, long long n, KP kp, ReduceState rs,
+                    MeshDims md, double* rho, cudaStream_t st) {
+    k_deposit<<<grid_for(n, 148 * 3), kThreads, 0, st>>>(r, ld, q, n, kp, rs, md, rho);
 }
-void launch_green_table(ReduceState rs, MeshDims md, Draws dr, double* gtab, double* h3, cudaStream_t st) {
+void launch_green_table(ReduceState rs, MeshDims md, KP kp, double* gtab, double* h3, cudaStream_t st) {
     StepSrc src;
     src.given = 0; src.h[0] = src.h[1] = src.h[2] = 0.0;
     long long total = (long long)(md.nx + 1) * (md.ny + 1) * (md.nz + 1);
-    k_green_table<<<grid_for(total, kGridCap), kThreads, 0, st>>>(src, rs, md, dr, gtab, h3);
+    k_green_table<<<grid_for(total, kGridCap), kThreads, 0, st>>>(src, rs, md, kp, gtab, h3);
 }
 void launch_green_table_steps(const double steps[3], MeshDims md, double* gtab, double* h3, cudaStream_t st) {
     StepSrc src;
     src.given = 1; src.h[0] = steps[0]; src.h[1] = steps[1]; src.h[2] = steps[2];
     ReduceState rs = {};
-    Draws dr = {0.0, 0.0};
+    KP kp = {};
     long long total = (long long)(md.nx + 1) * (md.ny + 1) * (md.nz + 1);
-    k_green_table<<<grid_for(total, kGridCap), kThreads, 0, st>>>(src, rs, md, dr, gtab, h3);
+    k_green_table<<<grid_for(total, kGridCap), kThreads, 0, st>>>(src, rs, md, kp, gtab, h3);
 }
 void launch_green_mirror(const double* gtab, MeshDims md, double* kpad, cudaStream_t st) {
     cudaMemsetAsync(kpad, 0, sizeof(double) * (size_t)md.mx * md.my * md.mz, st);
@@ -502,36 +517,35 @@ double four_pi_eps0_value() {
     const double eps0 = 1 / mu0 / (c * c);
     return 4 * pi * eps0;
 }
-void launch_crop_phi(const double* conv, ReduceState rs, MeshDims md, Draws dr, double* phi, cudaStream_t st) {
+void launch_crop_phi(const double* conv, ReduceState rs, MeshDims md, KP kp, double* phi, cudaStream_t st) {
     StepSrc src;
     src.given = 0; src.h[0] = src.h[1] = src.h[2] = 0.0;
     long long total = (long long)md.nx * md.ny * md.nz;
-    k_crop_phi<<<grid_for(total, kGridCap), kThreads, 0, st>>>(conv, src, rs, md, dr, four_pi_eps0(), phi);
+    k_crop_phi<<<grid_for(total, kGridCap), kThreads, 0, st>>>(conv, src, rs, md, kp, four_pi_eps0(), phi);
 }
 void launch_crop_phi_steps(const double* conv, const double steps[3], MeshDims md, double* phi, cudaStream_t st) {
     StepSrc src;
     src.given = 1; src.h[0] = steps[0]; src.h[1] = steps[1]; src.h[2] = steps[2];
     ReduceState rs = {};
-    Draws dr = {0.0, 0.0};
+    KP kp = {};
     long long total = (long long)md.nx * md.ny * md.nz;
-    k_crop_phi<<<grid_for(total, kGridCap), kThreads, 0, st>>>(conv, src, rs, md, dr, four_pi_eps0(), phi);
+    k_crop_phi<<<grid_for(total, kGridCap), kThreads, 0, st>>>(conv, src, rs, md, kp, four_pi_eps0(), phi);
 }
-void launch_field(const double* phi, ReduceState rs, MeshDims md, Draws dr, EQuad* equad, cudaStream_t st) {
+void launch_field(const double* phi, ReduceState rs, MeshDims md, KP kp, EQuad* equad, cudaStream_t st) {
     StepSrc src;
     src.given = 0; src.h[0] = src.h[1] = src.h[2] = 0.0;
     dim3 grid((md.ny * md.nz + kThreads - 1) / kThreads, md.nx, 3);
-    k_field<<<grid, kThreads, 0, st>>>(phi, src, rs, md, dr, equad);
+    k_field<<<grid, kThreads, 0, st>>>(phi, src, rs, md, kp, equad);
 }
-void launch_gather_kick(double* r, long long ld, long long n, RefParams rp, ReduceState rs, MeshDims md, Draws dr,
-                        const EQuad* equad, double dz, double* exyz_out, int do_kick, cudaStream_t st) {
-    const double cdT = dz / rp.betaref;   // sc.py:244
+void launch_gather_kick(double* r, long long ld, long long n, KP kp, ReduceState rs, MeshDims md,
+                        const EQuad* equad, double* exyz_out, int do_kick, cudaStream_t st) {
     int grid = grid_for(n, kGatherCap);
     if (do_kick && exyz_out)
-        k_gather_kick<true, true><<<grid, kThreads, 0, st>>>(r, ld, n, rp, rs, md, dr, equad, cdT, exyz_out);
+        k_gather_kick<true, true><<<grid, kThreads, 0, st>>>(r, ld, n, kp, rs, md, equad, exyz_out);
     else if (do_kick)
-        k_gather_kick<true, false><<<grid, kThreads, 0, st>>>(r, ld, n, rp, rs, md, dr, equad, cdT, nullptr);
+        k_gather_kick<true, false><<<grid, kThreads, 0, st>>>(r, ld, n, kp, rs, md, equad, nullptr);
     else
-        k_gather_kick<false, true><<<grid, kThreads, 0, st>>>(r, ld, n, rp, rs, md, dr, equad, cdT, exyz_out);
+        k_gather_kick<false, true><<<grid, kThreads, 0, st>>>(r, ld, n, kp, rs, md, equad, exyz_out);
 }
 void launch_mad_to_cart(const double* r, long long ld, long long n, RefParams rp, double* xp, long long ld_xp,
                         cudaStream_t st) {

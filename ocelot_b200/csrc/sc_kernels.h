@@ -22,27 +22,24 @@ struct MeshDims {
     int mx, my, mz;   // padded FFT lengths
 };
 
-struct Draws {
-    double scale;  // <= 0: random_mesh off
-    double shift;
-};
-
 int particle_grid(long long n, int max_blocks);
 
-void launch_momentum(const double* r, long long ld, long long n, RefParams rp, ReduceState rs, cudaStream_t st);
-void launch_extent(const double* r, long long ld, const double* q, long long n, RefParams rp, ReduceState rs,
+void launch_set_params(KickParams v, KickParams* dst, cudaStream_t st);
+const void* set_params_kernel();
+void launch_momentum(const double* r, long long ld, long long n, KP kp, ReduceState rs, cudaStream_t st);
+void launch_extent(const double* r, long long ld, const double* q, long long n, KP kp, ReduceState rs,
                    cudaStream_t st);
-void launch_deposit(const double* r, long long ld, const double* q, long long n, RefParams rp, ReduceState rs,
-                    MeshDims md, Draws dr, double* rho, cudaStream_t st);
-void launch_green_table(ReduceState rs, MeshDims md, Draws dr, double* gtab, double* h3, cudaStream_t st);
+void launch_deposit(const double* r, long long ld, const double* q, long long n, KP kp, ReduceState rs,
+                    MeshDims md, double* rho, cudaStream_t st);
+void launch_green_table(ReduceState rs, MeshDims md, KP kp, double* gtab, double* h3, cudaStream_t st);
 void launch_green_mirror(const double* gtab, MeshDims md, double* kpad, cudaStream_t st);
 void launch_green_compact(const double* gtab, MeshDims md, double* k1, cudaStream_t st);
 void launch_pad_rho(const double* rho, MeshDims md, double* pad, cudaStream_t st);
 void launch_multiply(cufftDoubleComplex* rho_hat, const cufftDoubleComplex* k_hat, MeshDims md, cudaStream_t st);
-void launch_crop_phi(const double* conv, ReduceState rs, MeshDims md, Draws dr, double* phi, cudaStream_t st);
-void launch_field(const double* phi, ReduceState rs, MeshDims md, Draws dr, EQuad* equad, cudaStream_t st);
-void launch_gather_kick(double* r, long long ld, long long n, RefParams rp, ReduceState rs, MeshDims md, Draws dr,
-                        const EQuad* equad, double dz, double* exyz_out, int do_kick, cudaStream_t st);
+void launch_crop_phi(const double* conv, ReduceState rs, MeshDims md, KP kp, double* phi, cudaStream_t st);
+void launch_field(const double* phi, ReduceState rs, MeshDims md, KP kp, EQuad* equad, cudaStream_t st);
+void launch_gather_kick(double* r, long long ld, long long n, KP kp, ReduceState rs, MeshDims md,
+                        const EQuad* equad, double* exyz_out, int do_kick, cudaStream_t st);
 void launch_mad_to_cart(const double* r, long long ld, long long n, RefParams rp, double* xp, long long ld_xp,
                         cudaStream_t st);
 void launch_cart_to_mad(const double* xp, long long ld_xp, long long n, RefParams rp, double* r, long long ld,
