@@ -83,9 +83,22 @@ enum {
     OCL_SC_BUF_MOMENTUM = 0,   /* 4 doubles, reduce SUM */
     OCL_SC_BUF_EXTENT_MAX = 1, /* 6 doubles, reduce MAX */
     OCL_SC_BUF_EXTENT_SUM = 2, /* 4 doubles, reduce SUM */
-    OCL_SC_BUF_RHO = 3         /* nx*ny*nz doubles, reduce SUM */
+    OCL_SC_BUF_RHO = 3,        /* nx*ny*nz doubles, reduce SUM */
+    OCL_SC_BUF_EXTENT = 4      /* the 10 doubles of EXTENT_MAX + EXTENT_SUM, contiguous (for all-gather) */
 };
 int ocl_sc_collective_buffer(ocl_sc_t* h, int which, double** d_ptr, long long* count);
+
+/* One-collective variant of the extent exchange: all-gather buffer EXTENT (10 doubles per rank)
+ * into d_all[world][10], then fold it (max over the first 6, sum over the last 4) back into the
+ * handle's EXTENT_MAX / EXTENT_SUM buffers. */
+int ocl_sc_combine_extents(ocl_sc_t* h, const double* d_all, int world, void* stream);
+
+/* CUDA-graph support for callers that capture the staged kick themselves (e.g. together with
+ * their NCCL collectives): with device params on, the stage kernels read E, dz and mesh draws
+ * from a device block that ocl_sc_set_kick_params refreshes (a 1-block kernel, launched outside
+ * the captured graph), so one captured graph serves every kick. */
+int ocl_sc_use_device_params(ocl_sc_t* h, int on);
+int ocl_sc_set_kick_params(ocl_sc_t* h, double E_GeV, double dz, const double* mesh_draws, void* stream);
 
 int ocl_sc_stage_momentum(ocl_sc_t* h, const double* d_r, long long ld, long long n, double E_GeV, void* stream);
 int ocl_sc_stage_extent(ocl_sc_t* h, const double* d_r, long long ld, const double* d_q, long long n,

@@ -359,8 +359,32 @@ int ocl_sc_collective_buffer(ocl_sc_t* h, int which, double** d_ptr, long long* 
         case OCL_SC_BUF_EXTENT_MAX: *d_ptr = h->rs.emax; *count = 6; return 0;
         case OCL_SC_BUF_EXTENT_SUM: *d_ptr = h->rs.esum; *count = 4; return 0;
         case OCL_SC_BUF_RHO: *d_ptr = h->rho; *count = (long long)h->md.nx * h->md.ny * h->md.nz; return 0;
+        case OCL_SC_BUF_EXTENT: *d_ptr = h->rs.emax; *count = 10; return 0;
     }
     return fail(h, "ocl_sc_collective_buffer", "unknown buffer id");
+}
+
+int ocl_sc_combine_extents(ocl_sc_t* h, const double* d_all, int world, void* stream) {
+    if (!h || !d_all || world < 1) return 1;
+    if (set_device(h)) return 1;
+    launch_combine_extents(d_all, world, h->rs, (cudaStream_t)stream);
+    h->launches += 1;
+    return check_launch(h, "k_combine_extents");
+}
+
+int ocl_sc_use_device_params(ocl_sc_t* h, int on) {
+    if (!h) return 1;
+    h->cur_pp = on ? h->kp_dev : nullptr;
+    return 0;
+}
+
+int ocl_sc_set_kick_params(ocl_sc_t* h, double E_GeV, double dz, const double* mesh_draws, void* stream) {
+    if (!h) return 1;
+    if (!(E_GeV > 0.0)) return fail(h, "ocl_sc_set_kick_params", "beam energy must be positive");
+    if (set_device(h)) return 1;
+    launch_set_params(kick_params(h, E_GeV, dz, mesh_draws), h->kp_dev, (cudaStream_t)stream);
+    h->launches += 1;
+    return check_launch(h, "k_set_params");
 }
 
 // ---- stages ---------------------------------------------------------------

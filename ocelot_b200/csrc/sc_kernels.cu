@@ -463,6 +463,22 @@ constexpr int kGridCap = 148 * 16;    // grid kernels
 __global__ void k_set_params(KickParams v, KickParams* dst) {
     if (threadIdx.x == 0 && blockIdx.x == 0) *dst = v;
 }
+// fold all-gathered extents: max over ranks of the first 6 doubles, sum of the last 4
+__global__ void k_combine_extents(const double* __restrict__ all, int world, double* __restrict__ emax,
+                                  double* __restrict__ esum) {
+    const int k = threadIdx.x;
+    if (k >= 10) return;
+    double v = all[k];
+    for (int w = 1; w < world; ++w) {
+        const double x = all[(size_t)w * 10 + k];
+        v = (k < 6) ? fmax(v, x) : v + x;
+    }
+    if (k < 6) emax[k] = v; else esum[k - 6] = v;
+}
+void launch_combine_extents(const double* all, int world, ReduceState rs, cudaStream_t st) {
+    k_combine_extents<<<1, 32, 0, st>>>(all, world, rs.emax, rs.esum);
+}
+
 void launch_set_params(KickParams v, KickParams* dst, cudaStream_t st) { k_set_params<<<1, 32, 0, st>>>(v, dst); }
 const void* set_params_kernel() { return (const void*)k_set_params; }
 

@@ -25,6 +25,7 @@ struct MeshDims {
 int particle_grid(long long n, int max_blocks);
 
 void launch_set_params(KickParams v, KickParams* dst, cudaStream_t st);
+void launch_combine_extents(const double* all, int world, ReduceState rs, cudaStream_t st);
 const void* set_params_kernel();
 void launch_momentum(const double* r, long long ld, long long n, KP kp, ReduceState rs, cudaStream_t st);
 void launch_extent(const double* r, long long ld, const double* q, long long n, KP kp, ReduceState rs,

@@ -3,10 +3,10 @@
 One process per GPU; rank r owns a contiguous range of the bunch's particles
 (SURVEY.md section 8e).  Per kick the ranks exchange only
 
-  1. sum of Cartesian momenta + particle count      4 doubles, SUM   (sc.py:224)
-  2. extents of the rotated, stretched coordinates  6 doubles, MAX   (sc.py:173,181)
-     and the charge centroid                         4 doubles, SUM   (sc.py:182)
-  3. the deposited charge grid rho                   nx*ny*nz doubles, SUM (sc.py:193)
+  1. sum of Cartesian momenta + particle count      4 doubles, all-reduce SUM   (sc.py:224)
+  2. extents of the rotated, stretched coordinates  6 doubles, MAX  }  one all-gather of 10
+     and the charge centroid                         4 doubles, SUM  }  doubles, folded on device
+  3. the deposited charge grid rho                   nx*ny*nz doubles, all-reduce SUM (sc.py:193)
 
 after which every rank holds the same rho and solves the Poisson problem
 redundantly ("small-mesh mode"); no particle ever crosses a link.  The
@@ -41,7 +41,19 @@ class NativeStageEngine:
             "extent_max": self.solver.collective_buffer(native.BUF_EXTENT_MAX),
             "extent_sum": self.solver.collective_buffer(native.BUF_EXTENT_SUM),
             "rho": self.solver.collective_buffer(native.BUF_RHO),
+            "extent": self.solver.collective_buffer(native.BUF_EXTENT),
         }
+        self._gathered = None
+
+    def combine_extents(self, dist, group):
+        """One all-gather of the 10 extent doubles + an on-device fold (instead of a MAX and a
+        SUM all-reduce)."""
+        import torch
+        world = dist.get_world_size(group)
+        if self._gathered is None or self._gathered.numel() != 10 * world:
+            self._gathered = torch.empty(10 * world, dtype=torch.float64, device=self.buffers["extent"].device)
+        dist.all_gather_into_tensor(self._gathered, self.buffers["extent"], group=group)
+        self.solver.combine_extents(self._gathered, world)
 
     def momentum(self, r, q, E):
         self.solver.stage_momentum(r, E)
@@ -74,8 +86,11 @@ def sharded_kick(engine, r, q, E_GeV, dz, draws=None, group=None, dist=None):
         dist.all_reduce(b["momentum"], op=SUM, group=group)
     engine.extent(r, q, E_GeV)
     if multi:
-        dist.all_reduce(b["extent_max"], op=MAX, group=group)
-        dist.all_reduce(b["extent_sum"], op=SUM, group=group)
+        if hasattr(engine, "combine_extents"):
+            engine.combine_extents(dist, group)
+        else:
+            dist.all_reduce(b["extent_max"], op=MAX, group=group)
+            dist.all_reduce(b["extent_sum"], op=SUM, group=group)
     engine.deposit(r, q, E_GeV, draws)
     if multi:
         dist.all_reduce(b["rho"], op=SUM, group=group)
@@ -93,7 +108,10 @@ class ShardedSpaceCharge:
         self.random_mesh = random_mesh
         self.random_seed = 10
         self.group = group
+        self.use_graph = True
         self._engine = None
+        self._graph = None
+        self._graph_key = None
 
     def prepare(self, lat):
         if self.random_seed is not None:
@@ -102,14 +120,49 @@ class ShardedSpaceCharge:
     def apply(self, p_shard, dz):
         if dz == 0:
             return
-        r = p_shard.rparticles
+        import torch
+        r, q = p_shard.rparticles, p_shard.q_array
         key = tuple(int(v) for v in self.nmesh_xyz)
         if self._engine is None or self._engine.solver.nmesh != key:
             self._engine = NativeStageEngine(r.device.index or 0, key)
+            self._graph, self._graph_key = None, None
         draws = None
         if self.random_mesh:
             draws = (np.random.uniform(low=1, high=1.1), np.random.uniform(low=-0.5, high=0.5))
-        sharded_kick(self._engine, r, p_shard.q_array, float(p_shard.E), float(dz), draws, self.group)
+        E = float(p_shard.E)
+        if not self.use_graph:
+            sharded_kick(self._engine, r, q, E, float(dz), draws, self.group)
+            return
+        # The staged kick *and* its NCCL collectives are captured once per particle buffer into a
+        # CUDA graph; E, dz and the mesh draws live in a device block refreshed before each replay.
+        solver = self._engine.solver
+        gkey = (r.data_ptr(), r.stride(0), q.data_ptr(), r.shape[1])
+        if self._graph is None or self._graph_key != gkey:
+            sharded_kick(self._engine, r, q, E, float(dz), draws, self.group)   # also warms NCCL up
+            torch.cuda.synchronize()
+            solver.set_kick_params(E, 0.0, draws)       # dz = 0 while capturing: replays are the real kicks
+            solver.use_device_params(True)
+            try:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    sharded_kick(self._engine, r, q, E, float(dz), draws, self.group)
+            finally:
+                solver.use_device_params(False)
+            self._graph, self._graph_key = g, gkey
+            return                                       # this call's kick was the direct one above
+        solver.set_kick_params(E, float(dz), draws)
+        self._graph.replay()
+
+    def release(self):
+        """Drop the captured graph.  NCCL requires graphs that captured its collectives to be
+        destroyed before the communicator: call this (or finalize) before destroy_process_group."""
+        self._graph, self._graph_key = None, None
 
     def finalize(self, *a, **k):
-        pass
+        self.release()
+
+    def __del__(self):
+        try:
+            self.release()
+        except Exception:  # noqa: BLE001
+            pass

@@ -17,7 +17,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libocelot_sc.so")
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "ocelot_sc.h")
 
-BUF_MOMENTUM, BUF_EXTENT_MAX, BUF_EXTENT_SUM, BUF_RHO = 0, 1, 2, 3
+BUF_MOMENTUM, BUF_EXTENT_MAX, BUF_EXTENT_SUM, BUF_RHO, BUF_EXTENT = 0, 1, 2, 3, 4
 
 _lib = None
 
@@ -35,6 +35,9 @@ _SIGNATURES = {
     "ocl_sc_kick_device": (C.c_int, [_vp, _vp, _ll, _vp, _ll, C.c_double, C.c_double, _dp, _vp]),
     "ocl_sc_kick_host": (C.c_int, [_vp, _vp, _ll, _vp, _ll, C.c_double, C.c_double, _dp]),
     "ocl_sc_collective_buffer": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_ll)]),
+    "ocl_sc_combine_extents": (C.c_int, [_vp, _vp, C.c_int, _vp]),
+    "ocl_sc_use_device_params": (C.c_int, [_vp, C.c_int]),
+    "ocl_sc_set_kick_params": (C.c_int, [_vp, C.c_double, C.c_double, _dp, _vp]),
     "ocl_sc_stage_momentum": (C.c_int, [_vp, _vp, _ll, _ll, C.c_double, _vp]),
     "ocl_sc_stage_extent": (C.c_int, [_vp, _vp, _ll, _vp, _ll, C.c_double, _vp]),
     "ocl_sc_stage_deposit": (C.c_int, [_vp, _vp, _ll, _vp, _ll, C.c_double, _dp, _vp]),
@@ -180,6 +183,17 @@ class Solver:
         self._check(self._lib.ocl_sc_collective_buffer(self._h, which, C.byref(ptr), C.byref(cnt)),
                     "ocl_sc_collective_buffer")
         return _wrap_device_doubles(ptr.value, cnt.value, self.device)
+
+    def combine_extents(self, gathered, world, stream=None):
+        self._check(self._lib.ocl_sc_combine_extents(self._h, gathered.data_ptr(), int(world), _stream_ptr(stream)),
+                    "ocl_sc_combine_extents")
+
+    def use_device_params(self, on: bool):
+        self._check(self._lib.ocl_sc_use_device_params(self._h, 1 if on else 0), "ocl_sc_use_device_params")
+
+    def set_kick_params(self, E_GeV, dz, mesh_draws=None, stream=None):
+        self._check(self._lib.ocl_sc_set_kick_params(self._h, float(E_GeV), float(dz), _draws(mesh_draws),
+                                                     _stream_ptr(stream)), "ocl_sc_set_kick_params")
 
     def stage_momentum(self, r, E_GeV, stream=None):
         ptr, ld, n = self._dev_rows(r)

@@ -58,9 +58,13 @@ def _worker(rank, world, port, n, nmesh, out):
         sc.prepare(None)
         for _ in range(2):
             sc.apply(shard, 0.1)
+        for _ in range(2):                     # capture, replay
+            sc.apply(shard, 0.1)
         torch.cuda.synchronize()
         out[rank] = (lo, hi, shard.to_host().rparticles.copy())
+        sc.finalize()                          # graphs holding NCCL work must go before the communicator
     finally:
+        torch.cuda.synchronize()
         dist.destroy_process_group()
 
 
@@ -82,7 +86,7 @@ def test_two_gpu_sharded_kick_matches_single_gpu():
     solver = native.Solver(0, nmesh)
     r = torch.from_numpy(r0).cuda()
     q = torch.from_numpy(q0).cuda()
-    for _ in range(2):
+    for _ in range(4):
         solver.kick_device(r, q, E, 0.1)
     ref = r.cpu().numpy()
     got = np.empty_like(ref)
