@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--slab", default="auto", choices=["auto", "on", "off"],
+                    help="multi-GPU Poisson solve: slab-decomposed FFT (on), redundant per rank (off), by mesh size (auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -208,7 +210,8 @@ def run_native(args):
     sharded = None
     if world > 1:
         # staged kick + NCCL collectives, captured into one CUDA graph (ocelot_b200/distributed.py)
-        sharded = ShardedSpaceCharge(step=1, nmesh_xyz=[mesh] * 3)
+        sharded = ShardedSpaceCharge(step=1, nmesh_xyz=[mesh] * 3,
+                                     slab={"auto": None, "on": True, "off": False}[args.slab])
         sharded.prepare(None)
         sharded.use_graph = False
         sharded.apply(p, DZ)
@@ -322,7 +325,9 @@ def run_native(args):
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": desc, "particles_per_gpu": n, "particles_total": n * world, "nmesh": [mesh] * 3,
                        "fft_box": [m] * 3, "E_GeV": E_GEV, "dz_m": DZ, "parallelism": f"particle-shard x{world}",
-                       "collectives_per_kick": 0 if world == 1 else 3,
+                       "collectives_per_kick": 0 if world == 1 else (6 if (sharded is not None and sharded._engine.slab) else 3),
+                       "poisson": "single GPU" if world == 1 else ("slab-decomposed FFT (reduce-scatter, 2 all-to-all, all-gather)"
+                                                                   if sharded._engine.slab else "redundant per rank after all-reduce of rho"),
                        "cuda_graph": "whole kick captured once; parameter node refreshed per kick",
                        "l2": "256 MiB buffer written between timed steps (untimed); per-step CUDA events"},
             "warm_l2": {"ms_per_step": warm_ms, "value": world * n / (warm_ms * 1e-3)},

@@ -84,7 +84,13 @@ enum {
     OCL_SC_BUF_EXTENT_MAX = 1, /* 6 doubles, reduce MAX */
     OCL_SC_BUF_EXTENT_SUM = 2, /* 4 doubles, reduce SUM */
     OCL_SC_BUF_RHO = 3,        /* nx*ny*nz doubles, reduce SUM */
-    OCL_SC_BUF_EXTENT = 4      /* the 10 doubles of EXTENT_MAX + EXTENT_SUM, contiguous (for all-gather) */
+    OCL_SC_BUF_EXTENT = 4,     /* the 10 doubles of EXTENT_MAX + EXTENT_SUM, contiguous (for all-gather) */
+    /* slab mode only (after ocl_sc_slab_init); RHO and PHI then have nx_pad = sx*world planes */
+    OCL_SC_BUF_RHO_SLAB = 5,   /* sx*ny*nz doubles: this rank's x-planes of rho (reduce-scatter output) */
+    OCL_SC_BUF_XCHG_A = 6,     /* 2*nx_pad*fs doubles (complex): y-pass output / inverse-y input, chunk layout */
+    OCL_SC_BUF_XCHG_B = 7,     /* 2*nx_pad*fs doubles (complex): x-pass lines of this rank, [nx_pad][fs] */
+    OCL_SC_BUF_PHI_SLAB = 8,   /* sx*ny*nz doubles: this rank's x-planes of phi (all-gather input) */
+    OCL_SC_BUF_PHI = 9         /* nx_pad*ny*nz doubles: the gathered potential */
 };
 int ocl_sc_collective_buffer(ocl_sc_t* h, int which, double** d_ptr, long long* count);
 
@@ -99,6 +105,21 @@ int ocl_sc_combine_extents(ocl_sc_t* h, const double* d_all, int world, void* st
  * the captured graph), so one captured graph serves every kick. */
 int ocl_sc_use_device_params(ocl_sc_t* h, int on);
 int ocl_sc_set_kick_params(ocl_sc_t* h, double E_GeV, double dz, const double* mesh_draws, void* stream);
+
+/* ---- slab-decomposed Poisson solve for large meshes ----
+ * Rank r of `world` owns sx = ceil(nx/world) x-planes of rho/phi and a chunk of
+ * fs = ceil(My*(Mz/2+1)/world) (ky,kz) lines of the x pass.  Per kick, instead of
+ * all-reduce(RHO) + ocl_sc_stage_solve:
+ *     reduce-scatter RHO -> RHO_SLAB ; ocl_sc_slab_forward   (z, y passes of the slab -> XCHG_A)
+ *     all-to-all XCHG_A -> XCHG_B     ; ocl_sc_slab_xpass     (x: forward FFT, * K_hat, inverse FFT)
+ *     all-to-all XCHG_B -> XCHG_A     ; ocl_sc_slab_inverse   (inverse y, z -> PHI_SLAB)
+ *     all-gather PHI_SLAB -> PHI      ; ocl_sc_slab_finish    (staggered field table)
+ * replaces sc.py:135-168 + :195-200 exactly as the single-GPU solve does. */
+int ocl_sc_slab_init(ocl_sc_t* h, int rank, int world);
+int ocl_sc_slab_forward(ocl_sc_t* h, void* stream);
+int ocl_sc_slab_xpass(ocl_sc_t* h, void* stream);
+int ocl_sc_slab_inverse(ocl_sc_t* h, void* stream);
+int ocl_sc_slab_finish(ocl_sc_t* h, const double* mesh_draws, void* stream);
 
 int ocl_sc_stage_momentum(ocl_sc_t* h, const double* d_r, long long ld, long long n, double E_GeV, void* stream);
 int ocl_sc_stage_extent(ocl_sc_t* h, const double* d_r, long long ld, const double* d_q, long long n,

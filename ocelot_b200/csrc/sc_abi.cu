@@ -42,6 +42,13 @@ struct ocl_sc {
     EQuad* equad = nullptr;   // 3*n^3 quads: the field table the gather reads
     cufftHandle plan_fwd = 0, plan_inv = 0;
     bool plans = false;
+    // slab mode (multi-GPU solve)
+    int slab_world = 0, slab_rank = 0, sx = 0, fs = 0, nx_pad = 0;
+    size_t rho_count = 0;                     // doubles in rho / phi (n^3, or nx_pad*ny*nz in slab mode)
+    double* rho_slab = nullptr;
+    double* phi_slab = nullptr;
+    double2* xchg_a = nullptr;
+    double2* xchg_b = nullptr;
     // host-mode staging
     double* stage_r = nullptr;
     double* stage_q = nullptr;
@@ -317,6 +324,7 @@ int ocl_sc_create(int device, int nx, int ny, int nz, long long max_particles, o
     TRY(cudaMalloc(&h->equad, sizeof(EQuad) * n3 * 3));
     TRY(cudaMemset(h->rho, 0, sizeof(double) * n3));
     TRY(cudaMemset(h->phi, 0, sizeof(double) * n3));
+    h->rho_count = n3;
     TRY(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
     TRY(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
     TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -344,6 +352,7 @@ void ocl_sc_destroy(ocl_sc_t* h) {
     cudaFree(h->fw.P); cudaFree(h->fw.Q); cudaFree(h->fw.khat); cudaFree(h->fw.A); cudaFree(h->fw.B);
     cudaFree(h->tw[0]); cudaFree(h->tw[1]); cudaFree(h->tw[2]); cudaFree(h->h3);
     cudaFree(h->stage_r); cudaFree(h->stage_q);
+    cudaFree(h->rho_slab); cudaFree(h->phi_slab); cudaFree(h->xchg_a); cudaFree(h->xchg_b);
     for (int i = 0; i < T_COUNT; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
@@ -358,7 +367,12 @@ int ocl_sc_collective_buffer(ocl_sc_t* h, int which, double** d_ptr, long long* 
         case OCL_SC_BUF_MOMENTUM: *d_ptr = h->rs.sums; *count = 4; return 0;
         case OCL_SC_BUF_EXTENT_MAX: *d_ptr = h->rs.emax; *count = 6; return 0;
         case OCL_SC_BUF_EXTENT_SUM: *d_ptr = h->rs.esum; *count = 4; return 0;
-        case OCL_SC_BUF_RHO: *d_ptr = h->rho; *count = (long long)h->md.nx * h->md.ny * h->md.nz; return 0;
+        case OCL_SC_BUF_RHO: *d_ptr = h->rho; *count = (long long)h->rho_count; return 0;
+        case OCL_SC_BUF_RHO_SLAB: if (!h->slab_world) break; *d_ptr = h->rho_slab; *count = (long long)h->sx * h->md.ny * h->md.nz; return 0;
+        case OCL_SC_BUF_PHI_SLAB: if (!h->slab_world) break; *d_ptr = h->phi_slab; *count = (long long)h->sx * h->md.ny * h->md.nz; return 0;
+        case OCL_SC_BUF_XCHG_A: if (!h->slab_world) break; *d_ptr = (double*)h->xchg_a; *count = 2LL * h->nx_pad * h->fs; return 0;
+        case OCL_SC_BUF_XCHG_B: if (!h->slab_world) break; *d_ptr = (double*)h->xchg_b; *count = 2LL * h->nx_pad * h->fs; return 0;
+        case OCL_SC_BUF_PHI: if (!h->slab_world) break; *d_ptr = h->phi; *count = (long long)h->rho_count; return 0;
         case OCL_SC_BUF_EXTENT: *d_ptr = h->rs.emax; *count = 10; return 0;
     }
     return fail(h, "ocl_sc_collective_buffer", "unknown buffer id");
@@ -385,6 +399,83 @@ int ocl_sc_set_kick_params(ocl_sc_t* h, double E_GeV, double dz, const double* m
     launch_set_params(kick_params(h, E_GeV, dz, mesh_draws), h->kp_dev, (cudaStream_t)stream);
     h->launches += 1;
     return check_launch(h, "k_set_params");
+}
+
+// ---- slab-decomposed solve ---------------------------------------------------
+int ocl_sc_slab_init(ocl_sc_t* h, int rank, int world) {
+    if (!h) return 1;
+    if (world < 1 || rank < 0 || rank >= world) return fail(h, "ocl_sc_slab_init", "bad rank/world");
+    if (h->solver != 0) return fail(h, "ocl_sc_slab_init", "slab mode needs the hand-written solver");
+    if (set_device(h)) return 1;
+    drop_graph(h);
+    const int hz1 = h->md.mz / 2 + 1;
+    const int F = h->md.my * hz1;
+    h->slab_world = world; h->slab_rank = rank;
+    h->sx = (h->md.nx + world - 1) / world;
+    h->nx_pad = h->sx * world;
+    h->fs = (F + world - 1) / world;
+    const size_t plane = (size_t)h->md.ny * h->md.nz;
+    cudaFree(h->rho); cudaFree(h->phi);
+    cudaFree(h->rho_slab); cudaFree(h->phi_slab); cudaFree(h->xchg_a); cudaFree(h->xchg_b);
+    h->rho = h->phi = h->rho_slab = h->phi_slab = nullptr; h->xchg_a = h->xchg_b = nullptr;
+    h->rho_count = (size_t)h->nx_pad * plane;
+    CU(h, cudaMalloc(&h->rho, sizeof(double) * h->rho_count));
+    CU(h, cudaMalloc(&h->phi, sizeof(double) * h->rho_count));
+    CU(h, cudaMalloc(&h->rho_slab, sizeof(double) * h->sx * plane));
+    CU(h, cudaMalloc(&h->phi_slab, sizeof(double) * h->sx * plane));
+    CU(h, cudaMalloc(&h->xchg_a, sizeof(double2) * (size_t)h->nx_pad * h->fs));
+    CU(h, cudaMalloc(&h->xchg_b, sizeof(double2) * (size_t)h->nx_pad * h->fs));
+    CU(h, cudaMemset(h->rho, 0, sizeof(double) * h->rho_count));
+    CU(h, cudaMemset(h->phi, 0, sizeof(double) * h->rho_count));
+    CU(h, cudaMemset(h->xchg_a, 0, sizeof(double2) * (size_t)h->nx_pad * h->fs));
+    CU(h, cudaMemset(h->xchg_b, 0, sizeof(double2) * (size_t)h->nx_pad * h->fs));
+    return 0;
+}
+
+int ocl_sc_slab_forward(ocl_sc_t* h, void* stream) {
+    if (!h || !h->slab_world) return h ? fail(h, "ocl_sc_slab_forward", "call ocl_sc_slab_init first") : 1;
+    if (set_device(h)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    h->last_stream = st;
+    launch_slab_forward(h->rho_slab, h->md, h->sx, h->fs, h->fw, h->xchg_a, st);
+    h->launches += 2;
+    return check_launch(h, "slab_forward");
+}
+
+int ocl_sc_slab_xpass(ocl_sc_t* h, void* stream) {
+    if (!h || !h->slab_world) return h ? fail(h, "ocl_sc_slab_xpass", "call ocl_sc_slab_init first") : 1;
+    if (set_device(h)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    h->last_stream = st;
+    if (h->khat_pending) {                      // join the Green's-function chain forked by stage_deposit
+        CU(h, cudaStreamWaitEvent(st, h->ev_khat, 0));
+        h->khat_pending = false;
+    } else {
+        return fail(h, "ocl_sc_slab_xpass", "K_hat not available: ocl_sc_stage_deposit must precede the solve");
+    }
+    launch_slab_xpass(h->xchg_b, h->md, h->fs, h->slab_rank * h->fs, h->fw, st);
+    h->launches += 1;
+    return check_launch(h, "slab_xpass");
+}
+
+int ocl_sc_slab_inverse(ocl_sc_t* h, void* stream) {
+    if (!h || !h->slab_world) return h ? fail(h, "ocl_sc_slab_inverse", "call ocl_sc_slab_init first") : 1;
+    if (set_device(h)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    h->last_stream = st;
+    launch_slab_inverse(h->xchg_a, h->md, h->sx, h->fs, h->fw, h->h3, four_pi_eps0_value(), h->phi_slab, st);
+    h->launches += 2;
+    return check_launch(h, "slab_inverse");
+}
+
+int ocl_sc_slab_finish(ocl_sc_t* h, const double* mesh_draws, void* stream) {
+    if (!h || !h->slab_world) return h ? fail(h, "ocl_sc_slab_finish", "call ocl_sc_slab_init first") : 1;
+    if (set_device(h)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    h->last_stream = st;
+    launch_field(h->phi, h->rs, h->md, kp_of(h, 1.0, 0.0, mesh_draws), h->equad, st);
+    h->launches += 1;
+    return check_launch(h, "slab_finish");
 }
 
 // ---- stages ---------------------------------------------------------------
@@ -423,7 +514,7 @@ int ocl_sc_stage_deposit(ocl_sc_t* h, const double* d_r, long long ld, const dou
     // the mesh steps are final once the extents are reduced: start the Green's-function / K_hat
     // chain now, concurrently with the deposit and the first two rho passes
     if (h->solver == 0 && fork_khat(h, kp_of(h, E_GeV, 0.0, mesh_draws), st)) return 1;
-    CU(h, cudaMemsetAsync(h->rho, 0, sizeof(double) * (size_t)h->md.nx * h->md.ny * h->md.nz, st));
+    CU(h, cudaMemsetAsync(h->rho, 0, sizeof(double) * h->rho_count, st));
     launch_deposit(d_r, ld, d_q, n, kp_of(h, E_GeV, 0.0, mesh_draws), h->rs, h->md, h->rho, st);
     h->launches += 2;
     mark(h, T_DEP, st);

@@ -338,15 +338,18 @@ template <int M, int MODE>
 __global__ void __launch_bounds__(kFftThreads) k_cplx_outer(const double2* in, double2* out,   // may alias (MODE 2)
                                                            int n_in, int n_out, int inner,
                                                            const double2* __restrict__ tw_g,
-                                                           const double* __restrict__ khat, MeshDims md) {
+                                                           const double* __restrict__ khat, MeshDims md, SlabMap sm) {
     constexpr int NL = Geom<M>::NL, NLP = Geom<M>::NLP;
     FftSmem<M> s = fft_smem<M>(tw_g);
     const int blocks_per_batch = (inner + NL - 1) / NL;
     const int batch = blockIdx.x / blocks_per_batch;
     const int f0 = (blockIdx.x - batch * blocks_per_batch) * NL;
-    const int nl = min(NL, inner - f0);
+    int nl = min(NL, inner - f0);
+    if (sm.mode == 3) nl = max(0, min(nl, sm.f_total - sm.f_base - f0));   // padding lines of the last chunk
     const double2* src = in + (size_t)batch * n_in * inner + f0;
     double2* dst = out + (size_t)batch * n_out * inner + f0;
+    // chunk-layout address of element (x plane = batch, line f)
+    auto chunk = [&](int f) -> size_t { return ((size_t)(f / sm.fs) * sm.sx + batch) * sm.fs + f % sm.fs; };
     {   // global -> shared, U independent 16-byte loads in flight per thread
         constexpr int PER = NL * M / kFftThreads, U = PER < 8 ? PER : 8;
         static_assert(PER % U == 0, "load batching");
@@ -358,7 +361,10 @@ __global__ void __launch_bounds__(kFftThreads) k_cplx_outer(const double2* in, d
 #pragma unroll
             for (int u = 0; u < U; ++u) {
                 const int o = o0 + (c + u) * OSTEP;
-                v[u] = (o < n_in && l < nl) ? col[(size_t)o * inner] : make_double2(0.0, 0.0);
+                if (sm.mode == 2)
+                    v[u] = (o < n_in && l < nl) ? in[chunk(o * inner + f0 + l)] : make_double2(0.0, 0.0);
+                else
+                    v[u] = (o < n_in && l < nl) ? col[(size_t)o * inner] : make_double2(0.0, 0.0);
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) s.a[(o0 + (c + u) * OSTEP) * NLP + l] = v[u];
@@ -370,7 +376,7 @@ __global__ void __launch_bounds__(kFftThreads) k_cplx_outer(const double2* in, d
         // each thread owns one line l for the multiply: its (ky, kz) is computed once
         const int l = threadIdx.x % NL;
         if (l < nl) {
-            const int f = f0 + l;
+            const int f = f0 + l + (sm.mode == 3 ? sm.f_base : 0);
             const int ky = f / hz1, kz = f - ky * hz1;
             const int sy = min(ky, md.my - ky);
             const double* kcol = khat + (size_t)sy * hz1 + kz;
@@ -397,7 +403,10 @@ __global__ void __launch_bounds__(kFftThreads) k_cplx_outer(const double2* in, d
     }
     for (int t = threadIdx.x; t < NL * n_out; t += kFftThreads) {
         const int o = t / NL, l = t % NL;
-        if (l < nl) dst[(size_t)o * inner + l] = X[o * NLP + l];
+        if (l < nl) {
+            if (sm.mode == 1) out[chunk(o * inner + f0 + l)] = X[o * NLP + l];
+            else dst[(size_t)o * inner + l] = X[o * NLP + l];
+        }
     }
 }
 
@@ -519,7 +528,7 @@ void launch_convolve_pre(const double* rho, MeshDims md, FftWork w, cudaStream_t
         const int lb = Geom<MM>::NL;
         const int bpb = (hz1 + lb - 1) / lb;
         k_cplx_outer<MM, 0><<<bpb * md.nx, kFftThreads, Geom<MM>::SMEM, st>>>(w.A, w.B, md.ny, md.my, hz1, w.tw_y,
-                                                                             nullptr, md);
+                                                                             nullptr, md, SlabMap{});
     )
 }
 
@@ -531,18 +540,71 @@ void launch_convolve_post(MeshDims md, FftWork w, const double* h3, double four_
         const int lb = Geom<MM>::NL;
         const int blocks = (inner + lb - 1) / lb;
         k_cplx_outer<MM, 2><<<blocks, kFftThreads, Geom<MM>::SMEM, st>>>(w.B, w.B, md.nx, md.nx, inner, w.tw_x, w.khat,
-                                                                        md);
+                                                                        md, SlabMap{});
     )
     OCL_FFT_DISPATCH(md.my,   // y inverse: per i, [My][hz1] -> [ny][hz1]
         const int lb = Geom<MM>::NL;
         const int bpb = (hz1 + lb - 1) / lb;
         k_cplx_outer<MM, 1><<<bpb * md.nx, kFftThreads, Geom<MM>::SMEM, st>>>(w.B, w.A, md.my, md.ny, hz1, w.tw_y,
-                                                                             nullptr, md);
+                                                                             nullptr, md, SlabMap{});
     )
     OCL_FFT_DISPATCH(md.mz,
         const int lbz = 2 * Geom<MM>::NL;
         const int zblocks = (md.nx * md.ny + lbz - 1) / lbz;
         k_inv_z<MM><<<zblocks, kFftThreads, Geom<MM>::SMEM, st>>>(w.A, md, w.tw_z, h3, four_pi_eps0, phi);
+    )
+}
+
+// ---------------------------------------------------------------------------
+// slab-decomposed solve: this rank owns sx x-planes of rho / phi and one chunk of fs (ky,kz)
+// lines of the x pass; the caller exchanges `xchg` between the calls (all-to-all).
+// ---------------------------------------------------------------------------
+void launch_slab_forward(const double* rho_slab, MeshDims md, int sx, int fs, FftWork w, double2* xchg,
+                         cudaStream_t st) {
+    MeshDims ms = md;
+    ms.nx = sx;
+    const int hz1 = md.mz / 2 + 1;
+    OCL_FFT_DISPATCH(md.mz,
+        const int lbz = 2 * Geom<MM>::NL;
+        const int zblocks = (sx * md.ny + lbz - 1) / lbz;
+        k_rho_z<MM><<<zblocks, kFftThreads, Geom<MM>::SMEM, st>>>(rho_slab, ms, w.tw_z, w.A);
+    )
+    SlabMap sm{1, fs, sx, 0, 0};
+    OCL_FFT_DISPATCH(md.my,   // y forward, stored in chunk layout for the all-to-all
+        const int lb = Geom<MM>::NL;
+        const int bpb = (hz1 + lb - 1) / lb;
+        k_cplx_outer<MM, 0><<<bpb * sx, kFftThreads, Geom<MM>::SMEM, st>>>(w.A, xchg, md.ny, md.my, hz1, w.tw_y,
+                                                                          nullptr, md, sm);
+    )
+}
+
+void launch_slab_xpass(double2* xchg, MeshDims md, int fs, int f_base, FftWork w, cudaStream_t st) {
+    const int hz1 = md.mz / 2 + 1;
+    SlabMap sm{3, fs, 0, f_base, md.my * hz1};
+    OCL_FFT_DISPATCH(md.mx,   // x: forward, * K_hat, inverse on this rank's chunk of lines, [nx_pad][fs] in place
+        const int lb = Geom<MM>::NL;
+        const int blocks = (fs + lb - 1) / lb;
+        k_cplx_outer<MM, 2><<<blocks, kFftThreads, Geom<MM>::SMEM, st>>>(xchg, xchg, md.nx, md.nx, fs, w.tw_x, w.khat,
+                                                                        md, sm);
+    )
+}
+
+void launch_slab_inverse(const double2* xchg, MeshDims md, int sx, int fs, FftWork w, const double* h3,
+                         double four_pi_eps0, double* phi_slab, cudaStream_t st) {
+    MeshDims ms = md;
+    ms.nx = sx;
+    const int hz1 = md.mz / 2 + 1;
+    SlabMap sm{2, fs, sx, 0, 0};
+    OCL_FFT_DISPATCH(md.my,   // y inverse, read from chunk layout
+        const int lb = Geom<MM>::NL;
+        const int bpb = (hz1 + lb - 1) / lb;
+        k_cplx_outer<MM, 1><<<bpb * sx, kFftThreads, Geom<MM>::SMEM, st>>>(xchg, w.A, md.my, md.ny, hz1, w.tw_y,
+                                                                          nullptr, md, sm);
+    )
+    OCL_FFT_DISPATCH(md.mz,
+        const int lbz = 2 * Geom<MM>::NL;
+        const int zblocks = (sx * md.ny + lbz - 1) / lbz;
+        k_inv_z<MM><<<zblocks, kFftThreads, Geom<MM>::SMEM, st>>>(w.A, ms, w.tw_z, h3, four_pi_eps0, phi_slab);
     )
 }
 

@@ -85,6 +85,9 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* part, unsig
 }
 
 constexpr int kPipeDepth = 3;
+#ifndef GK_BLOCKS
+#define GK_BLOCKS 2
+#endif
 
 // ---------------------------------------------------------------------------
 // sweep 1: mean momentum (sc.py:221,224)
@@ -371,7 +374,7 @@ __global__ void __launch_bounds__(kThreads) k_field(const double* __restrict__ p
 // sweep 4: gather, kick, back-transform (sc.py:201-204, :244-251)
 // ---------------------------------------------------------------------------
 template <bool KICK, bool TAP>
-__global__ void __launch_bounds__(kThreads, 2) k_gather_kick(double* __restrict__ r, long long ld, long long n,
+__global__ void __launch_bounds__(kThreads, GK_BLOCKS) k_gather_kick(double* __restrict__ r, long long ld, long long n,
                                                             KP kp, ReduceState rs, MeshDims md,
                                                             const EQuad* __restrict__ equad,
                                                             double* __restrict__ exyz_out) {
@@ -457,7 +460,7 @@ static inline int grid_for(long long total, int cap) {
     return (int)b;
 }
 constexpr int kSweepCap = 148 * 4;    // persistent grid-stride sweeps: 4 resident blocks per SM
-constexpr int kGatherCap = 148 * 2;   // gather/kick: 2 resident blocks per SM
+constexpr int kGatherCap = 148 * GK_BLOCKS;   // gather/kick: resident blocks per SM
 constexpr int kGridCap = 148 * 16;    // grid kernels
 
 __global__ void k_set_params(KickParams v, KickParams* dst) {

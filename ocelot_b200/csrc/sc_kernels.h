@@ -56,12 +56,27 @@ struct FftWork {
     double2* A;            // [nx][ny][Mz/2+1]            rho after pass z / before inverse z
     double2* B;            // [nx][My][Mz/2+1]            rho after pass y; pass x in place
 };
+// slab (multi-GPU) addressing of the y/x passes: the [i][f] array (f = ky*H + kz) is exchanged
+// between ranks in chunks of fs lines; chunk layout index = ((f / fs) * sx + i) * fs + f % fs.
+struct SlabMap {
+    int mode;      // 0 none | 1 chunked output (y forward) | 2 chunked input (y inverse) | 3 x pass on one f-chunk
+    int fs;        // lines per chunk
+    int sx;        // x planes per rank
+    int f_base;    // mode 3: global index of this rank's first line
+    int f_total;   // mode 3: number of real lines (My * H); beyond it the chunk is padding
+};
 void fft_init_kernels();
 int fft_max_length();
 void launch_khat(const double* gtab, MeshDims md, FftWork w, cudaStream_t st);
 void launch_convolve_pre(const double* rho, MeshDims md, FftWork w, cudaStream_t st);
 void launch_convolve_post(MeshDims md, FftWork w, const double* h3, double four_pi_eps0, double* phi,
                           cudaStream_t st);
+// slab-decomposed variants (this rank owns sx x-planes and one chunk of fs (ky,kz) lines)
+void launch_slab_forward(const double* rho_slab, MeshDims md, int sx, int fs, FftWork w, double2* xchg,
+                         cudaStream_t st);
+void launch_slab_xpass(double2* xchg, MeshDims md, int fs, int f_base, FftWork w, cudaStream_t st);
+void launch_slab_inverse(const double2* xchg, MeshDims md, int sx, int fs, FftWork w, const double* h3,
+                         double four_pi_eps0, double* phi_slab, cudaStream_t st);
 double four_pi_eps0_value();
 
 // potential KAT helpers: steps given explicitly instead of derived from particles

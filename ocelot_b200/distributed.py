@@ -9,7 +9,15 @@ One process per GPU; rank r owns a contiguous range of the bunch's particles
   3. the deposited charge grid rho                   nx*ny*nz doubles, all-reduce SUM (sc.py:193)
 
 after which every rank holds the same rho and solves the Poisson problem
-redundantly ("small-mesh mode"); no particle ever crosses a link.  The
+redundantly ("small-mesh mode"); no particle ever crosses a link.  For large
+meshes ("slab mode") step 3 becomes a reduce-scatter of rho into
+x-slabs, the FFT passes are split across ranks with two all-to-all transposes
+around the x pass, and the potential is all-gathered:
+
+  3'. reduce-scatter rho -> x-slab ; z,y passes ; all-to-all ; x pass (FFT * K_hat * IFFT) ;
+      all-to-all ; inverse y,z passes ; all-gather phi
+
+The
 collectives run in place on the native handle's device buffers, stream-ordered
 with the kernels, so a kick involves no host synchronisation.
 
@@ -32,10 +40,14 @@ def shard_bounds(n_total: int, world_size: int, rank: int):
 class NativeStageEngine:
     """The five stages of the kick on one GPU (include/ocelot_sc.h, ocl_sc_stage_*)."""
 
-    def __init__(self, device: int, nmesh_xyz):
+    def __init__(self, device: int, nmesh_xyz, slab=None):
+        """``slab`` = (rank, world) switches the Poisson solve to the slab-decomposed form."""
         from . import native
         self._native = native
         self.solver = native.Solver(device, nmesh_xyz)
+        self.slab = slab
+        if slab is not None:
+            self.solver.slab_init(*slab)
         self.buffers = {
             "momentum": self.solver.collective_buffer(native.BUF_MOMENTUM),
             "extent_max": self.solver.collective_buffer(native.BUF_EXTENT_MAX),
@@ -43,7 +55,24 @@ class NativeStageEngine:
             "rho": self.solver.collective_buffer(native.BUF_RHO),
             "extent": self.solver.collective_buffer(native.BUF_EXTENT),
         }
+        if slab is not None:
+            for name, which in (("rho_slab", native.BUF_RHO_SLAB), ("xchg_a", native.BUF_XCHG_A),
+                                ("xchg_b", native.BUF_XCHG_B), ("phi_slab", native.BUF_PHI_SLAB),
+                                ("phi", native.BUF_PHI)):
+                self.buffers[name] = self.solver.collective_buffer(which)
         self._gathered = None
+
+    def solve_slab(self, dist, group, draws):
+        """Slab-decomposed solve: rho (local partial sums, nx_pad planes) -> field table."""
+        b, s = self.buffers, self.solver
+        dist.reduce_scatter_tensor(b["rho_slab"], b["rho"], op=dist.ReduceOp.SUM, group=group)
+        s.slab_forward()
+        dist.all_to_all_single(b["xchg_b"], b["xchg_a"], group=group)
+        s.slab_xpass()
+        dist.all_to_all_single(b["xchg_a"], b["xchg_b"], group=group)
+        s.slab_inverse()
+        dist.all_gather_into_tensor(b["phi"], b["phi_slab"], group=group)
+        s.slab_finish(draws)
 
     def combine_extents(self, dist, group):
         """One all-gather of the 10 extent doubles + an on-device fold (instead of a MAX and a
@@ -92,9 +121,12 @@ def sharded_kick(engine, r, q, E_GeV, dz, draws=None, group=None, dist=None):
             dist.all_reduce(b["extent_max"], op=MAX, group=group)
             dist.all_reduce(b["extent_sum"], op=SUM, group=group)
     engine.deposit(r, q, E_GeV, draws)
-    if multi:
-        dist.all_reduce(b["rho"], op=SUM, group=group)
-    engine.solve(draws)
+    if getattr(engine, "slab", None) is not None:
+        engine.solve_slab(dist, group, draws)      # works for any world size >= 1
+    else:
+        if multi:
+            dist.all_reduce(b["rho"], op=SUM, group=group)
+        engine.solve(draws)
     engine.kick(r, E_GeV, dz, draws)
 
 
@@ -102,12 +134,15 @@ class ShardedSpaceCharge:
     """PhysProc-style wrapper for a particle-sharded bunch: same attributes as
     ``SpaceCharge``; ``apply`` takes this rank's ``DeviceParticleArray`` shard."""
 
-    def __init__(self, step=1, nmesh_xyz=(63, 63, 63), random_mesh=False, group=None):
+    SLAB_MIN_MESH = 200      # meshes with any axis >= this use the slab-decomposed solve by default
+
+    def __init__(self, step=1, nmesh_xyz=(63, 63, 63), random_mesh=False, group=None, slab=None):
         self.step = step
         self.nmesh_xyz = list(nmesh_xyz)
         self.random_mesh = random_mesh
         self.random_seed = 10
         self.group = group
+        self.slab = slab          # None: automatic (by mesh size); True / False: forced
         self.use_graph = True
         self._engine = None
         self._graph = None
@@ -124,7 +159,12 @@ class ShardedSpaceCharge:
         r, q = p_shard.rparticles, p_shard.q_array
         key = tuple(int(v) for v in self.nmesh_xyz)
         if self._engine is None or self._engine.solver.nmesh != key:
-            self._engine = NativeStageEngine(r.device.index or 0, key)
+            import torch.distributed as dist
+            slab = None
+            want = self.slab if self.slab is not None else max(key) >= self.SLAB_MIN_MESH
+            if want and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+                slab = (dist.get_rank(self.group), dist.get_world_size(self.group))
+            self._engine = NativeStageEngine(r.device.index or 0, key, slab=slab)
             self._graph, self._graph_key = None, None
         draws = None
         if self.random_mesh:

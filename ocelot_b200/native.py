@@ -14,10 +14,11 @@ import re
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libocelot_sc.so")
+LIB_PATH = os.environ.get("OCL_SC_LIB") or os.path.join(_HERE, "libocelot_sc.so")   # OCL_SC_LIB: A/B builds
 HEADER = os.path.join(os.path.dirname(_HERE), "include", "ocelot_sc.h")
 
 BUF_MOMENTUM, BUF_EXTENT_MAX, BUF_EXTENT_SUM, BUF_RHO, BUF_EXTENT = 0, 1, 2, 3, 4
+BUF_RHO_SLAB, BUF_XCHG_A, BUF_XCHG_B, BUF_PHI_SLAB, BUF_PHI = 5, 6, 7, 8, 9
 
 _lib = None
 
@@ -36,6 +37,11 @@ _SIGNATURES = {
     "ocl_sc_kick_host": (C.c_int, [_vp, _vp, _ll, _vp, _ll, C.c_double, C.c_double, _dp]),
     "ocl_sc_collective_buffer": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_ll)]),
     "ocl_sc_combine_extents": (C.c_int, [_vp, _vp, C.c_int, _vp]),
+    "ocl_sc_slab_init": (C.c_int, [_vp, C.c_int, C.c_int]),
+    "ocl_sc_slab_forward": (C.c_int, [_vp, _vp]),
+    "ocl_sc_slab_xpass": (C.c_int, [_vp, _vp]),
+    "ocl_sc_slab_inverse": (C.c_int, [_vp, _vp]),
+    "ocl_sc_slab_finish": (C.c_int, [_vp, _dp, _vp]),
     "ocl_sc_use_device_params": (C.c_int, [_vp, C.c_int]),
     "ocl_sc_set_kick_params": (C.c_int, [_vp, C.c_double, C.c_double, _dp, _vp]),
     "ocl_sc_stage_momentum": (C.c_int, [_vp, _vp, _ll, _ll, C.c_double, _vp]),
@@ -183,6 +189,22 @@ class Solver:
         self._check(self._lib.ocl_sc_collective_buffer(self._h, which, C.byref(ptr), C.byref(cnt)),
                     "ocl_sc_collective_buffer")
         return _wrap_device_doubles(ptr.value, cnt.value, self.device)
+
+    def slab_init(self, rank, world):
+        self._check(self._lib.ocl_sc_slab_init(self._h, int(rank), int(world)), "ocl_sc_slab_init")
+
+    def slab_forward(self, stream=None):
+        self._check(self._lib.ocl_sc_slab_forward(self._h, _stream_ptr(stream)), "ocl_sc_slab_forward")
+
+    def slab_xpass(self, stream=None):
+        self._check(self._lib.ocl_sc_slab_xpass(self._h, _stream_ptr(stream)), "ocl_sc_slab_xpass")
+
+    def slab_inverse(self, stream=None):
+        self._check(self._lib.ocl_sc_slab_inverse(self._h, _stream_ptr(stream)), "ocl_sc_slab_inverse")
+
+    def slab_finish(self, mesh_draws=None, stream=None):
+        self._check(self._lib.ocl_sc_slab_finish(self._h, _draws(mesh_draws), _stream_ptr(stream)),
+                    "ocl_sc_slab_finish")
 
     def combine_extents(self, gathered, world, stream=None):
         self._check(self._lib.ocl_sc_combine_extents(self._h, gathered.data_ptr(), int(world), _stream_ptr(stream)),

@@ -40,7 +40,7 @@ def test_sharded_wrapper_single_rank_equals_plugin():
     assert _row_err(b.to_host().rparticles, a.to_host().rparticles) < 1e-12
 
 
-def _worker(rank, world, port, n, nmesh, out):
+def _worker(rank, world, port, n, nmesh, out, slab=False):
     import torch.distributed as dist
     from ocelot_b200 import ParticleArray, DeviceParticleArray
     from ocelot_b200.distributed import ShardedSpaceCharge, shard_bounds
@@ -54,7 +54,7 @@ def _worker(rank, world, port, n, nmesh, out):
         host = ParticleArray(hi - lo)
         host.rparticles[:], host.q_array[:], host.E = r0[:, lo:hi], q0[lo:hi], E
         shard = DeviceParticleArray.from_host(host, device=f"cuda:{rank}")
-        sc = ShardedSpaceCharge(nmesh_xyz=list(nmesh))
+        sc = ShardedSpaceCharge(nmesh_xyz=list(nmesh), slab=slab)
         sc.prepare(None)
         for _ in range(2):
             sc.apply(shard, 0.1)
@@ -68,7 +68,8 @@ def _worker(rank, world, port, n, nmesh, out):
         dist.destroy_process_group()
 
 
-def test_two_gpu_sharded_kick_matches_single_gpu():
+@pytest.mark.parametrize("slab", [False, True])
+def test_two_gpu_sharded_kick_matches_single_gpu(slab):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     import torch.multiprocessing as mp
@@ -80,7 +81,7 @@ def test_two_gpu_sharded_kick_matches_single_gpu():
     ctx = mp.get_context("spawn")
     with ctx.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_worker, args=(world, port, n, nmesh, out), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, port, n, nmesh, out, slab), nprocs=world, join=True)
         parts = [out[k] for k in range(world)]
     r0, q0, E = _bunch(n, 4)
     solver = native.Solver(0, nmesh)
