@@ -150,6 +150,18 @@ int ocl_sc_cartesian_to_mad(ocl_sc_t* h, const double* d_xp, long long ld_xp, lo
 /* potential(q, steps) of sc.py:135-168 for a host rho[nx*ny*nz] and steps[3]; result to h_phi. */
 int ocl_sc_potential_host(ocl_sc_t* h, const double* h_rho, const double steps[3], double* h_phi);
 
+/* ---- the steps either side of the kick in the reference's tracking loop (track.py:470-482),
+ * so that a bunch can stay resident between kicks ---- */
+/* X <- R X + T:XX + B in place (TransferMap.mul_p_array, transformations/transfer_map.py:42-53;
+ * SecondTM.t_apply, transformations/second_order.py:31-39 with tm_utils.py:54-55).
+ * R[36] row-major; B[6] or NULL; T[216] (index a*36 + j*6 + k) or NULL for a first-order map. */
+int ocl_sc_map_apply(ocl_sc_t* h, double* d_r, long long ld, long long n, const double* R, const double* B,
+                     const double* T, void* stream);
+/* First and centred second moments of get_envelope's default path (beam/analysis.py:72-76,
+ * :121-166): h_out[18] = {x, px, y, py, tau, p, xx, xpx, pxpx, yy, ypy, pypy, tautau, pp, xy, pxpy,
+ * xpy, ypx} with the reference's px, py correction factor applied.  Synchronous. */
+int ocl_sc_beam_moments(ocl_sc_t* h, const double* d_r, long long ld, long long n, double* h_out, void* stream);
+
 /* Per-stage device timers.  enable=1 records CUDA events around each stage of
  * every following kick; get returns the last kick's milliseconds:
  * out[8] = {momentum, extent, deposit, green+fft, field, kick, total, reserved}. */

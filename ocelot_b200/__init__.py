@@ -2,5 +2,8 @@
 from .physproc import PhysProc
 from .particles import ParticleArray, DeviceParticleArray
 from .sc import SpaceCharge, install
+from .beam import apply_map, get_envelope, Moments
+from .track import track, replay_track
 
-__all__ = ["PhysProc", "ParticleArray", "DeviceParticleArray", "SpaceCharge", "install"]
+__all__ = ["PhysProc", "ParticleArray", "DeviceParticleArray", "SpaceCharge", "install",
+           "apply_map", "get_envelope", "Moments", "track", "replay_track"]

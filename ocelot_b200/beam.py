@@ -1,0 +1,86 @@
+"""Device-side neighbours of the space-charge kick in the tracking loop:
+
+* ``apply_map``     -- first/second-order transfer map on a resident bunch
+                       (``TransferMap.mul_p_array``, transformations/transfer_map.py:42-53;
+                       ``SecondTM.t_apply``, transformations/second_order.py:31-39)
+* ``get_envelope``  -- beam moments / Twiss from particles, default path of the reference's
+                       ``get_envelope`` (beam/analysis.py:27-222: no bounds, no dispersion correction)
+
+Both run as CUDA kernels behind the C ABI (``ocl_sc_map_apply``, ``ocl_sc_beam_moments``); the
+scalar post-processing of the 18 reduced moments (emittances, beta, alpha) is host arithmetic in
+the reference's own expressions.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import constants as _c
+
+_solvers = {}
+
+
+def _scratch_solver(device: int):
+    """A small native handle used only for its reduction scratch (mesh size irrelevant)."""
+    from . import native
+    s = _solvers.get(device)
+    if s is None:
+        s = native.Solver(device, (8, 8, 8))
+        _solvers[device] = s
+    return s
+
+
+def apply_map(p_array, R, B=None, T=None, delta_e=0.0, length=0.0):
+    """``rparticles <- R r + T:rr + B`` on a DeviceParticleArray, then ``E += delta_e``,
+    ``s += length`` as ``Transformation.apply`` does (transformations/transformation.py:123-131)."""
+    r = p_array.rparticles
+    _scratch_solver(r.device.index or 0).map_apply(r, R, B, T)
+    p_array.E += delta_e
+    p_array.s += length
+
+
+class Moments:
+    """Result of ``get_envelope``: the attributes of the reference's ``Twiss`` that the default
+    path fills (beam/analysis.py:81-83, :125-222)."""
+
+    def __init__(self):
+        self.E = self.q = self.p = self.s = 0.0
+        for k in ("x", "px", "y", "py", "tau", "xx", "xpx", "pxpx", "yy", "ypy", "pypy", "tautau", "pp", "xy",
+                  "pxpy", "xpy", "ypx", "emit_x", "emit_y", "emit_xn", "emit_yn", "beta_x", "beta_y", "alpha_x",
+                  "alpha_y"):
+            setattr(self, k, 0.0)
+
+    def __repr__(self):
+        return (f"<Moments E={self.E:.6g} emit_x={self.emit_x:.6g} emit_y={self.emit_y:.6g} "
+                f"beta_x={self.beta_x:.6g} beta_y={self.beta_y:.6g} sigma_tau={np.sqrt(self.tautau):.6g}>")
+
+
+def moments_from_sums(m: dict, E=0.0, q=0.0) -> Moments:
+    """Scalar post-processing of the 18 reduced moments (beam/analysis.py:179-220)."""
+    t = Moments()
+    t.E, t.q = float(E), float(q)
+    for k, v in m.items():
+        setattr(t, k, float(v))
+    t.emit_x = np.sqrt(t.xx * t.pxpx - t.xpx ** 2)
+    t.emit_y = np.sqrt(t.yy * t.pypy - t.ypy ** 2)
+    relgamma = t.E / _c.m_e_GeV
+    relbeta = np.sqrt(1 - relgamma ** -2) if relgamma != 0 else 1.
+    t.emit_xn = t.emit_x * relgamma * relbeta
+    t.emit_yn = t.emit_y * relgamma * relbeta
+    t.beta_x = t.xx / t.emit_x
+    t.beta_y = t.yy / t.emit_y
+    t.alpha_x = -t.xpx / t.emit_x
+    t.alpha_y = -t.ypy / t.emit_y
+    return t
+
+
+def get_envelope(p_array) -> Moments:
+    """Beam moments of a DeviceParticleArray (two streaming passes on the GPU, 18 doubles back)."""
+    r = p_array.rparticles
+    if r.shape[1] < 3:                       # analysis.py:86-88
+        t = Moments()
+        t.E = float(p_array.E)
+        return t
+    m = _scratch_solver(r.device.index or 0).beam_moments(r)
+    t = moments_from_sums(m, E=p_array.E, q=float(p_array.q_array.sum().item()))
+    t.s = float(getattr(p_array, "s", 0.0))
+    return t

@@ -35,6 +35,7 @@ struct ocl_sc {
     FftWork fw{};
     double2* tw[3] = {nullptr, nullptr, nullptr};
     double* h3 = nullptr;                     // mesh steps of the current kick
+    double* moments = nullptr;                // 18 doubles: beam moments (ocl_sc_beam_moments)
     double* real_buf = nullptr;               // M^3 real: K, then padded rho, then the convolution
     cufftDoubleComplex* k_hat = nullptr;      // M*M*(M/2+1)
     cufftDoubleComplex* rho_hat = nullptr;    // M*M*(M/2+1)
@@ -285,7 +286,7 @@ int ocl_sc_create(int device, int nx, int ny, int nz, long long max_particles, o
         }                                                                     \
     } while (0)
     TRY(cudaSetDevice(device));
-    TRY(cudaMalloc(&h->rs.part, sizeof(double) * 10 * h->rs.max_blocks));
+    TRY(cudaMalloc(&h->rs.part, sizeof(double) * 12 * h->rs.max_blocks));
     TRY(cudaMalloc(&h->rs.ticket, sizeof(unsigned int) * 4));
     TRY(cudaMemset(h->rs.ticket, 0, sizeof(unsigned int) * 4));
     TRY(cudaMalloc(&h->rs.sums, sizeof(double) * 40));
@@ -302,6 +303,7 @@ int ocl_sc_create(int device, int nx, int ny, int nz, long long max_particles, o
         if (h->md.mx > fft_max_length() || h->md.my > fft_max_length() || h->md.mz > fft_max_length()) h->solver = 1;
     }
     TRY(cudaMalloc(&h->h3, sizeof(double) * 4));
+    TRY(cudaMalloc(&h->moments, sizeof(double) * 18));
     TRY(cudaMalloc(&h->kp_dev, sizeof(KickParams)));
     {
         const char* env = getenv("OCL_SC_GRAPH");
@@ -350,7 +352,7 @@ void ocl_sc_destroy(ocl_sc_t* h) {
     cudaFree(h->rho); cudaFree(h->gtab); cudaFree(h->k1); cudaFree(h->real_buf);
     cudaFree(h->k_hat); cudaFree(h->rho_hat); cudaFree(h->phi); cudaFree(h->equad);
     cudaFree(h->fw.P); cudaFree(h->fw.Q); cudaFree(h->fw.khat); cudaFree(h->fw.A); cudaFree(h->fw.B);
-    cudaFree(h->tw[0]); cudaFree(h->tw[1]); cudaFree(h->tw[2]); cudaFree(h->h3);
+    cudaFree(h->tw[0]); cudaFree(h->tw[1]); cudaFree(h->tw[2]); cudaFree(h->h3); cudaFree(h->moments);
     cudaFree(h->stage_r); cudaFree(h->stage_q);
     cudaFree(h->rho_slab); cudaFree(h->phi_slab); cudaFree(h->xchg_a); cudaFree(h->xchg_b);
     for (int i = 0; i < T_COUNT; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
@@ -465,6 +467,7 @@ int ocl_sc_slab_inverse(ocl_sc_t* h, void* stream) {
     h->last_stream = st;
     launch_slab_inverse(h->xchg_a, h->md, h->sx, h->fs, h->fw, h->h3, four_pi_eps0_value(), h->phi_slab, st);
     h->launches += 2;
+    mark(h, T_SOLVE, st);
     return check_launch(h, "slab_inverse");
 }
 
@@ -475,6 +478,7 @@ int ocl_sc_slab_finish(ocl_sc_t* h, const double* mesh_draws, void* stream) {
     h->last_stream = st;
     launch_field(h->phi, h->rs, h->md, kp_of(h, 1.0, 0.0, mesh_draws), h->equad, st);
     h->launches += 1;
+    mark(h, T_FIELD, st);
     return check_launch(h, "slab_finish");
 }
 
@@ -768,6 +772,38 @@ int ocl_sc_potential_host(ocl_sc_t* h, const double* h_rho, const double steps[3
     }
     if (check_launch(h, "potential")) return 1;
     CU(h, cudaMemcpyAsync(h_phi, h->phi, sizeof(double) * n3, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    return 0;
+}
+
+int ocl_sc_map_apply(ocl_sc_t* h, double* d_r, long long ld, long long n, const double* R, const double* B,
+                     const double* T, void* stream) {
+    if (!h || !R) return 1;
+    if (n <= 0 || ld < n) return fail(h, "ocl_sc_map_apply", "need 0 < n <= ld");
+    if (set_device(h)) return 1;
+    MapCoef mc;
+    for (int i = 0; i < 36; ++i) mc.R[i] = R[i];
+    for (int i = 0; i < 6; ++i) mc.B[i] = B ? B[i] : 0.0;
+    mc.nt = 0;
+    if (T)
+        for (int c = 0; c < 216; ++c)
+            if (T[c] != 0.0) { mc.tval[mc.nt] = T[c]; mc.tidx[mc.nt] = (unsigned char)c; ++mc.nt; }
+    h->last_stream = (cudaStream_t)stream;
+    launch_map_apply(d_r, ld, n, mc, (cudaStream_t)stream);
+    h->launches += 1;
+    return check_launch(h, "k_map_apply");
+}
+
+int ocl_sc_beam_moments(ocl_sc_t* h, const double* d_r, long long ld, long long n, double* h_out, void* stream) {
+    if (!h || !h_out) return 1;
+    if (n <= 0 || ld < n) return fail(h, "ocl_sc_beam_moments", "need 0 < n <= ld");
+    if (set_device(h)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    h->last_stream = st;
+    launch_moments(d_r, ld, n, h->rs, h->moments, st);
+    h->launches += 2;
+    if (check_launch(h, "k_moments")) return 1;
+    CU(h, cudaMemcpyAsync(h_out, h->moments, sizeof(double) * 18, cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
     return 0;
 }

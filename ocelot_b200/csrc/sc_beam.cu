@@ -1,0 +1,160 @@
+// sc_beam.cu -- the two per-particle steps either side of the space-charge kick in the
+// reference's tracking loop, so that a bunch can stay
+// resident in HBM between kicks:
+//
+//   k_map_apply    X <- R X + T:XX + B     TransferMap.mul_p_array (transformations/transfer_map.py:42-53)
+//                                          SecondTM.t_apply        (transformations/second_order.py:31-39,
+//                                                                   tm_utils.py:54-55)
+//   k_moments_1/2  first moments, then centred second moments: get_envelope default path
+//                                          (beam/analysis.py:72-76, :121-123, :125-166)
+//
+// Both stream the six coordinate rows once (96 B resp. 48 B per particle) through the same
+// cp.async row pipeline as the kick sweeps.
+#include "sc_kernels.h"
+
+namespace ocl {
+
+constexpr int kBThreads = kSweepThreads;
+constexpr int kBWarps = kBThreads / 32;
+constexpr int kBDepth = 3;
+
+// ---- reductions (sum only), fixed order ------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void block_sum(double (&v)[NV], double* sh) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) {
+        v[k] = warp_reduce(v[k], OpSum());
+        if (lane == 0) sh[k * kBWarps + warp] = v[k];
+    }
+    __syncthreads();
+    if (warp == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) {
+            double x = (lane < kBWarps) ? sh[k * kBWarps + lane] : 0.0;
+            v[k] = warp_reduce(x, OpSum());
+        }
+    }
+    __syncthreads();
+}
+
+template <int NV>
+__device__ __forceinline__ bool grid_sum(double (&v)[NV], double* part, unsigned int* ticket, double* sh) {
+    __shared__ bool last;
+    block_sum<NV>(v, sh);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) part[(size_t)blockIdx.x * NV + k] = v[k];
+        __threadfence();
+        last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return false;
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += kBThreads) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) v[k] += __ldcg(part + (size_t)b * NV + k);
+    }
+    block_sum<NV>(v, sh);
+    if (threadIdx.x == 0) *ticket = 0;
+    return true;
+}
+
+// ---- f1: transfer map ----------------------------------------------------------------------
+__global__ void __launch_bounds__(kBThreads, 3) k_map_apply(double* __restrict__ r, long long ld, long long n,
+                                                           MapCoef mc) {
+    __shared__ double pipe[kBDepth * 6 * kBThreads];
+    const double* const base[6] = {r, r + ld, r + 2 * ld, r + 3 * ld, r + 4 * ld, r + 5 * ld};
+    pipelined_sweep<6, kBDepth>(base, (int)n, pipe, [&](int i, const double (&x)[6]) {
+        double y[6];
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            double s = mc.R[a * 6] * x[0];                       // R X (transfer_map.py:51)
+#pragma unroll
+            for (int b = 1; b < 6; ++b) s += mc.R[a * 6 + b] * x[b];
+            y[a] = s;
+        }
+        if (mc.nt > 0) {                                         // + T : X X, non-zero terms only (tm_utils.py:55)
+            double t[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+            for (int m = 0; m < mc.nt; ++m) {
+                const int c = mc.tidx[m];
+                const int a = c / 36, j = (c / 6) % 6, k = c % 6;
+                const double term = mc.tval[m] * x[j] * x[k];
+#pragma unroll
+                for (int q = 0; q < 6; ++q) t[q] += (q == a) ? term : 0.0;
+            }
+#pragma unroll
+            for (int a = 0; a < 6; ++a) y[a] += t[a];
+        }
+#pragma unroll
+        for (int a = 0; a < 6; ++a) r[a * ld + i] = y[a] + mc.B[a];   // + B (transfer_map.py:51, second_order.py:37)
+    });
+}
+
+// ---- f2: beam moments ----------------------------------------------------------------------
+// pass 1: sums of x, px*f, y, py*f, tau, p with f = 1 - p - p^2/2 + px^2/2 + py^2/2 (analysis.py:121-123)
+__global__ void __launch_bounds__(kBThreads, 4) k_moments_1(const double* __restrict__ r, long long ld, long long n,
+                                                           ReduceState rs, double* __restrict__ out) {
+    __shared__ double sh[6 * kBWarps];
+    __shared__ double pipe[kBDepth * 6 * kBThreads];
+    double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+    const double* const base[6] = {r, r + ld, r + 2 * ld, r + 3 * ld, r + 4 * ld, r + 5 * ld};
+    pipelined_sweep<6, kBDepth>(base, (int)n, pipe, [&](int, const double (&x)[6]) {
+        const double p = x[5];
+        const double f = 1. - p - 0.5 * p * p + 0.5 * x[1] * x[1] + 0.5 * x[3] * x[3];
+        v[0] += x[0]; v[1] += x[1] * f; v[2] += x[2]; v[3] += x[3] * f; v[4] += x[4]; v[5] += p;
+    });
+    if (grid_sum<6>(v, rs.part, rs.ticket + 2, sh) && threadIdx.x == 0) {
+        const double inv = 1.0 / (double)n;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) out[k] = v[k] * inv;        // np.mean
+    }
+}
+
+// pass 2: centred second moments (analysis.py:153-166), means from pass 1 in out[0..5]
+// out[6..17] = xx, xpx, pxpx, yy, ypy, pypy, tautau, pp, xy, pxpy, xpy, ypx
+__global__ void __launch_bounds__(kBThreads, 3) k_moments_2(const double* __restrict__ r, long long ld, long long n,
+                                                           ReduceState rs, double* __restrict__ out) {
+    __shared__ double sh[12 * kBWarps];
+    __shared__ double pipe[kBDepth * 6 * kBThreads];
+    const double mx = out[0], mpx = out[1], my = out[2], mpy = out[3], mt = out[4], mp = out[5];
+    double v[12];
+#pragma unroll
+    for (int k = 0; k < 12; ++k) v[k] = 0.0;
+    const double* const base[6] = {r, r + ld, r + 2 * ld, r + 3 * ld, r + 4 * ld, r + 5 * ld};
+    pipelined_sweep<6, kBDepth>(base, (int)n, pipe, [&](int, const double (&x)[6]) {
+        const double p = x[5];
+        const double f = 1. - p - 0.5 * p * p + 0.5 * x[1] * x[1] + 0.5 * x[3] * x[3];
+        const double dx = x[0] - mx, dpx = x[1] * f - mpx, dy = x[2] - my, dpy = x[3] * f - mpy;
+        const double dt = x[4] - mt, dp = p - mp;
+        v[0] += dx * dx; v[1] += dx * dpx; v[2] += dpx * dpx;
+        v[3] += dy * dy; v[4] += dy * dpy; v[5] += dpy * dpy;
+        v[6] += dt * dt; v[7] += dp * dp;
+        v[8] += dx * dy; v[9] += dpx * dpy; v[10] += dx * dpy; v[11] += dy * dpx;
+    });
+    if (grid_sum<12>(v, rs.part, rs.ticket + 3, sh) && threadIdx.x == 0) {
+        const double inv = 1.0 / (double)n;
+#pragma unroll
+        for (int k = 0; k < 12; ++k) out[6 + k] = v[k] * inv;
+    }
+}
+
+static int sweep_grid(long long n, int cap) {
+    long long b = (n + kBThreads - 1) / kBThreads;
+    if (b < 1) b = 1;
+    if (b > cap) b = cap;
+    return (int)b;
+}
+
+void launch_map_apply(double* r, long long ld, long long n, const MapCoef& mc, cudaStream_t st) {
+    k_map_apply<<<sweep_grid(n, 148 * 3), kBThreads, 0, st>>>(r, ld, n, mc);
+}
+
+void launch_moments(const double* r, long long ld, long long n, ReduceState rs, double* out18, cudaStream_t st) {
+    k_moments_1<<<sweep_grid(n, rs.max_blocks), kBThreads, 0, st>>>(r, ld, n, rs, out18);
+    k_moments_2<<<sweep_grid(n, 148 * 3), kBThreads, 0, st>>>(r, ld, n, rs, out18);
+}
+
+}  // namespace ocl

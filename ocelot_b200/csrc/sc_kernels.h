@@ -45,6 +45,17 @@ void launch_mad_to_cart(const double* r, long long ld, long long n, RefParams rp
                         cudaStream_t st);
 void launch_cart_to_mad(const double* xp, long long ld_xp, long long n, RefParams rp, double* r, long long ld,
                         cudaStream_t st);
+// ---- transfer maps and beam moments (sc_beam.cu) ----
+struct MapCoef {
+    double R[36];        // first-order matrix, row-major
+    double B[6];         // constant term
+    double tval[216];    // non-zero second-order coefficients ...
+    unsigned char tidx[216];   // ... and their flat index a*36 + j*6 + k
+    int nt;              // number of non-zero T terms (0: first-order map)
+};
+void launch_map_apply(double* r, long long ld, long long n, const MapCoef& mc, cudaStream_t st);
+void launch_moments(const double* r, long long ld, long long n, ReduceState rs, double* out18, cudaStream_t st);
+
 // ---- hand-written Hockney convolution (sc_fft.cu) ----
 struct FftWork {
     const double2* tw_x;   // exp(-2 pi i m / M) tables, one per axis

@@ -57,6 +57,8 @@ _SIGNATURES = {
     "ocl_sc_mad_to_cartesian": (C.c_int, [_vp, _vp, _ll, _ll, C.c_double, _vp, _ll, _vp]),
     "ocl_sc_cartesian_to_mad": (C.c_int, [_vp, _vp, _ll, _ll, C.c_double, _vp, _ll, _vp]),
     "ocl_sc_potential_host": (C.c_int, [_vp, _vp, _dp, _vp]),
+    "ocl_sc_map_apply": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _dp, _dp, _vp]),
+    "ocl_sc_beam_moments": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _vp]),
     "ocl_sc_enable_timers": (C.c_int, [_vp, C.c_int]),
     "ocl_sc_get_timers": (C.c_int, [_vp, _dp]),
     "ocl_sc_launch_count": (_ll, [_vp]),
@@ -297,6 +299,27 @@ class Solver:
         self._check(self._lib.ocl_sc_potential_host(self._h, rho.ctypes.data, st, out.ctypes.data),
                     "ocl_sc_potential_host")
         return out
+
+    # -- neighbours of the kick in the tracking loop -----------------------------
+    def map_apply(self, r, R, B=None, T=None, stream=None):
+        """rparticles <- R r + T:rr + B in place (first- or second-order transfer map)."""
+        ptr, ld, n = self._dev_rows(r)
+        Rc = np.ascontiguousarray(R, dtype=np.float64).reshape(36)
+        Bc = None if B is None else np.ascontiguousarray(B, dtype=np.float64).reshape(6)
+        Tc = None if T is None else np.ascontiguousarray(T, dtype=np.float64).reshape(216)
+        as_p = lambda a: None if a is None else a.ctypes.data_as(_dp)
+        self._check(self._lib.ocl_sc_map_apply(self._h, ptr, ld, n, as_p(Rc), as_p(Bc), as_p(Tc),
+                                               _stream_ptr(stream)), "ocl_sc_map_apply")
+
+    MOMENT_KEYS = ("x", "px", "y", "py", "tau", "p", "xx", "xpx", "pxpx", "yy", "ypy", "pypy", "tautau", "pp",
+                   "xy", "pxpy", "xpy", "ypx")
+
+    def beam_moments(self, r, stream=None) -> dict:
+        ptr, ld, n = self._dev_rows(r)
+        out = (C.c_double * 18)()
+        self._check(self._lib.ocl_sc_beam_moments(self._h, ptr, ld, n, out, _stream_ptr(stream)),
+                    "ocl_sc_beam_moments")
+        return dict(zip(self.MOMENT_KEYS, out[:]))
 
     # -- timers ---------------------------------------------------------------
     def enable_timers(self, on=True):

@@ -82,6 +82,25 @@ class DeviceParticleArray:
     def q_array(self):
         return self._q[:self._n]
 
+    # accessors of the reference container (particle.py:176-195), as device views
+    def x(self):
+        return self.rparticles[0]
+
+    def px(self):
+        return self.rparticles[1]
+
+    def y(self):
+        return self.rparticles[2]
+
+    def py(self):
+        return self.rparticles[3]
+
+    def tau(self):
+        return self.rparticles[4]
+
+    def p(self):
+        return self.rparticles[5]
+
     @classmethod
     def from_host(cls, p_array, device=None):
         """Copy any object with rparticles/q_array/E/s (e.g. Ocelot's ParticleArray) to the device."""

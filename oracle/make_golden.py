@@ -213,7 +213,7 @@ def _fodo(k1=5.0, ncell=10):
     return seq
 
 
-def _track_fixture(name, n, ncell, nmesh, sample_stride):
+def _track_fixture(name, n, ncell, nmesh, sample_stride, second_order=False):
     """Config-1 tracking: Gaussian bunch through ncell FODO cells (1 m each),
     first-order maps, SC kick every 0.1 m.  The per-step transfer matrices the
     reference used are stored so the run can be replayed without Ocelot."""
@@ -222,7 +222,11 @@ def _track_fixture(name, n, ncell, nmesh, sample_stride):
     np.random.seed(1)
     p_array = generate_parray(nparticles=n, energy=0.13, charge=250e-12)
     r0 = p_array.rparticles.copy()
-    lat = MagneticLattice(_fodo(ncell=ncell))
+    if second_order:
+        from ocelot import SecondTM
+        lat = MagneticLattice(_fodo(ncell=ncell), method={'global': SecondTM})
+    else:
+        lat = MagneticLattice(_fodo(ncell=ncell))
     navi = Navigator(lat)
     navi.unit_step = 0.1
     sc = SpaceCharge()
@@ -230,7 +234,7 @@ def _track_fixture(name, n, ncell, nmesh, sample_stride):
     sc.nmesh_xyz = list(nmesh)
     navi.add_physics_proc(sc, lat.sequence[0], lat.sequence[-1])
 
-    Rs, Bs, map_step, dzs, moments = [], [], [], [], []
+    Rs, Bs, Ts, map_step, dzs, moments = [], [], [], [], [], []
 
     def env(p):
         t = get_envelope(p)
@@ -242,7 +246,12 @@ def _track_fixture(name, n, ncell, nmesh, sample_stride):
     for t_maps, dz, proc_list, phys_steps in navi.get_next_step():
         for tm in t_maps:
             prm = tm.get_params(p_array.E)
-            Rs.append(np.array(prm.get_rotated_R(), dtype=float))
+            if second_order:                     # SecondTM.t_apply, second_order.py:31-39 (tilt == 0 here)
+                assert prm.tilt == 0
+                Rs.append(np.array(prm.R, dtype=float))
+                Ts.append(np.array(prm.T, dtype=float))
+            else:
+                Rs.append(np.array(prm.get_rotated_R(), dtype=float))
             Bs.append(np.array(prm.B, dtype=float).reshape(6))
             map_step.append(step)
             tm.apply(p_array)
@@ -257,7 +266,7 @@ def _track_fixture(name, n, ncell, nmesh, sample_stride):
     print(f"{name}: steps={step} maps={len(Rs)} kicks={int(np.count_nonzero(dzs))}")
     save(name, seed=1, n=n, E=p_array.E, charge=250e-12, nmesh=np.array(nmesh),
          r0_head=r0[:, :64], r0_checksum=np.array([r0.sum(), np.abs(r0).sum(), (r0 * r0).sum()]),
-         R=np.array(Rs), B=np.array(Bs), map_step=np.array(map_step), kick_dz=np.array(dzs),
+         R=np.array(Rs), B=np.array(Bs), T=np.array(Ts), map_step=np.array(map_step), kick_dz=np.array(dzs),
          moment_keys=np.array(MOMENT_KEYS), moments=np.array(moments),
          sample_stride=sample_stride, r_final_sample=p_array.rparticles[:, ::sample_stride].copy())
 
@@ -265,6 +274,7 @@ def _track_fixture(name, n, ncell, nmesh, sample_stride):
 def golden_track():
     _track_fixture("track_c1_small.npz", n=20000, ncell=2, nmesh=(31, 31, 31), sample_stride=10)
     _track_fixture("track_c1.npz", n=200000, ncell=10, nmesh=(31, 31, 31), sample_stride=100)
+    _track_fixture("track_second_order.npz", n=20000, ncell=2, nmesh=(31, 31, 31), sample_stride=10, second_order=True)
 
 
 if __name__ == "__main__":

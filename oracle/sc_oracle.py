@@ -416,7 +416,7 @@ def beam_moments(r: np.ndarray) -> dict:
 
 
 def replay_track(r: np.ndarray, q: np.ndarray, E_GeV: float, R, B, map_step, kick_dz, nmesh_xyz, kick,
-                 after_step=None) -> None:
+                 after_step=None, T=None) -> None:
     """Replay a recorded first-order tracking run in place: for every step apply
     its transfer maps ``r <- R r + B`` (transfer_map.py:51-52) and then
     ``kick(r, q, E, dz, nmesh)`` -- the loop body of ``track()``
@@ -424,7 +424,11 @@ def replay_track(r: np.ndarray, q: np.ndarray, E_GeV: float, R, B, map_step, kic
     map_step = np.asarray(map_step)
     for step, dz in enumerate(kick_dz):
         for m in np.nonzero(map_step == step)[0]:
-            r[:] = np.add(np.dot(R[m], r), B[m].reshape(6, 1))
+            if T is None:
+                r[:] = np.add(np.dot(R[m], r), B[m].reshape(6, 1))
+            else:   # SecondTM.t_apply (second_order.py:31-39) with SecondOrderMult.numpy_apply (tm_utils.py:54-55)
+                r[:] = np.matmul(R[m], r) + np.einsum('ijk,j...,k...->i...', T[m], r, r)
+                r[:] = np.add(r, B[m].reshape(6, 1))
         if dz != 0:
             kick(r, q, E_GeV, float(dz), nmesh_xyz)
         if after_step is not None:

@@ -1,0 +1,90 @@
+"""Rows f1/f2: device transfer maps and device beam moments, and the resident
+tracking loop built from them, against the reference's formulas and golden tracking runs."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import sc_oracle as orc  # noqa: E402
+
+
+def _moment_err(got, ref_row, keys):
+    ref = dict(zip(keys, ref_row))
+    sig = {"x": ref["xx"], "px": ref["pxpx"], "y": ref["yy"], "py": ref["pypy"], "tau": ref["tautau"], "p": ref["pp"]}
+    worst = 0.0
+    for k in keys:
+        g = got[k] if isinstance(got, dict) else getattr(got, k)
+        e = abs(g - ref[k]) / (np.sqrt(sig[k]) if k in sig else abs(ref[k]))
+        worst = max(worst, e)
+    return worst
+
+
+def _device_bunch(n, seed, energy=0.13):
+    from ocelot_b200 import ParticleArray, DeviceParticleArray
+    np.random.seed(seed)
+    r, q, E = orc.gaussian_bunch(n, energy=energy, charge=250e-12)
+    host = ParticleArray(n)
+    host.rparticles[:], host.q_array[:], host.E = r, q, E
+    return r, q, E, DeviceParticleArray.from_host(host)
+
+
+def test_map_apply_first_and_second_order():
+    from ocelot_b200 import apply_map
+    rng = np.random.RandomState(1)
+    r0, q0, E, dev = _device_bunch(100_003, 2)
+    R = np.eye(6) + rng.randn(6, 6) * 0.1
+    B = rng.randn(6) * 1e-6
+    T = rng.randn(6, 6, 6) * (rng.rand(6, 6, 6) < 0.3)          # sparse like real T matrices
+    # first order: TransferMap.mul_p_array (transfer_map.py:51)
+    apply_map(dev, R, B)
+    ref = np.add(np.dot(R, r0), B.reshape(6, 1))
+    got = dev.to_host().rparticles
+    assert np.max(np.abs(got - ref) / (np.abs(ref).max(axis=1, keepdims=True))) < 1e-14
+    # second order: SecondOrderMult.numpy_apply + B (tm_utils.py:55, second_order.py:37)
+    ref2 = np.matmul(R, ref) + np.einsum('ijk,j...,k...->i...', T, ref, ref)
+    ref2 = np.add(ref2, B.reshape(6, 1))
+    apply_map(dev, R, B, T, delta_e=0.001, length=0.5)
+    got2 = dev.to_host().rparticles
+    assert np.max(np.abs(got2 - ref2) / (np.abs(ref2).max(axis=1, keepdims=True))) < 1e-14
+    assert abs(dev.E - (E + 0.001)) < 1e-15 and dev.s == 0.5
+
+
+def test_beam_moments_vs_oracle():
+    from ocelot_b200 import get_envelope
+    for n in (3, 1000, 1_000_003):
+        r0, q0, E, dev = _device_bunch(n, 3)
+        dev.rparticles[0] += 3e-4                                  # non-zero means
+        dev.rparticles[5] += 1e-3
+        ref = orc.beam_moments(dev.to_host().rparticles)
+        t = get_envelope(dev)
+        keys = list(orc.MOMENT_KEYS)
+        assert _moment_err(t, [ref[k] for k in keys], keys) < 1e-12, n
+        assert abs(t.q / q0.sum() - 1) < 1e-12 and t.E == E
+
+
+@pytest.mark.parametrize("fixture,second", [("track_c1.npz", False), ("track_second_order.npz", True)])
+def test_resident_tracking_moments(golden, fixture, second):
+    """Maps, kicks and moments all on the device; only 18 doubles per step come back.
+    Moments against the reference's get_envelope after every step: north-star bound 1e-9."""
+    from ocelot_b200 import SpaceCharge, get_envelope, replay_track
+    g = golden(fixture)
+    keys = [str(k) for k in g["moment_keys"]]
+    r0, q0, E, dev = _device_bunch(int(g["n"]), int(g["seed"]), energy=float(g["E"]))
+    assert np.array_equal(r0[:, :64], g["r0_head"])
+    sc = SpaceCharge(step=1, nmesh_xyz=[int(v) for v in g["nmesh"]])
+    sc.prepare(None)
+    assert _moment_err(get_envelope(dev), g["moments"][0], keys) < 1e-12
+    worst = [0.0]
+
+    def check(step, p):
+        worst[0] = max(worst[0], _moment_err(get_envelope(p), g["moments"][step + 1], keys))
+
+    replay_track(dev, g["R"], g["B"], g["map_step"], g["kick_dz"], sc, T=g["T"] if second else None, after_step=check)
+    assert worst[0] < 1e-9, worst[0]
+    stride = int(g["sample_stride"])
+    final = dev.to_host().rparticles[:, ::stride]
+    for row in range(6):
+        ref = g["r_final_sample"][row]
+        assert np.max(np.abs(final[row] - ref)) / np.std(ref) < 1e-10

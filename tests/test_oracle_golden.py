@@ -166,3 +166,37 @@ def test_track_c1_small_replay(golden):
     for row in range(6):
         ref = g["r_final_sample"][row]
         assert np.max(np.abs(r[row, ::stride] - ref)) / np.std(ref) < 1e-10
+
+
+def test_track_second_order_replay(golden):
+    """Same lattice with SecondTM maps (R, T, B recorded from the reference): pins the
+    oracle's second-order map restatement (second_order.py:31-39, tm_utils.py:54-55)."""
+    g = golden("track_second_order.npz")
+    keys = [str(k) for k in g["moment_keys"]]
+    np.random.seed(int(g["seed"]))
+    r, q, E = orc.gaussian_bunch(int(g["n"]), energy=float(g["E"]), charge=float(g["charge"]))
+    worst = [0.0]
+
+    def check(step, rr):
+        worst[0] = max(worst[0], _moment_err(orc.beam_moments(rr), g["moments"][step + 1], keys))
+
+    orc.replay_track(r, q, E, g["R"], g["B"], g["map_step"], g["kick_dz"], g["nmesh"],
+                     lambda rr, qq, EE, dz, nm: orc.sc_kick(rr, qq, EE, dz, nm, fft="padded", workers=4), check,
+                     T=g["T"])
+    assert worst[0] < 1e-9, worst[0]
+    stride = int(g["sample_stride"])
+    for row in range(6):
+        ref = g["r_final_sample"][row]
+        assert np.max(np.abs(r[row, ::stride] - ref)) / np.std(ref) < 1e-10
+
+
+def test_moment_postprocessing_matches_oracle():
+    """Host arithmetic of ocelot_b200.beam.moments_from_sums (analysis.py:179-220)."""
+    from ocelot_b200.beam import moments_from_sums
+    rng = np.random.RandomState(0)
+    r = rng.randn(6, 5000) * np.array([1e-4, 2e-5, 1e-4, 2e-5, 1e-3, 1e-3]).reshape(6, 1)
+    m = orc.beam_moments(r)
+    sums = {k: m[k] for k in m if not k.startswith("emit")}
+    t = moments_from_sums(sums, E=0.13, q=1e-9)
+    assert t.emit_x == m["emit_x"] and t.emit_y == m["emit_y"]
+    assert t.beta_x == m["xx"] / m["emit_x"] and t.alpha_y == -m["ypy"] / m["emit_y"]
