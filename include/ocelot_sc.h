@@ -157,6 +157,13 @@ int ocl_sc_potential_host(ocl_sc_t* h, const double* h_rho, const double steps[3
  * R[36] row-major; B[6] or NULL; T[216] (index a*36 + j*6 + k) or NULL for a first-order map. */
 int ocl_sc_map_apply(ocl_sc_t* h, double* d_r, long long ld, long long n, const double* R, const double* B,
                      const double* T, void* stream);
+/* RF cavity body, CavityTM.map4cav (transformations/cavity.py:29-128): X <- R X + B, then
+ *   delta <- delta0*c[0] + c[1]*(cos(c[3] - c[2]*tau0) - cos(c[3]))        (cavity.py:81-84)
+ *   tau   += c[4]*delta0^2 + c[5]*tau0*delta0 + c[6]*tau0^2                 (cavity.py:126)
+ * with c[7] = {E0 b0/(E1 b1), V b0/(E1 b1), b0 k, phi, T566, T556, T555} computed by the host from the
+ * reference's scalar formulas; mode 1 = full, mode 2 = drift-like branch (cavity.py:67-69). */
+int ocl_sc_cavity_apply(ocl_sc_t* h, double* d_r, long long ld, long long n, const double* R, const double* B,
+                        const double* c, int mode, void* stream);
 /* First and centred second moments of get_envelope's default path (beam/analysis.py:72-76,
  * :121-166): h_out[18] = {x, px, y, py, tau, p, xx, xpx, pxpx, yy, ypy, pypy, tautau, pp, xy, pxpy,
  * xpy, ypx} with the reference's px, py correction factor applied.  Synchronous. */

@@ -785,6 +785,7 @@ int ocl_sc_map_apply(ocl_sc_t* h, double* d_r, long long ld, long long n, const 
     for (int i = 0; i < 36; ++i) mc.R[i] = R[i];
     for (int i = 0; i < 6; ++i) mc.B[i] = B ? B[i] : 0.0;
     mc.nt = 0;
+    mc.cav = 0;
     if (T)
         for (int c = 0; c < 216; ++c)
             if (T[c] != 0.0) { mc.tval[mc.nt] = T[c]; mc.tidx[mc.nt] = (unsigned char)c; ++mc.nt; }
@@ -792,6 +793,25 @@ int ocl_sc_map_apply(ocl_sc_t* h, double* d_r, long long ld, long long n, const 
     launch_map_apply(d_r, ld, n, mc, (cudaStream_t)stream);
     h->launches += 1;
     return check_launch(h, "k_map_apply");
+}
+
+int ocl_sc_cavity_apply(ocl_sc_t* h, double* d_r, long long ld, long long n, const double* R, const double* B,
+                        const double* c, int mode, void* stream) {
+    if (!h || !R || !c) return 1;
+    if (n <= 0 || ld < n) return fail(h, "ocl_sc_cavity_apply", "need 0 < n <= ld");
+    if (mode != 1 && mode != 2) return fail(h, "ocl_sc_cavity_apply", "mode must be 1 or 2");
+    if (set_device(h)) return 1;
+    MapCoef mc;
+    for (int i = 0; i < 36; ++i) mc.R[i] = R[i];
+    for (int i = 0; i < 6; ++i) mc.B[i] = B ? B[i] : 0.0;
+    mc.nt = 0;
+    mc.cav = mode;
+    mc.c1 = c[0]; mc.c2 = c[1]; mc.kb = c[2]; mc.phi = c[3]; mc.cosphi = std::cos(c[3]);
+    mc.t566 = c[4]; mc.t556 = c[5]; mc.t555 = c[6];
+    h->last_stream = (cudaStream_t)stream;
+    launch_map_apply(d_r, ld, n, mc, (cudaStream_t)stream);
+    h->launches += 1;
+    return check_launch(h, "k_map_apply(cavity)");
 }
 
 int ocl_sc_beam_moments(ocl_sc_t* h, const double* d_r, long long ld, long long n, double* h_out, void* stream) {

@@ -89,7 +89,13 @@ __global__ void __launch_bounds__(kBThreads, 3) k_map_apply(double* __restrict__
             for (int a = 0; a < 6; ++a) y[a] += t[a];
         }
 #pragma unroll
-        for (int a = 0; a < 6; ++a) r[a * ld + i] = y[a] + mc.B[a];   // + B (transfer_map.py:51, second_order.py:37)
+        for (int a = 0; a < 6; ++a) y[a] += mc.B[a];                   // + B (transfer_map.py:51, second_order.py:37)
+        if (mc.cav) {                                                  // cavity.py:56-126, x[4], x[5] are the saved X4, X5
+            if (mc.cav == 1) y[5] = x[5] * mc.c1 + mc.c2 * (cos(-x[4] * mc.kb + mc.phi) - mc.cosphi);   // :81-84
+            y[4] += mc.t566 * x[5] * x[5] + mc.t556 * x[4] * x[5] + mc.t555 * x[4] * x[4];              // :126
+        }
+#pragma unroll
+        for (int a = 0; a < 6; ++a) r[a * ld + i] = y[a];
     });
 }
 

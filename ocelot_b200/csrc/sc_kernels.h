@@ -52,6 +52,10 @@ struct MapCoef {
     double tval[216];    // non-zero second-order coefficients ...
     unsigned char tidx[216];   // ... and their flat index a*36 + j*6 + k
     int nt;              // number of non-zero T terms (0: first-order map)
+    // RF cavity body (CavityTM.map4cav, transformations/cavity.py:29-128), applied after R X + B:
+    //   delta <- delta0*c1 + c2*(cos(phi - kb*tau0) - cos(phi));  tau += t566 d0^2 + t556 tau0 d0 + t555 tau0^2
+    int cav;             // 0: no cavity step | 1: full | 2: drift-like (final energy non-physical, cavity.py:67-69)
+    double c1, c2, kb, phi, cosphi, t566, t556, t555;
 };
 void launch_map_apply(double* r, long long ld, long long n, const MapCoef& mc, cudaStream_t st);
 void launch_moments(const double* r, long long ld, long long n, ReduceState rs, double* out18, cudaStream_t st);

@@ -58,6 +58,7 @@ _SIGNATURES = {
     "ocl_sc_cartesian_to_mad": (C.c_int, [_vp, _vp, _ll, _ll, C.c_double, _vp, _ll, _vp]),
     "ocl_sc_potential_host": (C.c_int, [_vp, _vp, _dp, _vp]),
     "ocl_sc_map_apply": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _dp, _dp, _vp]),
+    "ocl_sc_cavity_apply": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _dp, _dp, C.c_int, _vp]),
     "ocl_sc_beam_moments": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _vp]),
     "ocl_sc_enable_timers": (C.c_int, [_vp, C.c_int]),
     "ocl_sc_get_timers": (C.c_int, [_vp, _dp]),
@@ -310,6 +311,16 @@ class Solver:
         as_p = lambda a: None if a is None else a.ctypes.data_as(_dp)
         self._check(self._lib.ocl_sc_map_apply(self._h, ptr, ld, n, as_p(Rc), as_p(Bc), as_p(Tc),
                                                _stream_ptr(stream)), "ocl_sc_map_apply")
+
+    def cavity_apply(self, r, R, B, coef, mode=1, stream=None):
+        """RF cavity body: R r + B, then the longitudinal RF map with the 7 host-computed scalars."""
+        ptr, ld, n = self._dev_rows(r)
+        Rc = np.ascontiguousarray(R, dtype=np.float64).reshape(36)
+        Bc = np.zeros(6) if B is None else np.ascontiguousarray(B, dtype=np.float64).reshape(6)
+        cc = np.ascontiguousarray(coef, dtype=np.float64).reshape(7)
+        self._check(self._lib.ocl_sc_cavity_apply(self._h, ptr, ld, n, Rc.ctypes.data_as(_dp), Bc.ctypes.data_as(_dp),
+                                                  cc.ctypes.data_as(_dp), int(mode), _stream_ptr(stream)),
+                    "ocl_sc_cavity_apply")
 
     MOMENT_KEYS = ("x", "px", "y", "py", "tau", "p", "xx", "xpx", "pxpx", "yy", "ypy", "pypy", "tautau", "pp",
                    "xy", "pxpy", "xpy", "ypx")

@@ -13,12 +13,12 @@ import logging
 
 import numpy as np
 
-from .beam import apply_map, get_envelope
+from .beam import apply_map, apply_cavity, get_envelope
 from .particles import DeviceParticleArray, ParticleArray
 
 logger = logging.getLogger(__name__)
 
-_DEVICE_MAPS = {"TransferMap", "SecondTM"}
+_DEVICE_MAPS = {"TransferMap", "SecondTM", "CavityTM"}
 
 
 def _apply_tm(tm, p_dev):
@@ -26,7 +26,10 @@ def _apply_tm(tm, p_dev):
     if name in _DEVICE_MAPS and hasattr(tm, "get_params"):
         prm = tm.get_params(p_dev.E)
         dl = tm.delta_length if getattr(tm, "delta_length", None) is not None else tm.length
-        if name == "TransferMap":
+        if name == "CavityTM" and getattr(tm.tm_type, "name", "") == "MAIN":                  # cavity.py:130-132
+            apply_cavity(p_dev, prm.get_rotated_R(), prm.B, prm.v, prm.phi, prm.freq, tm.delta_length, tm.length,
+                         delta_e=tm.get_delta_e())
+        elif name in ("TransferMap", "CavityTM"):
             apply_map(p_dev, prm.get_rotated_R(), prm.B, None, tm.get_delta_e(), dl)      # transfer_map.py:50-52
         else:
             R, T = prm.R, prm.T                                                           # second_order.py:32-36
@@ -96,3 +99,29 @@ def replay_track(p_array, R, B, map_step, kick_dz, sc, T=None, after_step=None):
         sc.apply(p_array, float(dz))
         if after_step is not None:
             after_step(step, p_array)
+
+
+def replay_recorded_maps(p_array, g, sc_for_step):
+    """Replay a recorded run (fixture layout of oracle/make_golden.py::golden_injector_track) entirely
+    on the device: ``g`` holds per map ``kind`` (0 first order, 1 second order, 2 RF cavity body),
+    ``R``, ``B``, ``Tidx``/``T``, ``cav`` = (v, phi, freq, delta_length|nan, length), ``delta_e``, ``dl``,
+    ``map_step`` and per step ``kick_dz``.  ``sc_for_step(step)`` returns the physics process to
+    apply after the maps of that step (or None)."""
+    map_step = np.asarray(g["map_step"])
+    order = np.argsort(map_step, kind="stable")
+    pos = 0
+    for step, dz in enumerate(g["kick_dz"]):
+        while pos < len(order) and map_step[order[pos]] == step:
+            m = int(order[pos])
+            pos += 1
+            kind = int(g["kind"][m])
+            if kind == 2:
+                v, phi, freq, dlen, length = (float(x) for x in g["cav"][m])
+                apply_cavity(p_array, g["R"][m], g["B"][m], v, phi, freq, None if np.isnan(dlen) else dlen, length,
+                             delta_e=float(g["delta_e"][m]))
+            else:
+                T = g["T"][int(g["Tidx"][m])] if kind == 1 else None
+                apply_map(p_array, g["R"][m], g["B"][m], T, float(g["delta_e"][m]), float(g["dl"][m]))
+        sc = sc_for_step(step)
+        if sc is not None and dz != 0:
+            sc.apply(p_array, float(dz))

@@ -203,6 +203,75 @@ def golden_injector():
                    "kicks": len(record), "max_abs_diff": diffs, "row_std": rms}, f, indent=1)
 
 
+def golden_injector_track():
+    """The reference's own golden test test_track_with_sp (space_charge_test.py:51-66) recorded map by
+    map: 8+8 cavities (CavityTM), drifts/quads (SecondTM), two SpaceCharge processes (63^3, step 1 then
+    5), unit_step 0.02, 10k particles.  The fixture lets the device path replay the whole run and be
+    compared with the reference's JSON golden particles."""
+    import importlib.util
+    conf_path = os.path.join(REF, "unit_tests", "ebeam_test", "space_charge", "space_charge_conf.py")
+    spec = importlib.util.spec_from_file_location("space_charge_conf", conf_path)
+    conf = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(conf)
+    from ocelot import MagneticLattice, Navigator, SecondTM
+
+    cell = (conf.Marker(), conf.D_14, conf.C_A1_1_1_I1, conf.D_15, conf.C_A1_1_2_I1, conf.D_15, conf.C_A1_1_3_I1,
+            conf.D_15, conf.C_A1_1_4_I1, conf.D_15, conf.C_A1_1_5_I1, conf.D_15, conf.C_A1_1_6_I1, conf.D_15,
+            conf.C_A1_1_7_I1, conf.D_15, conf.C_A1_1_8_I1, conf.D_22, conf.Q_37_I1, conf.D_23, conf.Q_38_I1)
+    lat = MagneticLattice(cell, method={'global': SecondTM})
+    p_array = conf.p_array.__wrapped__()
+    r0, q0, E0 = p_array.rparticles.copy(), p_array.q_array.copy(), float(p_array.E)
+    sc1, sc5 = SpaceCharge(), SpaceCharge()
+    sc1.nmesh_xyz = sc5.nmesh_xyz = [63, 63, 63]
+    sc1.step, sc5.step = 1, 5
+    navi = Navigator(lat)
+    navi.add_physics_proc(sc1, lat.sequence[0], conf.C_A1_1_2_I1)
+    navi.add_physics_proc(sc5, conf.C_A1_1_2_I1, lat.sequence[-1])
+    navi.unit_step = 0.02
+
+    kind, Rs, Bs, Tidx, Ts, cav, dE, dL, map_step, kick_dz, names = [], [], [], [], [], [], [], [], [], [], set()
+    step = 0
+    for t_maps, dz, proc_list, phys_steps in navi.get_next_step():      # body of track(), track.py:470-477
+        for tm in t_maps:
+            prm = tm.get_params(p_array.E)
+            name = type(tm).__name__
+            names.add(name + ":" + tm.tm_type.name)
+            dl = tm.delta_length if tm.delta_length is not None else tm.length
+            if name == "SecondTM":
+                R, T = (prm.R, prm.T) if prm.tilt == 0 else (prm.get_rotated_R(), prm.get_rotated_T())
+                kind.append(1); Tidx.append(len(Ts)); Ts.append(np.array(T, dtype=float))
+                cav.append([0, 0, 0, np.nan, 0])
+            elif name == "CavityTM" and tm.tm_type.name == "MAIN":
+                R = prm.get_rotated_R()
+                kind.append(2); Tidx.append(-1)
+                cav.append([prm.v, prm.phi, prm.freq, np.nan if tm.delta_length is None else tm.delta_length, tm.length])
+            else:                                                       # first-order (incl. cavity edges)
+                R = prm.get_rotated_R()
+                kind.append(0); Tidx.append(-1); cav.append([0, 0, 0, np.nan, 0])
+            Rs.append(np.array(R, dtype=float)); Bs.append(np.array(prm.B, dtype=float).reshape(6))
+            dE.append(float(tm.get_delta_e())); dL.append(float(dl)); map_step.append(step)
+            tm.apply(p_array)
+        dzk = 0.0
+        for p, z_step in zip(proc_list, phys_steps):
+            p.z0 = navi.z0
+            p.apply(p_array, z_step)
+            dzk = z_step
+        assert len(proc_list) <= 1
+        kick_dz.append(float(dzk))
+        step += 1
+    print("golden path maps:", sorted(names), "steps", step, "maps", len(kind), "kicks", int(np.count_nonzero(kick_dz)))
+    gpath = os.path.join(REF, "unit_tests", "ebeam_test", "space_charge", "ref_results", "test_track_with_sp.json")
+    with open(gpath) as f:
+        gp = json.load(f)["p_array"]
+    keys = ("x", "px", "y", "py", "tau", "p")
+    gold_r = np.array([[prt[k] for prt in gp] for k in keys])
+    print("reference-here vs JSON golden, max abs per row:", np.max(np.abs(gold_r - p_array.rparticles), axis=1))
+    save("track_injector_golden.npz", r0=r0, q=q0, E0=E0, nmesh=np.array((63, 63, 63)), kind=np.array(kind),
+         R=np.array(Rs), B=np.array(Bs), Tidx=np.array(Tidx), T=np.array(Ts), cav=np.array(cav, dtype=float),
+         delta_e=np.array(dE), dl=np.array(dL), map_step=np.array(map_step), kick_dz=np.array(kick_dz),
+         json_golden_final=gold_r, reference_here_final=p_array.rparticles.copy(), E_final=float(p_array.E))
+
+
 def _fodo(k1=5.0, ncell=10):
     from ocelot import Quadrupole, Drift, Marker
     seq = [Marker(eid="START")]
@@ -287,3 +356,5 @@ if __name__ == "__main__":
         golden_injector()
     if what in ("all", "track"):
         golden_track()
+    if what in ("all", "injector_track"):
+        golden_injector_track()

@@ -433,3 +433,78 @@ def replay_track(r: np.ndarray, q: np.ndarray, E_GeV: float, R, B, map_step, kic
             kick(r, q, E_GeV, float(dz), nmesh_xyz)
         if after_step is not None:
             after_step(step, r)
+
+
+# ---------------------------------------------------------------------------
+# RF cavity body and generic recorded-map replay (rows f1/f3 of SURVEY.md 8f)
+# ---------------------------------------------------------------------------
+def cavity_map(r: np.ndarray, R, B, v, phi_deg, freq, E, delta_length, length) -> float:
+    """In place: the MAIN map of an RF cavity.  Restates ``CavityTM.map4cav``
+    (ocelot/cpbd/transformations/cavity.py:29-128).  Returns the energy gain V cos(phi)."""
+    if delta_length is not None:
+        V = v * delta_length / length if length != 0 else v
+        z = delta_length
+    else:
+        V, z = v, length
+    beta0, igamma2, g0 = 1.0, 0.0, 1e10
+    if E != 0.0:
+        g0 = E / M_E_GEV
+        igamma2 = 1.0 / (g0 * g0)
+        beta0 = np.sqrt(1.0 - igamma2)
+    phi = phi_deg * np.pi / 180.0
+    X4, X5 = np.copy(r[4]), np.copy(r[5])
+    r[:] = np.add(np.dot(R, r), np.asarray(B).reshape(6, 1))
+    delta_e = V * np.cos(phi)
+    E1 = E + delta_e
+    T566, T556, T555 = 1.5 * z * igamma2 / (beta0 ** 3), 0.0, 0.0
+    if E1 <= 0.0:
+        r[4] += T566 * X5 * X5
+        return delta_e
+    k = 2.0 * np.pi * freq / C_LIGHT
+    g1 = E1 / M_E_GEV
+    beta1 = np.sqrt(1.0 - 1.0 / (g1 * g1))
+    r[5] = (X5 * E * beta0 / (E1 * beta1)
+            + V * beta0 / (E1 * beta1) * (np.cos(-X4 * beta0 * k + phi) - np.cos(phi)))
+    dgamma = V / M_E_GEV
+    dg = g1 - g0
+    if abs(dg) < 1e-8 * abs(g0):
+        if abs(np.cos(phi)) < 1e-3:
+            T556 = 1.5 * z * k * dgamma / (beta0 ** 3 * g0 ** 3)
+            T555 = 0.5 * z * k * k * dgamma * dgamma / (beta0 ** 3 * g0 ** 4)
+    else:
+        T566 = (z * (beta0 ** 3 * g0 ** 3 - beta1 ** 3 * g1 ** 3)
+                / (2.0 * beta0 * beta1 ** 3 * g0 * (g0 - g1) * g1 ** 3))
+        T556 = (beta0 * k * z * dgamma * g0 * (beta1 ** 3 * g1 ** 3 + beta0 * (g0 - g1 ** 3)) * np.sin(phi) /
+                (beta1 ** 3 * g1 ** 3 * (g0 - g1) ** 2))
+        T555 = (beta0 ** 2 * k ** 2 * z * dgamma / 2.0
+                * (dgamma * (2.0 * g0 * g1 ** 3 * (beta0 * beta1 ** 3 - 1.0)
+                             + g0 ** 2 + 3.0 * g1 ** 2 - 2.0) / (beta1 ** 3 * g1 ** 3 * (g0 - g1) ** 3) * np.sin(phi) ** 2
+                   - (g1 * g0 * (beta1 * beta0 - 1.0) + 1.0)
+                   / (beta1 * g1 * (g0 - g1) ** 2)
+                   * np.cos(phi)))
+    r[4] += T566 * X5 * X5 + T556 * X4 * X5 + T555 * X4 * X4
+    return delta_e
+
+
+def replay_recorded_maps(r, q, E, g, kick) -> float:
+    """Replay a fixture written by oracle/make_golden.py::golden_injector_track: per step the
+    recorded maps (kind 0 first order, 1 second order, 2 cavity body), then ``kick``.
+    Returns the final beam energy."""
+    map_step = np.asarray(g["map_step"])
+    for step, dz in enumerate(g["kick_dz"]):
+        for m in np.nonzero(map_step == step)[0]:
+            kind = int(g["kind"][m])
+            R, B = g["R"][m], g["B"][m]
+            if kind == 2:
+                v, phi, freq, dlen, length = g["cav"][m]
+                cavity_map(r, R, B, v, phi, freq, E, None if np.isnan(dlen) else dlen, length)
+            elif kind == 1:
+                T = g["T"][int(g["Tidx"][m])]
+                r[:] = np.matmul(R, r) + np.einsum('ijk,j...,k...->i...', T, r, r)
+                r[:] = np.add(r, B.reshape(6, 1))
+            else:
+                r[:] = np.add(np.dot(R, r), B.reshape(6, 1))
+            E += float(g["delta_e"][m])
+        if dz != 0:
+            kick(r, q, E, float(dz), g["nmesh"])
+    return E

@@ -88,3 +88,47 @@ def test_resident_tracking_moments(golden, fixture, second):
     for row in range(6):
         ref = g["r_final_sample"][row]
         assert np.max(np.abs(final[row] - ref)) / np.std(ref) < 1e-10
+
+
+def test_cavity_map_vs_oracle():
+    from ocelot_b200.beam import apply_cavity
+    rng = np.random.RandomState(5)
+    for (v, phi, freq, E, dlen, length) in ((0.02, 18.7, 1.3e9, 0.0065, 0.02, 1.0377), (0.0025, 180.0, 3.9e9, 0.15, None, 0.346),
+                                           (0.02, 90.0, 1.3e9, 0.1, 0.5, 1.0), (0.0, 0.0, 1.3e9, 0.05, 0.1, 1.0)):
+        r0, q0, _, dev = _device_bunch(50_001, 8, energy=E)
+        dev.rparticles[4] *= 1.0
+        R = np.eye(6) + rng.randn(6, 6) * 0.01
+        B = rng.randn(6) * 1e-7
+        ref = r0.copy()
+        de = orc.cavity_map(ref, R, B, v, phi, freq, E, dlen, length)
+        apply_cavity(dev, R, B, v, phi, freq, dlen, length)
+        got = dev.to_host().rparticles
+        assert np.max(np.abs(got - ref) / np.abs(ref).max(axis=1, keepdims=True)) < 1e-13
+        assert abs(dev.E - (E + de)) < 1e-15
+
+
+def test_reference_golden_test_on_device(golden):
+    """The reference's own golden test test_track_with_sp (space_charge_test.py:51-66): 16 RF cavities,
+    quadrupoles, second-order maps, 193 space-charge kicks at 63^3 -- replayed on the GPU from the maps
+    the reference used, particles never leaving HBM.  Checked against the reference's JSON golden
+    particles with that test's own tolerance (absolute 1e-12)."""
+    from ocelot_b200 import SpaceCharge, ParticleArray, DeviceParticleArray
+    from ocelot_b200.track import replay_recorded_maps
+    g = golden("track_injector_golden.npz")
+    host = ParticleArray(g["r0"].shape[1])
+    host.rparticles[:], host.q_array[:], host.E = g["r0"], g["q"], float(g["E0"])
+    dev = DeviceParticleArray.from_host(host)
+    sc = SpaceCharge(step=1, nmesh_xyz=[63, 63, 63])
+    sc.prepare(None)
+    replay_recorded_maps(dev, g, lambda step: sc)
+    got = dev.to_host().rparticles
+    assert abs(dev.E - float(g["E_final"])) < 1e-12
+    ref = g["reference_here_final"]
+    # after 193 kicks on a 10k-particle (shot-noise dominated) rho the reference run in the build
+    # container and the reference's own JSON golden differ by 1.3e-10 of the row rms (SURVEY 4, 8c);
+    # the device path is held to the same scale against both
+    for row in range(6):
+        assert np.max(np.abs(got[row] - ref[row])) / np.std(ref[row]) < 3e-10
+    self_agreement = np.max(np.abs(ref - g["json_golden_final"]))
+    assert np.max(np.abs(got - g["json_golden_final"])) < max(1e-12, 2 * self_agreement)
+    assert np.max(np.abs(got - g["json_golden_final"])) < 1e-12      # tolerance of space_charge_test.py:64

@@ -200,3 +200,19 @@ def test_moment_postprocessing_matches_oracle():
     t = moments_from_sums(sums, E=0.13, q=1e-9)
     assert t.emit_x == m["emit_x"] and t.emit_y == m["emit_y"]
     assert t.beta_x == m["xx"] / m["emit_x"] and t.alpha_y == -m["ypy"] / m["emit_y"]
+
+
+def test_reference_golden_test_replayed_by_oracle(golden):
+    """The reference's own golden test (test_track_with_sp: 16 cavities, quads, 193 SC kicks at 63^3)
+    replayed from its recorded maps by the oracle: pins the cavity-map restatement and the
+    whole chain against the reference run AND the reference's JSON golden particles."""
+    g = golden("track_injector_golden.npz")
+    r = g["r0"].copy()
+    E = orc.replay_recorded_maps(r, g["q"], float(g["E0"]), g,
+                                 lambda rr, qq, EE, dz, nm: orc.sc_kick(rr, qq, EE, dz, nm, fft="padded", workers=4))
+    assert abs(E - float(g["E_final"])) < 1e-12
+    ref = g["reference_here_final"]
+    for row in range(6):
+        assert np.max(np.abs(r[row] - ref[row])) / np.std(ref[row]) < 1e-10
+    # tolerance of the reference's own test: particles absolute 1e-12 (space_charge_test.py:64)
+    assert np.max(np.abs(r - g["json_golden_final"])) < 1e-12
