@@ -4,6 +4,9 @@ from .particles import ParticleArray, DeviceParticleArray
 from .sc import SpaceCharge, install
 from .beam import apply_map, get_envelope, Moments
 from .track import track, replay_track
+from .apertures import RectAperture, EllipticalAperture
+from .io import save_particle_array2npz, load_particle_array_from_npz
 
 __all__ = ["PhysProc", "ParticleArray", "DeviceParticleArray", "SpaceCharge", "install",
-           "apply_map", "get_envelope", "Moments", "track", "replay_track"]
+           "apply_map", "get_envelope", "Moments", "track", "replay_track",
+           "RectAperture", "EllipticalAperture", "save_particle_array2npz", "load_particle_array_from_npz"]

@@ -50,6 +50,11 @@ class ParticleArray:
     def p(self):
         return self.rparticles[5]
 
+    def delete_particles(self, inds, record=True):
+        """particle.py:323-333 (without the lost-particle recorder)."""
+        self.rparticles = np.delete(self.rparticles, inds, 1)
+        self.q_array = np.delete(self.q_array, inds, 0)
+
 
 class DeviceParticleArray:
     """Device-resident particles: ``rparticles`` is a (6, n) view into a
@@ -66,12 +71,19 @@ class DeviceParticleArray:
         self._n = int(n)
         self.s = 0.0
         self.E = 0.0
+        # lost-particle bookkeeping of the reference container (particle.py:24-45)
+        self.lost_particles = []
+        self.lp_to_pos_hist = []
+        self._current_particle = torch.arange(int(n), device=self.device)
 
     @property
     def n(self):
         return self._n
 
     def size(self):
+        return self._n
+
+    def __len__(self):
         return self._n
 
     @property
@@ -100,6 +112,28 @@ class DeviceParticleArray:
 
     def p(self):
         return self.rparticles[5]
+
+    def delete_particles(self, inds, record=True):
+        """Remove particles by index (or boolean mask), keeping the order of the survivors
+        (``ParticleArray.delete_particles``, beam/particle.py:323-333).  The buffer is compacted in place."""
+        import torch
+        inds = torch.as_tensor(inds, device=self.device)
+        keep = torch.ones(self._n, dtype=torch.bool, device=self.device)
+        if inds.dtype == torch.bool:
+            keep &= ~inds
+        elif inds.numel():
+            keep[inds.long()] = False
+        lost = torch.nonzero(~keep).flatten()
+        if record:
+            self.lost_particles += self._current_particle[lost].tolist()
+            self.lp_to_pos_hist.append((self.s, int(lost.numel())))
+            self._current_particle = self._current_particle[keep]
+        m = int(keep.sum().item())
+        if m == self._n:
+            return
+        self._buf[:, :m] = self._buf[:, :self._n][:, keep]
+        self._q[:m] = self._q[:self._n][keep]
+        self._n = m
 
     @classmethod
     def from_host(cls, p_array, device=None):
