@@ -99,6 +99,15 @@ int ocl_sc_collective_buffer(ocl_sc_t* h, int which, double** d_ptr, long long* 
  * handle's EXTENT_MAX / EXTENT_SUM buffers. */
 int ocl_sc_combine_extents(ocl_sc_t* h, const double* d_all, int world, void* stream);
 
+/* Fused scalar exchanges over NVLink peer memory, replacing the MOMENTUM all-reduce (which = 0) and
+ * the EXTENT all-gather + fold (which = 1) by one 32-thread kernel each: every rank passes the
+ * device pointers at which all `world` (<= 8) ranks' mailboxes (OCL_SC_MAILBOX_DOUBLES zeroed
+ * doubles of symmetric / IPC-mapped memory each) are mapped in ITS address space.  All ranks must
+ * issue the same sequence of exchanges. */
+#define OCL_SC_MAILBOX_DOUBLES 256
+int ocl_sc_mailbox_init(ocl_sc_t* h, int rank, int world, void* const* peer_ptrs);
+int ocl_sc_mailbox_exchange(ocl_sc_t* h, int which, void* stream);
+
 /* CUDA-graph support for callers that capture the staged kick themselves (e.g. together with
  * their NCCL collectives): with device params on, the stage kernels read E, dz and mesh draws
  * from a device block that ocl_sc_set_kick_params refreshes (a 1-block kernel, launched outside

@@ -50,6 +50,9 @@ struct ocl_sc {
     double* phi_slab = nullptr;
     double2* xchg_a = nullptr;
     double2* xchg_b = nullptr;
+    // peer-memory mailbox (multi-GPU scalar exchanges)
+    Mailbox mb{};
+    int* mb_err = nullptr;
     // host arrays page-locked in place on first use (numpy buffers persist across kicks)
     bool pin_host = true;
     void* pinned[2] = {nullptr, nullptr};
@@ -352,6 +355,7 @@ void ocl_sc_destroy(ocl_sc_t* h) {
     if (!h) return;
     cudaSetDevice(h->device);
     drop_graph(h);
+    cudaFree(h->mb.epoch); cudaFree(h->mb_err);
     for (int i = 0; i < 2; ++i) if (h->pinned[i]) cudaHostUnregister(h->pinned[i]);
     cudaGetLastError();
     cudaFree(h->kp_dev);
@@ -394,6 +398,32 @@ int ocl_sc_combine_extents(ocl_sc_t* h, const double* d_all, int world, void* st
     launch_combine_extents(d_all, world, h->rs, (cudaStream_t)stream);
     h->launches += 1;
     return check_launch(h, "k_combine_extents");
+}
+
+int ocl_sc_mailbox_init(ocl_sc_t* h, int rank, int world, void* const* peer_ptrs) {
+    if (!h || !peer_ptrs) return 1;
+    if (world < 1 || world > 8 || rank < 0 || rank >= world)
+        return fail(h, "ocl_sc_mailbox_init", "need 0 <= rank < world <= 8");
+    if (set_device(h)) return 1;
+    for (int w = 0; w < 8; ++w) h->mb.peer[w] = (w < world) ? (double*)peer_ptrs[w] : nullptr;
+    h->mb.rank = rank; h->mb.world = world;
+    if (!h->mb.epoch) {
+        CU(h, cudaMalloc(&h->mb.epoch, sizeof(unsigned long long) * 2));
+        CU(h, cudaMalloc(&h->mb_err, sizeof(int)));
+    }
+    CU(h, cudaMemset(h->mb.epoch, 0, sizeof(unsigned long long) * 2));
+    CU(h, cudaMemset(h->mb_err, 0, sizeof(int)));
+    return 0;
+}
+
+int ocl_sc_mailbox_exchange(ocl_sc_t* h, int which, void* stream) {
+    if (!h) return 1;
+    if (!h->mb.world) return fail(h, "ocl_sc_mailbox_exchange", "call ocl_sc_mailbox_init first");
+    if (which != 0 && which != 1) return fail(h, "ocl_sc_mailbox_exchange", "which must be 0 or 1");
+    if (set_device(h)) return 1;
+    launch_mailbox_exchange(h->mb, which, h->rs, h->mb_err, (cudaStream_t)stream);
+    h->launches += 1;
+    return check_launch(h, "k_mailbox_exchange");
 }
 
 int ocl_sc_use_device_params(ocl_sc_t* h, int on) {

@@ -466,6 +466,60 @@ constexpr int kGridCap = 148 * 16;    // grid kernels
 __global__ void k_set_params(KickParams v, KickParams* dst) {
     if (threadIdx.x == 0 && blockIdx.x == 0) *dst = v;
 }
+// ---------------------------------------------------------------------------
+// Fused exchange over NVLink peer memory (replaces an NCCL all-reduce / all-gather of a handful of
+// doubles): lane w stores this rank's values into rank w's mailbox, fences, raises its epoch flag
+// there; then waits for rank w's flag in the local mailbox; lane 0 folds the W slots in rank order
+// (bit-identical result on every rank) into the handle's reduced buffers.
+//   which 0: momentum {sum px, py, pz, count}        -> SUM
+//   which 1: extents  {max x6} MAX, {sum q x3, q} SUM
+// Slots are single-buffered: a rank can only push exchange e+1 after it has consumed everyone's
+// exchange e of the *other* kind, which in turn requires everyone to have consumed this kind's e.
+// ---------------------------------------------------------------------------
+__global__ void k_mailbox_exchange(Mailbox mb, int which, ReduceState rs, int* __restrict__ err_flag) {
+    const int lane = threadIdx.x;
+    const int nv = which == 0 ? 4 : 10;
+    const int vbase = which == 0 ? 0 : 32;
+    const int fbase = which == 0 ? 128 : 136;
+    const double* local_vals = which == 0 ? rs.sums : rs.emax;          // emax[6] and esum[4] are contiguous
+    const unsigned long long epoch = mb.epoch[which] + 1;
+    if (lane < mb.world) {
+        double* dst = mb.peer[lane] + vbase + mb.rank * nv;
+        for (int k = 0; k < nv; ++k) dst[k] = local_vals[k];
+        __threadfence_system();
+        volatile unsigned long long* flag = reinterpret_cast<unsigned long long*>(mb.peer[lane] + fbase) + mb.rank;
+        *flag = epoch;
+        // wait for rank `lane` to have delivered its values here
+        volatile unsigned long long* mine = reinterpret_cast<unsigned long long*>(mb.peer[mb.rank] + fbase) + lane;
+        const long long t0 = clock64();
+        while (*mine < epoch) {
+            if (clock64() - t0 > 8000000000LL) { atomicExch(err_flag, 1 + which); break; }   // ~4 s: a peer is gone
+        }
+        __threadfence_system();
+    }
+    __syncwarp();
+    if (lane == 0) {
+        const volatile double* box = mb.peer[mb.rank] + vbase;
+        double v[10];
+        for (int k = 0; k < nv; ++k) v[k] = box[k];
+        for (int w = 1; w < mb.world; ++w)
+            for (int k = 0; k < nv; ++k) {
+                const double x = box[w * nv + k];
+                v[k] = (which == 1 && k < 6) ? fmax(v[k], x) : v[k] + x;
+            }
+        if (which == 0) {
+            for (int k = 0; k < 4; ++k) rs.sums[k] = v[k];
+        } else {
+            for (int k = 0; k < 6; ++k) rs.emax[k] = v[k];
+            for (int k = 0; k < 4; ++k) rs.esum[k] = v[6 + k];
+        }
+        mb.epoch[which] = epoch;
+    }
+}
+void launch_mailbox_exchange(Mailbox mb, int which, ReduceState rs, int* err_flag, cudaStream_t st) {
+    k_mailbox_exchange<<<1, 32, 0, st>>>(mb, which, rs, err_flag);
+}
+
 // fold all-gathered extents: max over ranks of the first 6 doubles, sum of the last 4
 __global__ void k_combine_extents(const double* __restrict__ all, int world, double* __restrict__ emax,
                                   double* __restrict__ esum) {

@@ -22,6 +22,20 @@ struct MeshDims {
     int mx, my, mz;   // padded FFT lengths
 };
 
+// Peer-memory mailbox for the two scalar exchanges of a particle-sharded kick: every rank owns one
+// small symmetric buffer that all ranks have mapped (NVLink/NVSwitch peer access).
+//   doubles [0,32)    momentum slots   (4 per source rank)
+//   doubles [32,112)  extent slots     (10 per source rank)
+//   doubles [128,136) momentum flags   (one 64-bit epoch per source rank)
+//   doubles [136,144) extent flags
+struct Mailbox {
+    double* peer[8];                 // this mailbox as mapped on every rank (peer[rank] is the local one)
+    unsigned long long* epoch;       // local device counters {momentum, extent}
+    int rank, world;
+};
+constexpr int kMailboxDoubles = 256;
+void launch_mailbox_exchange(Mailbox mb, int which, ReduceState rs, int* err_flag, cudaStream_t st);
+
 int particle_grid(long long n, int max_blocks);
 
 void launch_set_params(KickParams v, KickParams* dst, cudaStream_t st);

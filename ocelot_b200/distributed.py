@@ -61,6 +61,25 @@ class NativeStageEngine:
                                 ("phi", native.BUF_PHI)):
                 self.buffers[name] = self.solver.collective_buffer(which)
         self._gathered = None
+        self.mailbox = None
+
+    def setup_mailbox(self, dist, group):
+        """Map one small symmetric buffer per rank into every rank (torch symmetric memory over
+        NVLink peer access) and hand the peer pointers to the native handle: the two scalar
+        exchanges then run as one tiny kernel each instead of an NCCL collective."""
+        import torch
+        import torch.distributed._symmetric_memory as symm
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+        if world > 8:
+            return False
+        box = symm.empty(self.solver.MAILBOX_DOUBLES, dtype=torch.float64, device=self.buffers["rho"].device)
+        box.zero_()
+        hdl = symm.rendezvous(box, group=group if group is not None else dist.group.WORLD)
+        torch.cuda.synchronize()
+        dist.barrier(group=group)
+        self.solver.mailbox_init(rank, world, list(hdl.buffer_ptrs))
+        self.mailbox = (box, hdl)              # keep the mapping alive
+        return True
 
     def solve_slab(self, dist, group, draws):
         """Slab-decomposed solve: rho (local partial sums, nx_pad planes) -> field table."""
@@ -110,11 +129,16 @@ def sharded_kick(engine, r, q, E_GeV, dz, draws=None, group=None, dist=None):
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     SUM, MAX = dist.ReduceOp.SUM, dist.ReduceOp.MAX
     b = engine.buffers
+    fused = multi and getattr(engine, "mailbox", None) is not None
     engine.momentum(r, q, E_GeV)
-    if multi:
+    if fused:
+        engine.solver.mailbox_exchange(0)
+    elif multi:
         dist.all_reduce(b["momentum"], op=SUM, group=group)
     engine.extent(r, q, E_GeV)
-    if multi:
+    if fused:
+        engine.solver.mailbox_exchange(1)
+    elif multi:
         if hasattr(engine, "combine_extents"):
             engine.combine_extents(dist, group)
         else:
@@ -143,6 +167,7 @@ class ShardedSpaceCharge:
         self.random_seed = 10
         self.group = group
         self.slab = slab          # None: automatic (by mesh size); True / False: forced
+        self.p2p = True           # scalar exchanges through NVLink peer memory instead of NCCL
         self.use_graph = True
         self._engine = None
         self._graph = None
@@ -165,6 +190,12 @@ class ShardedSpaceCharge:
             if want and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
                 slab = (dist.get_rank(self.group), dist.get_world_size(self.group))
             self._engine = NativeStageEngine(r.device.index or 0, key, slab=slab)
+            if self.p2p and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+                try:
+                    self._engine.setup_mailbox(dist, self.group)
+                except Exception as exc:  # noqa: BLE001  (no symmetric memory: stay on NCCL)
+                    import logging
+                    logging.getLogger(__name__).warning("peer-memory mailbox unavailable (%s); using NCCL", exc)
             self._graph, self._graph_key = None, None
         draws = None
         if self.random_mesh:
