@@ -107,6 +107,12 @@ int ocl_sc_combine_extents(ocl_sc_t* h, const double* d_all, int world, void* st
 #define OCL_SC_MAILBOX_DOUBLES 256
 int ocl_sc_mailbox_init(ocl_sc_t* h, int rank, int world, void* const* peer_ptrs);
 int ocl_sc_mailbox_exchange(ocl_sc_t* h, int which, void* stream);
+/* Fused reduction of the charge grid: the handle deposits into peer_rho[rank] (caller-owned symmetric
+ * memory of at least the RHO buffer's size, mapped on every rank) and, after
+ * ocl_sc_mailbox_exchange(h, 2, stream) -- a barrier: every rank's deposit is complete -- the first FFT
+ * pass of ocl_sc_stage_solve / ocl_sc_slab_forward sums the `world` grids in rank order while loading
+ * them over NVLink.  Replaces the all-reduce (or reduce-scatter) of RHO; no separate reduction kernel. */
+int ocl_sc_set_peer_rho(ocl_sc_t* h, int rank, int world, void* const* peer_rho);
 
 /* CUDA-graph support for callers that capture the staged kick themselves (e.g. together with
  * their NCCL collectives): with device params on, the stage kernels read E, dz and mesh draws

@@ -53,6 +53,8 @@ struct ocl_sc {
     // peer-memory mailbox (multi-GPU scalar exchanges)
     Mailbox mb{};
     int* mb_err = nullptr;
+    PeerRho peer_rho{};                       // world > 0: rho lives in caller-owned symmetric memory
+    double* own_rho = nullptr;                // the cudaMalloc'ed grid (kept for freeing)
     // host arrays page-locked in place on first use (numpy buffers persist across kicks)
     bool pin_host = true;
     void* pinned[2] = {nullptr, nullptr};
@@ -206,7 +208,7 @@ int make_twiddles(ocl_sc* h, int M, double2** out) {
 // If the K_hat chain was forked onto the side stream (khat_pending), join it before the x pass.
 int solve_fused(ocl_sc* h, cudaStream_t st) {
     if (!h->khat_pending) launch_khat(h->gtab, h->md, h->fw, st);
-    launch_convolve_pre(h->rho, h->md, h->fw, st);
+    launch_convolve_pre(h->rho, h->peer_rho, h->md, h->fw, st);
     if (h->khat_pending) {
         CU(h, cudaStreamWaitEvent(st, h->ev_khat, 0));
         h->khat_pending = false;
@@ -361,7 +363,7 @@ void ocl_sc_destroy(ocl_sc_t* h) {
     cudaFree(h->kp_dev);
     if (h->plans) { cufftDestroy(h->plan_fwd); cufftDestroy(h->plan_inv); }
     cudaFree(h->rs.part); cudaFree(h->rs.ticket); cudaFree(h->rs.sums);
-    cudaFree(h->rho); cudaFree(h->gtab); cudaFree(h->k1); cudaFree(h->real_buf);
+    cudaFree(h->own_rho ? h->own_rho : h->rho); cudaFree(h->gtab); cudaFree(h->k1); cudaFree(h->real_buf);
     cudaFree(h->k_hat); cudaFree(h->rho_hat); cudaFree(h->phi); cudaFree(h->equad);
     cudaFree(h->fw.P); cudaFree(h->fw.Q); cudaFree(h->fw.khat); cudaFree(h->fw.A); cudaFree(h->fw.B);
     cudaFree(h->tw[0]); cudaFree(h->tw[1]); cudaFree(h->tw[2]); cudaFree(h->h3); cudaFree(h->moments);
@@ -408,10 +410,10 @@ int ocl_sc_mailbox_init(ocl_sc_t* h, int rank, int world, void* const* peer_ptrs
     for (int w = 0; w < 8; ++w) h->mb.peer[w] = (w < world) ? (double*)peer_ptrs[w] : nullptr;
     h->mb.rank = rank; h->mb.world = world;
     if (!h->mb.epoch) {
-        CU(h, cudaMalloc(&h->mb.epoch, sizeof(unsigned long long) * 2));
+        CU(h, cudaMalloc(&h->mb.epoch, sizeof(unsigned long long) * 4));
         CU(h, cudaMalloc(&h->mb_err, sizeof(int)));
     }
-    CU(h, cudaMemset(h->mb.epoch, 0, sizeof(unsigned long long) * 2));
+    CU(h, cudaMemset(h->mb.epoch, 0, sizeof(unsigned long long) * 4));
     CU(h, cudaMemset(h->mb_err, 0, sizeof(int)));
     return 0;
 }
@@ -419,11 +421,25 @@ int ocl_sc_mailbox_init(ocl_sc_t* h, int rank, int world, void* const* peer_ptrs
 int ocl_sc_mailbox_exchange(ocl_sc_t* h, int which, void* stream) {
     if (!h) return 1;
     if (!h->mb.world) return fail(h, "ocl_sc_mailbox_exchange", "call ocl_sc_mailbox_init first");
-    if (which != 0 && which != 1) return fail(h, "ocl_sc_mailbox_exchange", "which must be 0 or 1");
+    if (which < 0 || which > 2) return fail(h, "ocl_sc_mailbox_exchange", "which must be 0, 1 or 2");
     if (set_device(h)) return 1;
     launch_mailbox_exchange(h->mb, which, h->rs, h->mb_err, (cudaStream_t)stream);
     h->launches += 1;
     return check_launch(h, "k_mailbox_exchange");
+}
+
+int ocl_sc_set_peer_rho(ocl_sc_t* h, int rank, int world, void* const* peer_rho) {
+    if (!h || !peer_rho) return 1;
+    if (world < 1 || world > 8 || rank < 0 || rank >= world)
+        return fail(h, "ocl_sc_set_peer_rho", "need 0 <= rank < world <= 8");
+    if (set_device(h)) return 1;
+    drop_graph(h);
+    if (!h->own_rho) h->own_rho = h->rho;
+    for (int w = 0; w < 8; ++w) h->peer_rho.p[w] = (w < world) ? (const double*)peer_rho[w] : nullptr;
+    h->peer_rho.world = world;
+    h->rho = (double*)peer_rho[rank];
+    CU(h, cudaMemset(h->rho, 0, sizeof(double) * h->rho_count));
+    return 0;
 }
 
 int ocl_sc_use_device_params(ocl_sc_t* h, int on) {
@@ -455,7 +471,8 @@ int ocl_sc_slab_init(ocl_sc_t* h, int rank, int world) {
     h->nx_pad = h->sx * world;
     h->fs = (F + world - 1) / world;
     const size_t plane = (size_t)h->md.ny * h->md.nz;
-    cudaFree(h->rho); cudaFree(h->phi);
+    cudaFree(h->own_rho ? h->own_rho : h->rho); cudaFree(h->phi);
+    h->own_rho = nullptr; h->peer_rho.world = 0;
     cudaFree(h->rho_slab); cudaFree(h->phi_slab); cudaFree(h->xchg_a); cudaFree(h->xchg_b);
     h->rho = h->phi = h->rho_slab = h->phi_slab = nullptr; h->xchg_a = h->xchg_b = nullptr;
     h->rho_count = (size_t)h->nx_pad * plane;
@@ -477,7 +494,8 @@ int ocl_sc_slab_forward(ocl_sc_t* h, void* stream) {
     if (set_device(h)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     h->last_stream = st;
-    launch_slab_forward(h->rho_slab, h->md, h->sx, h->fs, h->fw, h->xchg_a, st);
+    launch_slab_forward(h->rho_slab, h->peer_rho, (long long)h->slab_rank * h->sx * h->md.ny, h->md, h->sx, h->fs, h->fw,
+                        h->xchg_a, st);
     h->launches += 2;
     return check_launch(h, "slab_forward");
 }

@@ -25,7 +25,8 @@
 
 namespace ocl {
 
-constexpr int kFftThreads = 128;
+// threads per block: 128, except M = 512 where one block per SM is resident (147 KB of shared
+// memory) and 256 threads keep 8 warps on it
 
 // Shared-memory layout: complex point o of line l lives at x[o * NLP + l] with
 // NLP = NL + 1.  Lines run across lanes, so every butterfly stage reads and
@@ -34,7 +35,12 @@ constexpr int kFftThreads = 128;
 // (lanes along o) conflict-free per quarter-warp as well.
 template <int M>
 struct Geom {
-    static constexpr int NL = (M >= 256) ? 8 : ((2048 / M) > 32 ? 32 : (2048 / M));   // lines per block
+#ifndef OCL_FFT512_NL
+#define OCL_FFT512_NL 8
+#define OCL_FFT512_T 256
+#endif
+    static constexpr int T = (M >= 512) ? OCL_FFT512_T : 128;                           // threads per block
+    static constexpr int NL = (M >= 512) ? OCL_FFT512_NL : (M >= 256) ? 8 : ((2048 / M) > 32 ? 32 : (2048 / M));   // lines per block
     static constexpr int NLP = NL + 1;
     static constexpr int ELEMS = M * NLP;
     static constexpr size_t SMEM = sizeof(double2) * (2 * (size_t)ELEMS);
@@ -136,7 +142,7 @@ __device__ __forceinline__ void fft_stage(const double2* __restrict__ x, double2
     constexpr int nb = M / R;
     constexpr int step = M / (Ns * R);
     constexpr int total = nb * NL;
-    for (int t = threadIdx.x; t < total; t += kFftThreads) {
+    for (int t = threadIdx.x; t < total; t += Geom<M>::T) {
         const int j = t / NL, l = t % NL;       // NL is a power of two: shift / mask
         const int k = j & (Ns - 1);
         double2 v[R];
@@ -197,16 +203,16 @@ __device__ __forceinline__ double green_entry_dev(const double* __restrict__ G, 
 // out P[a][b][kz], kz <= Mz/2 (real).
 // ---------------------------------------------------------------------------
 template <int M>
-__global__ void __launch_bounds__(kFftThreads) k_khat_z(const double* __restrict__ gtab, MeshDims md,
+__global__ void __launch_bounds__(Geom<M>::T) k_khat_z(const double* __restrict__ gtab, MeshDims md,
                                                        const double2* __restrict__ tw_g, double* __restrict__ P) {
     constexpr int NL = Geom<M>::NL, NLP = Geom<M>::NLP, H = M / 2;
     const int n = md.nz;
     FftSmem<M> s = fft_smem<M>(tw_g);
     const int nlines = md.nx * md.ny;
     const int line0 = blockIdx.x * (2 * NL);              // 2 real lines per complex line
-    for (int t = threadIdx.x; t < M * NLP; t += kFftThreads) s.a[t] = make_double2(0.0, 0.0);
+    for (int t = threadIdx.x; t < M * NLP; t += Geom<M>::T) s.a[t] = make_double2(0.0, 0.0);
     __syncthreads();
-    for (int t = threadIdx.x; t < NL * n; t += kFftThreads) {
+    for (int t = threadIdx.x; t < NL * n; t += Geom<M>::T) {
         const int p = t / n, c = t - p * n;               // c fastest: contiguous table reads
         const int l1 = line0 + 2 * p, l2 = l1 + 1;
         if (l1 >= nlines) continue;
@@ -216,7 +222,7 @@ __global__ void __launch_bounds__(kFftThreads) k_khat_z(const double* __restrict
         if (c) s.a[(M - c) * NLP + p] = make_double2(e1, e2);
     }
     double2* X = block_fft<false, M>(s.a, s.b, s.tw);
-    for (int t = threadIdx.x; t < NL * (H + 1); t += kFftThreads) {
+    for (int t = threadIdx.x; t < NL * (H + 1); t += Geom<M>::T) {
         const int p = t / (H + 1), kz = t - p * (H + 1);
         const int l1 = line0 + 2 * p, l2 = l1 + 1;
         if (l1 >= nlines) continue;
@@ -232,7 +238,7 @@ __global__ void __launch_bounds__(kFftThreads) k_khat_z(const double* __restrict
 // per complex FFT.
 // ---------------------------------------------------------------------------
 template <int M>
-__global__ void __launch_bounds__(kFftThreads) k_real_even_outer(const double* __restrict__ in,
+__global__ void __launch_bounds__(Geom<M>::T) k_real_even_outer(const double* __restrict__ in,
                                                                 double* __restrict__ out, int n, int inner,
                                                                 const double2* __restrict__ tw_g) {
     constexpr int NL = Geom<M>::NL, NLP = Geom<M>::NLP, H = M / 2;
@@ -244,12 +250,12 @@ __global__ void __launch_bounds__(kFftThreads) k_real_even_outer(const double* _
     const int pairs = min(NL, pairs_total - pair0);
     const double* src = in + (size_t)batch * n * inner;
     double* dst = out + (size_t)batch * (H + 1) * inner;
-    for (int t = threadIdx.x; t < M * NLP; t += kFftThreads) s.a[t] = make_double2(0.0, 0.0);
+    for (int t = threadIdx.x; t < M * NLP; t += Geom<M>::T) s.a[t] = make_double2(0.0, 0.0);
     __syncthreads();
     {   // p fastest: adjacent inner indices; U independent load pairs in flight per thread
         constexpr int U = 4;
         const int p = threadIdx.x % NL, o0 = threadIdx.x / NL;
-        constexpr int OSTEP = kFftThreads / NL;
+        constexpr int OSTEP = Geom<M>::T / NL;
         const int f = 2 * (pair0 + p);
         const bool live = p < pairs, two = f + 1 < inner;
         for (int ob = o0; ob < n; ob += U * OSTEP) {
@@ -272,7 +278,7 @@ __global__ void __launch_bounds__(kFftThreads) k_real_even_outer(const double* _
         }
     }
     double2* X = block_fft<false, M>(s.a, s.b, s.tw);
-    for (int t = threadIdx.x; t < NL * (H + 1); t += kFftThreads) {
+    for (int t = threadIdx.x; t < NL * (H + 1); t += Geom<M>::T) {
         const int ko = t / NL, p = t % NL;
         if (p >= pairs) continue;
         const int f = 2 * (pair0 + p);
@@ -286,35 +292,47 @@ __global__ void __launch_bounds__(kFftThreads) k_real_even_outer(const double* _
 // rho, pass z: real lines rho[l][k<nz] zero-padded to Mz, two per complex FFT,
 // separated by Hermitian symmetry.  out A[l][kz], kz <= Mz/2 (complex).
 // ---------------------------------------------------------------------------
+// With pr.world > 0 the load is the fused all-reduce of the charge grid: every value is the sum, in
+// rank order, of the W ranks' partial grids read through NVLink peer mappings (line_offset selects this
+// rank's x-slab in slab mode).
 template <int M>
-__global__ void __launch_bounds__(kFftThreads) k_rho_z(const double* __restrict__ rho, MeshDims md,
-                                                      const double2* __restrict__ tw_g, double2* __restrict__ A) {
+__global__ void __launch_bounds__(Geom<M>::T) k_rho_z(const double* __restrict__ rho, PeerRho pr, long long line_offset,
+                                                      MeshDims md, const double2* __restrict__ tw_g,
+                                                      double2* __restrict__ A) {
     constexpr int NL = Geom<M>::NL, NLP = Geom<M>::NLP, H = M / 2;
     const int n = md.nz;
     FftSmem<M> s = fft_smem<M>(tw_g);
     const int nlines = md.nx * md.ny;
     const int line0 = blockIdx.x * (2 * NL);
     {   // k fastest: contiguous reads of rho; U independent loads in flight per thread
-        constexpr int PER = NL * M / kFftThreads, U = PER < 8 ? PER : 8;
+        constexpr int PER = NL * M / Geom<M>::T, U = PER < 8 ? PER : 8;
         for (int c = 0; c < PER; c += U) {
             double a[U], b[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int t = threadIdx.x + (c + u) * kFftThreads;
+                const int t = threadIdx.x + (c + u) * Geom<M>::T;
                 const int p = t / M, k = t % M;
                 const int l1 = line0 + 2 * p, l2 = l1 + 1;
-                a[u] = (k < n && l1 < nlines) ? __ldg(rho + (size_t)l1 * n + k) : 0.0;
-                b[u] = (k < n && l2 < nlines) ? __ldg(rho + (size_t)l2 * n + k) : 0.0;
+                a[u] = 0.0; b[u] = 0.0;
+                if (pr.world == 0) {
+                    if (k < n && l1 < nlines) a[u] = __ldg(rho + (size_t)l1 * n + k);
+                    if (k < n && l2 < nlines) b[u] = __ldg(rho + (size_t)l2 * n + k);
+                } else if (k < n) {
+                    for (int w = 0; w < pr.world; ++w) {
+                        if (l1 < nlines) a[u] += __ldcg(pr.p[w] + (size_t)(line_offset + l1) * n + k);
+                        if (l2 < nlines) b[u] += __ldcg(pr.p[w] + (size_t)(line_offset + l2) * n + k);
+                    }
+                }
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int t = threadIdx.x + (c + u) * kFftThreads;
+                const int t = threadIdx.x + (c + u) * Geom<M>::T;
                 s.a[(t % M) * NLP + t / M] = make_double2(a[u], b[u]);
             }
         }
     }
     double2* Z = block_fft<false, M>(s.a, s.b, s.tw);
-    for (int t = threadIdx.x; t < NL * (H + 1); t += kFftThreads) {
+    for (int t = threadIdx.x; t < NL * (H + 1); t += Geom<M>::T) {
         const int p = t / (H + 1), kz = t - p * (H + 1);
         const int l1 = line0 + 2 * p, l2 = l1 + 1;
         if (l1 >= nlines) continue;
@@ -335,7 +353,7 @@ __global__ void __launch_bounds__(kFftThreads) k_rho_z(const double* __restrict_
 // For MODE 2 inner = My*(Mz/2+1) and khat is [Mx/2+1][My/2+1][Mz/2+1].
 // ---------------------------------------------------------------------------
 template <int M, int MODE>
-__global__ void __launch_bounds__(kFftThreads) k_cplx_outer(const double2* in, double2* out,   // may alias (MODE 2)
+__global__ void __launch_bounds__(Geom<M>::T) k_cplx_outer(const double2* in, double2* out,   // may alias (MODE 2)
                                                            int n_in, int n_out, int inner,
                                                            const double2* __restrict__ tw_g,
                                                            const double* __restrict__ khat, MeshDims md, SlabMap sm) {
@@ -351,10 +369,10 @@ __global__ void __launch_bounds__(kFftThreads) k_cplx_outer(const double2* in, d
     // chunk-layout address of element (x plane = batch, line f)
     auto chunk = [&](int f) -> size_t { return ((size_t)(f / sm.fs) * sm.sx + batch) * sm.fs + f % sm.fs; };
     {   // global -> shared, U independent 16-byte loads in flight per thread
-        constexpr int PER = NL * M / kFftThreads, U = PER < 8 ? PER : 8;
+        constexpr int PER = NL * M / Geom<M>::T, U = PER < 8 ? PER : 8;
         static_assert(PER % U == 0, "load batching");
         const int l = threadIdx.x % NL, o0 = threadIdx.x / NL;          // l fastest: adjacent inner indices
-        constexpr int OSTEP = kFftThreads / NL;
+        constexpr int OSTEP = Geom<M>::T / NL;
         const double2* col = src + l;
         for (int c = 0; c < PER; c += U) {
             double2 v[U];
@@ -381,7 +399,7 @@ __global__ void __launch_bounds__(kFftThreads) k_cplx_outer(const double2* in, d
             const int sy = min(ky, md.my - ky);
             const double* kcol = khat + (size_t)sy * hz1 + kz;
             const size_t kplane = (size_t)hy1 * hz1;
-            constexpr int KSTEP = kFftThreads / NL, KPER = M / KSTEP, KU = KPER < 8 ? KPER : 8;
+            constexpr int KSTEP = Geom<M>::T / NL, KPER = M / KSTEP, KU = KPER < 8 ? KPER : 8;
             const int kx0 = threadIdx.x / NL;
             for (int c = 0; c < KPER; c += KU) {
                 double gk[KU];
@@ -401,7 +419,7 @@ __global__ void __launch_bounds__(kFftThreads) k_cplx_outer(const double2* in, d
         double2* Y = (X == s.a) ? s.b : s.a;
         X = block_fft<true, M>(X, Y, s.tw);
     }
-    for (int t = threadIdx.x; t < NL * n_out; t += kFftThreads) {
+    for (int t = threadIdx.x; t < NL * n_out; t += Geom<M>::T) {
         const int o = t / NL, l = t % NL;
         if (l < nl) {
             if (sm.mode == 1) out[chunk(o * inner + f0 + l)] = X[o * NLP + l];
@@ -415,7 +433,7 @@ __global__ void __launch_bounds__(kFftThreads) k_cplx_outer(const double2* in, d
 // phi[l][k<nz] = value / (Mx My Mz) / (4 pi eps0 hx hy hz)   (sc.py:164,167)
 // ---------------------------------------------------------------------------
 template <int M>
-__global__ void __launch_bounds__(kFftThreads) k_inv_z(const double2* __restrict__ D, MeshDims md,
+__global__ void __launch_bounds__(Geom<M>::T) k_inv_z(const double2* __restrict__ D, MeshDims md,
                                                       const double2* __restrict__ tw_g, const double* __restrict__ hsrc,
                                                       double four_pi_eps0, double* __restrict__ phi) {
     constexpr int NL = Geom<M>::NL, NLP = Geom<M>::NLP, H = M / 2;
@@ -425,11 +443,11 @@ __global__ void __launch_bounds__(kFftThreads) k_inv_z(const double2* __restrict
     const int line0 = blockIdx.x * (2 * NL);
     {   // k fastest: contiguous reads of D; U independent load pairs in flight per thread
         constexpr int TOTAL = NL * (H + 1), U = 4;
-        for (int t0 = threadIdx.x; t0 < TOTAL; t0 += U * kFftThreads) {
+        for (int t0 = threadIdx.x; t0 < TOTAL; t0 += U * Geom<M>::T) {
             double2 d1[U], d2[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int t = t0 + u * kFftThreads;
+                const int t = t0 + u * Geom<M>::T;
                 const int p = t / (H + 1), k = t - p * (H + 1);
                 const int l1 = line0 + 2 * p, l2 = l1 + 1;
                 d1[u] = (t < TOTAL && l1 < nlines) ? D[(size_t)l1 * (H + 1) + k] : make_double2(0.0, 0.0);
@@ -437,7 +455,7 @@ __global__ void __launch_bounds__(kFftThreads) k_inv_z(const double2* __restrict
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const int t = t0 + u * kFftThreads;
+                const int t = t0 + u * Geom<M>::T;
                 if (t >= TOTAL) continue;
                 const int p = t / (H + 1), k = t - p * (H + 1);
                 s.a[k * NLP + p] = make_double2(d1[u].x - d2[u].y, d1[u].y + d2[u].x);          // d1 + i d2
@@ -449,7 +467,7 @@ __global__ void __launch_bounds__(kFftThreads) k_inv_z(const double2* __restrict
     double2* X = block_fft<true, M>(s.a, s.b, s.tw);
     const double inv_m3 = 1.0 / ((double)md.mx * (double)md.my * (double)md.mz);
     const double denom = four_pi_eps0 * hsrc[0] * hsrc[1] * hsrc[2];
-    for (int t = threadIdx.x; t < NL * n; t += kFftThreads) {
+    for (int t = threadIdx.x; t < NL * n; t += Geom<M>::T) {
         const int p = t / n, k = t - p * n;
         const int l1 = line0 + 2 * p, l2 = l1 + 1;
         if (l1 >= nlines) continue;
@@ -499,35 +517,35 @@ void launch_khat(const double* gtab, MeshDims md, FftWork w, cudaStream_t st) {
     OCL_FFT_DISPATCH(md.mz,   // z: P[nx][ny][hz1]
         const int lb = 2 * Geom<MM>::NL;
         const int blocks = (md.nx * md.ny + lb - 1) / lb;
-        k_khat_z<MM><<<blocks, kFftThreads, Geom<MM>::SMEM, st>>>(gtab, md, w.tw_z, w.P);
+        k_khat_z<MM><<<blocks, Geom<MM>::T, Geom<MM>::SMEM, st>>>(gtab, md, w.tw_z, w.P);
     )
     OCL_FFT_DISPATCH(md.my,   // y: per a, in [ny][hz1] -> Q[a][hy1][hz1]
         const int pb = Geom<MM>::NL;
         const int blocks_per_batch = ((hz1 + 1) / 2 + pb - 1) / pb;
-        k_real_even_outer<MM><<<blocks_per_batch * md.nx, kFftThreads, Geom<MM>::SMEM, st>>>(w.P, w.Q, md.ny, hz1,
+        k_real_even_outer<MM><<<blocks_per_batch * md.nx, Geom<MM>::T, Geom<MM>::SMEM, st>>>(w.P, w.Q, md.ny, hz1,
                                                                                            w.tw_y);
     )
     OCL_FFT_DISPATCH(md.mx,   // x: in [nx][hy1*hz1] -> khat[hx1][hy1*hz1]
         const int inner = hy1 * hz1;
         const int pb = Geom<MM>::NL;
         const int blocks = ((inner + 1) / 2 + pb - 1) / pb;
-        k_real_even_outer<MM><<<blocks, kFftThreads, Geom<MM>::SMEM, st>>>(w.Q, w.khat, md.nx, inner, w.tw_x);
+        k_real_even_outer<MM><<<blocks, Geom<MM>::T, Geom<MM>::SMEM, st>>>(w.Q, w.khat, md.nx, inner, w.tw_x);
     )
 }
 
 // phi = (rho (*) K) / (4 pi eps0 hx hy hz) on [0,n)^3, in two halves: the forward z and y
 // passes of rho do not need K_hat, so the caller can overlap them with the K_hat chain.
-void launch_convolve_pre(const double* rho, MeshDims md, FftWork w, cudaStream_t st) {
+void launch_convolve_pre(const double* rho, PeerRho pr, MeshDims md, FftWork w, cudaStream_t st) {
     const int hz1 = md.mz / 2 + 1;
     OCL_FFT_DISPATCH(md.mz,
         const int lbz = 2 * Geom<MM>::NL;
         const int zblocks = (md.nx * md.ny + lbz - 1) / lbz;
-        k_rho_z<MM><<<zblocks, kFftThreads, Geom<MM>::SMEM, st>>>(rho, md, w.tw_z, w.A);
+        k_rho_z<MM><<<zblocks, Geom<MM>::T, Geom<MM>::SMEM, st>>>(rho, pr, 0, md, w.tw_z, w.A);
     )
     OCL_FFT_DISPATCH(md.my,   // y forward: per i, [ny][hz1] -> [My][hz1]
         const int lb = Geom<MM>::NL;
         const int bpb = (hz1 + lb - 1) / lb;
-        k_cplx_outer<MM, 0><<<bpb * md.nx, kFftThreads, Geom<MM>::SMEM, st>>>(w.A, w.B, md.ny, md.my, hz1, w.tw_y,
+        k_cplx_outer<MM, 0><<<bpb * md.nx, Geom<MM>::T, Geom<MM>::SMEM, st>>>(w.A, w.B, md.ny, md.my, hz1, w.tw_y,
                                                                              nullptr, md, SlabMap{});
     )
 }
@@ -539,19 +557,19 @@ void launch_convolve_post(MeshDims md, FftWork w, const double* h3, double four_
         const int inner = md.my * hz1;
         const int lb = Geom<MM>::NL;
         const int blocks = (inner + lb - 1) / lb;
-        k_cplx_outer<MM, 2><<<blocks, kFftThreads, Geom<MM>::SMEM, st>>>(w.B, w.B, md.nx, md.nx, inner, w.tw_x, w.khat,
+        k_cplx_outer<MM, 2><<<blocks, Geom<MM>::T, Geom<MM>::SMEM, st>>>(w.B, w.B, md.nx, md.nx, inner, w.tw_x, w.khat,
                                                                         md, SlabMap{});
     )
     OCL_FFT_DISPATCH(md.my,   // y inverse: per i, [My][hz1] -> [ny][hz1]
         const int lb = Geom<MM>::NL;
         const int bpb = (hz1 + lb - 1) / lb;
-        k_cplx_outer<MM, 1><<<bpb * md.nx, kFftThreads, Geom<MM>::SMEM, st>>>(w.B, w.A, md.my, md.ny, hz1, w.tw_y,
+        k_cplx_outer<MM, 1><<<bpb * md.nx, Geom<MM>::T, Geom<MM>::SMEM, st>>>(w.B, w.A, md.my, md.ny, hz1, w.tw_y,
                                                                              nullptr, md, SlabMap{});
     )
     OCL_FFT_DISPATCH(md.mz,
         const int lbz = 2 * Geom<MM>::NL;
         const int zblocks = (md.nx * md.ny + lbz - 1) / lbz;
-        k_inv_z<MM><<<zblocks, kFftThreads, Geom<MM>::SMEM, st>>>(w.A, md, w.tw_z, h3, four_pi_eps0, phi);
+        k_inv_z<MM><<<zblocks, Geom<MM>::T, Geom<MM>::SMEM, st>>>(w.A, md, w.tw_z, h3, four_pi_eps0, phi);
     )
 }
 
@@ -559,21 +577,21 @@ void launch_convolve_post(MeshDims md, FftWork w, const double* h3, double four_
 // slab-decomposed solve: this rank owns sx x-planes of rho / phi and one chunk of fs (ky,kz)
 // lines of the x pass; the caller exchanges `xchg` between the calls (all-to-all).
 // ---------------------------------------------------------------------------
-void launch_slab_forward(const double* rho_slab, MeshDims md, int sx, int fs, FftWork w, double2* xchg,
-                         cudaStream_t st) {
+void launch_slab_forward(const double* rho_slab, PeerRho pr, long long line_offset, MeshDims md, int sx, int fs,
+                         FftWork w, double2* xchg, cudaStream_t st) {
     MeshDims ms = md;
     ms.nx = sx;
     const int hz1 = md.mz / 2 + 1;
     OCL_FFT_DISPATCH(md.mz,
         const int lbz = 2 * Geom<MM>::NL;
         const int zblocks = (sx * md.ny + lbz - 1) / lbz;
-        k_rho_z<MM><<<zblocks, kFftThreads, Geom<MM>::SMEM, st>>>(rho_slab, ms, w.tw_z, w.A);
+        k_rho_z<MM><<<zblocks, Geom<MM>::T, Geom<MM>::SMEM, st>>>(rho_slab, pr, line_offset, ms, w.tw_z, w.A);
     )
     SlabMap sm{1, fs, sx, 0, 0};
     OCL_FFT_DISPATCH(md.my,   // y forward, stored in chunk layout for the all-to-all
         const int lb = Geom<MM>::NL;
         const int bpb = (hz1 + lb - 1) / lb;
-        k_cplx_outer<MM, 0><<<bpb * sx, kFftThreads, Geom<MM>::SMEM, st>>>(w.A, xchg, md.ny, md.my, hz1, w.tw_y,
+        k_cplx_outer<MM, 0><<<bpb * sx, Geom<MM>::T, Geom<MM>::SMEM, st>>>(w.A, xchg, md.ny, md.my, hz1, w.tw_y,
                                                                           nullptr, md, sm);
     )
 }
@@ -584,7 +602,7 @@ void launch_slab_xpass(double2* xchg, MeshDims md, int fs, int f_base, FftWork w
     OCL_FFT_DISPATCH(md.mx,   // x: forward, * K_hat, inverse on this rank's chunk of lines, [nx_pad][fs] in place
         const int lb = Geom<MM>::NL;
         const int blocks = (fs + lb - 1) / lb;
-        k_cplx_outer<MM, 2><<<blocks, kFftThreads, Geom<MM>::SMEM, st>>>(xchg, xchg, md.nx, md.nx, fs, w.tw_x, w.khat,
+        k_cplx_outer<MM, 2><<<blocks, Geom<MM>::T, Geom<MM>::SMEM, st>>>(xchg, xchg, md.nx, md.nx, fs, w.tw_x, w.khat,
                                                                         md, sm);
     )
 }
@@ -598,13 +616,13 @@ void launch_slab_inverse(const double2* xchg, MeshDims md, int sx, int fs, FftWo
     OCL_FFT_DISPATCH(md.my,   // y inverse, read from chunk layout
         const int lb = Geom<MM>::NL;
         const int bpb = (hz1 + lb - 1) / lb;
-        k_cplx_outer<MM, 1><<<bpb * sx, kFftThreads, Geom<MM>::SMEM, st>>>(xchg, w.A, md.my, md.ny, hz1, w.tw_y,
+        k_cplx_outer<MM, 1><<<bpb * sx, Geom<MM>::T, Geom<MM>::SMEM, st>>>(xchg, w.A, md.my, md.ny, hz1, w.tw_y,
                                                                           nullptr, md, sm);
     )
     OCL_FFT_DISPATCH(md.mz,
         const int lbz = 2 * Geom<MM>::NL;
         const int zblocks = (sx * md.ny + lbz - 1) / lbz;
-        k_inv_z<MM><<<zblocks, kFftThreads, Geom<MM>::SMEM, st>>>(w.A, ms, w.tw_z, h3, four_pi_eps0, phi_slab);
+        k_inv_z<MM><<<zblocks, Geom<MM>::T, Geom<MM>::SMEM, st>>>(w.A, ms, w.tw_z, h3, four_pi_eps0, phi_slab);
     )
 }
 

@@ -478,9 +478,9 @@ __global__ void k_set_params(KickParams v, KickParams* dst) {
 // ---------------------------------------------------------------------------
 __global__ void k_mailbox_exchange(Mailbox mb, int which, ReduceState rs, int* __restrict__ err_flag) {
     const int lane = threadIdx.x;
-    const int nv = which == 0 ? 4 : 10;
+    const int nv = which == 0 ? 4 : (which == 1 ? 10 : 0);      // which 2: barrier only ("rho ready")
     const int vbase = which == 0 ? 0 : 32;
-    const int fbase = which == 0 ? 128 : 136;
+    const int fbase = 128 + 8 * which;
     const double* local_vals = which == 0 ? rs.sums : rs.emax;          // emax[6] and esum[4] are contiguous
     const unsigned long long epoch = mb.epoch[which] + 1;
     if (lane < mb.world) {
@@ -498,7 +498,8 @@ __global__ void k_mailbox_exchange(Mailbox mb, int which, ReduceState rs, int* _
         __threadfence_system();
     }
     __syncwarp();
-    if (lane == 0) {
+    if (lane == 0 && which == 2) mb.epoch[which] = epoch;
+    if (lane == 0 && which < 2) {
         const volatile double* box = mb.peer[mb.rank] + vbase;
         double v[10];
         for (int k = 0; k < nv; ++k) v[k] = box[k];

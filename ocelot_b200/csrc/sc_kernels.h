@@ -33,7 +33,13 @@ struct Mailbox {
     unsigned long long* epoch;       // local device counters {momentum, extent}
     int rank, world;
 };
+//   doubles [144,152) "rho ready" flags (barrier before the fused rho reduction)
 constexpr int kMailboxDoubles = 256;
+// the charge grids of all ranks, as mapped in this rank's address space (world == 0: local rho only)
+struct PeerRho {
+    const double* p[8];
+    int world;
+};
 void launch_mailbox_exchange(Mailbox mb, int which, ReduceState rs, int* err_flag, cudaStream_t st);
 
 int particle_grid(long long n, int max_blocks);
@@ -97,12 +103,12 @@ struct SlabMap {
 void fft_init_kernels();
 int fft_max_length();
 void launch_khat(const double* gtab, MeshDims md, FftWork w, cudaStream_t st);
-void launch_convolve_pre(const double* rho, MeshDims md, FftWork w, cudaStream_t st);
+void launch_convolve_pre(const double* rho, PeerRho pr, MeshDims md, FftWork w, cudaStream_t st);
 void launch_convolve_post(MeshDims md, FftWork w, const double* h3, double four_pi_eps0, double* phi,
                           cudaStream_t st);
 // slab-decomposed variants (this rank owns sx x-planes and one chunk of fs (ky,kz) lines)
-void launch_slab_forward(const double* rho_slab, MeshDims md, int sx, int fs, FftWork w, double2* xchg,
-                         cudaStream_t st);
+void launch_slab_forward(const double* rho_slab, PeerRho pr, long long line_offset, MeshDims md, int sx, int fs,
+                         FftWork w, double2* xchg, cudaStream_t st);
 void launch_slab_xpass(double2* xchg, MeshDims md, int fs, int f_base, FftWork w, cudaStream_t st);
 void launch_slab_inverse(const double2* xchg, MeshDims md, int sx, int fs, FftWork w, const double* h3,
                          double four_pi_eps0, double* phi_slab, cudaStream_t st);

@@ -62,8 +62,9 @@ class NativeStageEngine:
                 self.buffers[name] = self.solver.collective_buffer(which)
         self._gathered = None
         self.mailbox = None
+        self.peer_rho = None
 
-    def setup_mailbox(self, dist, group):
+    def setup_mailbox(self, dist, group, peer_rho=True):
         """Map one small symmetric buffer per rank into every rank (torch symmetric memory over
         NVLink peer access) and hand the peer pointers to the native handle: the two scalar
         exchanges then run as one tiny kernel each instead of an NCCL collective."""
@@ -79,12 +80,27 @@ class NativeStageEngine:
         dist.barrier(group=group)
         self.solver.mailbox_init(rank, world, list(hdl.buffer_ptrs))
         self.mailbox = (box, hdl)              # keep the mapping alive
+        # the charge grid itself also lives in symmetric memory: the first FFT pass then sums the
+        # ranks' grids while loading them over NVLink (no all-reduce / reduce-scatter kernel)
+        if peer_rho:
+            native = self._native
+            grid = symm.empty(self.buffers["rho"].numel(), dtype=torch.float64, device=box.device)
+            grid.zero_()
+            ghdl = symm.rendezvous(grid, group=group if group is not None else dist.group.WORLD)
+            torch.cuda.synchronize()
+            dist.barrier(group=group)
+            self.solver.set_peer_rho(rank, world, list(ghdl.buffer_ptrs))
+            self.buffers["rho"] = self.solver.collective_buffer(native.BUF_RHO)
+            self.peer_rho = (grid, ghdl)
         return True
 
     def solve_slab(self, dist, group, draws):
         """Slab-decomposed solve: rho (local partial sums, nx_pad planes) -> field table."""
         b, s = self.buffers, self.solver
-        dist.reduce_scatter_tensor(b["rho_slab"], b["rho"], op=dist.ReduceOp.SUM, group=group)
+        if self.peer_rho is not None:
+            s.mailbox_exchange(2)              # barrier: every rank's deposit is complete
+        else:
+            dist.reduce_scatter_tensor(b["rho_slab"], b["rho"], op=dist.ReduceOp.SUM, group=group)
         s.slab_forward()
         dist.all_to_all_single(b["xchg_b"], b["xchg_a"], group=group)
         s.slab_xpass()
@@ -148,7 +164,9 @@ def sharded_kick(engine, r, q, E_GeV, dz, draws=None, group=None, dist=None):
     if getattr(engine, "slab", None) is not None:
         engine.solve_slab(dist, group, draws)      # works for any world size >= 1
     else:
-        if multi:
+        if multi and getattr(engine, "peer_rho", None) is not None:
+            engine.solver.mailbox_exchange(2)      # barrier; the solve's first pass sums the peers' grids
+        elif multi:
             dist.all_reduce(b["rho"], op=SUM, group=group)
         engine.solve(draws)
     engine.kick(r, E_GeV, dz, draws)
@@ -168,6 +186,11 @@ class ShardedSpaceCharge:
         self.group = group
         self.slab = slab          # None: automatic (by mesh size); True / False: forced
         self.p2p = True           # scalar exchanges through NVLink peer memory instead of NCCL
+        # Opt-in: fuse the charge-grid reduction into the first FFT pass (peer loads of every rank's
+        # grid).  Correct (bit-identical to the NCCL path at W = 2) but measured 40 us SLOWER than the
+        # NCCL all-reduce at 1M / 63^3 on 2 x B200 (8-byte peer loads in a latency-bound 125-block
+        # kernel), so the default keeps NCCL (NVLS) for rho.
+        self.p2p_rho = False
         self.use_graph = True
         self._engine = None
         self._graph = None
@@ -192,7 +215,7 @@ class ShardedSpaceCharge:
             self._engine = NativeStageEngine(r.device.index or 0, key, slab=slab)
             if self.p2p and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
                 try:
-                    self._engine.setup_mailbox(dist, self.group)
+                    self._engine.setup_mailbox(dist, self.group, peer_rho=self.p2p_rho)
                 except Exception as exc:  # noqa: BLE001  (no symmetric memory: stay on NCCL)
                     import logging
                     logging.getLogger(__name__).warning("peer-memory mailbox unavailable (%s); using NCCL", exc)

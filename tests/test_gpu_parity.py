@@ -95,7 +95,7 @@ def test_fused_solver_matches_cufft(native, golden, monkeypatch):
     """The hand-written pruned/symmetric convolution (sc_fft.cu) against the plain
     cuFFT D2Z/Z2D convolution on the full padded box, same handle API."""
     rng = np.random.RandomState(7)
-    for shape in ((9, 12, 7), (31, 31, 31), (63, 63, 63), (20, 33, 64)):
+    for shape in ((9, 12, 7), (31, 31, 31), (63, 63, 63), (20, 33, 64), (130, 6, 70), (5, 257, 4)):
         rho = rng.rand(*shape) * 1e-12
         steps = np.array([1.1e-4, 0.7e-4, 2.3e-3])
         monkeypatch.delenv("OCL_SC_SOLVER", raising=False)

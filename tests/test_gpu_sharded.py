@@ -40,7 +40,7 @@ def test_sharded_wrapper_single_rank_equals_plugin():
     assert _row_err(b.to_host().rparticles, a.to_host().rparticles) < 1e-12
 
 
-def _worker(rank, world, port, n, nmesh, out, slab=False):
+def _worker(rank, world, port, n, nmesh, out, slab=False, p2p_rho=False):
     import torch.distributed as dist
     from ocelot_b200 import ParticleArray, DeviceParticleArray
     from ocelot_b200.distributed import ShardedSpaceCharge, shard_bounds
@@ -55,6 +55,7 @@ def _worker(rank, world, port, n, nmesh, out, slab=False):
         host.rparticles[:], host.q_array[:], host.E = r0[:, lo:hi], q0[lo:hi], E
         shard = DeviceParticleArray.from_host(host, device=f"cuda:{rank}")
         sc = ShardedSpaceCharge(nmesh_xyz=list(nmesh), slab=slab)
+        sc.p2p_rho = p2p_rho
         sc.prepare(None)
         for _ in range(2):
             sc.apply(shard, 0.1)
@@ -68,8 +69,8 @@ def _worker(rank, world, port, n, nmesh, out, slab=False):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("slab", [False, True])
-def test_two_gpu_sharded_kick_matches_single_gpu(slab):
+@pytest.mark.parametrize("slab,p2p_rho", [(False, False), (True, False), (False, True), (True, True)])
+def test_two_gpu_sharded_kick_matches_single_gpu(slab, p2p_rho):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     import torch.multiprocessing as mp
@@ -81,7 +82,7 @@ def test_two_gpu_sharded_kick_matches_single_gpu(slab):
     ctx = mp.get_context("spawn")
     with ctx.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_worker, args=(world, port, n, nmesh, out, slab), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, port, n, nmesh, out, slab, p2p_rho), nprocs=world, join=True)
         parts = [out[k] for k in range(world)]
     r0, q0, E = _bunch(n, 4)
     solver = native.Solver(0, nmesh)
