@@ -65,7 +65,8 @@ struct ocl_sc {
     long long stage_cap = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t side_stream = nullptr;       // K_hat chain runs here, concurrent with the deposit
-    cudaEvent_t ev_fork = nullptr, ev_khat = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_khat = nullptr, ev_handoff = nullptr;
+    bool last_stream_valid = false;
     bool khat_pending = false;
     cudaStream_t last_stream = nullptr;
     // whole-kick CUDA graph (single-GPU ocl_sc_kick_device): captured once per (r, ld, q, n),
@@ -170,6 +171,26 @@ void mark(ocl_sc* h, int slot, cudaStream_t st) {
 
 int set_device(ocl_sc* h) {
     CU(h, cudaSetDevice(h->device));
+    return 0;
+}
+
+// The handle's scratch (reduction buffers, grids, FFT work space) is shared by consecutive kicks.
+// When a call arrives on a different stream than the previous one, order it after the work
+// already queued there, so callers may alternate streams (e.g. a device-resident kick on the
+// caller's stream followed by a host-array kick on the handle's own stream).
+int adopt_stream(ocl_sc* h, cudaStream_t st) {
+    if (h->last_stream_valid && h->last_stream != st) {
+        cudaStreamCaptureStatus a = cudaStreamCaptureStatusNone, b = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(h->last_stream, &a);
+        cudaStreamIsCapturing(st, &b);
+        cudaGetLastError();
+        if (a == cudaStreamCaptureStatusNone && b == cudaStreamCaptureStatusNone) {
+            CU(h, cudaEventRecord(h->ev_handoff, h->last_stream));
+            CU(h, cudaStreamWaitEvent(st, h->ev_handoff, 0));
+        }
+    }
+    h->last_stream = st;
+    h->last_stream_valid = true;
     return 0;
 }
 
@@ -342,6 +363,7 @@ int ocl_sc_create(int device, int nx, int ny, int nz, long long max_particles, o
     TRY(cudaStreamCreateWithFlags(&h->side_stream, cudaStreamNonBlocking));
     TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
     TRY(cudaEventCreateWithFlags(&h->ev_khat, cudaEventDisableTiming));
+    TRY(cudaEventCreateWithFlags(&h->ev_handoff, cudaEventDisableTiming));
     for (int i = 0; i < T_COUNT; ++i) TRY(cudaEventCreate(&h->ev[i]));
     if (max_particles > 0) {
         TRY(cudaMalloc(&h->stage_r, sizeof(double) * 6 * max_particles));
@@ -374,6 +396,7 @@ void ocl_sc_destroy(ocl_sc_t* h) {
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_khat) cudaEventDestroy(h->ev_khat);
+    if (h->ev_handoff) cudaEventDestroy(h->ev_handoff);
     delete h;
 }
 
@@ -493,7 +516,7 @@ int ocl_sc_slab_forward(ocl_sc_t* h, void* stream) {
     if (!h || !h->slab_world) return h ? fail(h, "ocl_sc_slab_forward", "call ocl_sc_slab_init first") : 1;
     if (set_device(h)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
-    h->last_stream = st;
+    if (adopt_stream(h, st)) return 1;
     launch_slab_forward(h->rho_slab, h->peer_rho, (long long)h->slab_rank * h->sx * h->md.ny, h->md, h->sx, h->fs, h->fw,
                         h->xchg_a, st);
     h->launches += 2;
@@ -504,7 +527,7 @@ int ocl_sc_slab_xpass(ocl_sc_t* h, void* stream) {
     if (!h || !h->slab_world) return h ? fail(h, "ocl_sc_slab_xpass", "call ocl_sc_slab_init first") : 1;
     if (set_device(h)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
-    h->last_stream = st;
+    if (adopt_stream(h, st)) return 1;
     if (h->khat_pending) {                      // join the Green's-function chain forked by stage_deposit
         CU(h, cudaStreamWaitEvent(st, h->ev_khat, 0));
         h->khat_pending = false;
@@ -520,7 +543,7 @@ int ocl_sc_slab_inverse(ocl_sc_t* h, void* stream) {
     if (!h || !h->slab_world) return h ? fail(h, "ocl_sc_slab_inverse", "call ocl_sc_slab_init first") : 1;
     if (set_device(h)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
-    h->last_stream = st;
+    if (adopt_stream(h, st)) return 1;
     launch_slab_inverse(h->xchg_a, h->md, h->sx, h->fs, h->fw, h->h3, four_pi_eps0_value(), h->phi_slab, st);
     h->launches += 2;
     mark(h, T_SOLVE, st);
@@ -531,7 +554,7 @@ int ocl_sc_slab_finish(ocl_sc_t* h, const double* mesh_draws, void* stream) {
     if (!h || !h->slab_world) return h ? fail(h, "ocl_sc_slab_finish", "call ocl_sc_slab_init first") : 1;
     if (set_device(h)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
-    h->last_stream = st;
+    if (adopt_stream(h, st)) return 1;
     launch_field(h->phi, h->rs, h->md, kp_of(h, 1.0, 0.0, mesh_draws), h->equad, st);
     h->launches += 1;
     mark(h, T_FIELD, st);
@@ -545,7 +568,7 @@ int ocl_sc_stage_momentum(ocl_sc_t* h, const double* d_r, long long ld, long lon
     if (n >= 2147483647LL - 2 * 148 * 4 * 256) return fail(h, "ocl_sc_stage_momentum", "more than 2^31 particles per GPU");
     if (set_device(h)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
-    h->last_stream = st;
+    if (adopt_stream(h, st)) return 1;
     mark(h, T_BEGIN, st);
     launch_momentum(d_r, ld, n, kp_of(h, E_GeV, 0.0, nullptr), h->rs, st);
     h->launches += 1;
@@ -558,7 +581,7 @@ int ocl_sc_stage_extent(ocl_sc_t* h, const double* d_r, long long ld, const doub
     if (!h) return 1;
     if (set_device(h)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
-    h->last_stream = st;
+    if (adopt_stream(h, st)) return 1;
     launch_extent(d_r, ld, d_q, n, kp_of(h, E_GeV, 0.0, nullptr), h->rs, st);
     h->launches += 1;
     mark(h, T_EXT, st);
@@ -570,7 +593,7 @@ int ocl_sc_stage_deposit(ocl_sc_t* h, const double* d_r, long long ld, const dou
     if (!h) return 1;
     if (set_device(h)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
-    h->last_stream = st;
+    if (adopt_stream(h, st)) return 1;
     // the mesh steps are final once the extents are reduced: start the Green's-function / K_hat
     // chain now, concurrently with the deposit and the first two rho passes
     if (h->solver == 0 && fork_khat(h, kp_of(h, E_GeV, 0.0, mesh_draws), st)) return 1;
@@ -585,7 +608,7 @@ int ocl_sc_stage_solve(ocl_sc_t* h, const double* mesh_draws, void* stream) {
     if (!h) return 1;
     if (set_device(h)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
-    h->last_stream = st;
+    if (adopt_stream(h, st)) return 1;
     KP dr = kp_of(h, 1.0, 0.0, mesh_draws);   // only the mesh draws are used by the solve
     if (!h->khat_pending) {
         launch_green_table(h->rs, h->md, dr, h->gtab, h->h3, st);
@@ -611,7 +634,7 @@ int ocl_sc_stage_kick(ocl_sc_t* h, double* d_r, long long ld, long long n, doubl
     if (!h) return 1;
     if (set_device(h)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
-    h->last_stream = st;
+    if (adopt_stream(h, st)) return 1;
     launch_gather_kick(d_r, ld, n, kp_of(h, E_GeV, dz, mesh_draws), h->rs, h->md, h->equad, nullptr, 1, st);
     h->launches += 1;
     mark(h, T_KICK, st);
@@ -691,8 +714,13 @@ int ocl_sc_kick_device(ocl_sc_t* h, double* d_r, long long ld, const double* d_q
     }
     if (!graph_ok) return run_stages(h, d_r, ld, d_q, n, E_GeV, dz, mesh_draws, stream);
     if (!h->graph_exec || h->g_r != d_r || h->g_q != d_q || h->g_ld != ld || h->g_n != n) {
-        if (capture_kick(h, d_r, ld, d_q, n, E_GeV, dz, mesh_draws)) return 1;
+        const cudaStream_t prev = h->last_stream;          // the capture pass runs the stages on own_stream
+        const bool prev_valid = h->last_stream_valid;      // without executing anything: keep the real history
+        const int rc = capture_kick(h, d_r, ld, d_q, n, E_GeV, dz, mesh_draws);
+        h->last_stream = prev; h->last_stream_valid = prev_valid;
+        if (rc) return 1;
     }
+    if (adopt_stream(h, st)) return 1;
     KickParams kp = kick_params(h, E_GeV, dz, mesh_draws);
     void* args[2] = {&kp, &h->kp_dev};
     cudaKernelNodeParams np = {};
@@ -702,7 +730,6 @@ int ocl_sc_kick_device(ocl_sc_t* h, double* d_r, long long ld, const double* d_q
     CU(h, cudaGraphExecKernelNodeSetParams(h->graph_exec, h->param_node, &np));
     CU(h, cudaGraphLaunch(h->graph_exec, st));
     h->launches += h->graph_launches_per_kick;
-    h->last_stream = st;
     return 0;
 }
 
@@ -828,7 +855,7 @@ int ocl_sc_mad_to_cartesian(ocl_sc_t* h, const double* d_r, long long ld, long l
                             long long ld_xp, void* stream) {
     if (!h) return 1;
     if (set_device(h)) return 1;
-    h->last_stream = (cudaStream_t)stream;
+    if (adopt_stream(h, (cudaStream_t)stream)) return 1;
     launch_mad_to_cart(d_r, ld, n, ref_params(h, E_GeV), d_xp, ld_xp, (cudaStream_t)stream);
     h->launches += 1;
     return check_launch(h, "k_mad_to_cart");
@@ -838,7 +865,7 @@ int ocl_sc_cartesian_to_mad(ocl_sc_t* h, const double* d_xp, long long ld_xp, lo
                             long long ld, void* stream) {
     if (!h) return 1;
     if (set_device(h)) return 1;
-    h->last_stream = (cudaStream_t)stream;
+    if (adopt_stream(h, (cudaStream_t)stream)) return 1;
     launch_cart_to_mad(d_xp, ld_xp, n, ref_params(h, E_GeV), d_r, ld, (cudaStream_t)stream);
     h->launches += 1;
     return check_launch(h, "k_cart_to_mad");
@@ -848,7 +875,7 @@ int ocl_sc_potential_host(ocl_sc_t* h, const double* h_rho, const double steps[3
     if (!h) return 1;
     if (set_device(h)) return 1;
     cudaStream_t st = h->own_stream;
-    h->last_stream = st;
+    if (adopt_stream(h, st)) return 1;
     const size_t n3 = (size_t)h->md.nx * h->md.ny * h->md.nz;
     CU(h, cudaMemcpyAsync(h->rho, h_rho, sizeof(double) * n3, cudaMemcpyHostToDevice, st));
     launch_green_table_steps(steps, h->md, h->gtab, h->h3, st);
@@ -879,7 +906,7 @@ int ocl_sc_map_apply(ocl_sc_t* h, double* d_r, long long ld, long long n, const 
     if (T)
         for (int c = 0; c < 216; ++c)
             if (T[c] != 0.0) { mc.tval[mc.nt] = T[c]; mc.tidx[mc.nt] = (unsigned char)c; ++mc.nt; }
-    h->last_stream = (cudaStream_t)stream;
+    if (adopt_stream(h, (cudaStream_t)stream)) return 1;
     launch_map_apply(d_r, ld, n, mc, (cudaStream_t)stream);
     h->launches += 1;
     return check_launch(h, "k_map_apply");
@@ -898,7 +925,7 @@ int ocl_sc_cavity_apply(ocl_sc_t* h, double* d_r, long long ld, long long n, con
     mc.cav = mode;
     mc.c1 = c[0]; mc.c2 = c[1]; mc.kb = c[2]; mc.phi = c[3]; mc.cosphi = std::cos(c[3]);
     mc.t566 = c[4]; mc.t556 = c[5]; mc.t555 = c[6];
-    h->last_stream = (cudaStream_t)stream;
+    if (adopt_stream(h, (cudaStream_t)stream)) return 1;
     launch_map_apply(d_r, ld, n, mc, (cudaStream_t)stream);
     h->launches += 1;
     return check_launch(h, "k_map_apply(cavity)");
@@ -909,7 +936,7 @@ int ocl_sc_beam_moments(ocl_sc_t* h, const double* d_r, long long ld, long long 
     if (n <= 0 || ld < n) return fail(h, "ocl_sc_beam_moments", "need 0 < n <= ld");
     if (set_device(h)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
-    h->last_stream = st;
+    if (adopt_stream(h, st)) return 1;
     launch_moments(d_r, ld, n, h->rs, h->moments, st);
     h->launches += 2;
     if (check_launch(h, "k_moments")) return 1;

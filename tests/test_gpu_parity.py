@@ -388,3 +388,33 @@ def test_track_config1_moments(native, golden):
     for row in range(6):
         ref = g["r_final_sample"][row]
         assert np.max(np.abs(final[row] - ref)) / np.std(ref) < 1e-10
+
+
+def test_one_handle_alternating_streams(native, golden):
+    """A device-resident kick (caller's stream) immediately followed by a host-array kick (the
+    handle's own stream) on the SAME SpaceCharge object: the handle orders its scratch use across
+    the two streams (found by compute-sanitizer timing, tools/sanitize_run.py)."""
+    from ocelot_b200 import SpaceCharge, ParticleArray, DeviceParticleArray
+    g = golden("kat_c1_31.npz")
+    n = g["r_in"].shape[1]
+
+    def fresh():
+        p = ParticleArray(n)
+        p.rparticles[:], p.q_array[:], p.E = g["r_in"], g["q"], float(g["E"])
+        return p
+
+    # reference: three kicks, fully synchronised between calls
+    ref = DeviceParticleArray.from_host(fresh())
+    s0 = SpaceCharge(nmesh_xyz=[31, 31, 31])
+    for _ in range(3):
+        s0.apply(ref, 0.1)
+        torch.cuda.synchronize()
+    expect = ref.to_host().rparticles
+    for _ in range(5):
+        sc = SpaceCharge(nmesh_xyz=[31, 31, 31])
+        dev, host = DeviceParticleArray.from_host(fresh()), fresh()
+        for _ in range(3):                      # no synchronisation between the two paths
+            sc.apply(dev, 0.1)
+            sc.apply(host, 0.1)
+        assert row_err(dev.to_host().rparticles, expect) < 1e-11
+        assert row_err(host.rparticles, expect) < 1e-11
