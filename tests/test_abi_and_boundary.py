@@ -145,3 +145,96 @@ def test_drop_in_under_reference_navigator_and_track(monkeypatch):
     # reset_position deep-copies the process table and calls prepare again (navi.py:142-156)
     navi.reset_position()
     assert navi.process_table.proc_list[0]._solvers == {}
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/ocelot"), reason="reference checkout not present")
+def test_resident_track_loop_drives_reference_navigator(monkeypatch):
+    """ocelot_b200.track.track (the device-resident loop) against the reference's track() on a lattice
+    with RF cavities (CavityTM entrance/main/exit), quadrupoles and drifts under SecondTM, with space
+    charge.  This box has no GPU, so the three device calls are replaced by the oracle's numpy
+    restatements; what is checked is the control flow: which parameters are pulled from each map
+    (tm.get_params(E)), the energy / path-length bookkeeping and the process scheduling."""
+    sys.path.insert(0, "/root/reference")
+    import logging
+    logging.disable(logging.WARNING)
+    from ocelot import MagneticLattice, Navigator, Drift, Quadrupole, Cavity, Marker, SecondTM, track as ref_track
+    from ocelot.cpbd.beam import ParticleArray as RefParticleArray
+    from ocelot.cpbd.sc import SpaceCharge as RefSpaceCharge
+    from oracle import sc_oracle as orc
+    import importlib
+    T = importlib.import_module("ocelot_b200.track")   # (the package also exports the function `track`)
+
+    class HostDev:                                       # stands in for DeviceParticleArray
+        def __init__(self, p):
+            self.rparticles, self.q_array = p.rparticles.copy(), p.q_array.copy()
+            self.E, self.s = float(p.E), float(p.s)
+
+        @property
+        def n(self):
+            return self.rparticles.shape[1]
+
+    def apply_map(p, R, B=None, T_=None, delta_e=0.0, length=0.0):
+        r = p.rparticles
+        if T_ is None:
+            r[:] = np.add(np.dot(R, r), np.zeros(6).reshape(6, 1) if B is None else np.asarray(B).reshape(6, 1))
+        else:
+            r[:] = np.matmul(R, r) + np.einsum('ijk,j...,k...->i...', T_, r, r)
+            r[:] = np.add(r, np.asarray(B).reshape(6, 1))
+        p.E += delta_e
+        p.s += length
+
+    def apply_cavity(p, R, B, v, phi, freq, dlen, length, delta_e=None):
+        de = orc.cavity_map(p.rparticles, R, B, v, phi, freq, p.E, dlen, length)
+        p.E += de if delta_e is None else delta_e
+        p.s += dlen if dlen is not None else length
+
+    class OracleSolver:
+        def __init__(self, device, nmesh):
+            self.nmesh = nmesh
+
+        def kick_host(self, r, q, E, dz, draws):
+            orc.sc_kick(r, q, E, dz, self.nmesh)
+
+    monkeypatch.setattr(T, "apply_map", apply_map)
+    monkeypatch.setattr(T, "apply_cavity", apply_cavity)
+    from ocelot_b200.beam import moments_from_sums
+
+    def envelope(p):
+        m = orc.beam_moments(p.rparticles)
+        return moments_from_sums({k: v for k, v in m.items() if not k.startswith("emit")}, E=p.E)
+
+    monkeypatch.setattr(T, "get_envelope", envelope)
+    monkeypatch.setattr(T, "DeviceParticleArray", HostDev)
+    monkeypatch.setattr(SpaceCharge, "_host_device", lambda self: 0)
+    monkeypatch.setattr(native, "Solver", OracleSolver)
+
+    def build(sc_cls):
+        m1, m2 = Marker(), Marker()
+        cav = Cavity(l=0.5, v=0.01, freq=1.3e9, phi=10.0)
+        cell = (m1, Drift(l=0.2), cav, Drift(l=0.1), Quadrupole(l=0.2, k1=3.0), Drift(l=0.2),
+                Quadrupole(l=0.2, k1=-3.0, tilt=0.3), Drift(l=0.1), m2)
+        lat = MagneticLattice(cell, method={'global': SecondTM})
+        navi = Navigator(lat)
+        navi.unit_step = 0.05
+        sc = sc_cls()
+        sc.step = 2
+        sc.nmesh_xyz = [15, 15, 15]
+        navi.add_physics_proc(sc, m1, m2)
+        np.random.seed(5)
+        p = RefParticleArray(n=2000)
+        p.rparticles[:] = orc.gaussian_bunch(2000, energy=0.02, charge=2e-10)[0]
+        p.q_array[:] = 2e-10 / 2000
+        p.E = 0.02
+        return lat, navi, p
+
+    lat, navi, p = build(RefSpaceCharge)
+    tws_ref, p_ref = ref_track(lat, p, navi, print_progress=False)
+    lat2, navi2, p2 = build(SpaceCharge)
+    dev = HostDev(p2)
+    tws, dev = T.track(lat2, dev, navi2)
+    assert len(tws) == len(tws_ref)
+    assert abs(dev.E - p_ref.E) < 1e-15 and abs(dev.s - p_ref.s) < 1e-12
+    for row in range(6):
+        assert np.max(np.abs(dev.rparticles[row] - p_ref.rparticles[row])) <= 1e-13 * np.std(p_ref.rparticles[row])
+    assert abs(tws[-1].xx / tws_ref[-1].xx - 1) < 1e-12 and abs(tws[-1].emit_x / tws_ref[-1].emit_x - 1) < 1e-9
+    assert abs(tws[-1].s - tws_ref[-1].s) < 1e-12
