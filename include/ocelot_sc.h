@@ -90,7 +90,11 @@ enum {
     OCL_SC_BUF_XCHG_A = 6,     /* 2*nx_pad*fs doubles (complex): y-pass output / inverse-y input, chunk layout */
     OCL_SC_BUF_XCHG_B = 7,     /* 2*nx_pad*fs doubles (complex): x-pass lines of this rank, [nx_pad][fs] */
     OCL_SC_BUF_PHI_SLAB = 8,   /* sx*ny*nz doubles: this rank's x-planes of phi (all-gather input) */
-    OCL_SC_BUF_PHI = 9         /* nx_pad*ny*nz doubles: the gathered potential */
+    OCL_SC_BUF_PHI = 9,        /* nx_pad*ny*nz doubles: the gathered potential */
+    /* longitudinal space charge (after ocl_sc_lsc_deposit) */
+    OCL_SC_BUF_LSC_BINS = 10,      /* nb 64-bit integers (fixed-point CIC counts), reduce SUM as int64 */
+    OCL_SC_BUF_LSC_SLICE_MAX = 11, /* 4 doubles, reduce MAX */
+    OCL_SC_BUF_LSC_SLICE_SUM = 12  /* 5 doubles, reduce SUM */
 };
 int ocl_sc_collective_buffer(ocl_sc_t* h, int which, double** d_ptr, long long* count);
 
@@ -183,6 +187,27 @@ int ocl_sc_cavity_apply(ocl_sc_t* h, double* d_r, long long ld, long long n, con
  * :121-166): h_out[18] = {x, px, y, py, tau, p, xx, xpx, pxpx, yy, ypy, pypy, tautau, pp, xy, pxpy,
  * xpy, ypx} with the reference's px, py correction factor applied.  Synchronous. */
 int ocl_sc_beam_moments(ocl_sc_t* h, const double* d_r, long long ld, long long n, double* h_out, void* stream);
+
+/* ---- longitudinal space charge: class LSC (ocelot/cpbd/sc.py:261-599), the 1-D sibling of the
+ * kick.  One LSC.apply = ocl_sc_lsc_stats (sweep A, synchronous) -> the host derives the 1-D grid like
+ * s_to_cur (beam/analysis.py:293-333) -> ocl_sc_lsc_kick (deposit, smoothing, impedance, wake, energy
+ * kick; asynchronous).  Only row 5 (delta) of the particles is modified (sc.py:599). ---- */
+/* h_out[8] = {n, mean(tau), sum (tau-mean)^2, min(tau), max(tau), sum(q), sum(x), sum(y)}
+ * (np.mean / np.std / np.sum of sc.py:576-577, :590; np.min / np.max of analysis.py:296-297). */
+int ocl_sc_lsc_stats(ocl_sc_t* h, const double* d_r, long long ld, long long n, const double* d_q, double h_out[8],
+                     void* stream);
+/* params[17] = {slice_min, slice_max (sc.py:579-580), x_shift, y_shift (centroid, shifts of the slice
+ * sums), a, ds, nb (grid x_j = j*ds + a, analysis.py:318-322), sigma_s, K (Gaussian taps -K..K,
+ * analysis.py:330-333; K < 0: no smoothing), q = sum(q_array), v, gamma, dz, 1 + K_max^2 fill/2
+ * (sc.py:460-463), pc_ref [GeV] (sc.py:597), step_profile (0/1), n_total (all ranks)}. */
+int ocl_sc_lsc_kick(ocl_sc_t* h, double* d_r, long long ld, long long n, const double* params, void* stream);
+/* The two halves of ocl_sc_lsc_kick for a particle-sharded bunch: after the deposit the caller
+ * all-reduces OCL_SC_BUF_LSC_BINS (int64 SUM: exact), _SLICE_MAX (MAX) and _SLICE_SUM (SUM). */
+int ocl_sc_lsc_deposit(ocl_sc_t* h, const double* d_r, long long ld, long long n, const double* params, void* stream);
+int ocl_sc_lsc_solve_kick(ocl_sc_t* h, double* d_r, long long ld, long long n, const double* params, void* stream);
+/* taps of the last LSC kick (any pointer may be NULL): current profile I(s_j) [A] (s_to_cur's B[:,1]),
+ * wake W(s_j)*q [V] (sc.py:592), transverse size sigma or rb used by the impedance (sc.py:584-589). */
+int ocl_sc_lsc_get_profile(ocl_sc_t* h, int nb, double* h_current, double* h_wake, double* h_sigma);
 
 /* Per-stage device timers.  enable=1 records CUDA events around each stage of
  * every following kick; get returns the last kick's milliseconds:

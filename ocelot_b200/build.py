@@ -15,8 +15,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libocelot_sc.so")
-SOURCES = ["sc_kernels.cu", "sc_fft.cu", "sc_beam.cu", "sc_abi.cu"]
-HEADERS = ["sc_device.cuh", "sc_kernels.h", os.path.join("..", "..", "include", "ocelot_sc.h")]
+SOURCES = ["sc_kernels.cu", "sc_fft.cu", "sc_beam.cu", "sc_lsc.cu", "sc_abi.cu"]
+HEADERS = ["sc_device.cuh", "sc_kernels.h", "sc_special.h", os.path.join("..", "..", "include", "ocelot_sc.h")]
 
 
 def nvcc_path() -> str:

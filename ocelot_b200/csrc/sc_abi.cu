@@ -1,4 +1,5 @@
 // sc_abi.cu -- handle management and the extern "C" entry points of include/ocelot_sc.h.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -79,6 +80,12 @@ struct ocl_sc {
     const void* g_r = nullptr; const void* g_q = nullptr; long long g_ld = 0, g_n = 0;
     long long graph_launches_per_kick = 0;
     const KickParams* cur_pp = nullptr;       // non-null while stages are being captured
+    // longitudinal space charge (sc_lsc.cu): 1-D work space, grown on demand
+    LscWork lw{};
+    int lsc_cap = 0;                          // grid points the buffers hold
+    long long lsc_spread_cap = 0;             // 64-bit words of the spread histogram
+    int lsc_tw_nb = 0;                        // nb the twiddle table was built for
+    int lsc_nb = 0;                           // nb of the last deposit / solve
     // timers
     bool timers = false;
     cudaEvent_t ev[T_COUNT] = {};
@@ -390,6 +397,9 @@ void ocl_sc_destroy(ocl_sc_t* h) {
     cudaFree(h->fw.P); cudaFree(h->fw.Q); cudaFree(h->fw.khat); cudaFree(h->fw.A); cudaFree(h->fw.B);
     cudaFree(h->tw[0]); cudaFree(h->tw[1]); cudaFree(h->tw[2]); cudaFree(h->h3); cudaFree(h->moments);
     cudaFree(h->stage_r); cudaFree(h->stage_q);
+    cudaFree(h->lw.ticket); cudaFree(h->lw.stats); cudaFree(h->lw.bins); cudaFree(h->lw.cnt); cudaFree(h->lw.Z);
+    cudaFree(h->lw.spread);
+    cudaFree(h->lw.tw);
     cudaFree(h->rho_slab); cudaFree(h->phi_slab); cudaFree(h->xchg_a); cudaFree(h->xchg_b);
     for (int i = 0; i < T_COUNT; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -413,6 +423,9 @@ int ocl_sc_collective_buffer(ocl_sc_t* h, int which, double** d_ptr, long long* 
         case OCL_SC_BUF_XCHG_B: if (!h->slab_world) break; *d_ptr = (double*)h->xchg_b; *count = 2LL * h->nx_pad * h->fs; return 0;
         case OCL_SC_BUF_PHI: if (!h->slab_world) break; *d_ptr = h->phi; *count = (long long)h->rho_count; return 0;
         case OCL_SC_BUF_EXTENT: *d_ptr = h->rs.emax; *count = 10; return 0;
+        case OCL_SC_BUF_LSC_BINS: if (!h->lsc_nb) break; *d_ptr = (double*)h->lw.bins; *count = h->lsc_nb; return 0;
+        case OCL_SC_BUF_LSC_SLICE_MAX: if (!h->lsc_cap) break; *d_ptr = h->lw.slice; *count = 4; return 0;
+        case OCL_SC_BUF_LSC_SLICE_SUM: if (!h->lsc_cap) break; *d_ptr = h->lw.slice + 4; *count = 5; return 0;
     }
     return fail(h, "ocl_sc_collective_buffer", "unknown buffer id");
 }
@@ -942,6 +955,134 @@ int ocl_sc_beam_moments(ocl_sc_t* h, const double* d_r, long long ld, long long 
     if (check_launch(h, "k_moments")) return 1;
     CU(h, cudaMemcpyAsync(h_out, h->moments, sizeof(double) * 18, cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
+    return 0;
+}
+
+/* ---- longitudinal space charge (LSC, sc.py:261-599) ---- */
+static int ensure_lsc(ocl_sc* h, int nb) {
+    if (nb <= h->lsc_cap) return 0;
+    int cap = 1024;
+    while (cap < nb) cap *= 2;
+    cudaFree(h->lw.bins); cudaFree(h->lw.cnt); cudaFree(h->lw.Z); cudaFree(h->lw.tw); cudaFree(h->lw.spread);
+    h->lw.bins = nullptr; h->lw.cnt = nullptr; h->lw.Z = nullptr; h->lw.tw = nullptr; h->lw.spread = nullptr;
+    h->lsc_cap = 0; h->lsc_tw_nb = 0;
+    if (!h->lw.ticket) {
+        CU(h, cudaMalloc(&h->lw.ticket, sizeof(unsigned int) * 2));
+        CU(h, cudaMemset(h->lw.ticket, 0, sizeof(unsigned int) * 2));
+        CU(h, cudaMalloc(&h->lw.stats, sizeof(double) * 32));
+        CU(h, cudaMemset(h->lw.stats, 0, sizeof(double) * 32));
+        h->lw.slice = h->lw.stats + 16;
+        h->lw.sigma = h->lw.stats + 26;
+    }
+    h->lw.part = h->rs.part;
+    h->lw.max_blocks = h->rs.max_blocks;
+    CU(h, cudaMalloc(&h->lw.bins, sizeof(unsigned long long) * cap));
+    CU(h, cudaMemset(h->lw.bins, 0, sizeof(unsigned long long) * cap));
+    {   // the spread histogram holds any nb <= cap (replicas shrink as nb grows)
+        long long words = std::max<long long>(1 << 20, cap);    // nb * replicas <= 2^20 by construction
+        CU(h, cudaMalloc(&h->lw.spread, sizeof(unsigned long long) * words));
+        CU(h, cudaMemset(h->lw.spread, 0, sizeof(unsigned long long) * words));
+        h->lsc_spread_cap = words;
+    }
+    CU(h, cudaMalloc(&h->lw.cnt, sizeof(double) * 5 * cap));
+    h->lw.prof = h->lw.cnt + cap; h->lw.cur = h->lw.cnt + 2 * (size_t)cap; h->lw.W = h->lw.cnt + 3 * (size_t)cap;
+    h->lw.A = h->lw.cnt + 4 * (size_t)cap;
+    CU(h, cudaMalloc(&h->lw.Z, sizeof(double2) * cap));
+    CU(h, cudaMalloc(&h->lw.tw, sizeof(double2) * 2 * cap));
+    h->lsc_cap = cap;
+    return 0;
+}
+
+static int lsc_params(ocl_sc* h, const double* p, LscParams& lp) {
+    if (!p) return fail(h, "lsc", "params is NULL");
+    lp.slice_min = p[0]; lp.slice_max = p[1]; lp.x_shift = p[2]; lp.y_shift = p[3];
+    lp.a = p[4]; lp.ds = p[5]; lp.nb = (int)p[6]; lp.sigma_s = p[7]; lp.K = (int)p[8];
+    lp.q = p[9]; lp.v = p[10]; lp.gamma = p[11]; lp.dz = p[12]; lp.und = p[13]; lp.pc_ref = p[14];
+    lp.step_profile = p[15] != 0.0;
+    double ntot = p[16] < 2.0 ? 2.0 : p[16];
+    int bits = 0;
+    while ((double)(1ull << bits) < ntot && bits < 62) ++bits;      // ceil(log2 n_total)
+    lp.fx_shift = 62 - bits > 52 ? 52 : 62 - bits;
+    if (!(lp.ds > 0.0) || lp.nb < 2 || lp.nb > (1 << 20)) return fail(h, "lsc", "bad grid (need ds > 0, 2 <= nb <= 2^20)");
+    if (lp.K >= 0 && !(lp.sigma_s > 0.0)) return fail(h, "lsc", "smoothing taps need sigma_s > 0");
+    return 0;
+}
+
+int ocl_sc_lsc_stats(ocl_sc_t* h, const double* d_r, long long ld, long long n, const double* d_q, double h_out[8],
+                     void* stream) {
+    if (!h || !h_out) return 1;
+    if (n <= 0 || ld < n) return fail(h, "ocl_sc_lsc_stats", "need 0 < n <= ld");
+    if (set_device(h)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (adopt_stream(h, st)) return 1;
+    if (ensure_lsc(h, 1)) return 1;
+    launch_lsc_stats(d_r, ld, d_q, n, h->lw, st);
+    h->launches += 1;
+    if (check_launch(h, "k_lsc_stats")) return 1;
+    double raw[9];
+    CU(h, cudaMemcpyAsync(raw, h->lw.stats, sizeof raw, cudaMemcpyDeviceToHost, st));
+    CU(h, cudaStreamSynchronize(st));
+    const double cnt = raw[2], s1 = raw[3], s2 = raw[4], t0 = raw[8];
+    h_out[0] = cnt;
+    h_out[1] = t0 + s1 / cnt;                 // mean tau
+    h_out[2] = s2 - s1 * s1 / cnt;            // sum (tau - mean)^2
+    if (h_out[2] < 0.0) h_out[2] = 0.0;
+    h_out[3] = -raw[1];                       // min tau
+    h_out[4] = raw[0];                        // max tau
+    h_out[5] = raw[5];                        // sum q
+    h_out[6] = raw[6];                        // sum x
+    h_out[7] = raw[7];                        // sum y
+    return 0;
+}
+
+int ocl_sc_lsc_deposit(ocl_sc_t* h, const double* d_r, long long ld, long long n, const double* params, void* stream) {
+    if (!h) return 1;
+    if (n <= 0 || ld < n) return fail(h, "ocl_sc_lsc_deposit", "need 0 < n <= ld");
+    LscParams lp;
+    if (lsc_params(h, params, lp)) return 1;
+    if (set_device(h)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (adopt_stream(h, st)) return 1;
+    if (ensure_lsc(h, lp.nb)) return 1;
+    h->lsc_nb = lp.nb;
+    launch_lsc_deposit(d_r, ld, n, lp, h->lw, st);
+    h->launches += 2;
+    return check_launch(h, "k_lsc_deposit");
+}
+
+int ocl_sc_lsc_solve_kick(ocl_sc_t* h, double* d_r, long long ld, long long n, const double* params, void* stream) {
+    if (!h) return 1;
+    if (n <= 0 || ld < n) return fail(h, "ocl_sc_lsc_solve_kick", "need 0 < n <= ld");
+    LscParams lp;
+    if (lsc_params(h, params, lp)) return 1;
+    if (lp.nb != h->lsc_nb) return fail(h, "ocl_sc_lsc_solve_kick", "grid differs from the deposited one");
+    if (set_device(h)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (adopt_stream(h, st)) return 1;
+    if (h->lsc_tw_nb != lp.nb) {
+        launch_lsc_twiddles(lp.nb, h->lw, st);
+        h->lsc_tw_nb = lp.nb;
+        h->launches += 1;
+    }
+    if (launch_lsc_solve(lp, h->lw, st)) return fail(h, "ocl_sc_lsc_solve_kick", "too many smoothing taps (K > 2559)");
+    launch_lsc_kick(d_r, ld, n, lp, h->lw, st);
+    h->launches += 5;
+    return check_launch(h, "k_lsc_kick");
+}
+
+int ocl_sc_lsc_kick(ocl_sc_t* h, double* d_r, long long ld, long long n, const double* params, void* stream) {
+    if (ocl_sc_lsc_deposit(h, d_r, ld, n, params, stream)) return 1;
+    return ocl_sc_lsc_solve_kick(h, d_r, ld, n, params, stream);
+}
+
+int ocl_sc_lsc_get_profile(ocl_sc_t* h, int nb, double* h_current, double* h_wake, double* h_sigma) {
+    if (!h) return 1;
+    if (nb <= 0 || nb != h->lsc_nb) return fail(h, "ocl_sc_lsc_get_profile", "nb differs from the last LSC kick");
+    if (set_device(h)) return 1;
+    if (sync_last(h)) return 1;
+    if (h_current) CU(h, cudaMemcpy(h_current, h->lw.cur, sizeof(double) * nb, cudaMemcpyDeviceToHost));
+    if (h_wake) CU(h, cudaMemcpy(h_wake, h->lw.W, sizeof(double) * nb, cudaMemcpyDeviceToHost));
+    if (h_sigma) CU(h, cudaMemcpy(h_sigma, h->lw.sigma, sizeof(double), cudaMemcpyDeviceToHost));
     return 0;
 }
 

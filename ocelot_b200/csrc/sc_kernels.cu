@@ -30,60 +30,6 @@ int particle_grid(long long n, int max_blocks) {
     return (int)b;
 }
 
-// ---------------------------------------------------------------------------
-// reductions: first NMAX slots reduce with max, the rest with +
-// ---------------------------------------------------------------------------
-template <int NV, int NMAX>
-__device__ __forceinline__ void block_reduce(double (&v)[NV], double* sh /* [NV*kWarps] */) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int k = 0; k < NV; ++k) {
-        v[k] = (k < NMAX) ? warp_reduce(v[k], OpMax()) : warp_reduce(v[k], OpSum());
-        if (lane == 0) sh[k * kWarps + warp] = v[k];
-    }
-    __syncthreads();
-    if (warp == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            double ident = (k < NMAX) ? -INFINITY : 0.0;
-            double x = (lane < kWarps) ? sh[k * kWarps + lane] : ident;
-            v[k] = (k < NMAX) ? warp_reduce(x, OpMax()) : warp_reduce(x, OpSum());
-        }
-    }
-    __syncthreads();
-}
-
-// every block stores its partial; the block that draws the last ticket folds
-// all partials in a fixed order and writes the result (deterministic for a
-// fixed grid).  Returns true in the finishing block (v valid in thread 0).
-template <int NV, int NMAX>
-__device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* part, unsigned int* ticket, double* sh) {
-    __shared__ bool last;
-    block_reduce<NV, NMAX>(v, sh);
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) part[(size_t)blockIdx.x * NV + k] = v[k];
-        __threadfence();
-        unsigned int t = atomicAdd(ticket, 1u);
-        last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!last) return false;
-    __threadfence();
-#pragma unroll
-    for (int k = 0; k < NV; ++k) v[k] = (k < NMAX) ? -INFINITY : 0.0;
-    for (int b = threadIdx.x; b < (int)gridDim.x; b += kThreads) {
-#pragma unroll
-        for (int k = 0; k < NV; ++k) {
-            double x = __ldcg(part + (size_t)b * NV + k);
-            v[k] = (k < NMAX) ? fmax(v[k], x) : v[k] + x;
-        }
-    }
-    block_reduce<NV, NMAX>(v, sh);
-    if (threadIdx.x == 0) *ticket = 0;
-    return true;
-}
-
 constexpr int kPipeDepth = 3;
 #ifndef GK_BLOCKS
 #define GK_BLOCKS 2

@@ -80,6 +80,54 @@ struct MapCoef {
 void launch_map_apply(double* r, long long ld, long long n, const MapCoef& mc, cudaStream_t st);
 void launch_moments(const double* r, long long ld, long long n, ReduceState rs, double* out18, cudaStream_t st);
 
+// ---- longitudinal space charge (sc_lsc.cu) ----
+// physical constants of ocelot/common/globals.py:13-36 (same expressions as the host code)
+constexpr double kPi = 3.141592653589793;
+constexpr double kSpeedOfLight = 299792458.0;
+constexpr double kEpsilon0 = 1 / (4 * kPi * 1e-7) / (kSpeedOfLight * kSpeedOfLight);
+// per-kick scalars the host derives from the sweep-A statistics exactly like the reference
+// (LSC.apply sc.py:575-592, s_to_cur analysis.py:293-333)
+struct LscParams {
+    double slice_min, slice_max;   // central slice, sc.py:579-582
+    double x_shift, y_shift;       // shifts of the slice sums (bunch centroid)
+    double a, ds;                  // grid x_j = j*ds + a
+    double sigma_s;                // smoothing width sigma_tau * smooth_param
+    double q, v, gamma, dz;        // sum(q_array), mean velocity, E/m_e, step length
+    double und;                    // 1 + K_max^2 fill_factor / 2 (undulator factor)
+    double pc_ref;                 // sqrt(E^2/m_e^2 - 1) m_e [GeV]
+    int nb;                        // grid points (N + 1)
+    int K;                         // smoothing taps -K..K; < 0: no smoothing
+    int step_profile;              // 0: round Gaussian beam | 1: uniform beam of radius rb
+    int fx_shift;                  // fixed-point scale of the CIC counts: one particle = 2^fx_shift
+};
+// packed deposit word: (count << cshift) | fraction sum with fbits fractional bits
+struct LscPack {
+    int replicas, cshift, fbits;
+};
+struct LscWork {
+    double* part;                  // per-block partials (shared with the kick sweeps)
+    unsigned int* ticket;          // [2]
+    double* stats;                 // [16] sweep A results
+    double* slice;                 // [9]  slice maxima (4) and sums (5)
+    double* sigma;                 // [1]  transverse size used by the impedance
+    unsigned long long* spread;    // [replica][nb] packed deposit counters
+    unsigned long long* bins;      // [cap] the replicas folded: C[j] * 2^fx_shift
+    double* A;                     // [cap] impedance Za = i A
+    double* cnt;                   // [cap] counts as doubles
+    double* prof;                  // [cap] bunch * c
+    double* cur;                   // [cap] I(s) [A]
+    double* W;                     // [cap] wake * q [eV... V]
+    double2* Z;                    // [cap]
+    double2* tw;                   // [2 cap] exp(2 pi i m / n)
+    int max_blocks;
+};
+void launch_lsc_stats(const double* r, long long ld, const double* q, long long n, LscWork w, cudaStream_t st);
+void launch_lsc_twiddles(int nb, LscWork w, cudaStream_t st);
+void launch_lsc_deposit(const double* r, long long ld, long long n, const LscParams& lp, LscWork w, cudaStream_t st);
+int launch_lsc_solve(const LscParams& lp, LscWork w, cudaStream_t st);
+long long lsc_spread_words(int nb);
+void launch_lsc_kick(double* r, long long ld, long long n, const LscParams& lp, LscWork w, cudaStream_t st);
+
 // ---- hand-written Hockney convolution (sc_fft.cu) ----
 struct FftWork {
     const double2* tw_x;   // exp(-2 pi i m / M) tables, one per axis

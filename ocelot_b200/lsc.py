@@ -1,0 +1,238 @@
+"""B200-native drop-in for Ocelot's longitudinal space-charge process ``LSC``.
+
+Same constructor, attributes and ``prepare/apply/finalize`` protocol as the reference class
+(ocelot/cpbd/sc.py:261-599), so ``Navigator.add_physics_proc`` / ``track()`` drive it unchanged.
+Every per-particle operation (bunch statistics, the first-order current deposit, the slice
+size, the wake interpolation and the energy kick) and the 1-D impedance solve run in the sm_100a
+kernels of ``csrc/sc_lsc.cu`` behind ``ocl_sc_lsc_*`` (include/ocelot_sc.h).  The host only
+derives a dozen scalars per kick -- the grid definition of ``s_to_cur``
+(ocelot/cpbd/beam/analysis.py:293-333) and the undulator factor -- with the reference's own
+float expressions.  There is no CPU path: without the native library or a CUDA device
+``apply`` raises.
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+
+from .constants import m_e_GeV, speed_of_light
+from .physproc import PhysProc
+
+logger = logging.getLogger(__name__)
+
+
+def _is_undulator(elem) -> bool:
+    """The reference tests ``isinstance(elem, Undulator)`` (sc.py:502); this package does not
+    import Ocelot, so the class is recognised by name anywhere in its MRO."""
+    return any(c.__name__ == "Undulator" for c in type(elem).__mro__)
+
+
+class LSC(PhysProc):
+    """Longitudinal Space Charge impedance model (API of ocelot/cpbd/sc.py:261-297).
+
+    Attributes:
+        step          -- kick every ``step`` Navigator.unit_step
+        step_profile  -- uniform transverse profile (imp_step_lsc) instead of round Gaussian (imp_lsc)
+        smooth_param  -- current-profile smoothing: resolution = std(tau) * smooth_param
+        bounds        -- [min, max] in units of std(tau): central slice that defines the beam size
+        slice         -- stored, unused (as in the reference)
+        device        -- CUDA device index used for host-array kicks (default: current)
+    """
+
+    def __init__(self, step=1, **kwargs):
+        PhysProc.__init__(self, step)
+        self.K_s_func = None
+        self.step_profile = kwargs.get("step_profile", False)
+        self.smooth_param = kwargs.get("smooth_param", 0.1)
+        self.bounds = kwargs.get("bounds", [-0.4, 0.4])
+        self.slice = kwargs.get("slice", None)
+        self._is_undul_in_beam_line = False
+        self.device = kwargs.get("device", None)
+        self._solvers = {}
+
+    # -- protocol -----------------------------------------------------------
+    def prepare(self, lat):
+        """Undulator strength profile K(s) between start_elem and end_elem (sc.py:476-508)."""
+        from scipy.interpolate import interp1d
+        self.check_step()
+        seq = lat.get_sequence_part(self.start_elem, self.end_elem)
+        s, k = [], []
+        s_current = self.s_start
+        for elem in seq:
+            s_next = s_current + elem.l
+            s.extend([s_current, s_next])
+            if _is_undulator(elem) and not (elem.Kx != 0 and elem.Ky != 0):
+                k.extend([elem.Kx + elem.Ky, elem.Kx + elem.Ky])
+                self._is_undul_in_beam_line = True
+            else:
+                k.extend([0.0, 0.0])
+            s_current = s_next
+        self.K_s_func = interp1d(s, k, kind='linear', bounds_error=False, fill_value=(k[0], k[-1]))
+
+    def compute_filling_factor(self, x0, x1, num_points=100):
+        """Fraction of [x0, x1] inside an undulator field (sc.py:510-544)."""
+        x = np.linspace(x0, x1, num_points)
+        k_vals = self.K_s_func(x)
+        nonzero_intervals = (k_vals[:-1] != 0) | (k_vals[1:] != 0)
+        dx = (x1 - x0) / (num_points - 1)
+        filled_length = np.sum(nonzero_intervals) * dx
+        total_length = x1 - x0
+        return filled_length / total_length
+
+    def undulator_factor(self, dz):
+        """(K_max, fill_factor) of the step that ends at z0 (sc.py:569-574)."""
+        if self._is_undul_in_beam_line:
+            fill_factor = self.compute_filling_factor(self.z0 - dz, self.z0, num_points=200)
+            K_max = np.max(self.K_s_func(np.linspace(self.z0 - dz, self.z0, num=200)))
+        else:
+            fill_factor = 0
+            K_max = 0
+        return K_max, fill_factor
+
+    def kick_parameters(self, stats: dict, E, dz) -> dict:
+        """The scalars of one kick, from the bunch statistics of sweep A, with the reference's own
+        expressions: slice bounds (sc.py:579-580), charge and velocity (:590-592), the grid of
+        s_to_cur (analysis.py:293-321) and its smoothing taps (:330-331)."""
+        n = stats["n"]
+        mean_tau = stats["mean_tau"]
+        sigma_tau = np.sqrt(stats["m2_tau"] / n)                       # np.std
+        K_max, fill_factor = self.undulator_factor(dz)
+        q = stats["sum_q"]
+        gamma = E / m_e_GeV
+        v = np.sqrt(1 - 1 / gamma ** 2) * speed_of_light
+        sigma = sigma_tau * self.smooth_param
+        Nsigma = 3
+        a = stats["min_tau"] - Nsigma * sigma
+        b = stats["max_tau"] + Nsigma * sigma
+        if sigma > 0:
+            ds = 0.25 * sigma
+        else:
+            ds = (b - a) / 1000.0
+        N = int(np.ceil((b - a) / ds))
+        ds = (b - a) / N
+        K = int(np.floor(Nsigma * sigma / ds + 0.5)) if sigma > 0 else -1
+        return dict(
+            slice_min=mean_tau + sigma_tau * self.bounds[0], slice_max=mean_tau + sigma_tau * self.bounds[1],
+            x_shift=stats["sum_x"] / n, y_shift=stats["sum_y"] / n,
+            a=a, ds=ds, nb=N + 1, sigma_s=sigma, K=K, q=q, v=v, gamma=gamma, dz=dz,
+            und=1 + 0.5 * K_max * K_max * fill_factor,
+            pc_ref=np.sqrt(E ** 2 / m_e_GeV ** 2 - 1) * m_e_GeV,
+            step_profile=1.0 if self.step_profile else 0.0, n_total=n)
+
+    def apply(self, p_array, dz):
+        if dz < 1e-10:                                                   # sc.py:566-568
+            logger.debug(" LSC applied, dz < 1e-10, dz = " + str(dz))
+            return
+        r = p_array.rparticles
+        if r.shape[1] == 0:
+            return
+        E = float(p_array.E)
+        if isinstance(r, np.ndarray):
+            self._apply_host(r, p_array.q_array, E, float(dz))
+        else:
+            dev = r.device.index if r.device.index is not None else 0
+            solver = self._solver(dev)
+            params = self.kick_parameters(solver.lsc_stats(r, p_array.q_array), E, float(dz))
+            solver.lsc_kick(r, params)
+            self.last_params = params
+
+    def _apply_host(self, r, q_array, E, dz):
+        """Host numpy arrays: stage the four rows LSC reads (x, y, tau, delta) to the device, kick,
+        and copy row 5 back in place (the only row LSC writes, sc.py:599)."""
+        import torch
+        dev = self._host_device()
+        solver = self._solver(dev)
+        with torch.cuda.device(dev):
+            d_r = torch.empty((6, r.shape[1]), dtype=torch.float64, device=f"cuda:{dev}")
+            for row in (0, 2, 4, 5):
+                d_r[row].copy_(torch.from_numpy(r[row]), non_blocking=False)
+            d_q = torch.from_numpy(np.ascontiguousarray(q_array, dtype=np.float64)).to(d_r.device)
+            params = self.kick_parameters(solver.lsc_stats(d_r, d_q), E, dz)
+            solver.lsc_kick(d_r, params)
+            r[5][:] = d_r[5].cpu().numpy()
+        self.last_params = params
+
+    # -- host-side utilities of the reference class (plotting / analysis helpers; ``apply`` does not
+    #    use them: the kick evaluates the same formulas on the device, csrc/sc_lsc.cu) -------------
+    def imp_lsc(self, gamma, sigma, w, dz):
+        """Round-Gaussian-beam LSC impedance Z(w) [Ohm] over a length dz (sc.py:299-340)."""
+        from scipy.special import exp1, factorial
+        from .constants import epsilon_0, pi
+        Z0 = 1. / (speed_of_light * epsilon_0)
+        alpha2 = (w * sigma / (gamma * speed_of_light)) ** 2
+        T = np.zeros(w.shape)
+        mid = (alpha2 <= 40.0) & (alpha2 >= 1e-16)
+        far = alpha2 > 40.0
+        T[mid] = np.exp(alpha2[mid]) * exp1(alpha2[mid])
+        T[far] = sum((-1) ** i * factorial(i) / alpha2[far] ** (i + 1) for i in range(10))
+        return 1j * Z0 / (4 * pi * speed_of_light * gamma ** 2) * w * T * dz
+
+    def imp_step_lsc(self, gamma, rb, w, dz):
+        """Uniform-beam LSC impedance (sc.py:342-369); clamps ``w`` in place like the reference."""
+        from scipy.special import k1
+        from .constants import epsilon_0
+        Z0 = 1. / (speed_of_light * epsilon_0)
+        low = np.where(w < 1e-7)[0]
+        w[low] = 1e-7
+        x = w * rb / (speed_of_light * gamma)
+        Z = 1j * Z0 * speed_of_light / (4 * w * rb * rb) * dz * (1 - x * k1(x))
+        Z[low] = 0
+        return Z
+
+    def wake2impedance(self, s, w):
+        """Spectrum of a signal on a uniform grid, exp(+iwt) convention (sc.py:371-398,
+        beam/analysis.py:343-383): returns (f [Hz], y)."""
+        dt = (s[1] - s[0]) / speed_of_light
+        n = len(s)
+        return 1 / dt * np.arange(0, n) / n, dt * np.fft.fft(w, n)
+
+    def impedance2wake(self, f, y):
+        """Inverse of wake2impedance for a Hermitian spectrum (sc.py:401-416): returns (s [m], w)."""
+        df = f[1] - f[0]
+        n = len(f)
+        return 1 / df * np.arange(0, n) / n * speed_of_light, n * df * np.fft.irfft(y, n)
+
+    # -- native handle management (as SpaceCharge) ------------------------------
+    def _host_device(self):
+        if self.device is not None:
+            return int(self.device)
+        import torch
+        if not torch.cuda.is_available():
+            raise RuntimeError("ocelot_b200.LSC needs a CUDA device; there is no CPU fallback")
+        return torch.cuda.current_device()
+
+    def _solver(self, device):
+        from . import native
+        s = self._solvers.get(int(device))
+        if s is None:
+            s = native.Solver(int(device), (4, 4, 4))      # LSC uses none of the 3-D grids
+            self._solvers = {int(device): s}
+        return s
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_solvers"] = {}
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._solvers = {}
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = {} if k == "_solvers" else copy.deepcopy(v, memo)
+        return new
+
+
+def install():
+    """Replace ``ocelot.cpbd.sc.LSC`` (and the re-export ``ocelot.LSC``) with this class."""
+    import ocelot
+    import ocelot.cpbd.sc as ref_sc
+    ref_sc.LSC = LSC
+    if hasattr(ocelot, "LSC"):
+        ocelot.LSC = LSC
+    return LSC

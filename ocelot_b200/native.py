@@ -19,6 +19,7 @@ HEADER = os.path.join(os.path.dirname(_HERE), "include", "ocelot_sc.h")
 
 BUF_MOMENTUM, BUF_EXTENT_MAX, BUF_EXTENT_SUM, BUF_RHO, BUF_EXTENT = 0, 1, 2, 3, 4
 BUF_RHO_SLAB, BUF_XCHG_A, BUF_XCHG_B, BUF_PHI_SLAB, BUF_PHI = 5, 6, 7, 8, 9
+BUF_LSC_BINS, BUF_LSC_SLICE_MAX, BUF_LSC_SLICE_SUM = 10, 11, 12
 
 _lib = None
 
@@ -63,6 +64,11 @@ _SIGNATURES = {
     "ocl_sc_map_apply": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _dp, _dp, _vp]),
     "ocl_sc_cavity_apply": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _dp, _dp, C.c_int, _vp]),
     "ocl_sc_beam_moments": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _vp]),
+    "ocl_sc_lsc_stats": (C.c_int, [_vp, _vp, _ll, _ll, _vp, _dp, _vp]),
+    "ocl_sc_lsc_kick": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _vp]),
+    "ocl_sc_lsc_deposit": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _vp]),
+    "ocl_sc_lsc_solve_kick": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _vp]),
+    "ocl_sc_lsc_get_profile": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp]),
     "ocl_sc_enable_timers": (C.c_int, [_vp, C.c_int]),
     "ocl_sc_get_timers": (C.c_int, [_vp, _dp]),
     "ocl_sc_launch_count": (_ll, [_vp]),
@@ -348,6 +354,46 @@ class Solver:
         self._check(self._lib.ocl_sc_beam_moments(self._h, ptr, ld, n, out, _stream_ptr(stream)),
                     "ocl_sc_beam_moments")
         return dict(zip(self.MOMENT_KEYS, out[:]))
+
+    # -- longitudinal space charge (sc.py:261-599) ----------------------------------
+    LSC_STAT_KEYS = ("n", "mean_tau", "m2_tau", "min_tau", "max_tau", "sum_q", "sum_x", "sum_y")
+    LSC_PARAM_KEYS = ("slice_min", "slice_max", "x_shift", "y_shift", "a", "ds", "nb", "sigma_s", "K", "q", "v",
+                      "gamma", "dz", "und", "pc_ref", "step_profile", "n_total")
+
+    def lsc_stats(self, r, q, stream=None) -> dict:
+        """Sweep A of an LSC kick (synchronous): this buffer's n, mean and centred square sum of tau,
+        min/max tau, sum q, sum x, sum y."""
+        ptr, ld, n = self._dev_rows(r, q)
+        out = (C.c_double * 8)()
+        self._check(self._lib.ocl_sc_lsc_stats(self._h, ptr, ld, n, q.data_ptr(), out, _stream_ptr(stream)),
+                    "ocl_sc_lsc_stats")
+        return dict(zip(self.LSC_STAT_KEYS, out[:]))
+
+    def _lsc_params(self, params: dict):
+        return (C.c_double * 17)(*[float(params[k]) for k in self.LSC_PARAM_KEYS])
+
+    def lsc_kick(self, r, params: dict, stream=None):
+        ptr, ld, n = self._dev_rows(r)
+        self._check(self._lib.ocl_sc_lsc_kick(self._h, ptr, ld, n, self._lsc_params(params), _stream_ptr(stream)),
+                    "ocl_sc_lsc_kick")
+
+    def lsc_deposit(self, r, params: dict, stream=None):
+        ptr, ld, n = self._dev_rows(r)
+        self._check(self._lib.ocl_sc_lsc_deposit(self._h, ptr, ld, n, self._lsc_params(params),
+                                                 _stream_ptr(stream)), "ocl_sc_lsc_deposit")
+
+    def lsc_solve_kick(self, r, params: dict, stream=None):
+        ptr, ld, n = self._dev_rows(r)
+        self._check(self._lib.ocl_sc_lsc_solve_kick(self._h, ptr, ld, n, self._lsc_params(params),
+                                                    _stream_ptr(stream)), "ocl_sc_lsc_solve_kick")
+
+    def lsc_profile(self, nb: int) -> dict:
+        cur, wake = np.empty(nb), np.empty(nb)
+        sig = C.c_double()
+        self._check(self._lib.ocl_sc_lsc_get_profile(self._h, int(nb), cur.ctypes.data_as(_dp),
+                                                     wake.ctypes.data_as(_dp), C.byref(sig)),
+                    "ocl_sc_lsc_get_profile")
+        return dict(current=cur, W=wake, sigma=sig.value)
 
     # -- timers ---------------------------------------------------------------
     def enable_timers(self, on=True):
