@@ -260,3 +260,106 @@ class ShardedSpaceCharge:
             self.release()
         except Exception:  # noqa: BLE001
             pass
+
+
+# ---------------------------------------------------------------------------
+# particle-sharded longitudinal space charge
+# ---------------------------------------------------------------------------
+def combine_lsc_stats(per_rank):
+    """Fold the sweep-A statistics of the ranks (rows of [n, mean, M2, min, max, sum q, sum x, sum y])
+    into those of the whole bunch; mean and centred square sum by the pairwise update of Chan et al."""
+    a = np.asarray(per_rank, dtype=np.float64).reshape(-1, 8)
+    a = a[a[:, 0] > 0]
+    n = a[:, 0].sum()
+    mean = np.sum(a[:, 0] * a[:, 1]) / n
+    m2 = np.sum(a[:, 2] + a[:, 0] * (a[:, 1] - mean) ** 2)
+    return dict(n=n, mean_tau=mean, m2_tau=m2, min_tau=a[:, 3].min(), max_tau=a[:, 4].max(),
+                sum_q=a[:, 5].sum(), sum_x=a[:, 6].sum(), sum_y=a[:, 7].sum())
+
+
+class NativeLscEngine:
+    """The stages of an LSC kick on one GPU (include/ocelot_sc.h, ocl_sc_lsc_*)."""
+
+    def __init__(self, device: int):
+        from . import native
+        self._native = native
+        self.solver = native.Solver(device, (4, 4, 4))
+
+    def stats(self, r, q):
+        import torch
+        s = self.solver.lsc_stats(r, q)
+        return torch.tensor([s[k] for k in self.solver.LSC_STAT_KEYS], dtype=torch.float64, device=r.device)
+
+    def deposit(self, r, params):
+        import torch
+        self.solver.lsc_deposit(r, params)
+        nat = self._native
+        return (self.solver.collective_buffer(nat.BUF_LSC_BINS).view(torch.int64),     # exact integer counts
+                self.solver.collective_buffer(nat.BUF_LSC_SLICE_MAX),
+                self.solver.collective_buffer(nat.BUF_LSC_SLICE_SUM))
+
+    def solve_kick(self, r, params):
+        self.solver.lsc_solve_kick(r, params)
+
+
+def sharded_lsc_kick(engine, lsc, r, q, E_GeV, dz, group=None, dist=None):
+    """One LSC.apply on this rank's shard (in place).  Exchanges per kick: one all-gather of 8
+    statistics, then all-reduces of the integer current histogram (SUM, exact) and of the 4 + 5
+    slice scalars (MAX, SUM).  ``lsc`` supplies the host-side scalars (ocelot_b200.LSC)."""
+    if dz < 1e-10:                                                 # sc.py:566-568
+        return None
+    import torch
+    if dist is None:
+        import torch.distributed as dist
+    multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+    mine = engine.stats(r, q)
+    if multi:
+        world = dist.get_world_size(group)
+        allst = torch.empty(8 * world, dtype=torch.float64, device=mine.device)
+        dist.all_gather_into_tensor(allst, mine, group=group)
+        stats = combine_lsc_stats(allst.cpu().numpy())
+    else:
+        stats = combine_lsc_stats(mine.cpu().numpy())
+    params = lsc.kick_parameters(stats, float(E_GeV), float(dz))
+    bins, smax, ssum = engine.deposit(r, params)
+    if multi:
+        dist.all_reduce(bins, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(smax, op=dist.ReduceOp.MAX, group=group)
+        dist.all_reduce(ssum, op=dist.ReduceOp.SUM, group=group)
+    engine.solve_kick(r, params)
+    return params
+
+
+class ShardedLSC:
+    """PhysProc-style wrapper of ``LSC`` for a particle-sharded bunch: same constructor and
+    attributes; ``apply`` takes this rank's ``DeviceParticleArray`` shard."""
+
+    def __init__(self, step=1, group=None, **kwargs):
+        from .lsc import LSC
+        self.lsc = LSC(step=step, **kwargs)
+        self.group = group
+        self._engine = None
+
+    def __getattr__(self, name):                    # step, bounds, smooth_param, z0, ... live on the LSC
+        if name in ("lsc", "group", "_engine"):
+            raise AttributeError(name)
+        return getattr(self.lsc, name)
+
+    def __setattr__(self, name, value):
+        if name in ("lsc", "group", "_engine"):
+            object.__setattr__(self, name, value)
+        else:
+            setattr(self.lsc, name, value)
+
+    def prepare(self, lat):
+        self.lsc.prepare(lat)
+
+    def apply(self, p_shard, dz):
+        r = p_shard.rparticles
+        if self._engine is None:
+            self._engine = NativeLscEngine(r.device.index or 0)
+        self.lsc.last_params = sharded_lsc_kick(self._engine, self.lsc, r, p_shard.q_array, float(p_shard.E),
+                                                float(dz), self.group)
+
+    def finalize(self, *a, **k):
+        pass

@@ -144,3 +144,105 @@ def test_shard_bounds_cover_everything():
             assert spans[0][0] == 0 and spans[-1][1] == n
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+# ---------------------------------------------------------------------------
+# particle-sharded longitudinal space charge
+# ---------------------------------------------------------------------------
+class OracleLscEngine:
+    """The device stages of the LSC kick restated with numpy (test double for NativeLscEngine):
+    integer fixed-point histogram like csrc/sc_lsc.cu, so the all-reduce is exact."""
+    SHIFT = 40
+
+    def stats(self, r, q):
+        r, q = r.numpy(), q.numpy()
+        tau = r[4]
+        m = tau.mean()
+        return torch.tensor([tau.size, m, np.sum((tau - m) ** 2), tau.min(), tau.max(), q.sum(), r[0].sum(),
+                             r[2].sum()], dtype=torch.float64)
+
+    def deposit(self, r, params):
+        from oracle import lsc_oracle as lo
+        r = r.numpy()
+        nb = int(params["nb"])
+        C = lo.cic_counts(r[4], params["a"], params["ds"], nb)
+        self.bins = torch.from_numpy(np.rint(C * 2.0 ** self.SHIFT).astype(np.int64))
+        sl = (r[4] >= params["slice_min"]) & (r[4] < params["slice_max"])
+        x, y = r[0][sl], r[2][sl]
+        dx, dy = x - params["x_shift"], y - params["y_shift"]
+        self.smax = torch.tensor([x.max(), -x.min(), y.max(), -y.min()], dtype=torch.float64)
+        self.ssum = torch.tensor([x.size, dx.sum(), (dx * dx).sum(), dy.sum(), (dy * dy).sum()], dtype=torch.float64)
+        return self.bins, self.smax, self.ssum
+
+    def solve_kick(self, r, params):
+        from oracle import lsc_oracle as lo
+        r = r.numpy()
+        nb, a, ds, K = int(params["nb"]), params["a"], params["ds"], int(params["K"])
+        C = self.bins.numpy().astype(np.float64) / 2.0 ** self.SHIFT
+        if K >= 0:
+            G = np.exp(-0.5 * (np.arange(-K, K + 1) * ds / params["sigma_s"]) ** 2)
+            C = np.convolve(C, G / G.sum())[K:nb + K]
+        s = self.ssum.numpy()
+        if params["step_profile"]:
+            m = self.smax.numpy()
+            sigma = min(m[0] + m[1], m[2] + m[3]) / 2
+        else:
+            sigma = (np.sqrt(s[2] / s[0] - (s[1] / s[0]) ** 2) + np.sqrt(s[4] / s[0] - (s[3] / s[0]) ** 2)) / 2
+        x = np.arange(nb) * ds + a
+        bunch = params["v"] * C / (ds * C.sum()) / lo.C_LIGHT
+        W = -lo.wake_lsc(x, bunch, params["gamma"], sigma, params["dz"], bool(params["step_profile"])) * params["q"]
+        r[5] += np.interp(r[4], x, W) * 1e-9 / params["pc_ref"]
+
+
+def _lsc_worker(rank, world, port, n, step_profile, out):
+    from ocelot_b200 import LSC
+    from ocelot_b200.distributed import sharded_lsc_kick
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        np.random.seed(3)
+        r0, q0, E = orc.gaussian_bunch(n, energy=0.05, charge=1e-10)
+        r0[0] += 2e-4
+        lo_, hi = shard_bounds(n, world, rank)
+        r = torch.from_numpy(r0[:, lo_:hi].copy())
+        q = torch.from_numpy(q0[lo_:hi].copy())
+        sharded_lsc_kick(OracleLscEngine(), LSC(step_profile=step_profile), r, q, E, 0.3)
+        out[rank] = (lo_, hi, r.numpy().copy())
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("step_profile", [False, True])
+def test_two_rank_sharded_lsc_matches_single_process(step_profile):
+    from oracle import lsc_oracle as lo
+    n, world = 20001, 2
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_lsc_worker, args=(world, port, n, step_profile, out), nprocs=world, join=True)
+        parts = [out[k] for k in range(world)]
+    np.random.seed(3)
+    r0, q0, E = orc.gaussian_bunch(n, energy=0.05, charge=1e-10)
+    r0[0] += 2e-4
+    ref = r0.copy()
+    lo.lsc_kick(ref, q0, E, 0.3, step_profile=step_profile)
+    got = np.empty_like(ref)
+    for lo_, hi, rr in parts:
+        got[:, lo_:hi] = rr
+    d_ref = ref[5] - r0[5]
+    assert np.abs((got[5] - r0[5]) - d_ref).max() <= 1e-10 * np.abs(d_ref).max()
+    assert np.array_equal(got[:5], r0[:5])
+
+
+def test_combine_lsc_stats_is_the_global_statistic():
+    from ocelot_b200.distributed import combine_lsc_stats
+    rng = np.random.default_rng(0)
+    tau = rng.normal(1e-3, 2e-4, 1000)
+    parts = np.split(tau, [100, 350, 351])
+    rows = [[p.size, p.mean(), np.sum((p - p.mean()) ** 2), p.min(), p.max(), p.size * 1.0, 0.0, 0.0] for p in parts]
+    rows.append([0, 0, 0, 0, 0, 0, 0, 0])                      # an empty shard
+    st = combine_lsc_stats(rows)
+    assert st["n"] == 1000 and st["mean_tau"] == pytest.approx(tau.mean(), rel=1e-14)
+    assert np.sqrt(st["m2_tau"] / st["n"]) == pytest.approx(np.std(tau), rel=1e-13)
+    assert (st["min_tau"], st["max_tau"]) == (tau.min(), tau.max())

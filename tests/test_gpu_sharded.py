@@ -97,3 +97,75 @@ def test_two_gpu_sharded_kick_matches_single_gpu(slab, p2p_rho):
     # different reduction order across ranks: agreement to summation round-off (and its
     # amplification through the Green's function when the mesh step moves by an ulp)
     assert _row_err(got, ref) < 1e-10
+
+
+# ---------------------------------------------------------------------------
+# particle-sharded longitudinal space charge
+# ---------------------------------------------------------------------------
+def test_sharded_lsc_single_rank_equals_plugin():
+    from ocelot_b200 import LSC, ParticleArray, DeviceParticleArray
+    from ocelot_b200.distributed import ShardedLSC
+    r0, q0, E = _bunch(100_000, 4)
+    host = ParticleArray(r0.shape[1])
+    host.rparticles[:], host.q_array[:], host.E = r0, q0, E
+    a, b = DeviceParticleArray.from_host(host), DeviceParticleArray.from_host(host)
+    LSC(step_profile=True).apply(a, 0.1)
+    sh = ShardedLSC(step_profile=True)
+    assert sh.step_profile is True and sh.bounds == [-0.4, 0.4]
+    sh.apply(b, 0.1)
+    assert np.array_equal(b.to_host().rparticles, a.to_host().rparticles)    # integer deposit: same bits
+
+
+def _lsc_worker(rank, world, port, n, out):
+    import torch.distributed as dist
+    from ocelot_b200 import ParticleArray, DeviceParticleArray
+    from ocelot_b200.distributed import ShardedLSC, shard_bounds
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        r0, q0, E = _bunch(n, 4)
+        lo, hi = shard_bounds(n, world, rank)
+        host = ParticleArray(hi - lo)
+        host.rparticles[:], host.q_array[:], host.E = r0[:, lo:hi], q0[lo:hi], E
+        shard = DeviceParticleArray.from_host(host, device=f"cuda:{rank}")
+        lsc = ShardedLSC()
+        for _ in range(3):
+            lsc.apply(shard, 0.1)
+        torch.cuda.synchronize()
+        out[rank] = (lo, hi, shard.to_host().rparticles.copy())
+    finally:
+        torch.cuda.synchronize()
+        dist.destroy_process_group()
+
+
+def test_two_gpu_sharded_lsc_matches_single_gpu():
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import torch.multiprocessing as mp
+    from ocelot_b200 import LSC, ParticleArray, DeviceParticleArray
+    n, world = 400_001, 2
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    with ctx.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_lsc_worker, args=(world, port, n, out), nprocs=world, join=True)
+        parts = [out[k] for k in range(world)]
+    r0, q0, E = _bunch(n, 4)
+    host = ParticleArray(n)
+    host.rparticles[:], host.q_array[:], host.E = r0, q0, E
+    dev = DeviceParticleArray.from_host(host)
+    lsc = LSC()
+    for _ in range(3):
+        lsc.apply(dev, 0.1)
+    ref = dev.to_host().rparticles
+    got = np.empty_like(ref)
+    for lo, hi, rr in parts:
+        got[:, lo:hi] = rr
+    d_ref = ref[5] - r0[5]
+    # the histogram is summed exactly; only the 8 + 9 floating-point statistics differ in rounding
+    assert np.abs((got[5] - r0[5]) - d_ref).max() <= 1e-11 * np.abs(d_ref).max()
+    assert np.array_equal(got[:5], ref[:5])

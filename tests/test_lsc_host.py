@@ -132,3 +132,74 @@ def test_special_functions_against_scipy(tmp_path):
     kk = k1(x)
     ok = kk > 1e-300
     assert np.max(np.abs(k[ok] - kk[ok]) / kk[ok]) < 5e-15
+
+
+def _emulated_device_kick(r, params):
+    """What csrc/sc_lsc.cu does with the host-derived parameters, in numpy (oracle pieces): used
+    where no GPU is present to check the host logic end to end."""
+    nb, a, ds, K = int(params["nb"]), params["a"], params["ds"], int(params["K"])
+    tau = r[4]
+    sl = (tau >= params["slice_min"]) & (tau < params["slice_max"])
+    if params["step_profile"]:
+        sigma = min(np.ptp(r[0][sl]), np.ptp(r[2][sl])) / 2
+    else:
+        sigma = (np.std(r[0][sl]) + np.std(r[2][sl])) / 2.
+    C = lo.cic_counts(tau, a, ds, nb)
+    if K >= 0:
+        G = np.exp(-0.5 * (np.arange(-K, K + 1) * ds / params["sigma_s"]) ** 2)
+        G = G / G.sum()
+        C = np.convolve(C, G)[K:nb + K]
+    x = np.arange(nb) * ds + a
+    bunch = params["v"] * C / (ds * C.sum()) / lo.C_LIGHT
+    und = params["und"]
+    res = lo.wake_lsc(x, bunch, params["gamma"], sigma, params["dz"], bool(params["step_profile"]),
+                      K_max=np.sqrt(2 * (und - 1)), fill_factor=1.0 if und != 1 else 0.0)
+    W = -res * params["q"]
+    r[5] += np.interp(tau, x, W) * 1e-9 / params["pc_ref"]
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/ocelot"), reason="reference checkout not present")
+def test_drop_in_under_reference_navigator_with_undulators(monkeypatch):
+    """The unmodified Navigator/track() drive ocelot_b200.LSC through the reference's own LSC test
+    lattice (quadrupoles, drifts, two undulators): lattice scan in prepare(), z0 injection, undulator
+    factor and per-kick scalars are the product's host code; the device kernels are emulated with
+    numpy because this box has no GPU.  Result against the reference LSC on the same bunch."""
+    import sys
+    sys.path.insert(0, "/root/reference")
+    import logging
+    logging.disable(logging.WARNING)
+    from ocelot import MagneticLattice, Navigator, Drift, Quadrupole, Marker, Undulator, track
+    from ocelot.cpbd.beam import generate_parray, Twiss
+    from ocelot.cpbd.sc import LSC as RefLSC
+    from ocelot_b200 import LSC
+
+    kicks = []
+
+    def apply_host(self, r, q_array, E, dz):
+        tau = r[4]
+        stats = dict(n=float(len(tau)), mean_tau=np.mean(tau), m2_tau=np.sum((tau - np.mean(tau)) ** 2),
+                     min_tau=tau.min(), max_tau=tau.max(), sum_q=np.sum(q_array), sum_x=r[0].sum(), sum_y=r[2].sum())
+        params = self.kick_parameters(stats, E, dz)
+        kicks.append(params["und"])
+        _emulated_device_kick(r, params)
+
+    monkeypatch.setattr(LSC, "_apply_host", apply_host)
+
+    def run(cls):
+        tws0 = Twiss(beta_x=6.6, beta_y=16.4, emit_xn=0.5e-6, emit_yn=0.5e-6, E=1)
+        d, qf, qd = Drift(l=1), Quadrupole(l=0.5, k1=0.6), Quadrupole(l=0.25, k1=-0.6)
+        u = Undulator(lperiod=0.04, nperiods=50, Kx=4, Ky=0.)
+        m1, m2 = Marker(), Marker()
+        lat = MagneticLattice((m1, qd, d, u, d, qf, d, u, d, qd, m2))
+        np.random.seed(10)
+        p = generate_parray(sigma_tau=3e-6, sigma_p=1e-4, chirp=0.01, charge=250e-12, nparticles=4000, tws=tws0)
+        navi = Navigator(lat, unit_step=0.1)
+        navi.add_physics_proc(cls(step=1), m1, m2)
+        track(lat, p, navi, print_progress=False)
+        return p.rparticles
+
+    got, ref = run(LSC), run(RefLSC)
+    assert len(kicks) > 50 and max(kicks) > 1.0 and min(kicks) == 1.0      # kicks inside and outside undulators
+    d_ref = ref[5]
+    assert np.abs(got[5] - d_ref).max() <= 1e-10 * np.abs(d_ref).max()
+    assert np.abs(got[4] - ref[4]).max() <= 1e-10 * np.abs(ref[4]).max()
