@@ -55,6 +55,9 @@ def parse():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--slab", default="auto", choices=["auto", "on", "off"],
                     help="multi-GPU Poisson solve: slab-decomposed FFT (on), redundant per rank (off), by mesh size (auto)")
+    ap.add_argument("--rho-reduce", default="nvls", choices=["nvls", "nccl"],
+                    help="multi-GPU charge-grid reduction: the library's in-switch multimem kernel (falls back to "
+                         "NCCL without a multicast mapping) or NCCL")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -212,6 +215,7 @@ def run_native(args):
         # staged kick + NCCL collectives, captured into one CUDA graph (ocelot_b200/distributed.py)
         sharded = ShardedSpaceCharge(step=1, nmesh_xyz=[mesh] * 3,
                                      slab={"auto": None, "on": True, "off": False}[args.slab])
+        sharded.nvls_rho = args.rho_reduce == "nvls"
         sharded.prepare(None)
         sharded.use_graph = False
         sharded.apply(p, DZ)
@@ -328,6 +332,8 @@ def run_native(args):
                        "collectives_per_kick": 0 if world == 1 else (6 if (sharded is not None and sharded._engine.slab) else 3),
                        "poisson": "single GPU" if world == 1 else ("slab-decomposed FFT (reduce-scatter, 2 all-to-all, all-gather)"
                                                                    if sharded._engine.slab else "redundant per rank after all-reduce of rho"),
+                       "rho_reduce": "n/a" if world == 1 else ("in-switch multimem kernel (NVLS)" if sharded._engine.nvls
+                                                               is not None else "NCCL"),
                        "cuda_graph": "whole kick captured once; parameter node refreshed per kick",
                        "l2": "256 MiB buffer written between timed steps (untimed); per-step CUDA events"},
             "warm_l2": {"ms_per_step": warm_ms, "value": world * n / (warm_ms * 1e-3)},

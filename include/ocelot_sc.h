@@ -117,6 +117,14 @@ int ocl_sc_mailbox_exchange(ocl_sc_t* h, int which, void* stream);
  * pass of ocl_sc_stage_solve / ocl_sc_slab_forward sums the `world` grids in rank order while loading
  * them over NVLink.  Replaces the all-reduce (or reduce-scatter) of RHO; no separate reduction kernel. */
 int ocl_sc_set_peer_rho(ocl_sc_t* h, int rank, int world, void* const* peer_rho);
+/* NVLS variant of the charge-grid reduction: `local_rho` is this rank's part of a symmetric allocation
+ * of nx_pad*ny*nz doubles that is also mapped as one multicast range `multicast_rho` (e.g. torch
+ * symmetric memory: buffer_ptrs[rank], multicast_ptr).  ocl_sc_nvls_reduce_rho then replaces the NCCL
+ * all-reduce (redundant solve) or reduce-scatter (slab solve) of OCL_SC_BUF_RHO: barrier over the
+ * mailbox, one kernel of multimem.ld_reduce / multimem.st (the NVSwitch sums each element once, so
+ * every rank ends up with bit-identical sums), barrier.  Needs ocl_sc_mailbox_init. */
+int ocl_sc_set_multicast_rho(ocl_sc_t* h, void* local_rho, void* multicast_rho);
+int ocl_sc_nvls_reduce_rho(ocl_sc_t* h, void* stream);
 
 /* CUDA-graph support for callers that capture the staged kick themselves (e.g. together with
  * their NCCL collectives): with device params on, the stage kernels read E, dz and mesh draws

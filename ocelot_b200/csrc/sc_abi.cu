@@ -56,6 +56,7 @@ struct ocl_sc {
     int* mb_err = nullptr;
     PeerRho peer_rho{};                       // world > 0: rho lives in caller-owned symmetric memory
     double* own_rho = nullptr;                // the cudaMalloc'ed grid (kept for freeing)
+    double* mc_rho = nullptr;                 // multicast mapping of every rank's rho (NVLS reduction)
     // host arrays page-locked in place on first use (numpy buffers persist across kicks)
     bool pin_host = true;
     void* pinned[2] = {nullptr, nullptr};
@@ -476,6 +477,43 @@ int ocl_sc_set_peer_rho(ocl_sc_t* h, int rank, int world, void* const* peer_rho)
     h->rho = (double*)peer_rho[rank];
     CU(h, cudaMemset(h->rho, 0, sizeof(double) * h->rho_count));
     return 0;
+}
+
+int ocl_sc_set_multicast_rho(ocl_sc_t* h, void* local_rho, void* multicast_rho) {
+    if (!h || !local_rho || !multicast_rho) return 1;
+    if (!h->mb.world) return fail(h, "ocl_sc_set_multicast_rho", "call ocl_sc_mailbox_init first");
+    if (set_device(h)) return 1;
+    drop_graph(h);
+    if (!h->own_rho) h->own_rho = h->rho;
+    h->peer_rho.world = 0;                     // the solve reads the local (already reduced) grid
+    h->rho = (double*)local_rho;
+    h->mc_rho = (double*)multicast_rho;
+    CU(h, cudaMemset(h->rho, 0, sizeof(double) * h->rho_count));
+    return 0;
+}
+
+int ocl_sc_nvls_reduce_rho(ocl_sc_t* h, void* stream) {
+    if (!h) return 1;
+    if (!h->mc_rho) return fail(h, "ocl_sc_nvls_reduce_rho", "call ocl_sc_set_multicast_rho first");
+    if (set_device(h)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (adopt_stream(h, st)) return 1;
+    const int world = h->mb.world, rank = h->mb.rank;
+    launch_mailbox_exchange(h->mb, 2, h->rs, h->mb_err, st);            // every rank's deposit is complete
+    if (h->slab_world) {                                               // reduce-scatter into this rank's x-slab
+        const long long plane = (long long)h->md.ny * h->md.nz;
+        const long long lo = (long long)h->slab_rank * h->sx * plane;
+        launch_nvls_reduce(h->mc_rho, lo, lo + (long long)h->sx * plane, h->rho_slab, st);
+        h->launches += 2;
+    } else {                                                           // all-reduce in place
+        const long long n3 = (long long)h->rho_count;
+        const long long chunk = (n3 + world - 1) / world;
+        const long long lo = std::min(n3, (long long)rank * chunk), hi = std::min(n3, lo + chunk);
+        launch_nvls_reduce(h->mc_rho, lo, hi, nullptr, st);
+        launch_mailbox_exchange(h->mb, 2, h->rs, h->mb_err, st);        // every rank's slice has been broadcast
+        h->launches += 3;
+    }
+    return check_launch(h, "k_nvls_reduce");
 }
 
 int ocl_sc_use_device_params(ocl_sc_t* h, int on) {

@@ -25,8 +25,10 @@
 
 namespace ocl {
 
-// threads per block: 128, except M = 512 where one block per SM is resident (147 KB of shared
-// memory) and 256 threads keep 8 warps on it
+// threads per block: 128, except M = 512: 256 threads, in-place stages (74 KB of shared memory), two
+// resident blocks per SM.  Measured at 255^3 on B200: 3.06 -> 1.90 ms per solve against the two-buffer
+// version with one resident block; in-place stages at M <= 256 change nothing (three blocks of the
+// two-buffer version are already resident).
 
 // Shared-memory layout: complex point o of line l lives at x[o * NLP + l] with
 // NLP = NL + 1.  Lines run across lanes, so every butterfly stage reads and
@@ -43,7 +45,19 @@ struct Geom {
     static constexpr int NL = (M >= 512) ? OCL_FFT512_NL : (M >= 256) ? 8 : ((2048 / M) > 32 ? 32 : (2048 / M));   // lines per block
     static constexpr int NLP = NL + 1;
     static constexpr int ELEMS = M * NLP;
-    static constexpr size_t SMEM = sizeof(double2) * (2 * (size_t)ELEMS);
+    // In-place stages (one shared buffer instead of Stockham's two): every thread reads all the
+    // butterflies it owns into registers, the block synchronises, and the results go back into the same
+    // buffer.  Halves the shared memory per block (M = 512: 147 -> 74 KB, 1 -> 3 resident blocks per SM),
+    // which is what lets the load, transform and store phases of different blocks overlap.
+#ifndef OCL_FFT_INPLACE_MIN
+#define OCL_FFT_INPLACE_MIN 512
+#endif
+    static constexpr bool INPLACE = M >= OCL_FFT_INPLACE_MIN;
+    static constexpr size_t SMEM = sizeof(double2) * ((INPLACE ? 1 : 2) * (size_t)ELEMS);
+#ifndef OCL_FFT512_MINB
+#define OCL_FFT512_MINB 2
+#endif
+    static constexpr int MINB = (M >= 512 && INPLACE) ? OCL_FFT512_MINB : 1;             // resident blocks asked of ptxas
 };
 
 __device__ __forceinline__ double2 cmul(double2 a, double2 b) {
@@ -133,6 +147,14 @@ __device__ __forceinline__ FftSmem<M> fft_smem(const double2* __restrict__ tw_g)
 }
 
 __host__ __device__ constexpr int radix_for(int rem) { return (rem % 16 == 0) ? 16 : (rem % 8 == 0) ? 8 : (rem % 4 == 0) ? 4 : 2; }
+// in-place stages keep ITEMS butterflies per thread in registers: radix 8 (512 = 8 * 8 * 8) bounds that
+// at 2 x 8 complex values per thread for 256 threads and 8 lines
+#ifndef OCL_FFT_INPLACE_RADIX
+#define OCL_FFT_INPLACE_RADIX 8
+#endif
+__host__ __device__ constexpr int radix_inplace(int rem) {
+    return (OCL_FFT_INPLACE_RADIX >= 16 && rem % 16 == 0) ? 16 : (rem % 8 == 0) ? 8 : (rem % 4 == 0) ? 4 : 2;
+}
 
 // One Stockham stage of radix R on all NL lines: work item t -> (butterfly j, line l), l fastest.
 template <bool INV, int M, int Ns, int R>
@@ -164,14 +186,64 @@ __device__ __forceinline__ void fft_stage(const double2* __restrict__ x, double2
     }
 }
 
+// The same stage with source == destination: all reads, a barrier, all writes.
+template <bool INV, int M, int Ns, int R>
+__device__ __forceinline__ void fft_stage_inplace(double2* __restrict__ x, const double2* __restrict__ tw) {
+    constexpr int NL = Geom<M>::NL, NLP = Geom<M>::NLP, T = Geom<M>::T;
+    constexpr int nb = M / R;
+    constexpr int step = M / (Ns * R);
+    constexpr int total = nb * NL;
+    constexpr int ITEMS = (total + T - 1) / T;
+    double2 v[ITEMS][R];
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        const int t = threadIdx.x + it * T;
+        if (total % T == 0 || t < total) {
+            const int j = t / NL, l = t % NL;
+            const int k = j & (Ns - 1);
+            const double2* src = x + j * NLP + l;
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[it][r] = src[r * nb * NLP];
+            if (Ns > 1) {
+#pragma unroll
+                for (int r = 1; r < R; ++r) {
+                    double2 w = __ldg(tw + r * k * step);
+                    if (INV) w.y = -w.y;
+                    v[it][r] = cmul(v[it][r], w);
+                }
+            }
+            dft<INV, R>(v[it]);
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        const int t = threadIdx.x + it * T;
+        if (total % T == 0 || t < total) {
+            const int j = t / NL, l = t % NL;
+            const int k = j & (Ns - 1);
+            double2* dst = x + ((j - k) * R + k) * NLP + l;
+#pragma unroll
+            for (int r = 0; r < R; ++r) dst[r * Ns * NLP] = v[it][r];
+        }
+    }
+}
+
 template <bool INV, int M, int Ns>
 __device__ __forceinline__ void fft_stages(double2*& x, double2*& y, const double2* tw) {
     if constexpr (Ns < M) {
-        constexpr int R = radix_for(M / Ns);
-        fft_stage<INV, M, Ns, R>(x, y, tw);
-        __syncthreads();
-        double2* tmp = x; x = y; y = tmp;
-        fft_stages<INV, M, Ns * R>(x, y, tw);
+        if constexpr (Geom<M>::INPLACE) {
+            constexpr int R = radix_inplace(M / Ns);
+            fft_stage_inplace<INV, M, Ns, R>(x, tw);
+            __syncthreads();
+            fft_stages<INV, M, Ns * R>(x, y, tw);
+        } else {
+            constexpr int R = radix_for(M / Ns);
+            fft_stage<INV, M, Ns, R>(x, y, tw);
+            __syncthreads();
+            double2* tmp = x; x = y; y = tmp;
+            fft_stages<INV, M, Ns * R>(x, y, tw);
+        }
     }
 }
 
@@ -203,7 +275,7 @@ __device__ __forceinline__ double green_entry_dev(const double* __restrict__ G, 
 // out P[a][b][kz], kz <= Mz/2 (real).
 // ---------------------------------------------------------------------------
 template <int M>
-__global__ void __launch_bounds__(Geom<M>::T) k_khat_z(const double* __restrict__ gtab, MeshDims md,
+__global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_khat_z(const double* __restrict__ gtab, MeshDims md,
                                                        const double2* __restrict__ tw_g, double* __restrict__ P) {
     constexpr int NL = Geom<M>::NL, NLP = Geom<M>::NLP, H = M / 2;
     const int n = md.nz;
@@ -238,7 +310,7 @@ __global__ void __launch_bounds__(Geom<M>::T) k_khat_z(const double* __restrict_
 // per complex FFT.
 // ---------------------------------------------------------------------------
 template <int M>
-__global__ void __launch_bounds__(Geom<M>::T) k_real_even_outer(const double* __restrict__ in,
+__global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_real_even_outer(const double* __restrict__ in,
                                                                 double* __restrict__ out, int n, int inner,
                                                                 const double2* __restrict__ tw_g) {
     constexpr int NL = Geom<M>::NL, NLP = Geom<M>::NLP, H = M / 2;
@@ -296,7 +368,7 @@ __global__ void __launch_bounds__(Geom<M>::T) k_real_even_outer(const double* __
 // rank order, of the W ranks' partial grids read through NVLink peer mappings (line_offset selects this
 // rank's x-slab in slab mode).
 template <int M>
-__global__ void __launch_bounds__(Geom<M>::T) k_rho_z(const double* __restrict__ rho, PeerRho pr, long long line_offset,
+__global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_rho_z(const double* __restrict__ rho, PeerRho pr, long long line_offset,
                                                       MeshDims md, const double2* __restrict__ tw_g,
                                                       double2* __restrict__ A) {
     constexpr int NL = Geom<M>::NL, NLP = Geom<M>::NLP, H = M / 2;
@@ -353,7 +425,7 @@ __global__ void __launch_bounds__(Geom<M>::T) k_rho_z(const double* __restrict__
 // For MODE 2 inner = My*(Mz/2+1) and khat is [Mx/2+1][My/2+1][Mz/2+1].
 // ---------------------------------------------------------------------------
 template <int M, int MODE>
-__global__ void __launch_bounds__(Geom<M>::T) k_cplx_outer(const double2* in, double2* out,   // may alias (MODE 2)
+__global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_cplx_outer(const double2* in, double2* out,   // may alias (MODE 2)
                                                            int n_in, int n_out, int inner,
                                                            const double2* __restrict__ tw_g,
                                                            const double* __restrict__ khat, MeshDims md, SlabMap sm) {
@@ -433,7 +505,7 @@ __global__ void __launch_bounds__(Geom<M>::T) k_cplx_outer(const double2* in, do
 // phi[l][k<nz] = value / (Mx My Mz) / (4 pi eps0 hx hy hz)   (sc.py:164,167)
 // ---------------------------------------------------------------------------
 template <int M>
-__global__ void __launch_bounds__(Geom<M>::T) k_inv_z(const double2* __restrict__ D, MeshDims md,
+__global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_inv_z(const double2* __restrict__ D, MeshDims md,
                                                       const double2* __restrict__ tw_g, const double* __restrict__ hsrc,
                                                       double four_pi_eps0, double* __restrict__ phi) {
     constexpr int NL = Geom<M>::NL, NLP = Geom<M>::NLP, H = M / 2;

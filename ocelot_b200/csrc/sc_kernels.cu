@@ -467,6 +467,34 @@ void launch_mailbox_exchange(Mailbox mb, int which, ReduceState rs, int* err_fla
     k_mailbox_exchange<<<1, 32, 0, st>>>(mb, which, rs, err_flag);
 }
 
+// ---------------------------------------------------------------------------
+// charge-grid reduction inside the NVSwitch (NVLS): every rank's rho lives at the same offset of a
+// symmetric allocation that is also mapped as ONE multicast address range.  A multimem.ld_reduce on
+// that range makes the switch fetch the element from all ranks and return the sum (LDGMC.E.ADD.F64);
+// a multimem.st broadcasts the result back into every rank's copy.  Each rank reduces 1/world of the
+// grid, so a full all-reduce moves 2 x n^3 x 8 / world bytes per link; every element is summed once,
+// by the switch, so all ranks end up with bit-identical grids.
+//   out == nullptr : all-reduce in place (redundant solve on every rank)
+//   out != nullptr : reduce-scatter: elements [lo, hi) of the sum go to out[0 .. hi-lo) (slab solve)
+// Ordering: the caller brackets the kernel with the mailbox barrier (k_mailbox_exchange which = 2).
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_nvls_reduce(double* __restrict__ mc, long long lo, long long hi,
+                                                    double* __restrict__ out) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
+        double v;
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(v) : "l"(mc + i) : "memory");
+        if (out) out[i - lo] = v;
+        else asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc + i), "d"(v) : "memory");
+    }
+}
+void launch_nvls_reduce(double* mc, long long lo, long long hi, double* out, cudaStream_t st) {
+    if (hi <= lo) return;
+    long long blocks = (hi - lo + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    k_nvls_reduce<<<(int)blocks, 256, 0, st>>>(mc, lo, hi, out);
+}
+
 // fold all-gathered extents: max over ranks of the first 6 doubles, sum of the last 4
 __global__ void k_combine_extents(const double* __restrict__ all, int world, double* __restrict__ emax,
                                   double* __restrict__ esum) {

@@ -41,6 +41,7 @@ struct PeerRho {
     int world;
 };
 void launch_mailbox_exchange(Mailbox mb, int which, ReduceState rs, int* err_flag, cudaStream_t st);
+void launch_nvls_reduce(double* mc, long long lo, long long hi, double* out, cudaStream_t st);
 
 int particle_grid(long long n, int max_blocks);
 

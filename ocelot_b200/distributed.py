@@ -63,8 +63,9 @@ class NativeStageEngine:
         self._gathered = None
         self.mailbox = None
         self.peer_rho = None
+        self.nvls = None
 
-    def setup_mailbox(self, dist, group, peer_rho=True):
+    def setup_mailbox(self, dist, group, peer_rho=True, nvls=False):
         """Map one small symmetric buffer per rank into every rank (torch symmetric memory over
         NVLink peer access) and hand the peer pointers to the native handle: the two scalar
         exchanges then run as one tiny kernel each instead of an NCCL collective."""
@@ -82,6 +83,22 @@ class NativeStageEngine:
         self.mailbox = (box, hdl)              # keep the mapping alive
         # the charge grid itself also lives in symmetric memory: the first FFT pass then sums the
         # ranks' grids while loading them over NVLink (no all-reduce / reduce-scatter kernel)
+        if nvls:
+            # rho in symmetric memory that is also mapped as one multicast range: the NVSwitch sums the
+            # ranks' grids (multimem.ld_reduce) inside ocl_sc_nvls_reduce_rho -- no NCCL on the grid
+            native = self._native
+            grid = symm.empty(self.buffers["rho"].numel(), dtype=torch.float64, device=box.device)
+            grid.zero_()
+            ghdl = symm.rendezvous(grid, group=group if group is not None else dist.group.WORLD)
+            mc = int(getattr(ghdl, "multicast_ptr", 0) or 0)
+            torch.cuda.synchronize()
+            dist.barrier(group=group)
+            if mc:
+                self.solver.set_multicast_rho(ghdl.buffer_ptrs[rank], mc)
+                self.buffers["rho"] = self.solver.collective_buffer(native.BUF_RHO)
+                self.nvls = (grid, ghdl)
+                return True
+            peer_rho = False                   # no multicast mapping on this system: stay on NCCL for rho
         if peer_rho:
             native = self._native
             grid = symm.empty(self.buffers["rho"].numel(), dtype=torch.float64, device=box.device)
@@ -97,7 +114,9 @@ class NativeStageEngine:
     def solve_slab(self, dist, group, draws):
         """Slab-decomposed solve: rho (local partial sums, nx_pad planes) -> field table."""
         b, s = self.buffers, self.solver
-        if self.peer_rho is not None:
+        if self.nvls is not None:
+            s.nvls_reduce_rho()                # barrier + in-switch reduce-scatter into this rank's x-slab
+        elif self.peer_rho is not None:
             s.mailbox_exchange(2)              # barrier: every rank's deposit is complete
         else:
             dist.reduce_scatter_tensor(b["rho_slab"], b["rho"], op=dist.ReduceOp.SUM, group=group)
@@ -164,7 +183,9 @@ def sharded_kick(engine, r, q, E_GeV, dz, draws=None, group=None, dist=None):
     if getattr(engine, "slab", None) is not None:
         engine.solve_slab(dist, group, draws)      # works for any world size >= 1
     else:
-        if multi and getattr(engine, "peer_rho", None) is not None:
+        if multi and getattr(engine, "nvls", None) is not None:
+            engine.solver.nvls_reduce_rho()        # barrier, in-switch all-reduce (multimem), barrier
+        elif multi and getattr(engine, "peer_rho", None) is not None:
             engine.solver.mailbox_exchange(2)      # barrier; the solve's first pass sums the peers' grids
         elif multi:
             dist.all_reduce(b["rho"], op=SUM, group=group)
@@ -191,6 +212,10 @@ class ShardedSpaceCharge:
         # NCCL all-reduce at 1M / 63^3 on 2 x B200 (8-byte peer loads in a latency-bound 125-block
         # kernel), so the default keeps NCCL (NVLS) for rho.
         self.p2p_rho = False
+        # Default: the charge grid is summed inside the NVSwitch by the library's own kernel
+        # (multimem.ld_reduce / multimem.st on a multicast mapping of the ranks' grids); falls back to the
+        # NCCL all-reduce / reduce-scatter when the system offers no multicast mapping.
+        self.nvls_rho = True
         self.use_graph = True
         self._engine = None
         self._graph = None
@@ -215,7 +240,8 @@ class ShardedSpaceCharge:
             self._engine = NativeStageEngine(r.device.index or 0, key, slab=slab)
             if self.p2p and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
                 try:
-                    self._engine.setup_mailbox(dist, self.group, peer_rho=self.p2p_rho)
+                    self._engine.setup_mailbox(dist, self.group, peer_rho=self.p2p_rho,
+                                               nvls=self.nvls_rho and not self.p2p_rho)
                 except Exception as exc:  # noqa: BLE001  (no symmetric memory: stay on NCCL)
                     import logging
                     logging.getLogger(__name__).warning("peer-memory mailbox unavailable (%s); using NCCL", exc)

@@ -46,6 +46,8 @@ _SIGNATURES = {
     "ocl_sc_mailbox_init": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
     "ocl_sc_mailbox_exchange": (C.c_int, [_vp, C.c_int, _vp]),
     "ocl_sc_set_peer_rho": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "ocl_sc_set_multicast_rho": (C.c_int, [_vp, _vp, _vp]),
+    "ocl_sc_nvls_reduce_rho": (C.c_int, [_vp, _vp]),
     "ocl_sc_use_device_params": (C.c_int, [_vp, C.c_int]),
     "ocl_sc_set_kick_params": (C.c_int, [_vp, C.c_double, C.c_double, _dp, _vp]),
     "ocl_sc_stage_momentum": (C.c_int, [_vp, _vp, _ll, _ll, C.c_double, _vp]),
@@ -231,6 +233,13 @@ class Solver:
     def set_peer_rho(self, rank, world, peer_ptrs):
         arr = (_vp * int(world))(*[int(p) for p in peer_ptrs])
         self._check(self._lib.ocl_sc_set_peer_rho(self._h, int(rank), int(world), arr), "ocl_sc_set_peer_rho")
+
+    def set_multicast_rho(self, local_ptr, multicast_ptr):
+        self._check(self._lib.ocl_sc_set_multicast_rho(self._h, int(local_ptr), int(multicast_ptr)),
+                    "ocl_sc_set_multicast_rho")
+
+    def nvls_reduce_rho(self, stream=None):
+        self._check(self._lib.ocl_sc_nvls_reduce_rho(self._h, _stream_ptr(stream)), "ocl_sc_nvls_reduce_rho")
 
     def mailbox_exchange(self, which, stream=None):
         self._check(self._lib.ocl_sc_mailbox_exchange(self._h, int(which), _stream_ptr(stream)),

@@ -418,3 +418,18 @@ def test_one_handle_alternating_streams(native, golden):
             sc.apply(host, 0.1)
         assert row_err(dev.to_host().rparticles, expect) < 1e-11
         assert row_err(host.rparticles, expect) < 1e-11
+
+
+def test_fft_512_box_matches_cufft(native, monkeypatch):
+    """255^3 mesh = 512^3 padded box (BASELINE configs[4]): the hand-written convolution with in-place
+    shared-memory stages against the cuFFT convolution on the full box."""
+    rng = np.random.RandomState(11)
+    shape = (255, 255, 255)
+    rho = rng.rand(*shape) * 1e-12
+    steps = np.array([1.1e-4, 0.7e-4, 2.3e-3])
+    monkeypatch.delenv("OCL_SC_SOLVER", raising=False)
+    phi_own = native.Solver(0, shape).potential_host(rho, steps)
+    monkeypatch.setenv("OCL_SC_SOLVER", "cufft")
+    phi_lib = native.Solver(0, shape).potential_host(rho, steps)
+    monkeypatch.delenv("OCL_SC_SOLVER", raising=False)
+    assert rel_to_max(phi_own, phi_lib) < 1e-13
