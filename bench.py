@@ -370,6 +370,29 @@ def run_native(args):
                            "call": "ocelot_b200.SpaceCharge.apply(p_array, dz) on pinned host arrays "
                                    "(independent replica per rank)"}
 
+    # ---- the 1-D sibling on the same resident bunch, reported beside the headline ----
+    if line is not None and world == 1:
+        from ocelot_b200 import LSC
+        import types
+        dp = types.SimpleNamespace(rparticles=r, q_array=q, E=E_GEV)     # apply() duck-types these three
+        if True:
+            lsc = LSC(step=1, device=local)
+            for _ in range(3):
+                lsc.apply(dp, DZ)
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            kl = max(3, min(K, 20))
+            a.record()
+            for _ in range(kl):
+                lsc.apply(dp, DZ)
+            b.record()
+            torch.cuda.synchronize()
+            lms = a.elapsed_time(b) / kl
+            line["lsc"] = {"value": n / (lms * 1e-3), "unit": "LSC particle-kicks/s", "ms_per_step": lms,
+                           "grid_points": int(lsc.last_params["nb"]),
+                           "note": "ocelot_b200.LSC.apply on the resident bunch (one host sync per kick for the "
+                                   "grid definition); not part of `value`"}
+
     # ---- CPU baseline on the host cores (rank 0, N = 1 only) ----
     if line is not None and world == 1 and not args.no_cpu_baseline:
         ns = cpu_sample_size(n)

@@ -277,6 +277,7 @@ __device__ __forceinline__ double green_entry_dev(const double* __restrict__ G, 
 template <int M>
 __global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_khat_z(const double* __restrict__ gtab, MeshDims md,
                                                        const double2* __restrict__ tw_g, double* __restrict__ P) {
+    pdl_enter();
     constexpr int NL = Geom<M>::NL, NLP = Geom<M>::NLP, H = M / 2;
     const int n = md.nz;
     FftSmem<M> s = fft_smem<M>(tw_g);
@@ -294,6 +295,7 @@ __global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_khat_z(const doub
         if (c) s.a[(M - c) * NLP + p] = make_double2(e1, e2);
     }
     double2* X = block_fft<false, M>(s.a, s.b, s.tw);
+    pdl_trigger();
     for (int t = threadIdx.x; t < NL * (H + 1); t += Geom<M>::T) {
         const int p = t / (H + 1), kz = t - p * (H + 1);
         const int l1 = line0 + 2 * p, l2 = l1 + 1;
@@ -313,6 +315,7 @@ template <int M>
 __global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_real_even_outer(const double* __restrict__ in,
                                                                 double* __restrict__ out, int n, int inner,
                                                                 const double2* __restrict__ tw_g) {
+    pdl_enter();
     constexpr int NL = Geom<M>::NL, NLP = Geom<M>::NLP, H = M / 2;
     FftSmem<M> s = fft_smem<M>(tw_g);
     const int pairs_total = (inner + 1) / 2;
@@ -350,6 +353,7 @@ __global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_real_even_outer(c
         }
     }
     double2* X = block_fft<false, M>(s.a, s.b, s.tw);
+    pdl_trigger();
     for (int t = threadIdx.x; t < NL * (H + 1); t += Geom<M>::T) {
         const int ko = t / NL, p = t % NL;
         if (p >= pairs) continue;
@@ -371,6 +375,7 @@ template <int M>
 __global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_rho_z(const double* __restrict__ rho, PeerRho pr, long long line_offset,
                                                       MeshDims md, const double2* __restrict__ tw_g,
                                                       double2* __restrict__ A) {
+    pdl_enter();
     constexpr int NL = Geom<M>::NL, NLP = Geom<M>::NLP, H = M / 2;
     const int n = md.nz;
     FftSmem<M> s = fft_smem<M>(tw_g);
@@ -404,6 +409,7 @@ __global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_rho_z(const doubl
         }
     }
     double2* Z = block_fft<false, M>(s.a, s.b, s.tw);
+    pdl_trigger();
     for (int t = threadIdx.x; t < NL * (H + 1); t += Geom<M>::T) {
         const int p = t / (H + 1), kz = t - p * (H + 1);
         const int l1 = line0 + 2 * p, l2 = l1 + 1;
@@ -429,6 +435,7 @@ __global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_cplx_outer(const 
                                                            int n_in, int n_out, int inner,
                                                            const double2* __restrict__ tw_g,
                                                            const double* __restrict__ khat, MeshDims md, SlabMap sm) {
+    pdl_enter();
     constexpr int NL = Geom<M>::NL, NLP = Geom<M>::NLP;
     FftSmem<M> s = fft_smem<M>(tw_g);
     const int blocks_per_batch = (inner + NL - 1) / NL;
@@ -491,6 +498,7 @@ __global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_cplx_outer(const 
         double2* Y = (X == s.a) ? s.b : s.a;
         X = block_fft<true, M>(X, Y, s.tw);
     }
+    pdl_trigger();
     for (int t = threadIdx.x; t < NL * n_out; t += Geom<M>::T) {
         const int o = t / NL, l = t % NL;
         if (l < nl) {
@@ -508,6 +516,7 @@ template <int M>
 __global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_inv_z(const double2* __restrict__ D, MeshDims md,
                                                       const double2* __restrict__ tw_g, const double* __restrict__ hsrc,
                                                       double four_pi_eps0, double* __restrict__ phi) {
+    pdl_enter();
     constexpr int NL = Geom<M>::NL, NLP = Geom<M>::NLP, H = M / 2;
     const int n = md.nz;
     FftSmem<M> s = fft_smem<M>(tw_g);
@@ -537,6 +546,7 @@ __global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_inv_z(const doubl
         }
     }
     double2* X = block_fft<true, M>(s.a, s.b, s.tw);
+    pdl_trigger();
     const double inv_m3 = 1.0 / ((double)md.mx * (double)md.my * (double)md.mz);
     const double denom = four_pi_eps0 * hsrc[0] * hsrc[1] * hsrc[2];
     for (int t = threadIdx.x; t < NL * n; t += Geom<M>::T) {
@@ -589,19 +599,19 @@ void launch_khat(const double* gtab, MeshDims md, FftWork w, cudaStream_t st) {
     OCL_FFT_DISPATCH(md.mz,   // z: P[nx][ny][hz1]
         const int lb = 2 * Geom<MM>::NL;
         const int blocks = (md.nx * md.ny + lb - 1) / lb;
-        k_khat_z<MM><<<blocks, Geom<MM>::T, Geom<MM>::SMEM, st>>>(gtab, md, w.tw_z, w.P);
+        launch_k(k_khat_z<MM>, dim3(blocks), dim3(Geom<MM>::T), Geom<MM>::SMEM, st, gtab, md, w.tw_z, w.P);
     )
     OCL_FFT_DISPATCH(md.my,   // y: per a, in [ny][hz1] -> Q[a][hy1][hz1]
         const int pb = Geom<MM>::NL;
         const int blocks_per_batch = ((hz1 + 1) / 2 + pb - 1) / pb;
-        k_real_even_outer<MM><<<blocks_per_batch * md.nx, Geom<MM>::T, Geom<MM>::SMEM, st>>>(w.P, w.Q, md.ny, hz1,
+        launch_k(k_real_even_outer<MM>, dim3(blocks_per_batch * md.nx), dim3(Geom<MM>::T), Geom<MM>::SMEM, st, w.P, w.Q, md.ny, hz1,
                                                                                            w.tw_y);
     )
     OCL_FFT_DISPATCH(md.mx,   // x: in [nx][hy1*hz1] -> khat[hx1][hy1*hz1]
         const int inner = hy1 * hz1;
         const int pb = Geom<MM>::NL;
         const int blocks = ((inner + 1) / 2 + pb - 1) / pb;
-        k_real_even_outer<MM><<<blocks, Geom<MM>::T, Geom<MM>::SMEM, st>>>(w.Q, w.khat, md.nx, inner, w.tw_x);
+        launch_k(k_real_even_outer<MM>, dim3(blocks), dim3(Geom<MM>::T), Geom<MM>::SMEM, st, w.Q, w.khat, md.nx, inner, w.tw_x);
     )
 }
 
@@ -612,12 +622,12 @@ void launch_convolve_pre(const double* rho, PeerRho pr, MeshDims md, FftWork w, 
     OCL_FFT_DISPATCH(md.mz,
         const int lbz = 2 * Geom<MM>::NL;
         const int zblocks = (md.nx * md.ny + lbz - 1) / lbz;
-        k_rho_z<MM><<<zblocks, Geom<MM>::T, Geom<MM>::SMEM, st>>>(rho, pr, 0, md, w.tw_z, w.A);
+        launch_k(k_rho_z<MM>, dim3(zblocks), dim3(Geom<MM>::T), Geom<MM>::SMEM, st, rho, pr, 0, md, w.tw_z, w.A);
     )
     OCL_FFT_DISPATCH(md.my,   // y forward: per i, [ny][hz1] -> [My][hz1]
         const int lb = Geom<MM>::NL;
         const int bpb = (hz1 + lb - 1) / lb;
-        k_cplx_outer<MM, 0><<<bpb * md.nx, Geom<MM>::T, Geom<MM>::SMEM, st>>>(w.A, w.B, md.ny, md.my, hz1, w.tw_y,
+        launch_k(k_cplx_outer<MM, 0>, dim3(bpb * md.nx), dim3(Geom<MM>::T), Geom<MM>::SMEM, st, w.A, w.B, md.ny, md.my, hz1, w.tw_y,
                                                                              nullptr, md, SlabMap{});
     )
 }
@@ -629,19 +639,19 @@ void launch_convolve_post(MeshDims md, FftWork w, const double* h3, double four_
         const int inner = md.my * hz1;
         const int lb = Geom<MM>::NL;
         const int blocks = (inner + lb - 1) / lb;
-        k_cplx_outer<MM, 2><<<blocks, Geom<MM>::T, Geom<MM>::SMEM, st>>>(w.B, w.B, md.nx, md.nx, inner, w.tw_x, w.khat,
+        launch_k(k_cplx_outer<MM, 2>, dim3(blocks), dim3(Geom<MM>::T), Geom<MM>::SMEM, st, w.B, w.B, md.nx, md.nx, inner, w.tw_x, w.khat,
                                                                         md, SlabMap{});
     )
     OCL_FFT_DISPATCH(md.my,   // y inverse: per i, [My][hz1] -> [ny][hz1]
         const int lb = Geom<MM>::NL;
         const int bpb = (hz1 + lb - 1) / lb;
-        k_cplx_outer<MM, 1><<<bpb * md.nx, Geom<MM>::T, Geom<MM>::SMEM, st>>>(w.B, w.A, md.my, md.ny, hz1, w.tw_y,
+        launch_k(k_cplx_outer<MM, 1>, dim3(bpb * md.nx), dim3(Geom<MM>::T), Geom<MM>::SMEM, st, w.B, w.A, md.my, md.ny, hz1, w.tw_y,
                                                                              nullptr, md, SlabMap{});
     )
     OCL_FFT_DISPATCH(md.mz,
         const int lbz = 2 * Geom<MM>::NL;
         const int zblocks = (md.nx * md.ny + lbz - 1) / lbz;
-        k_inv_z<MM><<<zblocks, Geom<MM>::T, Geom<MM>::SMEM, st>>>(w.A, md, w.tw_z, h3, four_pi_eps0, phi);
+        launch_k(k_inv_z<MM>, dim3(zblocks), dim3(Geom<MM>::T), Geom<MM>::SMEM, st, w.A, md, w.tw_z, h3, four_pi_eps0, phi);
     )
 }
 
@@ -657,13 +667,13 @@ void launch_slab_forward(const double* rho_slab, PeerRho pr, long long line_offs
     OCL_FFT_DISPATCH(md.mz,
         const int lbz = 2 * Geom<MM>::NL;
         const int zblocks = (sx * md.ny + lbz - 1) / lbz;
-        k_rho_z<MM><<<zblocks, Geom<MM>::T, Geom<MM>::SMEM, st>>>(rho_slab, pr, line_offset, ms, w.tw_z, w.A);
+        launch_k(k_rho_z<MM>, dim3(zblocks), dim3(Geom<MM>::T), Geom<MM>::SMEM, st, rho_slab, pr, line_offset, ms, w.tw_z, w.A);
     )
     SlabMap sm{1, fs, sx, 0, 0};
     OCL_FFT_DISPATCH(md.my,   // y forward, stored in chunk layout for the all-to-all
         const int lb = Geom<MM>::NL;
         const int bpb = (hz1 + lb - 1) / lb;
-        k_cplx_outer<MM, 0><<<bpb * sx, Geom<MM>::T, Geom<MM>::SMEM, st>>>(w.A, xchg, md.ny, md.my, hz1, w.tw_y,
+        launch_k(k_cplx_outer<MM, 0>, dim3(bpb * sx), dim3(Geom<MM>::T), Geom<MM>::SMEM, st, w.A, xchg, md.ny, md.my, hz1, w.tw_y,
                                                                           nullptr, md, sm);
     )
 }
@@ -674,7 +684,7 @@ void launch_slab_xpass(double2* xchg, MeshDims md, int fs, int f_base, FftWork w
     OCL_FFT_DISPATCH(md.mx,   // x: forward, * K_hat, inverse on this rank's chunk of lines, [nx_pad][fs] in place
         const int lb = Geom<MM>::NL;
         const int blocks = (fs + lb - 1) / lb;
-        k_cplx_outer<MM, 2><<<blocks, Geom<MM>::T, Geom<MM>::SMEM, st>>>(xchg, xchg, md.nx, md.nx, fs, w.tw_x, w.khat,
+        launch_k(k_cplx_outer<MM, 2>, dim3(blocks), dim3(Geom<MM>::T), Geom<MM>::SMEM, st, xchg, xchg, md.nx, md.nx, fs, w.tw_x, w.khat,
                                                                         md, sm);
     )
 }
@@ -688,13 +698,13 @@ void launch_slab_inverse(const double2* xchg, MeshDims md, int sx, int fs, FftWo
     OCL_FFT_DISPATCH(md.my,   // y inverse, read from chunk layout
         const int lb = Geom<MM>::NL;
         const int bpb = (hz1 + lb - 1) / lb;
-        k_cplx_outer<MM, 1><<<bpb * sx, Geom<MM>::T, Geom<MM>::SMEM, st>>>(xchg, w.A, md.my, md.ny, hz1, w.tw_y,
+        launch_k(k_cplx_outer<MM, 1>, dim3(bpb * sx), dim3(Geom<MM>::T), Geom<MM>::SMEM, st, xchg, w.A, md.my, md.ny, hz1, w.tw_y,
                                                                           nullptr, md, sm);
     )
     OCL_FFT_DISPATCH(md.mz,
         const int lbz = 2 * Geom<MM>::NL;
         const int zblocks = (sx * md.ny + lbz - 1) / lbz;
-        k_inv_z<MM><<<zblocks, Geom<MM>::T, Geom<MM>::SMEM, st>>>(w.A, ms, w.tw_z, h3, four_pi_eps0, phi_slab);
+        launch_k(k_inv_z<MM>, dim3(zblocks), dim3(Geom<MM>::T), Geom<MM>::SMEM, st, w.A, ms, w.tw_z, h3, four_pi_eps0, phi_slab);
     )
 }
 

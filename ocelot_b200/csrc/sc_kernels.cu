@@ -16,9 +16,20 @@
 // No kernel needs a host round trip: the scalar state (frame, mesh) is
 // re-derived on the device by every block from the tiny reduced buffers, which
 // is also what lets a multi-GPU caller all-reduce those buffers in between.
+#include <cstdlib>
+
 #include "sc_kernels.h"
 
 namespace ocl {
+
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("OCL_SC_PDL");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
+}
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
@@ -40,6 +51,7 @@ constexpr int kPipeDepth = 3;
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 4) k_momentum(const double* __restrict__ r, long long ld, long long n,
                                                          KP kp, ReduceState rs) {
+    pdl_enter();
     const RefParams rp = kp_ref(kp);
     __shared__ double sh[3 * kWarps];
     __shared__ double pipe[kPipeDepth * 3 * kThreads];
@@ -50,6 +62,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_momentum(const double* __restri
         const double pzr = mad_pz_rel(rp, w[0], w[1], w[2], gam);
         v[0] += w[0]; v[1] += w[1]; v[2] += pzr;       // p = (x', y', pz_rel) * pc: scaled once at the end
     });
+    pdl_trigger();
     if (grid_reduce<3, 0>(v, rs.part, rs.ticket + 0, sh) && threadIdx.x == 0) {
         rs.sums[0] = v[0] * rp.pc; rs.sums[1] = v[1] * rp.pc; rs.sums[2] = v[2] * rp.pc;
         rs.sums[3] = (double)n;
@@ -62,6 +75,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_momentum(const double* __restri
 __global__ void __launch_bounds__(kThreads, 3) k_extent(const double* __restrict__ r, long long ld,
                                                        const double* __restrict__ q, long long n, KP kp,
                                                        ReduceState rs) {
+    pdl_enter();
     const RefParams rp = kp_ref(kp);
     __shared__ double sh[10 * kWarps];
     __shared__ double pipe[kPipeDepth * 7 * kThreads];
@@ -80,6 +94,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_extent(const double* __restrict
         v[3] = fmax(v[3], -a); v[4] = fmax(v[4], -b); v[5] = fmax(v[5], -g);
         v[6] += qi * a; v[7] += qi * b; v[8] += qi * g; v[9] += qi;
     });
+    pdl_trigger();
     if (grid_reduce<10, 6>(v, rs.part, rs.ticket + 1, sh) && threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) rs.emax[k] = v[k];
@@ -94,6 +109,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_extent(const double* __restrict
 __global__ void __launch_bounds__(kThreads, 3) k_deposit(const double* __restrict__ r, long long ld,
                                                         const double* __restrict__ q, long long n, KP kp,
                                                         ReduceState rs, MeshDims md, double* __restrict__ rho) {
+    pdl_enter();
     const RefParams rp = kp_ref(kp);
     const Draws dr = kp_draws(kp);
     __shared__ double pipe[kPipeDepth * 7 * kThreads];
@@ -167,6 +183,7 @@ __device__ __forceinline__ void resolve_steps(const StepSrc& src, const ReduceSt
 // antiderivative on the (n+1)^3 half-offset points (sc.py:116-126)
 __global__ void __launch_bounds__(kThreads) k_green_table(StepSrc src, ReduceState rs, MeshDims md, KP kp,
                                                          double* __restrict__ gtab, double* __restrict__ h3) {
+    pdl_enter();
     const Draws dr = kp_draws(kp);
     __shared__ double h[3];
     resolve_steps(src, rs, md, dr, h);
@@ -297,6 +314,7 @@ __device__ __forceinline__ double field_value(const double* __restrict__ phi, co
 // grid = (ceil(nz*ny / threads), nx, 3): no integer division by runtime strides per thread
 __global__ void __launch_bounds__(kThreads) k_field(const double* __restrict__ phi, StepSrc src, ReduceState rs,
                                                    MeshDims md, KP kp, EQuad* __restrict__ equad) {
+    pdl_enter();
     const Draws dr = kp_draws(kp);
     __shared__ double h[3];
     __shared__ double ih[3];
@@ -324,6 +342,7 @@ __global__ void __launch_bounds__(kThreads, GK_BLOCKS) k_gather_kick(double* __r
                                                             KP kp, ReduceState rs, MeshDims md,
                                                             const EQuad* __restrict__ equad,
                                                             double* __restrict__ exyz_out) {
+    pdl_enter();
     const RefParams rp = kp_ref(kp);
     const Draws dr = kp_draws(kp);
     const double cdT = kp_cdT(kp);
@@ -410,6 +429,7 @@ constexpr int kGatherCap = 148 * GK_BLOCKS;   // gather/kick: resident blocks pe
 constexpr int kGridCap = 148 * 16;    // grid kernels
 
 __global__ void k_set_params(KickParams v, KickParams* dst) {
+    pdl_enter();
     if (threadIdx.x == 0 && blockIdx.x == 0) *dst = v;
 }
 // ---------------------------------------------------------------------------
@@ -511,25 +531,25 @@ void launch_combine_extents(const double* all, int world, ReduceState rs, cudaSt
     k_combine_extents<<<1, 32, 0, st>>>(all, world, rs.emax, rs.esum);
 }
 
-void launch_set_params(KickParams v, KickParams* dst, cudaStream_t st) { k_set_params<<<1, 32, 0, st>>>(v, dst); }
+void launch_set_params(KickParams v, KickParams* dst, cudaStream_t st) { launch_k(k_set_params, dim3(1), dim3(32), 0, st, v, dst); }
 const void* set_params_kernel() { return (const void*)k_set_params; }
 
 void launch_momentum(const double* r, long long ld, long long n, KP kp, ReduceState rs, cudaStream_t st) {
-    k_momentum<<<particle_grid(n, rs.max_blocks), kThreads, 0, st>>>(r, ld, n, kp, rs);
+    launch_k(k_momentum, dim3(particle_grid(n, rs.max_blocks)), dim3(kThreads), 0, st, r, ld, n, kp, rs);
 }
 void launch_extent(const double* r, long long ld, const double* q, long long n, KP kp, ReduceState rs,
                    cudaStream_t st) {
-    k_extent<<<particle_grid(n, 148 * 3), kThreads, 0, st>>>(r, ld, q, n, kp, rs);
+    launch_k(k_extent, dim3(particle_grid(n, 148 * 3)), dim3(kThreads), 0, st, r, ld, q, n, kp, rs);
 }
 void launch_deposit(const double* r, long long ld, const double* q, long long n, KP kp, ReduceState rs,
                     MeshDims md, double* rho, cudaStream_t st) {
-    k_deposit<<<grid_for(n, 148 * 3), kThreads, 0, st>>>(r, ld, q, n, kp, rs, md, rho);
+    launch_k(k_deposit, dim3(grid_for(n, 148 * 3)), dim3(kThreads), 0, st, r, ld, q, n, kp, rs, md, rho);
 }
 void launch_green_table(ReduceState rs, MeshDims md, KP kp, double* gtab, double* h3, cudaStream_t st) {
     StepSrc src;
     src.given = 0; src.h[0] = src.h[1] = src.h[2] = 0.0;
     long long total = (long long)(md.nx + 1) * (md.ny + 1) * (md.nz + 1);
-    k_green_table<<<grid_for(total, kGridCap), kThreads, 0, st>>>(src, rs, md, kp, gtab, h3);
+    launch_k(k_green_table, dim3(grid_for(total, kGridCap)), dim3(kThreads), 0, st, src, rs, md, kp, gtab, h3);
 }
 void launch_green_table_steps(const double steps[3], MeshDims md, double* gtab, double* h3, cudaStream_t st) {
     StepSrc src;
@@ -537,7 +557,7 @@ void launch_green_table_steps(const double steps[3], MeshDims md, double* gtab, 
     ReduceState rs = {};
     KP kp = {};
     long long total = (long long)(md.nx + 1) * (md.ny + 1) * (md.nz + 1);
-    k_green_table<<<grid_for(total, kGridCap), kThreads, 0, st>>>(src, rs, md, kp, gtab, h3);
+    launch_k(k_green_table, dim3(grid_for(total, kGridCap)), dim3(kThreads), 0, st, src, rs, md, kp, gtab, h3);
 }
 void launch_green_mirror(const double* gtab, MeshDims md, double* kpad, cudaStream_t st) {
     cudaMemsetAsync(kpad, 0, sizeof(double) * (size_t)md.mx * md.my * md.mz, st);
@@ -583,17 +603,17 @@ void launch_field(const double* phi, ReduceState rs, MeshDims md, KP kp, EQuad* 
     StepSrc src;
     src.given = 0; src.h[0] = src.h[1] = src.h[2] = 0.0;
     dim3 grid((md.ny * md.nz + kThreads - 1) / kThreads, md.nx, 3);
-    k_field<<<grid, kThreads, 0, st>>>(phi, src, rs, md, kp, equad);
+    launch_k(k_field, dim3(grid), dim3(kThreads), 0, st, phi, src, rs, md, kp, equad);
 }
 void launch_gather_kick(double* r, long long ld, long long n, KP kp, ReduceState rs, MeshDims md,
                         const EQuad* equad, double* exyz_out, int do_kick, cudaStream_t st) {
     int grid = grid_for(n, kGatherCap);
     if (do_kick && exyz_out)
-        k_gather_kick<true, true><<<grid, kThreads, 0, st>>>(r, ld, n, kp, rs, md, equad, exyz_out);
+        launch_k(k_gather_kick<true, true>, dim3(grid), dim3(kThreads), 0, st, r, ld, n, kp, rs, md, equad, exyz_out);
     else if (do_kick)
-        k_gather_kick<true, false><<<grid, kThreads, 0, st>>>(r, ld, n, kp, rs, md, equad, nullptr);
+        launch_k(k_gather_kick<true, false>, dim3(grid), dim3(kThreads), 0, st, r, ld, n, kp, rs, md, equad, nullptr);
     else
-        k_gather_kick<false, true><<<grid, kThreads, 0, st>>>(r, ld, n, kp, rs, md, equad, exyz_out);
+        launch_k(k_gather_kick<false, true>, dim3(grid), dim3(kThreads), 0, st, r, ld, n, kp, rs, md, equad, exyz_out);
 }
 void launch_mad_to_cart(const double* r, long long ld, long long n, RefParams rp, double* xp, long long ld_xp,
                         cudaStream_t st) {
