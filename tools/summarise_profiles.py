@@ -2,7 +2,8 @@
 import csv, glob, io, json, os, subprocess, sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-OUT = os.path.join(ROOT, "profiles")
+OUT = os.environ.get("PROFILES_OUT") or os.path.join(ROOT, "profiles")
+os.makedirs(OUT, exist_ok=True)
 TAG = sys.argv[1] if len(sys.argv) > 1 else "r1"
 KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
@@ -44,17 +45,26 @@ for rep in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"{TAG}_*.ncu-rep")
                 traffic.setdefault(wl, {})[kn] = tb
     print("wrote", name + "_summary.csv")
 if traffic:
+    old = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            old = json.load(f)
+    except Exception:  # noqa: BLE001
+        pass
+    for wl, d in traffic.items():
+        old.setdefault(wl, {}).update(d)
+    traffic = old
     with open(os.path.join(OUT, "traffic.json"), "w") as f:
         json.dump(traffic, f, indent=1, sort_keys=True)
-for lst in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"{TAG}_bench_launches.csv"))):
+for lst in sorted(glob.glob(os.path.join(ROOT, "gpurun_out", f"{TAG}_*launches*.csv"))):
     rows = list(csv.reader(open(lst)))
     h = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
     cols = rows[h]
     ki, vi, ui = cols.index("Kernel Name"), cols.index("Metric Value"), cols.index("Metric Unit")
-    with open(os.path.join(OUT, f"{TAG}_bench_launches.csv"), "w", newline="") as f:
+    with open(os.path.join(OUT, os.path.basename(lst)), "w", newline="") as f:
         w = csv.writer(f)
         w.writerow(["launch", "kernel", "gpu__time_duration.sum", "unit"])
         for n, r in enumerate(rows[h + 1:]):
             if len(r) > vi:
                 w.writerow([n, r[ki][:70], r[vi], r[ui]])
-    print("wrote", f"{TAG}_bench_launches.csv")
+    print("wrote", os.path.basename(lst))
