@@ -443,6 +443,7 @@ __global__ void k_set_params(KickParams v, KickParams* dst) {
 // exchange e of the *other* kind, which in turn requires everyone to have consumed this kind's e.
 // ---------------------------------------------------------------------------
 __global__ void k_mailbox_exchange(Mailbox mb, int which, ReduceState rs, int* __restrict__ err_flag) {
+    pdl_enter();
     const int lane = threadIdx.x;
     const int nv = which == 0 ? 4 : (which == 1 ? 10 : 0);      // which 2: barrier only ("rho ready")
     const int vbase = which == 0 ? 0 : 32;
@@ -484,7 +485,7 @@ __global__ void k_mailbox_exchange(Mailbox mb, int which, ReduceState rs, int* _
     }
 }
 void launch_mailbox_exchange(Mailbox mb, int which, ReduceState rs, int* err_flag, cudaStream_t st) {
-    k_mailbox_exchange<<<1, 32, 0, st>>>(mb, which, rs, err_flag);
+    launch_k(k_mailbox_exchange, dim3(1), dim3(32), 0, st, mb, which, rs, err_flag);
 }
 
 // ---------------------------------------------------------------------------
@@ -500,6 +501,7 @@ void launch_mailbox_exchange(Mailbox mb, int which, ReduceState rs, int* err_fla
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_nvls_reduce(double* __restrict__ mc, long long lo, long long hi,
                                                     double* __restrict__ out) {
+    pdl_enter();
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
         double v;
@@ -512,12 +514,13 @@ void launch_nvls_reduce(double* mc, long long lo, long long hi, double* out, cud
     if (hi <= lo) return;
     long long blocks = (hi - lo + 255) / 256;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    k_nvls_reduce<<<(int)blocks, 256, 0, st>>>(mc, lo, hi, out);
+    launch_k(k_nvls_reduce, dim3((int)blocks), dim3(256), 0, st, mc, lo, hi, out);
 }
 
 // fold all-gathered extents: max over ranks of the first 6 doubles, sum of the last 4
 __global__ void k_combine_extents(const double* __restrict__ all, int world, double* __restrict__ emax,
                                   double* __restrict__ esum) {
+    pdl_enter();
     const int k = threadIdx.x;
     if (k >= 10) return;
     double v = all[k];
@@ -528,7 +531,7 @@ __global__ void k_combine_extents(const double* __restrict__ all, int world, dou
     if (k < 6) emax[k] = v; else esum[k - 6] = v;
 }
 void launch_combine_extents(const double* all, int world, ReduceState rs, cudaStream_t st) {
-    k_combine_extents<<<1, 32, 0, st>>>(all, world, rs.emax, rs.esum);
+    launch_k(k_combine_extents, dim3(1), dim3(32), 0, st, all, world, rs.emax, rs.esum);
 }
 
 void launch_set_params(KickParams v, KickParams* dst, cudaStream_t st) { launch_k(k_set_params, dim3(1), dim3(32), 0, st, v, dst); }
