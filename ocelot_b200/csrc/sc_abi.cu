@@ -1083,7 +1083,8 @@ int ocl_sc_lsc_deposit(ocl_sc_t* h, const double* d_r, long long ld, long long n
     if (adopt_stream(h, st)) return 1;
     if (ensure_lsc(h, lp.nb)) return 1;
     h->lsc_nb = lp.nb;
-    launch_lsc_deposit(d_r, ld, n, lp, h->lw, st);
+    if (launch_lsc_deposit(d_r, ld, n, lp, h->lw, st))
+        return fail(h, "ocl_sc_lsc_deposit", "grid too fine for this particle count (fewer than 24 fractional bits left)");
     h->launches += 2;
     return check_launch(h, "k_lsc_deposit");
 }

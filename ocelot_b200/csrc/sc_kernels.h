@@ -124,7 +124,7 @@ struct LscWork {
 };
 void launch_lsc_stats(const double* r, long long ld, const double* q, long long n, LscWork w, cudaStream_t st);
 void launch_lsc_twiddles(int nb, LscWork w, cudaStream_t st);
-void launch_lsc_deposit(const double* r, long long ld, long long n, const LscParams& lp, LscWork w, cudaStream_t st);
+int launch_lsc_deposit(const double* r, long long ld, long long n, const LscParams& lp, LscWork w, cudaStream_t st);
 int launch_lsc_solve(const LscParams& lp, LscWork w, cudaStream_t st);
 long long lsc_spread_words(int nb);
 void launch_lsc_kick(double* r, long long ld, long long n, const LscParams& lp, LscWork w, cudaStream_t st);

@@ -397,8 +397,11 @@ int lsc_replicas(int nb) {
 
 long long lsc_spread_words(int nb) { return (long long)nb * lsc_replicas(nb); }
 
-void launch_lsc_deposit(const double* r, long long ld, long long n, const LscParams& lp, LscWork w,
-                        cudaStream_t st) {
+// returns 1 (nothing launched) if the packed word cannot hold 24 fractional bits: a grid so fine that the
+// histogram has few replicas, combined with so many particles per replica that the count field crowds
+// out the fraction (e.g. nb = 2^20 with 4e8 particles)
+int launch_lsc_deposit(const double* r, long long ld, long long n, const LscParams& lp, LscWork w,
+                       cudaStream_t st) {
     const int grid = lsc_grid(n, w.max_blocks);
     LscPack pk;
     pk.replicas = lsc_replicas(lp.nb);
@@ -411,11 +414,13 @@ void launch_lsc_deposit(const double* r, long long ld, long long n, const LscPar
     pk.cshift = 64 - cbits;
     pk.fbits = pk.cshift - cbits;                                    // F_i < 2^cshift for any fill
     if (pk.fbits > lp.fx_shift) pk.fbits = lp.fx_shift;
+    if (pk.fbits < 24) return 1;
     cudaMemsetAsync(w.spread, 0, sizeof(unsigned long long) * (size_t)lp.nb * pk.replicas, st);
     cudaMemsetAsync(w.bins, 0, sizeof(unsigned long long) * lp.nb, st);
     k_lsc_deposit<<<grid, kLscThreads, 0, st>>>(r, ld, n, lp, pk, w.part, w.ticket + 1, w.spread, w.slice);
     k_lsc_compact<<<dim3((lp.nb + 31) / 32, (pk.replicas + 63) / 64), dim3(32, 8), 0, st>>>(w.spread, lp.nb, pk,
                                                                                          lp.fx_shift, w.bins);
+    return 0;
 }
 
 int launch_lsc_solve(const LscParams& lp, LscWork w, cudaStream_t st) {

@@ -53,32 +53,28 @@ class LSC(PhysProc):
 
     # -- protocol -----------------------------------------------------------
     def prepare(self, lat):
-        """Undulator strength profile K(s) between start_elem and end_elem (sc.py:476-508)."""
+        """Piecewise-constant undulator strength K(s) over [start_elem, end_elem], as a linear interpolant
+        through both edges of every element (what sc.py:476-508 builds): K = Kx + Ky inside planar
+        undulators (at most one of Kx, Ky non-zero), 0 elsewhere, end values held outside the range."""
         from scipy.interpolate import interp1d
         self.check_step()
-        seq = lat.get_sequence_part(self.start_elem, self.end_elem)
-        s, k = [], []
-        s_current = self.s_start
-        for elem in seq:
-            s_next = s_current + elem.l
-            s.extend([s_current, s_next])
-            if _is_undulator(elem) and not (elem.Kx != 0 and elem.Ky != 0):
-                k.extend([elem.Kx + elem.Ky, elem.Kx + elem.Ky])
-                self._is_undul_in_beam_line = True
-            else:
-                k.extend([0.0, 0.0])
-            s_current = s_next
+        elems = list(lat.get_sequence_part(self.start_elem, self.end_elem))
+        # element edges by sequential addition from s_start (same rounding as a running sum)
+        edges = np.cumsum([self.s_start] + [e.l for e in elems])
+        strength = []
+        for e in elems:
+            planar = _is_undulator(e) and not (e.Kx != 0 and e.Ky != 0)
+            strength.append(e.Kx + e.Ky if planar else 0.0)
+            self._is_undul_in_beam_line = self._is_undul_in_beam_line or planar
+        s = np.repeat(edges, 2)[1:-1]               # entry and exit edge of every element
+        k = np.repeat(np.asarray(strength, dtype=float), 2)
         self.K_s_func = interp1d(s, k, kind='linear', bounds_error=False, fill_value=(k[0], k[-1]))
 
     def compute_filling_factor(self, x0, x1, num_points=100):
-        """Fraction of [x0, x1] inside an undulator field (sc.py:510-544)."""
-        x = np.linspace(x0, x1, num_points)
-        k_vals = self.K_s_func(x)
-        nonzero_intervals = (k_vals[:-1] != 0) | (k_vals[1:] != 0)
-        dx = (x1 - x0) / (num_points - 1)
-        filled_length = np.sum(nonzero_intervals) * dx
-        total_length = x1 - x0
-        return filled_length / total_length
+        """Fraction of [x0, x1] with a non-zero K at either end of a sampling interval (sc.py:510-544)."""
+        on = self.K_s_func(np.linspace(x0, x1, num_points)) != 0
+        covered = np.sum(on[:-1] | on[1:]) * ((x1 - x0) / (num_points - 1))
+        return covered / (x1 - x0)
 
     def undulator_factor(self, dz):
         """(K_max, fill_factor) of the step that ends at z0 (sc.py:569-574)."""
