@@ -414,8 +414,8 @@ def run_native(args):
             lms = a.elapsed_time(b) / kl
             line["lsc"] = {"value": n / (lms * 1e-3), "unit": "LSC particle-kicks/s", "ms_per_step": lms,
                            "grid_points": int(lsc.last_params["nb"]),
-                           "note": "ocelot_b200.LSC.apply on the resident bunch (one host sync per kick for the "
-                                   "grid definition); not part of `value`"}
+                           "note": "ocelot_b200.LSC.apply on the resident bunch (grid derived on the device, no host "
+                                   "synchronisation); not part of `value`"}
 
     # ---- CPU baseline on the host cores (rank 0, N = 1 only) ----
     if line is not None and world == 1 and not args.no_cpu_baseline:

@@ -213,6 +213,17 @@ int ocl_sc_lsc_kick(ocl_sc_t* h, double* d_r, long long ld, long long n, const d
  * all-reduces OCL_SC_BUF_LSC_BINS (int64 SUM: exact), _SLICE_MAX (MAX) and _SLICE_SUM (SUM). */
 int ocl_sc_lsc_deposit(ocl_sc_t* h, const double* d_r, long long ld, long long n, const double* params, void* stream);
 int ocl_sc_lsc_solve_kick(ocl_sc_t* h, double* d_r, long long ld, long long n, const double* params, void* stream);
+/* The same kick with no host synchronisation (CUDA-graph capturable): sweep A, then a one-thread kernel
+ * derives the grid on the device with the arithmetic of s_to_cur, then deposit, solve and kick read it
+ * from device memory.  hostp[10] = {gamma, v, pc_ref [GeV], dz, 1 + K_max^2 fill/2, bounds[0], bounds[1],
+ * smooth_param, step_profile (0/1), n_total (0: n)}.  Sized for grids of up to 8192 points and 127
+ * smoothing taps; a kick whose grid does not fit is skipped and reported by the next ocl_sc_lsc_* call
+ * on the handle (the synchronous form has no such limit). */
+int ocl_sc_lsc_kick_async(ocl_sc_t* h, double* d_r, long long ld, long long n, const double* d_q, const double* hostp,
+                          void* stream);
+/* scalars the device derived for the last asynchronous kick, in the layout of ocl_sc_lsc_kick's params
+ * (n_total not filled).  Synchronises; makes ocl_sc_lsc_get_profile usable with nb = out[6]. */
+int ocl_sc_lsc_last_params(ocl_sc_t* h, double out[17]);
 /* taps of the last LSC kick (any pointer may be NULL): current profile I(s_j) [A] (s_to_cur's B[:,1]),
  * wake W(s_j)*q [V] (sc.py:592), transverse size sigma or rb used by the impedance (sc.py:584-589). */
 int ocl_sc_lsc_get_profile(ocl_sc_t* h, int nb, double* h_current, double* h_wake, double* h_sigma);

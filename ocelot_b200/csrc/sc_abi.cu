@@ -87,6 +87,8 @@ struct ocl_sc {
     long long lsc_spread_cap = 0;             // 64-bit words of the spread histogram
     int lsc_tw_nb = 0;                        // nb the twiddle table was built for
     int lsc_nb = 0;                           // nb of the last deposit / solve
+    int* lsc_err_host = nullptr;              // mapped host flag the asynchronous form raises (grid too large ...)
+    bool lsc_async_pending = false;           // last kick was asynchronous: nb lives on the device
     // timers
     bool timers = false;
     cudaEvent_t ev[T_COUNT] = {};
@@ -997,6 +999,7 @@ int ocl_sc_beam_moments(ocl_sc_t* h, const double* d_r, long long ld, long long 
 }
 
 /* ---- longitudinal space charge (LSC, sc.py:261-599) ---- */
+static int lsc_async_error(ocl_sc* h, const char* who);
 static int ensure_lsc(ocl_sc* h, int nb) {
     if (nb <= h->lsc_cap) return 0;
     int cap = 1024;
@@ -1011,6 +1014,12 @@ static int ensure_lsc(ocl_sc* h, int nb) {
         CU(h, cudaMemset(h->lw.stats, 0, sizeof(double) * 32));
         h->lw.slice = h->lw.stats + 16;
         h->lw.sigma = h->lw.stats + 26;
+        CU(h, cudaMalloc(&h->lw.dparams, sizeof(LscParams)));
+        CU(h, cudaMalloc(&h->lw.dpack, sizeof(LscPack)));
+        CU(h, cudaMemset(h->lw.dparams, 0, sizeof(LscParams)));
+        CU(h, cudaHostAlloc(&h->lsc_err_host, sizeof(int), cudaHostAllocMapped));
+        *h->lsc_err_host = 0;
+        CU(h, cudaHostGetDevicePointer((void**)&h->lw.err, h->lsc_err_host, 0));
     }
     h->lw.part = h->rs.part;
     h->lw.max_blocks = h->rs.max_blocks;
@@ -1054,6 +1063,7 @@ int ocl_sc_lsc_stats(ocl_sc_t* h, const double* d_r, long long ld, long long n, 
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
     if (ensure_lsc(h, 1)) return 1;
+    if (lsc_async_error(h, "ocl_sc_lsc_stats")) return 1;
     launch_lsc_stats(d_r, ld, d_q, n, h->lw, st);
     h->launches += 1;
     if (check_launch(h, "k_lsc_stats")) return 1;
@@ -1083,6 +1093,7 @@ int ocl_sc_lsc_deposit(ocl_sc_t* h, const double* d_r, long long ld, long long n
     if (adopt_stream(h, st)) return 1;
     if (ensure_lsc(h, lp.nb)) return 1;
     h->lsc_nb = lp.nb;
+    h->lsc_async_pending = false;
     if (launch_lsc_deposit(d_r, ld, n, lp, h->lw, st))
         return fail(h, "ocl_sc_lsc_deposit", "grid too fine for this particle count (fewer than 24 fractional bits left)");
     h->launches += 2;
@@ -1112,6 +1123,58 @@ int ocl_sc_lsc_solve_kick(ocl_sc_t* h, double* d_r, long long ld, long long n, c
 int ocl_sc_lsc_kick(ocl_sc_t* h, double* d_r, long long ld, long long n, const double* params, void* stream) {
     if (ocl_sc_lsc_deposit(h, d_r, ld, n, params, stream)) return 1;
     return ocl_sc_lsc_solve_kick(h, d_r, ld, n, params, stream);
+}
+
+static int lsc_async_error(ocl_sc* h, const char* who) {
+    if (h->lsc_err_host && *h->lsc_err_host) {
+        const int e = *h->lsc_err_host;
+        *h->lsc_err_host = 0;
+        return fail(h, who, e == 2 ? "an earlier asynchronous LSC kick was skipped: grid too fine for the particle count"
+                                   : "an earlier asynchronous LSC kick was skipped: its grid exceeds the buffer "
+                                     "capacity (use the synchronous form, ocl_sc_lsc_stats + ocl_sc_lsc_kick)");
+    }
+    return 0;
+}
+
+int ocl_sc_lsc_kick_async(ocl_sc_t* h, double* d_r, long long ld, long long n, const double* d_q, const double* hostp,
+                          void* stream) {
+    if (!h || !hostp) return 1;
+    if (n <= 0 || ld < n) return fail(h, "ocl_sc_lsc_kick_async", "need 0 < n <= ld");
+    if (set_device(h)) return 1;
+    if (ensure_lsc(h, kLscAsyncCap)) return 1;
+    if (lsc_async_error(h, "ocl_sc_lsc_kick_async")) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (adopt_stream(h, st)) return 1;
+    LscHost hp;
+    hp.gamma = hostp[0]; hp.v = hostp[1]; hp.pc_ref = hostp[2]; hp.dz = hostp[3]; hp.und = hostp[4];
+    hp.bound_lo = hostp[5]; hp.bound_hi = hostp[6]; hp.smooth_param = hostp[7];
+    hp.step_profile = hostp[8] != 0.0;
+    double ntot = hostp[9] < 2.0 ? (n < 2 ? 2.0 : (double)n) : hostp[9];
+    int bits = 0;
+    while ((double)(1ull << bits) < ntot && bits < 62) ++bits;
+    hp.fx_shift = 62 - bits > 52 ? 52 : 62 - bits;
+    hp.cap_nb = kLscAsyncCap;
+    hp.warps = hp.iters = 0;
+    launch_lsc_kick_async(d_r, ld, d_q, n, hp, h->lw, st);
+    h->launches += 10;
+    h->lsc_async_pending = true;
+    h->lsc_tw_nb = 0;                          // the twiddle table now belongs to a device-defined grid
+    return check_launch(h, "ocl_sc_lsc_kick_async");
+}
+
+int ocl_sc_lsc_last_params(ocl_sc_t* h, double out[17]) {
+    if (!h || !out) return 1;
+    if (!h->lsc_async_pending) return fail(h, "ocl_sc_lsc_last_params", "no asynchronous LSC kick recorded");
+    if (set_device(h)) return 1;
+    if (sync_last(h)) return 1;
+    if (lsc_async_error(h, "ocl_sc_lsc_last_params")) return 1;
+    LscParams lp;
+    CU(h, cudaMemcpy(&lp, h->lw.dparams, sizeof lp, cudaMemcpyDeviceToHost));
+    const double v[17] = {lp.slice_min, lp.slice_max, lp.x_shift, lp.y_shift, lp.a, lp.ds, (double)lp.nb, lp.sigma_s,
+                          (double)lp.K, lp.q, lp.v, lp.gamma, lp.dz, lp.und, lp.pc_ref, (double)lp.step_profile, 0.0};
+    for (int i = 0; i < 17; ++i) out[i] = v[i];
+    h->lsc_nb = lp.nb;
+    return 0;
 }
 
 int ocl_sc_lsc_get_profile(ocl_sc_t* h, int nb, double* h_current, double* h_wake, double* h_sigma) {

@@ -105,6 +105,27 @@ struct LscParams {
 struct LscPack {
     int replicas, cshift, fbits;
 };
+// Kernels receive the per-kick scalars either by value (host-derived grid, after the one host
+// synchronisation of ocl_sc_lsc_stats) or through a device-resident copy that k_lsc_params derives from
+// the sweep-A statistics (ocl_sc_lsc_kick_async: no host synchronisation).
+struct LP {
+    LscParams v;
+    const LscParams* p;    // nullptr: use v
+};
+struct PKP {
+    LscPack v;
+    const LscPack* p;
+};
+// what the host still supplies in the asynchronous form (everything that does not depend on the particles)
+struct LscHost {
+    double gamma, v, pc_ref, dz, und;     // from p_array.E, dz and the undulator profile
+    double bound_lo, bound_hi;            // LSC.bounds
+    double smooth_param;
+    int step_profile;
+    int fx_shift;                         // 62 - ceil(log2 n_total), <= 52
+    int cap_nb;                           // grid points the buffers hold
+    long long warps, iters;               // deposit launch shape: warps in the grid, particles per thread
+};
 struct LscWork {
     double* part;                  // per-block partials (shared with the kick sweeps)
     unsigned int* ticket;          // [2]
@@ -120,6 +141,9 @@ struct LscWork {
     double* W;                     // [cap] wake * q [eV... V]
     double2* Z;                    // [cap]
     double2* tw;                   // [2 cap] exp(2 pi i m / n)
+    LscParams* dparams;            // device-derived scalars of the asynchronous form
+    LscPack* dpack;
+    int* err;                      // device flag: 1 = grid larger than the buffers, 2 = packed word too narrow
     int max_blocks;
 };
 void launch_lsc_stats(const double* r, long long ld, const double* q, long long n, LscWork w, cudaStream_t st);
@@ -128,6 +152,10 @@ int launch_lsc_deposit(const double* r, long long ld, long long n, const LscPara
 int launch_lsc_solve(const LscParams& lp, LscWork w, cudaStream_t st);
 long long lsc_spread_words(int nb);
 void launch_lsc_kick(double* r, long long ld, long long n, const LscParams& lp, LscWork w, cudaStream_t st);
+// asynchronous form: stats, device-side grid definition, deposit, solve, kick -- no host synchronisation
+void launch_lsc_kick_async(double* r, long long ld, const double* q, long long n, LscHost hp, LscWork w,
+                           cudaStream_t st);
+constexpr int kLscAsyncCap = 8192;        // grid points the asynchronous form is sized for
 
 // ---- hand-written Hockney convolution (sc_fft.cu) ----
 struct FftWork {

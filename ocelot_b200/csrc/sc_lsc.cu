@@ -74,12 +74,14 @@ __global__ void __launch_bounds__(kLscThreads, 4) k_lsc_stats(const double* __re
 // ---------------------------------------------------------------------------
 // slice[0..3] = max x, max -x, max y, max -y ; slice[4..8] = count, sum dx, sum dx^2, sum dy, sum dy^2
 __global__ void __launch_bounds__(kLscThreads, 3) k_lsc_deposit(const double* __restrict__ r, long long ld,
-                                                               long long n, LscParams lp, LscPack pk,
+                                                               long long n, LP lpk, PKP pkk,
                                                                double* part, unsigned int* ticket,
                                                                unsigned long long* __restrict__ spread,
                                                                double* __restrict__ slice) {
     __shared__ double sh[9 * kSweepWarps];
     __shared__ double pipe[kLscDepth * 3 * kLscThreads];
+    const LscParams lp = lpk.p ? *lpk.p : lpk.v;
+    const LscPack pk = pkk.p ? *pkk.p : pkk.v;
     // replica-major layout: counter (replica, j) at word replica * nb + j; one replica per warp in flight
     unsigned long long* const dst =
         spread + (size_t)((blockIdx.x * kSweepWarps + (threadIdx.x >> 5)) & (pk.replicas - 1)) * lp.nb;
@@ -113,33 +115,41 @@ __global__ void __launch_bounds__(kLscThreads, 3) k_lsc_deposit(const double* __
 }
 
 // fold the replicas: bins[j] += sum over replicas of (N_j << s) - (F_j << d) + (F_{j-1} << d), d = s - fbits
-// (bins zeroed by the caller).  grid (ceil(nb/32), replicas/64), block (32, 8): coalesced rows of 32 bins.
-__global__ void __launch_bounds__(256) k_lsc_compact(const unsigned long long* __restrict__ spread, int nb,
-                                                    LscPack pk, int s_out, unsigned long long* __restrict__ bins) {
+// (bins zeroed by the caller).  Tiles of 32 bins x 64 replicas, block (32, 8): coalesced rows of 32 bins;
+// the blocks stride over the tiles, so one launch shape serves any (nb, replicas).
+__global__ void __launch_bounds__(256) k_lsc_compact(const unsigned long long* __restrict__ spread, LP lpk, PKP pkk,
+                                                    unsigned long long* __restrict__ bins) {
     __shared__ unsigned long long sm[8][32];
-    const int j = blockIdx.x * 32 + threadIdx.x;
-    const int rep0 = blockIdx.y * 64;
+    const LscParams lp = lpk.p ? *lpk.p : lpk.v;
+    const LscPack pk = pkk.p ? *pkk.p : pkk.v;
+    const int nb = lp.nb, s_out = lp.fx_shift;
     const unsigned long long fmask = (1ull << pk.cshift) - 1ull;
     const int d = s_out - pk.fbits;
-    unsigned long long c = 0ull;                                    // modulo 2^64; the total is non-negative
-    if (j < nb) {
+    const int tiles_x = (nb + 31) / 32, tiles_y = (pk.replicas + 63) / 64;
+    for (int tile = blockIdx.x; tile < tiles_x * tiles_y; tile += gridDim.x) {
+        const int j = (tile % tiles_x) * 32 + threadIdx.x;
+        const int rep0 = (tile / tiles_x) * 64;
+        unsigned long long c = 0ull;                                // modulo 2^64; the total is non-negative
+        if (j < nb) {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const int rep = rep0 + k * 8 + threadIdx.y;
-            if (rep < pk.replicas) {
-                const unsigned long long* p = spread + (size_t)rep * nb + j;
-                const unsigned long long v = p[0];
-                const unsigned long long vm = (j > 0) ? p[-1] : 0ull;
-                c += ((v >> pk.cshift) << s_out) - ((v & fmask) << d) + ((vm & fmask) << d);
+            for (int k = 0; k < 8; ++k) {
+                const int rep = rep0 + k * 8 + threadIdx.y;
+                if (rep < pk.replicas) {
+                    const unsigned long long* p = spread + (size_t)rep * nb + j;
+                    const unsigned long long v = p[0];
+                    const unsigned long long vm = (j > 0) ? p[-1] : 0ull;
+                    c += ((v >> pk.cshift) << s_out) - ((v & fmask) << d) + ((vm & fmask) << d);
+                }
             }
         }
-    }
-    sm[threadIdx.y][threadIdx.x] = c;
-    __syncthreads();
-    if (threadIdx.y == 0 && j < nb) {
+        __syncthreads();
+        sm[threadIdx.y][threadIdx.x] = c;
+        __syncthreads();
+        if (threadIdx.y == 0 && j < nb) {
 #pragma unroll
-        for (int k = 1; k < 8; ++k) c += sm[k][threadIdx.x];
-        if (c) atomicAdd(bins + j, c);
+            for (int k = 1; k < 8; ++k) c += sm[k][threadIdx.x];
+            if (c) atomicAdd(bins + j, c);
+        }
     }
 }
 
@@ -149,13 +159,14 @@ __global__ void __launch_bounds__(256) k_lsc_compact(const unsigned long long* _
 // prof[j] = bunch[j] * c  (the array the reference feeds to signal_to_spectrum, sc.py:461-463)
 // cur[j]  = I(s_j) [A]    (B[:, 1] of s_to_cur; tap)
 // Also derives the transverse size from the slice sums.
-__global__ void __launch_bounds__(1024, 1) k_lsc_profile(const unsigned long long* __restrict__ bins, LscParams lp,
+__global__ void __launch_bounds__(1024, 1) k_lsc_profile(const unsigned long long* __restrict__ bins, LP lpk,
                                                         const double* __restrict__ slice, double* __restrict__ cnt,
                                                         double* __restrict__ prof, double* __restrict__ cur,
                                                         double* __restrict__ sigma_out) {
     __shared__ double red[32];
     __shared__ double total;
     extern __shared__ double G[];                                   // 2K+1 taps
+    const LscParams lp = lpk.p ? *lpk.p : lpk.v;
     const int nb = lp.nb, K = lp.K;
     const double inv_unit = 1.0 / (double)(1ull << lp.fx_shift);
     for (int j = threadIdx.x; j < nb; j += blockDim.x) {
@@ -222,7 +233,8 @@ __global__ void __launch_bounds__(1024, 1) k_lsc_profile(const unsigned long lon
 }
 
 // twiddle table tw[m] = exp(+2 pi i m / n), m = 0..n-1
-__global__ void k_lsc_twiddles(int n, double2* __restrict__ tw) {
+__global__ void k_lsc_twiddles(int n_host, const LscParams* __restrict__ dp, double2* __restrict__ tw) {
+    const int n = dp ? 2 * dp->nb : n_host;
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= n) return;
     double s, c;
@@ -233,8 +245,9 @@ __global__ void k_lsc_twiddles(int n, double2* __restrict__ tw) {
 // Za(w_k) = i A[k]: impedance of the step at the grid frequencies (imp_lsc sc.py:299-340,
 // imp_step_lsc :342-369, undulator factor :460-463).  One warp per frequency: the lanes share the
 // quadrature of K1.
-__global__ void __launch_bounds__(256) k_lsc_impedance(LscParams lp, const double* __restrict__ sigma_p,
+__global__ void __launch_bounds__(256) k_lsc_impedance(LP lpk, const double* __restrict__ sigma_p,
                                                       double* __restrict__ A) {
+    const LscParams lp = lpk.p ? *lpk.p : lpk.v;
     const int lane = threadIdx.x & 31;
     const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (k >= lp.nb) return;
@@ -276,9 +289,10 @@ __global__ void __launch_bounds__(256) k_lsc_impedance(LscParams lp, const doubl
 
 // Z[k] = Za(w_k) * Zb[k], k = 0..nb-1, with Zb = dt * fft(prof, n)  (sc.py:453-469, analysis.py:376-383)
 // One warp per frequency, lanes stride over the grid points.
-__global__ void __launch_bounds__(256) k_lsc_spectrum(const double* __restrict__ prof, LscParams lp,
+__global__ void __launch_bounds__(256) k_lsc_spectrum(const double* __restrict__ prof, LP lpk,
                                                      const double* __restrict__ A,
                                                      const double2* __restrict__ tw, double2* __restrict__ Z) {
+    const LscParams lp = lpk.p ? *lpk.p : lpk.v;
     const int lane = threadIdx.x & 31;
     const int nb = lp.nb, n = 2 * nb;
     const int k = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -304,8 +318,9 @@ __global__ void __launch_bounds__(256) k_lsc_spectrum(const double* __restrict__
 
 // W[j] = q / dt * irfft(Z, n)[j], j = 0..nb-1, with Z[nb] = conj(Z[nb-1]) (sc.py:466-473, :401-416, :592)
 // One warp per grid point, lanes stride over the frequencies.
-__global__ void __launch_bounds__(256) k_lsc_wake(const double2* __restrict__ Z, LscParams lp,
+__global__ void __launch_bounds__(256) k_lsc_wake(const double2* __restrict__ Z, LP lpk,
                                                  const double2* __restrict__ tw, double* __restrict__ W) {
+    const LscParams lp = lpk.p ? *lpk.p : lpk.v;
     const int lane = threadIdx.x & 31;
     const int nb = lp.nb, n = 2 * nb;
     const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -334,9 +349,11 @@ __global__ void __launch_bounds__(256) k_lsc_wake(const double2* __restrict__ Z,
 // ---------------------------------------------------------------------------
 template <bool SMEM>
 __global__ void __launch_bounds__(kLscThreads, 4) k_lsc_kick(double* __restrict__ r, long long ld, long long n,
-                                                            LscParams lp, const double* __restrict__ Wg) {
+                                                            LP lpk, const double* __restrict__ Wg) {
     __shared__ double pipe[kLscDepth * 2 * kLscThreads];
     extern __shared__ double Ws[];
+    const LscParams lp = lpk.p ? *lpk.p : lpk.v;
+    if (lp.nb < 2) return;                                           // rejected grid (asynchronous form): no kick
     if (SMEM) {
         for (int j = threadIdx.x; j < lp.nb; j += kLscThreads) Ws[j] = Wg[j];
         __syncthreads();
@@ -366,6 +383,58 @@ __global__ void __launch_bounds__(kLscThreads, 4) k_lsc_kick(double* __restrict_
 }
 
 // ---------------------------------------------------------------------------
+// asynchronous form: the grid definition on the device
+// ---------------------------------------------------------------------------
+// What ocelot_b200/lsc.py::kick_parameters does on the host after ocl_sc_lsc_stats, with the same
+// IEEE operations in the same order (explicitly rounded, so nothing is contracted into an FMA):
+// mean / sigma of tau (sc.py:576-580), the grid of s_to_cur (analysis.py:293-321), its smoothing taps
+// (:330-331), the packed-word layout of the deposit.  One thread.
+__global__ void k_lsc_params(const double* __restrict__ raw, LscHost hp, LscParams* __restrict__ out,
+                             LscPack* __restrict__ pk, int* __restrict__ err) {
+    if (threadIdx.x || blockIdx.x) return;
+    const double cnt = raw[2], s1 = raw[3], s2 = raw[4], t0 = raw[8];
+    const double mean = __dadd_rn(t0, __ddiv_rn(s1, cnt));
+    double m2 = __dsub_rn(s2, __ddiv_rn(__dmul_rn(s1, s1), cnt));
+    if (m2 < 0.0) m2 = 0.0;
+    const double sigma_tau = __dsqrt_rn(__ddiv_rn(m2, cnt));
+    const double tmin = -raw[1], tmax = raw[0];
+    const double sigma = __dmul_rn(sigma_tau, hp.smooth_param);
+    const double a = __dsub_rn(tmin, __dmul_rn(3.0, sigma));
+    const double b = __dadd_rn(tmax, __dmul_rn(3.0, sigma));
+    double ds = sigma > 0.0 ? __dmul_rn(0.25, sigma) : __ddiv_rn(__dsub_rn(b, a), 1000.0);
+    const double span = __dsub_rn(b, a);
+    const double Nf = ceil(__ddiv_rn(span, ds));
+    LscParams lp;
+    int bad = 0;
+    if (!(Nf >= 1.0) || Nf + 1.0 > (double)hp.cap_nb) { bad = 1; lp.nb = 0; ds = 1.0; }
+    else { lp.nb = (int)Nf + 1; ds = __ddiv_rn(span, Nf); }
+    lp.a = a; lp.ds = ds; lp.sigma_s = sigma;
+    lp.K = sigma > 0.0 ? (int)floor(__dadd_rn(__ddiv_rn(__dmul_rn(3.0, sigma), ds), 0.5)) : -1;
+    if (lp.K > 63) { bad = 1; lp.nb = 0; lp.K = -1; }
+    lp.slice_min = __dadd_rn(mean, __dmul_rn(sigma_tau, hp.bound_lo));
+    lp.slice_max = __dadd_rn(mean, __dmul_rn(sigma_tau, hp.bound_hi));
+    lp.x_shift = __ddiv_rn(raw[6], cnt); lp.y_shift = __ddiv_rn(raw[7], cnt);
+    lp.q = raw[5]; lp.v = hp.v; lp.gamma = hp.gamma; lp.dz = hp.dz; lp.und = hp.und; lp.pc_ref = hp.pc_ref;
+    lp.step_profile = hp.step_profile; lp.fx_shift = hp.fx_shift;
+    // packed deposit word (see launch_lsc_deposit)
+    LscPack p;
+    int rep = 2048;
+    while (rep > 1 && (long long)lp.nb * rep > (1 << 20)) rep >>= 1;
+    p.replicas = rep;
+    const long long share = (hp.warps + rep - 1) / rep;
+    const long long per_replica = share * 32 * hp.iters;
+    int cbits = 1;
+    while ((1ll << cbits) <= per_replica) ++cbits;
+    p.cshift = 64 - cbits;
+    p.fbits = p.cshift - cbits;
+    if (p.fbits > lp.fx_shift) p.fbits = lp.fx_shift;
+    if (p.fbits < 24) { bad = 2; lp.nb = 0; p.fbits = 24; }
+    *out = lp;
+    *pk = p;
+    if (bad) *err = bad;
+}
+
+// ---------------------------------------------------------------------------
 // launchers
 // ---------------------------------------------------------------------------
 static int lsc_grid(long long n, int cap) {
@@ -381,7 +450,7 @@ void launch_lsc_stats(const double* r, long long ld, const double* q, long long 
 
 void launch_lsc_twiddles(int nb, LscWork w, cudaStream_t st) {
     const int n = 2 * nb;
-    k_lsc_twiddles<<<(n + 255) / 256, 256, 0, st>>>(n, w.tw);
+    k_lsc_twiddles<<<(n + 255) / 256, 256, 0, st>>>(n, nullptr, w.tw);
 }
 
 int lsc_replicas(int nb) {
@@ -417,29 +486,58 @@ int launch_lsc_deposit(const double* r, long long ld, long long n, const LscPara
     if (pk.fbits < 24) return 1;
     cudaMemsetAsync(w.spread, 0, sizeof(unsigned long long) * (size_t)lp.nb * pk.replicas, st);
     cudaMemsetAsync(w.bins, 0, sizeof(unsigned long long) * lp.nb, st);
-    k_lsc_deposit<<<grid, kLscThreads, 0, st>>>(r, ld, n, lp, pk, w.part, w.ticket + 1, w.spread, w.slice);
-    k_lsc_compact<<<dim3((lp.nb + 31) / 32, (pk.replicas + 63) / 64), dim3(32, 8), 0, st>>>(w.spread, lp.nb, pk,
-                                                                                         lp.fx_shift, w.bins);
+    const LP lpk = {lp, nullptr};
+    const PKP pkk = {pk, nullptr};
+    k_lsc_deposit<<<grid, kLscThreads, 0, st>>>(r, ld, n, lpk, pkk, w.part, w.ticket + 1, w.spread, w.slice);
+    const int tiles = ((lp.nb + 31) / 32) * ((pk.replicas + 63) / 64);
+    k_lsc_compact<<<tiles, dim3(32, 8), 0, st>>>(w.spread, lpk, pkk, w.bins);
     return 0;
 }
 
 int launch_lsc_solve(const LscParams& lp, LscWork w, cudaStream_t st) {
     const size_t taps = lp.K >= 0 ? sizeof(double) * (2 * (size_t)lp.K + 1) : 0;
     if (taps > 40 * 1024) return 1;                                  // K <= 2559
-    k_lsc_profile<<<1, 1024, taps, st>>>(w.bins, lp, w.slice, w.cnt, w.prof, w.cur, w.sigma);
+    const LP lpk = {lp, nullptr};
+    k_lsc_profile<<<1, 1024, taps, st>>>(w.bins, lpk, w.slice, w.cnt, w.prof, w.cur, w.sigma);
     const int blocks = (lp.nb + 7) / 8;
-    k_lsc_impedance<<<blocks, 256, 0, st>>>(lp, w.sigma, w.A);
-    k_lsc_spectrum<<<blocks, 256, 0, st>>>(w.prof, lp, w.A, w.tw, w.Z);
-    k_lsc_wake<<<blocks, 256, 0, st>>>(w.Z, lp, w.tw, w.W);
+    k_lsc_impedance<<<blocks, 256, 0, st>>>(lpk, w.sigma, w.A);
+    k_lsc_spectrum<<<blocks, 256, 0, st>>>(w.prof, lpk, w.A, w.tw, w.Z);
+    k_lsc_wake<<<blocks, 256, 0, st>>>(w.Z, lpk, w.tw, w.W);
     return 0;
 }
 
 void launch_lsc_kick(double* r, long long ld, long long n, const LscParams& lp, LscWork w, cudaStream_t st) {
     const int grid = lsc_grid(n, 148 * 4);
     if (lp.nb <= kLscSmemBins)
-        k_lsc_kick<true><<<grid, kLscThreads, sizeof(double) * lp.nb, st>>>(r, ld, n, lp, w.W);
+        k_lsc_kick<true><<<grid, kLscThreads, sizeof(double) * lp.nb, st>>>(r, ld, n, LP{lp, nullptr}, w.W);
     else
-        k_lsc_kick<false><<<grid, kLscThreads, 0, st>>>(r, ld, n, lp, w.W);
+        k_lsc_kick<false><<<grid, kLscThreads, 0, st>>>(r, ld, n, LP{lp, nullptr}, w.W);
+}
+
+// One LSC.apply without a host round trip: sweep A, k_lsc_params, then the same kernels reading the
+// device-resident scalars.  Launch shapes are those of the largest grid the buffers hold
+// (hp.cap_nb <= kLscAsyncCap); blocks beyond the actual grid exit at once.
+void launch_lsc_kick_async(double* r, long long ld, const double* q, long long n, LscHost hp, LscWork w,
+                           cudaStream_t st) {
+    const int grid = lsc_grid(n, w.max_blocks);
+    hp.warps = (long long)grid * kSweepWarps;
+    hp.iters = (n + (long long)grid * kLscThreads - 1) / ((long long)grid * kLscThreads);
+    const int cap = hp.cap_nb;
+    k_lsc_stats<<<grid, kLscThreads, 0, st>>>(r, ld, q, n, w.part, w.ticket, w.stats);
+    k_lsc_params<<<1, 32, 0, st>>>(w.stats, hp, w.dparams, w.dpack, w.err);
+    const LP lpk = {LscParams{}, w.dparams};
+    const PKP pkk = {LscPack{}, w.dpack};
+    cudaMemsetAsync(w.spread, 0, sizeof(unsigned long long) * (size_t)(1 << 20), st);
+    cudaMemsetAsync(w.bins, 0, sizeof(unsigned long long) * cap, st);
+    k_lsc_deposit<<<grid, kLscThreads, 0, st>>>(r, ld, n, lpk, pkk, w.part, w.ticket + 1, w.spread, w.slice);
+    k_lsc_compact<<<512, dim3(32, 8), 0, st>>>(w.spread, lpk, pkk, w.bins);
+    k_lsc_twiddles<<<(2 * cap + 255) / 256, 256, 0, st>>>(0, w.dparams, w.tw);
+    k_lsc_profile<<<1, 1024, sizeof(double) * 127, st>>>(w.bins, lpk, w.slice, w.cnt, w.prof, w.cur, w.sigma);
+    const int blocks = (cap + 7) / 8;
+    k_lsc_impedance<<<blocks, 256, 0, st>>>(lpk, w.sigma, w.A);
+    k_lsc_spectrum<<<blocks, 256, 0, st>>>(w.prof, lpk, w.A, w.tw, w.Z);
+    k_lsc_wake<<<blocks, 256, 0, st>>>(w.Z, lpk, w.tw, w.W);
+    k_lsc_kick<false><<<lsc_grid(n, 148 * 4), kLscThreads, 0, st>>>(r, ld, n, lpk, w.W);
 }
 
 }  // namespace ocl

@@ -362,7 +362,7 @@ class ShardedLSC:
 
     def __init__(self, step=1, group=None, **kwargs):
         from .lsc import LSC
-        self.lsc = LSC(step=step, **kwargs)
+        self.lsc = LSC(step=step, **kwargs)        # host scalars; the sharded kick always uses the staged form
         self.group = group
         self._engine = None
 

@@ -38,6 +38,9 @@ class LSC(PhysProc):
         bounds        -- [min, max] in units of std(tau): central slice that defines the beam size
         slice         -- stored, unused (as in the reference)
         device        -- CUDA device index used for host-array kicks (default: current)
+        async_grid    -- True (default): the 1-D grid is derived on the device from the bunch statistics, so a
+                         kick involves no host synchronisation (grids of up to 8192 points); False: the host
+                         derives it after one small device->host read (any grid size)
     """
 
     def __init__(self, step=1, **kwargs):
@@ -49,7 +52,22 @@ class LSC(PhysProc):
         self.slice = kwargs.get("slice", None)
         self._is_undul_in_beam_line = False
         self.device = kwargs.get("device", None)
+        self.async_grid = kwargs.get("async_grid", True)
         self._solvers = {}
+        self._last_params = None
+        self._last_solver = None
+
+    @property
+    def last_params(self):
+        """Scalars of the last kick (grid a, ds, nb, taps K, slice bounds, charge ...).  After an asynchronous
+        kick they are read back from the device on first use."""
+        if self._last_params is None and self._last_solver is not None:
+            self._last_params = self._last_solver.lsc_last_params()
+        return self._last_params
+
+    @last_params.setter
+    def last_params(self, value):
+        self._last_params = value
 
     # -- protocol -----------------------------------------------------------
     def prepare(self, lat):
@@ -128,10 +146,7 @@ class LSC(PhysProc):
             self._apply_host(r, p_array.q_array, E, float(dz))
         else:
             dev = r.device.index if r.device.index is not None else 0
-            solver = self._solver(dev)
-            params = self.kick_parameters(solver.lsc_stats(r, p_array.q_array), E, float(dz))
-            solver.lsc_kick(r, params)
-            self.last_params = params
+            self._kick_device(self._solver(dev), r, p_array.q_array, E, float(dz))
 
     def _apply_host(self, r, q_array, E, dz):
         """Host numpy arrays: stage the four rows LSC reads (x, y, tau, delta) to the device, kick,
@@ -144,10 +159,22 @@ class LSC(PhysProc):
             for row in (0, 2, 4, 5):
                 d_r[row].copy_(torch.from_numpy(r[row]), non_blocking=False)
             d_q = torch.from_numpy(np.ascontiguousarray(q_array, dtype=np.float64)).to(d_r.device)
-            params = self.kick_parameters(solver.lsc_stats(d_r, d_q), E, dz)
-            solver.lsc_kick(d_r, params)
+            self._kick_device(solver, d_r, d_q, E, dz)
             r[5][:] = d_r[5].cpu().numpy()
-        self.last_params = params
+
+    def _kick_device(self, solver, r, q, E, dz):
+        if self.async_grid:
+            K_max, fill_factor = self.undulator_factor(dz)
+            gamma = E / m_e_GeV
+            solver.lsc_kick_async(r, q, gamma, np.sqrt(1 - 1 / gamma ** 2) * speed_of_light,
+                                  np.sqrt(E ** 2 / m_e_GeV ** 2 - 1) * m_e_GeV, dz,
+                                  1 + 0.5 * K_max * K_max * fill_factor, self.bounds, self.smooth_param,
+                                  self.step_profile)
+            self._last_params, self._last_solver = None, solver
+        else:
+            params = self.kick_parameters(solver.lsc_stats(r, q), E, dz)
+            solver.lsc_kick(r, params)
+            self._last_params, self._last_solver = params, None
 
     # -- host-side utilities of the reference class (plotting / analysis helpers; ``apply`` does not
     #    use them: the kick evaluates the same formulas on the device, csrc/sc_lsc.cu) -------------
@@ -209,6 +236,7 @@ class LSC(PhysProc):
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_solvers"] = {}
+        state["_last_solver"] = None
         return state
 
     def __setstate__(self, state):
@@ -220,7 +248,7 @@ class LSC(PhysProc):
         new = self.__class__.__new__(self.__class__)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            new.__dict__[k] = {} if k == "_solvers" else copy.deepcopy(v, memo)
+            new.__dict__[k] = {} if k == "_solvers" else (None if k == "_last_solver" else copy.deepcopy(v, memo))
         return new
 
 

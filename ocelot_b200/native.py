@@ -71,6 +71,8 @@ _SIGNATURES = {
     "ocl_sc_lsc_deposit": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _vp]),
     "ocl_sc_lsc_solve_kick": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _vp]),
     "ocl_sc_lsc_get_profile": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp]),
+    "ocl_sc_lsc_kick_async": (C.c_int, [_vp, _vp, _ll, _ll, _vp, _dp, _vp]),
+    "ocl_sc_lsc_last_params": (C.c_int, [_vp, _dp]),
     "ocl_sc_enable_timers": (C.c_int, [_vp, C.c_int]),
     "ocl_sc_get_timers": (C.c_int, [_vp, _dp]),
     "ocl_sc_launch_count": (_ll, [_vp]),
@@ -395,6 +397,23 @@ class Solver:
         ptr, ld, n = self._dev_rows(r)
         self._check(self._lib.ocl_sc_lsc_solve_kick(self._h, ptr, ld, n, self._lsc_params(params),
                                                     _stream_ptr(stream)), "ocl_sc_lsc_solve_kick")
+
+    def lsc_kick_async(self, r, q, gamma, v, pc_ref, dz, und, bounds, smooth_param, step_profile, n_total=0,
+                       stream=None):
+        """One LSC kick with the grid derived on the device: no host synchronisation."""
+        ptr, ld, n = self._dev_rows(r, q)
+        hp = (C.c_double * 10)(float(gamma), float(v), float(pc_ref), float(dz), float(und), float(bounds[0]),
+                               float(bounds[1]), float(smooth_param), 1.0 if step_profile else 0.0, float(n_total))
+        self._check(self._lib.ocl_sc_lsc_kick_async(self._h, ptr, ld, n, q.data_ptr(), hp, _stream_ptr(stream)),
+                    "ocl_sc_lsc_kick_async")
+
+    def lsc_last_params(self) -> dict:
+        """Scalars the device derived for the last asynchronous kick (synchronises)."""
+        out = (C.c_double * 17)()
+        self._check(self._lib.ocl_sc_lsc_last_params(self._h, out), "ocl_sc_lsc_last_params")
+        d = dict(zip(self.LSC_PARAM_KEYS, out[:]))
+        d["nb"], d["K"] = int(d["nb"]), int(d["K"])
+        return d
 
     def lsc_profile(self, nb: int) -> dict:
         cur, wake = np.empty(nb), np.empty(nb)

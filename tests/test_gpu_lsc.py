@@ -23,9 +23,16 @@ GOLD = os.path.join(os.path.dirname(__file__), "golden")
 TOL = 1e-10
 
 
-def _lsc(sc):
+@pytest.fixture(params=[True, False], ids=["device-grid", "host-grid"])
+def async_grid(request):
+    """Both forms of the kick: grid derived on the device (no host sync) / on the host after ocl_sc_lsc_stats."""
+    return request.param
+
+
+def _lsc(sc, async_grid=True):
     from ocelot_b200 import LSC
-    return LSC(step=1, step_profile=bool(sc[6]), smooth_param=float(sc[7]), bounds=[float(sc[8]), float(sc[9])])
+    return LSC(step=1, step_profile=bool(sc[6]), smooth_param=float(sc[7]), bounds=[float(sc[8]), float(sc[9])],
+               async_grid=async_grid)
 
 
 def _with_undulator(lsc, K_max, fill):
@@ -41,11 +48,11 @@ def _host_parray(r, q, E):
     return p
 
 
-def test_reference_golden_kicks_host_arrays():
+def test_reference_golden_kicks_host_arrays(async_grid):
     g = np.load(os.path.join(GOLD, "lsc_kicks.npz"))
     for name in g["names"]:
         sc = g[f"{name}_scalars"]
-        lsc = _with_undulator(_lsc(sc), float(sc[4]), float(sc[5]))
+        lsc = _with_undulator(_lsc(sc, async_grid), float(sc[4]), float(sc[5]))
         p = _host_parray(g[f"{name}_r_in"], g[f"{name}_q"], float(sc[0]))
         lsc.apply(p, float(sc[1]))
         for row in range(5):
@@ -66,12 +73,12 @@ def test_reference_golden_kicks_host_arrays():
         assert np.abs(d - d_ref).max() <= TOL * np.abs(d_ref).max(), (name, np.abs(d - d_ref).max() / np.abs(d_ref).max())
 
 
-def test_reference_lsc_test_lattice_kicks_device_resident():
+def test_reference_lsc_test_lattice_kicks_device_resident(async_grid):
     """Three kicks recorded from the reference's own LSC test (quadrupoles, drifts, two undulators)."""
     from ocelot_b200 import LSC, DeviceParticleArray
     g = np.load(os.path.join(GOLD, "lsc_track.npz"))
     for j, k in enumerate(g["kept"]):
-        lsc = _with_undulator(LSC(step=1), float(g["K_max"][k]), float(g["fill"][k]))
+        lsc = _with_undulator(LSC(step=1, async_grid=async_grid), float(g["K_max"][k]), float(g["fill"][k]))
         dev = DeviceParticleArray.from_host(_host_parray(g["r_in"][j], g["q"], float(g["E"][k])))
         lsc.apply(dev, float(g["dz"][k]))
         out = dev.to_host().rparticles
@@ -82,7 +89,7 @@ def test_reference_lsc_test_lattice_kicks_device_resident():
 
 
 @pytest.mark.parametrize("n,step_profile", [(1_000_000, False), (1_000_000, True), (37, False), (2, False)])
-def test_kick_vs_oracle(n, step_profile):
+def test_kick_vs_oracle(n, step_profile, async_grid):
     from ocelot_b200 import LSC, DeviceParticleArray
     np.random.seed(11)
     r, q, E = orc.gaussian_bunch(max(n, 64), energy=0.13, charge=250e-12)
@@ -90,7 +97,7 @@ def test_kick_vs_oracle(n, step_profile):
     ref = r.copy()
     st = lo.lsc_kick(ref, q, E, 0.25, step_profile=step_profile)
     dev = DeviceParticleArray.from_host(_host_parray(r, q, E))
-    lsc = LSC(step=1, step_profile=step_profile)
+    lsc = LSC(step=1, step_profile=step_profile, async_grid=async_grid)
     lsc.apply(dev, 0.25)
     out = dev.to_host().rparticles
     prm = lsc.last_params
@@ -122,8 +129,14 @@ def test_long_grid():
     for sp in (0.004,):
         ref = r.copy()
         st = lo.lsc_kick(ref, q, E, 1.0, smooth_param=sp)
+        # the device-derived grid is sized for 8192 points: the kick is skipped and the handle says so
         dev = DeviceParticleArray.from_host(_host_parray(r, q, E))
-        lsc = LSC(step=1, smooth_param=sp)
+        lsc = LSC(step=1, smooth_param=sp, async_grid=True)
+        lsc.apply(dev, 1.0)
+        with pytest.raises(RuntimeError, match="exceeds the buffer capacity"):
+            lsc.last_params
+        assert np.array_equal(dev.to_host().rparticles, r)
+        lsc = LSC(step=1, smooth_param=sp, async_grid=False)
         lsc.apply(dev, 1.0)
         assert lsc.last_params["nb"] == len(st["x"]) > 3072
         d_ref = ref[5] - r[5]
@@ -136,14 +149,15 @@ def test_deposit_is_bit_reproducible_and_dz_threshold():
     np.random.seed(6)
     r, q, E = orc.gaussian_bunch(300_000, energy=0.13, charge=250e-12)
     outs = []
-    for _ in range(2):
+    for _ in range(2):                                          # host-derived grid, then device-derived grid
         dev = DeviceParticleArray.from_host(_host_parray(r, q, E))
-        lsc = LSC()
+        lsc = LSC(async_grid=bool(_))
         lsc.apply(dev, 5e-11)                                   # below 1e-10: untouched (sc.py:566-568)
         assert np.array_equal(dev.to_host().rparticles, r)
         lsc.apply(dev, 0.1)
         outs.append(lsc._solver(0).lsc_profile(lsc.last_params["nb"])["current"])
-    assert np.array_equal(outs[0], outs[1])                     # integer accumulation: order independent
+    # integer accumulation: order independent; and the device derives bit-identical grid scalars
+    assert np.array_equal(outs[0], outs[1])
 
 
 def test_resident_tracking_with_sc_and_lsc_together():

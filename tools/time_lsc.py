@@ -15,8 +15,8 @@ for n in (1_000_000, 12_500_000):
     p = ParticleArray(n)
     p.rparticles[:], p.q_array[:], p.E = r, q, E
     dev = DeviceParticleArray.from_host(p)
-    for sp in (False, True):
-        lsc = LSC(step_profile=sp)
+    for sp, ag in ((False, True), (False, False), (True, True)):
+        lsc = LSC(step_profile=sp, async_grid=ag)
         for _ in range(3):
             lsc.apply(dev, 0.1)
         torch.cuda.synchronize()
@@ -27,11 +27,5 @@ for n in (1_000_000, 12_500_000):
         torch.cuda.synchronize()
         dt = (time.perf_counter() - t0) / K
         s = lsc._solver(0)
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
-        st = s.lsc_stats(dev.rparticles, dev.q_array)
-        prm = lsc.kick_parameters(st, E, 0.1)
-        e0.record(); s.lsc_deposit(dev.rparticles, prm); e1.record(); s.lsc_solve_kick(dev.rparticles, prm); e2.record()
-        torch.cuda.synchronize()
-        print(f"n={n} step_profile={sp} nb={prm['nb']}: {dt*1e6:.1f} us/kick wall "
-              f"(deposit {e0.elapsed_time(e1)*1e3:.1f} us, solve+kick {e1.elapsed_time(e2)*1e3:.1f} us) "
+        print(f"n={n} step_profile={sp} device_grid={ag} nb={lsc.last_params['nb']}: {dt*1e6:.1f} us/kick wall "
               f"= {n/dt:.3e} particle-kicks/s")
