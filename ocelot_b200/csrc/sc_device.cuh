@@ -223,16 +223,13 @@ __device__ __forceinline__ double trilinear(const EQuad* __restrict__ F, int nx,
     const size_t row = (size_t)i1 * nz + i2, plane = (size_t)ny * nz;
     const EQuad A = F[(size_t)i0 * plane + row];
     const EQuad B = F[(size_t)j0 * plane + row];
+    // three nested linear interpolations (z, then y, then x): 14 fp64 operations in a dependent chain of 6,
+    // against 32 in a chain of 10 for the sum of eight weighted corners; the two agree to a few ulp
     const double a0 = 1.0 - t0, b0 = 1.0 - t1, d0 = 1.0 - t2;
-    double acc = A.v00 * a0 * b0 * d0;
-    acc = acc + A.v01 * a0 * b0 * t2;
-    acc = acc + A.v10 * a0 * t1 * d0;
-    acc = acc + A.v11 * a0 * t1 * t2;
-    acc = acc + B.v00 * t0 * b0 * d0;
-    acc = acc + B.v01 * t0 * b0 * t2;
-    acc = acc + B.v10 * t0 * t1 * d0;
-    acc = acc + B.v11 * t0 * t1 * t2;
-    return acc;
+    const double za0 = fma(A.v01, t2, A.v00 * d0), za1 = fma(A.v11, t2, A.v10 * d0);
+    const double zb0 = fma(B.v01, t2, B.v00 * d0), zb1 = fma(B.v11, t2, B.v10 * d0);
+    const double ya = fma(za1, t1, za0 * b0), yb = fma(zb1, t1, zb0 * b0);
+    return fma(yb, t0, ya * a0);
 }
 
 // ---- asynchronous row pipeline -------------------------------------------------
