@@ -213,9 +213,15 @@ struct __align__(32) EQuad {
 // fastest.  Two 256-bit loads fetch the eight corners.
 __device__ __forceinline__ double trilinear(const EQuad* __restrict__ F, int nx, int ny, int nz, double c0,
                                             double c1, double c2) {
-    if (!(c0 >= 0.0 && c0 <= (double)(nx - 1) && c1 >= 0.0 && c1 <= (double)(ny - 1) && c2 >= 0.0 &&
-          c2 <= (double)(nz - 1)))
-        return 0.0;
+    // map_coordinates(mode='constant', cval=0): any coordinate outside [0, n-1] (or NaN) gives 0.
+    // Branch-free on purpose: with an early return each of the three components of the gather sits in
+    // its own reconvergence region, the compiler cannot hoist the next component's loads above the
+    // previous component's arithmetic, and a particle pays three exposed L2 latencies in a row (60 % of
+    // the kernel's stall samples, profiles/r1_gather_kick_c4_stalls.csv).  Out-of-range coordinates are
+    // replaced by 0 so the loads stay inside the table, and the result is discarded by the select.
+    const bool in = c0 >= 0.0 && c0 <= (double)(nx - 1) && c1 >= 0.0 && c1 <= (double)(ny - 1) && c2 >= 0.0 &&
+                    c2 <= (double)(nz - 1);
+    c0 = in ? c0 : 0.0; c1 = in ? c1 : 0.0; c2 = in ? c2 : 0.0;
     double f0 = floor(c0), f1 = floor(c1), f2 = floor(c2);
     int i0 = (int)f0, i1 = (int)f1, i2 = (int)f2;
     double t0 = c0 - f0, t1 = c1 - f1, t2 = c2 - f2;
@@ -229,7 +235,8 @@ __device__ __forceinline__ double trilinear(const EQuad* __restrict__ F, int nx,
     const double za0 = fma(A.v01, t2, A.v00 * d0), za1 = fma(A.v11, t2, A.v10 * d0);
     const double zb0 = fma(B.v01, t2, B.v00 * d0), zb1 = fma(B.v11, t2, B.v10 * d0);
     const double ya = fma(za1, t1, za0 * b0), yb = fma(zb1, t1, zb0 * b0);
-    return fma(yb, t0, ya * a0);
+    const double acc = fma(yb, t0, ya * a0);
+    return in ? acc : 0.0;
 }
 
 // ---- asynchronous row pipeline -------------------------------------------------
