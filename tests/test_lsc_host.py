@@ -203,3 +203,24 @@ def test_drop_in_under_reference_navigator_with_undulators(monkeypatch):
     d_ref = ref[5]
     assert np.abs(got[5] - d_ref).max() <= 1e-10 * np.abs(d_ref).max()
     assert np.abs(got[4] - ref[4]).max() <= 1e-10 * np.abs(ref[4]).max()
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/ocelot"), reason="reference checkout not present")
+def test_install_swaps_both_reference_classes():
+    import sys
+    sys.path.insert(0, "/root/reference")
+    import logging
+    logging.disable(logging.WARNING)
+    import ocelot
+    import ocelot.cpbd.sc as ref_sc
+    import ocelot_b200
+    saved = (ref_sc.SpaceCharge, ref_sc.LSC, ocelot.SpaceCharge, getattr(ocelot, "LSC", None))
+    try:
+        sc_cls, lsc_cls = ocelot_b200.install()
+        assert ref_sc.SpaceCharge is ocelot_b200.SpaceCharge is sc_cls and ocelot.SpaceCharge is sc_cls
+        assert ref_sc.LSC is ocelot_b200.LSC is lsc_cls
+        assert ref_sc.SpaceCharge().nmesh_xyz == [63, 63, 63] and ref_sc.LSC().smooth_param == 0.1
+    finally:
+        ref_sc.SpaceCharge, ref_sc.LSC, ocelot.SpaceCharge = saved[:3]
+        if saved[3] is not None:
+            ocelot.LSC = saved[3]
