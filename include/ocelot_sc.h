@@ -63,9 +63,15 @@ int ocl_sc_kick_host(ocl_sc_t* h, double* h_r, long long ld, const double* h_q, 
                      double E_GeV, double dz, const double* mesh_draws);
 
 /* ---- staged form of the same kick, for particle-sharded multi-GPU runs ----
- * Between stages the caller all-reduces the handle's small device buffers
- * (ocl_sc_collective_buffer) across ranks; with one rank the five stages in
- * order are exactly ocl_sc_kick_device.
+ * With one rank the five stages in order are exactly ocl_sc_kick_device.  Across ranks the two scalar
+ * reductions happen either
+ *   (a) INSIDE stage_momentum / stage_extent: after ocl_sc_mailbox_init the block that finishes the
+ *       sweep's reduction pushes the rank's partial sums into every peer's mailbox over NVLink, waits
+ *       for the peers' and folds them in rank order -- no collective call, no extra kernel launch; or
+ *   (b) by the caller (e.g. NCCL without peer mappings): ocl_sc_defer_finish(h, 1), all-reduce the
+ *       handle's small device buffers (ocl_sc_collective_buffer) after each of the two stages, then
+ *       ocl_sc_stage_finish(h, which, ...) derives the frame (which = 0) / the mesh (which = 1).
+ * The frame and the mesh are derived once per kick on the device and read by all later stages.
  *   stage_momentum : lab->Cartesian momenta (coord_transform.py:57-96), sums
  *                    -> buffer MOMENTUM {sum px, sum py, sum pz, count}   [SUM]
  *   stage_extent   : bunch frame (sc.py:224-239), rotate, gamma-stretch
@@ -120,9 +126,9 @@ int ocl_sc_set_peer_rho(ocl_sc_t* h, int rank, int world, void* const* peer_rho)
 /* NVLS variant of the charge-grid reduction: `local_rho` is this rank's part of a symmetric allocation
  * of nx_pad*ny*nz doubles that is also mapped as one multicast range `multicast_rho` (e.g. torch
  * symmetric memory: buffer_ptrs[rank], multicast_ptr).  ocl_sc_nvls_reduce_rho then replaces the NCCL
- * all-reduce (redundant solve) or reduce-scatter (slab solve) of OCL_SC_BUF_RHO: barrier over the
- * mailbox, one kernel of multimem.ld_reduce / multimem.st (the NVSwitch sums each element once, so
- * every rank ends up with bit-identical sums), barrier.  Needs ocl_sc_mailbox_init. */
+ * all-reduce (redundant solve) or reduce-scatter (slab solve) of OCL_SC_BUF_RHO by ONE kernel: entry
+ * barrier over the mailbox, multimem.ld_reduce / multimem.st (the NVSwitch sums each element once, so
+ * every rank ends up with bit-identical sums), exit barrier.  Needs ocl_sc_mailbox_init. */
 int ocl_sc_set_multicast_rho(ocl_sc_t* h, void* local_rho, void* multicast_rho);
 int ocl_sc_nvls_reduce_rho(ocl_sc_t* h, void* stream);
 
@@ -150,7 +156,9 @@ int ocl_sc_slab_finish(ocl_sc_t* h, const double* mesh_draws, void* stream);
 
 int ocl_sc_stage_momentum(ocl_sc_t* h, const double* d_r, long long ld, long long n, double E_GeV, void* stream);
 int ocl_sc_stage_extent(ocl_sc_t* h, const double* d_r, long long ld, const double* d_q, long long n,
-                        double E_GeV, void* stream);
+                        double E_GeV, const double* mesh_draws, void* stream);
+int ocl_sc_defer_finish(ocl_sc_t* h, int on);
+int ocl_sc_stage_finish(ocl_sc_t* h, int which, double E_GeV, const double* mesh_draws, void* stream);
 int ocl_sc_stage_deposit(ocl_sc_t* h, const double* d_r, long long ld, const double* d_q, long long n,
                          double E_GeV, const double* mesh_draws, void* stream);
 int ocl_sc_stage_solve(ocl_sc_t* h, const double* mesh_draws, void* stream);

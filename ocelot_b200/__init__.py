@@ -2,15 +2,15 @@
 from .physproc import PhysProc
 from .particles import ParticleArray, DeviceParticleArray
 from .sc import SpaceCharge
-from .sc import install as install_space_charge
+from .sc import install as install_space_charge, uninstall as uninstall_space_charge
 from .lsc import LSC
-from .lsc import install as install_lsc
+from .lsc import install as install_lsc, uninstall as uninstall_lsc
 from .beam import apply_map, get_envelope, Moments
 from .track import track, replay_track
 from .apertures import RectAperture, EllipticalAperture
 from .io import save_particle_array2npz, load_particle_array_from_npz
 
-__all__ = ["PhysProc", "ParticleArray", "DeviceParticleArray", "SpaceCharge", "LSC", "install", "install_space_charge", "install_lsc",
+__all__ = ["PhysProc", "ParticleArray", "DeviceParticleArray", "SpaceCharge", "LSC", "install", "uninstall", "install_space_charge", "install_lsc",
            "apply_map", "get_envelope", "Moments", "track", "replay_track",
            "RectAperture", "EllipticalAperture", "save_particle_array2npz", "load_particle_array_from_npz"]
 
@@ -19,3 +19,9 @@ def install():
     """Replace Ocelot's ``SpaceCharge`` and ``LSC`` (``ocelot.cpbd.sc`` and the ``ocelot`` re-exports) with the
     B200 classes, so unmodified Ocelot scripts pick them up.  Returns the two classes."""
     return install_space_charge(), install_lsc()
+
+
+def uninstall():
+    """Undo ``install()``: every rebound name gets the reference class back."""
+    uninstall_space_charge()
+    uninstall_lsc()

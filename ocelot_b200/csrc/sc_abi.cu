@@ -41,7 +41,8 @@ struct ocl_sc {
     cufftDoubleComplex* k_hat = nullptr;      // M*M*(M/2+1)
     cufftDoubleComplex* rho_hat = nullptr;    // M*M*(M/2+1)
     double* phi = nullptr;    // n^3
-    EQuad* equad = nullptr;   // 3*n^3 quads: the field table the gather reads
+    EQuad* equad = nullptr;   // 3*n^3 (+1 pad) quads: the field table the gather reads
+    int layout = 1;           // 0: z-fastest table, independent gathers | 1: x-fastest table, lane-pair gathers
     cufftHandle plan_fwd = 0, plan_inv = 0;
     bool plans = false;
     // slab mode (multi-GPU solve)
@@ -250,10 +251,10 @@ int solve_fused(ocl_sc* h, cudaStream_t st) {
 }
 
 // Green's function table + K_hat on the side stream, ordered after everything already in st
-int fork_khat(ocl_sc* h, KP kp, cudaStream_t st) {
+int fork_khat(ocl_sc* h, cudaStream_t st) {
     CU(h, cudaEventRecord(h->ev_fork, st));
     CU(h, cudaStreamWaitEvent(h->side_stream, h->ev_fork, 0));
-    launch_green_table(h->rs, h->md, kp, h->gtab, h->h3, h->side_stream);
+    launch_green_table(h->rs, h->md, h->gtab, h->h3, h->side_stream);
     launch_khat(h->gtab, h->md, h->fw, h->side_stream);
     CU(h, cudaEventRecord(h->ev_khat, h->side_stream));
     h->khat_pending = true;
@@ -326,9 +327,12 @@ int ocl_sc_create(int device, int nx, int ny, int nz, long long max_particles, o
         }                                                                     \
     } while (0)
     TRY(cudaSetDevice(device));
-    TRY(cudaMalloc(&h->rs.part, sizeof(double) * 12 * h->rs.max_blocks));
-    TRY(cudaMalloc(&h->rs.ticket, sizeof(unsigned int) * 4));
-    TRY(cudaMemset(h->rs.ticket, 0, sizeof(unsigned int) * 4));
+    TRY(cudaMalloc(&h->rs.part, sizeof(double) * 16 * h->rs.max_blocks));
+    TRY(cudaMalloc(&h->rs.ticket, sizeof(unsigned int) * 8));
+    TRY(cudaMemset(h->rs.ticket, 0, sizeof(unsigned int) * 8));
+    TRY(cudaMalloc(&h->rs.geo, sizeof(Geo)));
+    TRY(cudaMemset(h->rs.geo, 0, sizeof(Geo)));
+    h->rs.defer = 0;
     TRY(cudaMalloc(&h->rs.sums, sizeof(double) * 40));
     TRY(cudaMemset(h->rs.sums, 0, sizeof(double) * 40));
     h->rs.emax = h->rs.sums + 4;
@@ -365,7 +369,13 @@ int ocl_sc_create(int device, int nx, int ny, int nz, long long max_particles, o
         TRY(cudaMalloc(&h->fw.B, sizeof(double2) * nx * h->md.my * hz1));
     }
     TRY(cudaMalloc(&h->phi, sizeof(double) * n3));
-    TRY(cudaMalloc(&h->equad, sizeof(EQuad) * n3 * 3));
+    TRY(cudaMalloc(&h->equad, sizeof(EQuad) * (n3 * 3 + 1)));
+    TRY(cudaMemset(h->equad + n3 * 3, 0, sizeof(EQuad)));          // pad record behind the x-fastest table
+    {
+        const char* env = getenv("OCL_SC_GATHER");
+        if (env) h->layout = atoi(env) ? 1 : 0;
+        field_init_kernels();
+    }
     TRY(cudaMemset(h->rho, 0, sizeof(double) * n3));
     TRY(cudaMemset(h->phi, 0, sizeof(double) * n3));
     h->rho_count = n3;
@@ -394,7 +404,7 @@ void ocl_sc_destroy(ocl_sc_t* h) {
     cudaGetLastError();
     cudaFree(h->kp_dev);
     if (h->plans) { cufftDestroy(h->plan_fwd); cufftDestroy(h->plan_inv); }
-    cudaFree(h->rs.part); cudaFree(h->rs.ticket); cudaFree(h->rs.sums);
+    cudaFree(h->rs.part); cudaFree(h->rs.ticket); cudaFree(h->rs.sums); cudaFree(h->rs.geo);
     cudaFree(h->own_rho ? h->own_rho : h->rho); cudaFree(h->gtab); cudaFree(h->k1); cudaFree(h->real_buf);
     cudaFree(h->k_hat); cudaFree(h->rho_hat); cudaFree(h->phi); cudaFree(h->equad);
     cudaFree(h->fw.P); cudaFree(h->fw.Q); cudaFree(h->fw.khat); cudaFree(h->fw.A); cudaFree(h->fw.B);
@@ -501,20 +511,18 @@ int ocl_sc_nvls_reduce_rho(ocl_sc_t* h, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
     const int world = h->mb.world, rank = h->mb.rank;
-    launch_mailbox_exchange(h->mb, 2, h->rs, h->mb_err, st);            // every rank's deposit is complete
+    // one kernel: barrier ("every rank's deposit is complete"), in-switch reduction, barrier ("every slice final")
     if (h->slab_world) {                                               // reduce-scatter into this rank's x-slab
         const long long plane = (long long)h->md.ny * h->md.nz;
         const long long lo = (long long)h->slab_rank * h->sx * plane;
-        launch_nvls_reduce(h->mc_rho, lo, lo + (long long)h->sx * plane, h->rho_slab, st);
-        h->launches += 2;
+        launch_nvls_reduce(h->mc_rho, lo, lo + (long long)h->sx * plane, h->rho_slab, h->mb, h->rs.ticket + 4, h->mb_err, st);
     } else {                                                           // all-reduce in place
         const long long n3 = (long long)h->rho_count;
         const long long chunk = (n3 + world - 1) / world;
         const long long lo = std::min(n3, (long long)rank * chunk), hi = std::min(n3, lo + chunk);
-        launch_nvls_reduce(h->mc_rho, lo, hi, nullptr, st);
-        launch_mailbox_exchange(h->mb, 2, h->rs, h->mb_err, st);        // every rank's slice has been broadcast
-        h->launches += 3;
+        launch_nvls_reduce(h->mc_rho, lo, hi, nullptr, h->mb, h->rs.ticket + 4, h->mb_err, st);
     }
+    h->launches += 1;
     return check_launch(h, "k_nvls_reduce");
 }
 
@@ -522,6 +530,23 @@ int ocl_sc_use_device_params(ocl_sc_t* h, int on) {
     if (!h) return 1;
     h->cur_pp = on ? h->kp_dev : nullptr;
     return 0;
+}
+
+int ocl_sc_defer_finish(ocl_sc_t* h, int on) {
+    if (!h) return 1;
+    h->rs.defer = on ? 1 : 0;
+    return 0;
+}
+
+int ocl_sc_stage_finish(ocl_sc_t* h, int which, double E_GeV, const double* mesh_draws, void* stream) {
+    if (!h) return 1;
+    if (which != 0 && which != 1) return fail(h, "ocl_sc_stage_finish", "which must be 0 (momentum) or 1 (extent)");
+    if (set_device(h)) return 1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (adopt_stream(h, st)) return 1;
+    launch_finish(which, kp_of(h, E_GeV, 0.0, mesh_draws), h->rs, h->md, st);
+    h->launches += 1;
+    return check_launch(h, "k_finish");
 }
 
 int ocl_sc_set_kick_params(ocl_sc_t* h, double E_GeV, double dz, const double* mesh_draws, void* stream) {
@@ -608,7 +633,8 @@ int ocl_sc_slab_finish(ocl_sc_t* h, const double* mesh_draws, void* stream) {
     if (set_device(h)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
-    launch_field(h->phi, h->rs, h->md, kp_of(h, 1.0, 0.0, mesh_draws), h->equad, st);
+    (void)mesh_draws;
+    launch_field(h->phi, h->rs, h->md, h->equad, h->layout, st);
     h->launches += 1;
     mark(h, T_FIELD, st);
     return check_launch(h, "slab_finish");
@@ -617,25 +643,26 @@ int ocl_sc_slab_finish(ocl_sc_t* h, const double* mesh_draws, void* stream) {
 // ---- stages ---------------------------------------------------------------
 int ocl_sc_stage_momentum(ocl_sc_t* h, const double* d_r, long long ld, long long n, double E_GeV, void* stream) {
     if (!h) return 1;
-    if (n <= 0 || ld < n) return fail(h, "ocl_sc_stage_momentum", "need 0 < n <= ld");
+    if (n < 0 || ld < n) return fail(h, "ocl_sc_stage_momentum", "need 0 <= n <= ld");
+    if (n == 0 && h->mb.world <= 1 && !h->rs.defer) return fail(h, "ocl_sc_stage_momentum", "empty bunch");
     if (n >= 2147483647LL - 2 * 148 * 4 * 256) return fail(h, "ocl_sc_stage_momentum", "more than 2^31 particles per GPU");
     if (set_device(h)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
     mark(h, T_BEGIN, st);
-    launch_momentum(d_r, ld, n, kp_of(h, E_GeV, 0.0, nullptr), h->rs, st);
+    launch_momentum(d_r, ld, n, kp_of(h, E_GeV, 0.0, nullptr), h->rs, h->mb, h->mb_err, st);
     h->launches += 1;
     mark(h, T_MOM, st);
     return check_launch(h, "k_momentum");
 }
 
 int ocl_sc_stage_extent(ocl_sc_t* h, const double* d_r, long long ld, const double* d_q, long long n, double E_GeV,
-                        void* stream) {
+                        const double* mesh_draws, void* stream) {
     if (!h) return 1;
     if (set_device(h)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
-    launch_extent(d_r, ld, d_q, n, kp_of(h, E_GeV, 0.0, nullptr), h->rs, st);
+    launch_extent(d_r, ld, d_q, n, kp_of(h, E_GeV, 0.0, mesh_draws), h->rs, h->md, h->mb, h->mb_err, st);
     h->launches += 1;
     mark(h, T_EXT, st);
     return check_launch(h, "k_extent");
@@ -649,7 +676,7 @@ int ocl_sc_stage_deposit(ocl_sc_t* h, const double* d_r, long long ld, const dou
     if (adopt_stream(h, st)) return 1;
     // the mesh steps are final once the extents are reduced: start the Green's-function / K_hat
     // chain now, concurrently with the deposit and the first two rho passes
-    if (h->solver == 0 && fork_khat(h, kp_of(h, E_GeV, 0.0, mesh_draws), st)) return 1;
+    if (h->solver == 0 && fork_khat(h, st)) return 1;
     CU(h, cudaMemsetAsync(h->rho, 0, sizeof(double) * h->rho_count, st));
     launch_deposit(d_r, ld, d_q, n, kp_of(h, E_GeV, 0.0, mesh_draws), h->rs, h->md, h->rho, st);
     h->launches += 2;
@@ -662,9 +689,9 @@ int ocl_sc_stage_solve(ocl_sc_t* h, const double* mesh_draws, void* stream) {
     if (set_device(h)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
-    KP dr = kp_of(h, 1.0, 0.0, mesh_draws);   // only the mesh draws are used by the solve
+    (void)mesh_draws;                         // the mesh (incl. random_mesh draws) was fixed by the extent stage
     if (!h->khat_pending) {
-        launch_green_table(h->rs, h->md, dr, h->gtab, h->h3, st);
+        launch_green_table(h->rs, h->md, h->gtab, h->h3, st);
         h->launches += 1;
     }
     if (h->solver == 0) {
@@ -673,10 +700,10 @@ int ocl_sc_stage_solve(ocl_sc_t* h, const double* mesh_draws, void* stream) {
     } else {
         if (convolve(h, st)) return 1;
         mark(h, T_SOLVE, st);
-        launch_crop_phi(h->real_buf, h->rs, h->md, dr, h->phi, st);
+        launch_crop_phi(h->real_buf, h->rs, h->md, h->phi, st);
         h->launches += 1;
     }
-    launch_field(h->phi, h->rs, h->md, dr, h->equad, st);
+    launch_field(h->phi, h->rs, h->md, h->equad, h->layout, st);
     h->launches += 1;
     mark(h, T_FIELD, st);
     return check_launch(h, "stage_solve");
@@ -688,7 +715,7 @@ int ocl_sc_stage_kick(ocl_sc_t* h, double* d_r, long long ld, long long n, doubl
     if (set_device(h)) return 1;
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
-    launch_gather_kick(d_r, ld, n, kp_of(h, E_GeV, dz, mesh_draws), h->rs, h->md, h->equad, nullptr, 1, st);
+    launch_gather_kick(d_r, ld, n, kp_of(h, E_GeV, dz, mesh_draws), h->rs, h->md, h->equad, nullptr, 1, h->layout, st);
     h->launches += 1;
     mark(h, T_KICK, st);
     return check_launch(h, "k_gather_kick");
@@ -697,7 +724,7 @@ int ocl_sc_stage_kick(ocl_sc_t* h, double* d_r, long long ld, long long n, doubl
 static int run_stages(ocl_sc_t* h, double* d_r, long long ld, const double* d_q, long long n, double E_GeV,
                       double dz, const double* mesh_draws, void* stream) {
     if (ocl_sc_stage_momentum(h, d_r, ld, n, E_GeV, stream)) return 1;
-    if (ocl_sc_stage_extent(h, d_r, ld, d_q, n, E_GeV, stream)) return 1;
+    if (ocl_sc_stage_extent(h, d_r, ld, d_q, n, E_GeV, mesh_draws, stream)) return 1;
     if (ocl_sc_stage_deposit(h, d_r, ld, d_q, n, E_GeV, mesh_draws, stream)) return 1;
     if (ocl_sc_stage_solve(h, mesh_draws, stream)) return 1;
     return ocl_sc_stage_kick(h, d_r, ld, n, E_GeV, dz, mesh_draws, stream);
@@ -895,11 +922,11 @@ int ocl_sc_field_at_particles(ocl_sc_t* h, const double* d_r, long long ld, cons
                               double E_GeV, const double* mesh_draws, double* d_exyz, void* stream) {
     if (!h) return 1;
     if (ocl_sc_stage_momentum(h, d_r, ld, n, E_GeV, stream)) return 1;
-    if (ocl_sc_stage_extent(h, d_r, ld, d_q, n, E_GeV, stream)) return 1;
+    if (ocl_sc_stage_extent(h, d_r, ld, d_q, n, E_GeV, mesh_draws, stream)) return 1;
     if (ocl_sc_stage_deposit(h, d_r, ld, d_q, n, E_GeV, mesh_draws, stream)) return 1;
     if (ocl_sc_stage_solve(h, mesh_draws, stream)) return 1;
     launch_gather_kick(const_cast<double*>(d_r), ld, n, kp_of(h, E_GeV, 0.0, mesh_draws), h->rs, h->md, h->equad,
-                       d_exyz, 0, (cudaStream_t)stream);
+                       d_exyz, 0, h->layout, (cudaStream_t)stream);
     h->launches += 1;
     return check_launch(h, "k_gather");
 }

@@ -66,6 +66,15 @@ struct Cart {
     double x, y, z, px, py, pz;
 };
 
+// Frame and mesh of the current kick, derived ONCE per kick on the device (by the block that finishes the
+// momentum / extent reduction, after the cross-rank exchange in a sharded kick) and read by every
+// later kernel: no kernel repeats the serial fp64 divisions / square roots of derive_frame / derive_mesh
+// in its prologue, and all of them see bit-identical geometry.
+struct Geo {
+    Frame f;
+    Mesh m;
+};
+
 // Branch-free fp64 reciprocal and square root for normal, positive-range operands
 // (every use below is on gamma, momenta or mesh steps): hardware seed (MUFU.RCP64H /
 // MUFU.RSQ64H, ~2^-20) plus Newton / Goldschmidt steps in FMA arithmetic.  Results
@@ -183,6 +192,50 @@ __device__ __forceinline__ void derive_mesh(const double* emax, const double* es
     }
 }
 
+// block-wide copy of the kick geometry into shared memory (ends with a barrier)
+__device__ __forceinline__ void load_geo(const Geo* __restrict__ g, Geo* s) {
+    constexpr int W = (int)(sizeof(Geo) / sizeof(double));
+    static_assert(sizeof(Geo) % sizeof(double) == 0, "Geo is copied as 8-byte words");
+    if (threadIdx.x < W) reinterpret_cast<double*>(s)[threadIdx.x] = __ldcg(reinterpret_cast<const double*>(g) + threadIdx.x);
+    __syncthreads();
+}
+
+// 1 / g^2 rounded to nearest: numpy evaluates `gamma ** -2` (coord_transform.py:69) with libm / SVML pow,
+// which is (nearly always) the correctly rounded value; a plain 1/(g*g) carries two roundings.
+__device__ __forceinline__ double inv_square_rn(double g) {
+    const double g2 = __dmul_rn(g, g);
+    const double e = __fma_rn(g, g, -g2);                 // g*g = g2 + e exactly
+    const double r0 = __ddiv_rn(1.0, g2);
+    const double res = __fma_rn(-g2, r0, 1.0) - e * r0;   // 1 - (g2 + e) r0
+    return __fma_rn(res, r0, r0);
+}
+
+// ---- coord_transform.py:68-92 + sc.py:233,172 in the REFERENCE's operation order ------------------------
+// Position of one particle in the bunch frame (z stretched by gamma0), every operation rounded separately
+// as numpy does; the 3x3 rotation accumulates like the BLAS kernel behind np.dot (k-sequential FMAs).
+// Used only for the <= 6 particles that define the mesh extents: the mesh step h = extent / (n - 3) feeds
+// the integrated Green's function, whose 8-corner cancellation amplifies a one-ulp change of h to ~1e-10
+// of the field, so the extremal coordinates are re-evaluated exactly like the reference does
+// (DESIGN.md section 5).  All other per-particle work uses the reduced forms above.
+__device__ __forceinline__ void exact_frame_position(const RefParams& rp, const Frame& f, double x, double xs, double y,
+                                                     double ys, double tau, double delta, double& a, double& b,
+                                                     double& c) {
+    const double gam = __dmul_rn(__dadd_rn(__dmul_rn(rp.betaref, delta), 1.0), rp.gamref);            // :68
+    const double bet = __dsqrt_rn(__dsub_rn(1.0, inv_square_rn(gam)));                                 // :69
+    const double t = __ddiv_rn(__dmul_rn(gam, bet), rp.gb_ref);
+    const double pz = __dsqrt_rn(__dsub_rn(__dsub_rn(__dmul_rn(t, t), __dmul_rn(xs, xs)), __dmul_rn(ys, ys)));   // :70
+    const double d0 = __ddiv_rn(xs, pz), d1 = __ddiv_rn(ys, pz);                                       // :72
+    const double nrm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), 1.0));    // :74
+    const double u0 = __ddiv_rn(d0, nrm), u1 = __ddiv_rn(d1, nrm), u2 = __ddiv_rn(1.0, nrm);           // :77
+    const double X = __dsub_rn(x, __dmul_rn(__dmul_rn(u0, bet), tau));                                 // :90
+    const double Y = __dsub_rn(y, __dmul_rn(__dmul_rn(u1, bet), tau));                                 // :91
+    const double Z = __dmul_rn(__dmul_rn(-u2, bet), tau);                                              // :92
+    a = __fma_rn(Z, f.T[2][0], __fma_rn(Y, f.T[1][0], __dmul_rn(X, f.T[0][0])));                       // sc.py:233
+    b = __fma_rn(Z, f.T[2][1], __fma_rn(Y, f.T[1][1], __dmul_rn(X, f.T[0][1])));
+    c = __fma_rn(Z, f.T[2][2], __fma_rn(Y, f.T[1][2], __dmul_rn(X, f.T[0][2])));
+    c = __dmul_rn(c, f.gamma0);                                                                        // sc.py:172
+}
+
 // rotate into the bunch frame and stretch z (sc.py:233, :172)
 __device__ __forceinline__ void rotate_stretch(const Frame& f, double x, double y, double z, double& a, double& b,
                                                double& c) {
@@ -231,6 +284,44 @@ __device__ __forceinline__ double trilinear(const EQuad* __restrict__ F, int nx,
     const EQuad B = F[(size_t)j0 * plane + row];
     // three nested linear interpolations (z, then y, then x): 14 fp64 operations in a dependent chain of 6,
     // against 32 in a chain of 10 for the sum of eight weighted corners; the two agree to a few ulp
+    const double a0 = 1.0 - t0, b0 = 1.0 - t1, d0 = 1.0 - t2;
+    const double za0 = fma(A.v01, t2, A.v00 * d0), za1 = fma(A.v11, t2, A.v10 * d0);
+    const double zb0 = fma(B.v01, t2, B.v00 * d0), zb1 = fma(B.v11, t2, B.v10 * d0);
+    const double ya = fma(za1, t1, za0 * b0), yb = fma(zb1, t1, zb0 * b0);
+    const double acc = fma(yb, t0, ya * a0);
+    return in ? acc : 0.0;
+}
+
+// ---- x-fastest field table, fetched by lane pairs ----------------------------------------------------------
+// The gather is bound by L1TEX wavefronts (one per distinct 128-byte line per warp instruction), not by bytes
+// (profiles/r1_gather_kick_c4_summary.csv): with the z-fastest table above every particle touches six lines.
+// Here the quad records of one component are stored x-fastest, rec(i, j, k) at F[(j*nz + k)*nx + i], so the two
+// records a particle needs (x = i0 and i0 + 1) are adjacent, 64 contiguous bytes that share a 128-byte line three
+// times out of four.  A lane pair fetches them with ONE request per particle: in the first load instruction the
+// even lane reads record i0 and the odd lane record i0 + 1 of the EVEN lane's particle, in the second both read
+// the ODD lane's particle; one exchange (8 x SHFL.32 per component) then hands every lane the two records of its
+// own particle.  Wavefronts per particle: 3 x 1.25 instead of 6.  Must be called by all 32 lanes.
+__device__ __forceinline__ double shfl_xor1(double v) { return __shfl_xor_sync(0xffffffffu, v, 1); }
+
+__device__ __forceinline__ double trilinear_pair(const EQuad* __restrict__ F, int nx, int ny, int nz, double c0,
+                                                 double c1, double c2) {
+    const bool in = c0 >= 0.0 && c0 <= (double)(nx - 1) && c1 >= 0.0 && c1 <= (double)(ny - 1) && c2 >= 0.0 &&
+                    c2 <= (double)(nz - 1);
+    c0 = in ? c0 : 0.0; c1 = in ? c1 : 0.0; c2 = in ? c2 : 0.0;
+    const double f0 = floor(c0), f1 = floor(c1), f2 = floor(c2);
+    const int i0 = (int)f0, i1 = (int)f1, i2 = (int)f2;
+    const double t0 = c0 - f0, t1 = c1 - f1, t2 = c2 - f2;
+    // record i0 + 1 of the last plane (i0 == nx - 1, t0 == 0) is the next row's first record (or the zeroed
+    // pad record behind the table): finite, and its weight is exactly zero
+    const int mine = (i1 * nz + i2) * nx + i0;
+    const int other = __shfl_xor_sync(0xffffffffu, mine, 1);
+    const int odd = (int)(threadIdx.x & 1);
+    const EQuad L1 = F[(odd ? other : mine) + odd];        // even lane's particle: records i0 | i0 + 1
+    const EQuad L2 = F[(odd ? mine : other) + odd];        // odd lane's particle
+    EQuad S = odd ? L1 : L2, R;
+    R.v00 = shfl_xor1(S.v00); R.v01 = shfl_xor1(S.v01); R.v10 = shfl_xor1(S.v10); R.v11 = shfl_xor1(S.v11);
+    const EQuad A = odd ? R : L1;
+    const EQuad B = odd ? L2 : R;
     const double a0 = 1.0 - t0, b0 = 1.0 - t1, d0 = 1.0 - t2;
     const double za0 = fma(A.v01, t2, A.v00 * d0), za1 = fma(A.v11, t2, A.v10 * d0);
     const double zb0 = fma(B.v01, t2, B.v00 * d0), zb1 = fma(B.v11, t2, B.v10 * d0);
@@ -295,11 +386,14 @@ inline void launch_k(void (*kernel)(Exp...), dim3 grid, dim3 block, size_t smem,
 constexpr int kSweepThreads = 256;
 
 // body(i, v) is called once per particle i with v[k] = base[k][i].  n < 2^31.
-template <int NR, int D, typename F>
+// UNIFORM: the trip count is uniform across each warp (lanes beyond n run the body with v = 0 and
+// valid = false), so the body may use warp shuffles: body(i, v, valid).
+template <int NR, int D, bool UNIFORM = false, typename F>
 __device__ __forceinline__ void pipelined_sweep(const double* const (&base)[NR], int n, double* sm, F&& body) {
     const int stride = (int)gridDim.x * kSweepThreads;
     int i = (int)blockIdx.x * kSweepThreads + (int)threadIdx.x;
     int ip = i;
+    const int lane = UNIFORM ? (int)(threadIdx.x & 31) : 0;      // i - lane: index of the warp's first particle
     double* slot = sm + threadIdx.x;
 #pragma unroll
     for (int d = 0; d < D - 1; ++d) {
@@ -310,11 +404,10 @@ __device__ __forceinline__ void pipelined_sweep(const double* const (&base)[NR],
         cp_async_commit();
         ip += stride;
     }
-    while (i < n) {
+    while (i - lane < n) {
 #pragma unroll
         for (int st = 0; st < D; ++st) {           // static stage index: all shared-memory offsets are immediates
-            if (i < n) {
-                constexpr int dummy = 0; (void)dummy;
+            if (i - lane < n) {
                 const int sp = (st + D - 1) % D;
                 if (ip < n) {
 #pragma unroll
@@ -324,9 +417,16 @@ __device__ __forceinline__ void pipelined_sweep(const double* const (&base)[NR],
                 ip += stride;
                 cp_async_wait<D - 1>();
                 double v[NR];
+                if constexpr (UNIFORM) {
+                    const bool valid = i < n;
 #pragma unroll
-                for (int k = 0; k < NR; ++k) v[k] = slot[(st * NR + k) * kSweepThreads];
-                body(i, v);
+                    for (int k = 0; k < NR; ++k) v[k] = valid ? slot[(st * NR + k) * kSweepThreads] : 0.0;
+                    body(i, v, valid);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NR; ++k) v[k] = slot[(st * NR + k) * kSweepThreads];
+                    body(i, v);
+                }
                 i += stride;
             }
         }
@@ -396,6 +496,69 @@ __device__ __forceinline__ bool grid_reduce(double (&v)[NV], double* part, unsig
         }
     }
     block_reduce<NV, NMAX>(v, sh);
+    if (threadIdx.x == 0) *ticket = 0;
+    return true;
+}
+
+// The extent reduction with the owner of every extremum: v[0..5] reduce with max and carry the index of the
+// particle that attains them (ix), v[6..9] reduce with +.  Same fixed-order two-level scheme as grid_reduce;
+// per-block partials are 16 doubles {10 values, 6 indices}.  Returns true in the finishing block, where
+// thread 0 holds the results.
+constexpr int kExtentPartial = 16;
+__device__ __forceinline__ void block_reduce_arg(double (&v)[10], int (&ix)[6], double* sh /* [10*kSweepWarps] */,
+                                                 double* shv /* [6] */, int* shi /* [6] */) {
+    double mine[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) mine[k] = v[k];
+    block_reduce<10, 6>(v, sh);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) { shv[k] = v[k]; shi[k] = -1; }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+        if (mine[k] == shv[k] && ix[k] >= 0) shi[k] = ix[k];          // ties: any owner will do
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 6; ++k) ix[k] = shi[k];
+    __syncthreads();
+}
+
+__device__ __forceinline__ bool grid_reduce_extent(double (&v)[10], int (&ix)[6], double* part, unsigned int* ticket,
+                                                   double* sh, double* shv, int* shi) {
+    __shared__ bool last;
+    block_reduce_arg(v, ix, sh, shv, shi);
+    if (threadIdx.x == 0) {
+        double* dst = part + (size_t)blockIdx.x * kExtentPartial;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) dst[k] = v[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) dst[10 + k] = (double)ix[k];
+        __threadfence();
+        unsigned int t = atomicAdd(ticket, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!last) return false;
+    __threadfence();
+#pragma unroll
+    for (int k = 0; k < 10; ++k) v[k] = (k < 6) ? -INFINITY : 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) ix[k] = -1;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += kSweepThreads) {
+        const double* src = part + (size_t)b * kExtentPartial;
+#pragma unroll
+        for (int k = 0; k < 10; ++k) {
+            const double x = __ldcg(src + k);
+            if (k < 6) {
+                if (x > v[k]) { v[k] = x; ix[k] = (int)__ldcg(src + 10 + k); }
+            } else {
+                v[k] += x;
+            }
+        }
+    }
+    block_reduce_arg(v, ix, sh, shv, shi);
     if (threadIdx.x == 0) *ticket = 0;
     return true;
 }

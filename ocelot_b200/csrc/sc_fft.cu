@@ -41,8 +41,17 @@ struct Geom {
 #define OCL_FFT512_NL 8
 #define OCL_FFT512_T 256
 #endif
-    static constexpr int T = (M >= 512) ? OCL_FFT512_T : 128;                           // threads per block
-    static constexpr int NL = (M >= 512) ? OCL_FFT512_NL : (M >= 256) ? 8 : ((2048 / M) > 32 ? 32 : (2048 / M));   // lines per block
+    // M <= 128: the grids are small (63^3: 3969 z lines), so the lines per block decide how many blocks there
+    // are to spread over 148 SMs.  Round 1 used 2048/M lines (125 blocks of 128 threads at M = 128: 6 % of the
+    // warp slots busy, 8-16 us per pass); OCL_FFT_LINES_SMALL lines per block with one thread per 8 points
+    // gives 4x the blocks, each with a quarter of the loads in front of its first butterfly.
+#ifndef OCL_FFT_LINES_SMALL
+#define OCL_FFT_LINES_SMALL 4
+#endif
+    static constexpr int NL_SMALL = (OCL_FFT_LINES_SMALL * M > 2048) ? (2048 / M) : OCL_FFT_LINES_SMALL;
+    static constexpr int T_SMALL = (NL_SMALL * M / 8 > 128) ? 128 : ((NL_SMALL * M / 8 < 32) ? 32 : NL_SMALL * M / 8);
+    static constexpr int T = (M >= 512) ? OCL_FFT512_T : (M >= 256 ? 128 : T_SMALL);    // threads per block
+    static constexpr int NL = (M >= 512) ? OCL_FFT512_NL : (M >= 256) ? 8 : NL_SMALL;   // lines per block
     static constexpr int NLP = NL + 1;
     static constexpr int ELEMS = M * NLP;
     // In-place stages (one shared buffer instead of Stockham's two): every thread reads all the

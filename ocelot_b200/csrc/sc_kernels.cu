@@ -5,8 +5,8 @@
 // (mean momentum -> frame; extents/centroid -> mesh; rho -> potential), plus
 // the grid work in between:
 //
-//   k_momentum     sweep 1  rows x',y',delta            -> sums[4]
-//   k_extent       sweep 2  6 rows + q                  -> emax[6], esum[4]
+//   k_momentum     sweep 1  rows x',y',delta            -> sums[4]; tail: exchange, frame -> Geo
+//   k_extent       sweep 2  6 rows + q                  -> emax[6], esum[4]; tail: exchange, mesh -> Geo
 //   k_deposit      sweep 3  6 rows + q                  -> rho (NGP, fp64 RED)
 //   k_green_table / k_green_mirror                      -> K on the padded grid
 //   cuFFT D2Z x2, k_multiply, cuFFT Z2D                 -> convolution
@@ -47,10 +47,97 @@ constexpr int kPipeDepth = 3;
 #endif
 
 // ---------------------------------------------------------------------------
-// sweep 1: mean momentum (sc.py:221,224)
+// Fused exchange over NVLink peer memory (replaces an NCCL all-reduce / all-gather of a handful of
+// doubles): lane w stores this rank's values into rank w's mailbox, fences, raises its epoch flag
+// there; then waits for rank w's flag in the local mailbox; lane 0 folds the W slots in rank order
+// (bit-identical result on every rank) into the handle's reduced buffers.
+//   which 0: momentum {sum px, py, pz, count}        -> SUM
+//   which 1: extents  {max x6} MAX, {sum q x3, q} SUM
+//   which 2: barrier only
+// Slots are single-buffered: a rank can only push exchange e+1 after it has consumed everyone's
+// exchange e of the *other* kind, which in turn requires everyone to have consumed this kind's e.
+// Runs in ONE warp (all 32 lanes): either the warp that finishes a sweep's grid reduction (no extra
+// launch on the critical path) or the stand-alone k_mailbox_exchange.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void mailbox_exchange_warp(const Mailbox& mb, int which, const ReduceState& rs,
+                                                      int* __restrict__ err_flag) {
+    const int lane = threadIdx.x & 31;
+    const int nv = which == 0 ? 4 : (which == 1 ? 10 : 0);
+    const int vbase = which == 0 ? 0 : 32;
+    const int fbase = 128 + 8 * which;
+    const double* local_vals = which == 0 ? rs.sums : rs.emax;          // emax[6] and esum[4] are contiguous
+    const unsigned long long epoch = mb.epoch[which] + 1;
+    __syncwarp();
+    if (lane < mb.world) {
+        double* dst = mb.peer[lane] + vbase + mb.rank * nv;
+        for (int k = 0; k < nv; ++k) dst[k] = __ldcg(local_vals + k);
+        __threadfence_system();
+        volatile unsigned long long* flag = reinterpret_cast<unsigned long long*>(mb.peer[lane] + fbase) + mb.rank;
+        *flag = epoch;
+        // wait for rank `lane` to have delivered its values here
+        volatile unsigned long long* mine = reinterpret_cast<unsigned long long*>(mb.peer[mb.rank] + fbase) + lane;
+        const long long t0 = clock64();
+        while (*mine < epoch) {
+            if (clock64() - t0 > 8000000000LL) { atomicExch(err_flag, 1 + which); break; }   // ~4 s: a peer is gone
+        }
+        __threadfence_system();
+    }
+    __syncwarp();
+    if (lane == 0) {
+        if (which < 2) {
+            const volatile double* box = mb.peer[mb.rank] + vbase;
+            double v[10];
+            for (int k = 0; k < nv; ++k) v[k] = box[k];
+            for (int w = 1; w < mb.world; ++w)
+                for (int k = 0; k < nv; ++k) {
+                    const double x = box[w * nv + k];
+                    v[k] = (which == 1 && k < 6) ? fmax(v[k], x) : v[k] + x;
+                }
+            if (which == 0) {
+                for (int k = 0; k < 4; ++k) rs.sums[k] = v[k];
+            } else {
+                for (int k = 0; k < 6; ++k) rs.emax[k] = v[k];
+                for (int k = 0; k < 4; ++k) rs.esum[k] = v[6 + k];
+            }
+        }
+        mb.epoch[which] = epoch;
+        __threadfence();
+    }
+    __syncwarp();
+}
+
+// frame of the kick from the (globally) reduced momentum sums -> rs.geo->f        (one thread)
+__device__ __forceinline__ void finish_momentum(const ReduceState& rs, const RefParams& rp) {
+    Frame f;
+    double sums[4];
+    for (int k = 0; k < 4; ++k) sums[k] = __ldcg(rs.sums + k);
+    derive_frame(sums, rp.m_e_eV, f);
+    rs.geo->f = f;
+}
+
+// mesh of the kick from the (globally) reduced extents -> rs.geo->m, geometry tap   (one thread)
+__device__ __forceinline__ void finish_extent(const ReduceState& rs, const MeshDims& md, const Draws& dr) {
+    Mesh m;
+    double e[10];
+    for (int k = 0; k < 10; ++k) e[k] = __ldcg(rs.emax + k);              // emax[6] and esum[4] are contiguous
+    derive_mesh(e, e + 6, md.nx, md.ny, md.nz, dr.scale, dr.shift, m);
+    rs.geo->m = m;
+    const Frame f = rs.geo->f;
+    double* g = rs.geom;
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) g[i * 3 + j] = f.T[i][j];
+    g[9] = f.pav; g[10] = f.gamma0; g[11] = f.beta0;
+    for (int c = 0; c < 3; ++c) { g[12 + c] = m.steps[c]; g[15 + c] = m.xoff[c]; }
+    g[18] = m.sumq; g[19] = __ldcg(rs.sums + 3);
+}
+
+// ---------------------------------------------------------------------------
+// sweep 1: mean momentum (sc.py:221,224).  The block that finishes the reduction also runs the
+// cross-rank exchange (sharded kick) and derives the frame, unless the caller defers that
+// (NCCL fallback: all-reduce of rs.sums, then k_finish).
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 4) k_momentum(const double* __restrict__ r, long long ld, long long n,
-                                                         KP kp, ReduceState rs) {
+                                                         KP kp, ReduceState rs, Mailbox mb, int* mb_err) {
     pdl_enter();
     const RefParams rp = kp_ref(kp);
     __shared__ double sh[3 * kWarps];
@@ -63,44 +150,95 @@ __global__ void __launch_bounds__(kThreads, 4) k_momentum(const double* __restri
         v[0] += w[0]; v[1] += w[1]; v[2] += pzr;       // p = (x', y', pz_rel) * pc: scaled once at the end
     });
     pdl_trigger();
-    if (grid_reduce<3, 0>(v, rs.part, rs.ticket + 0, sh) && threadIdx.x == 0) {
+    if (!grid_reduce<3, 0>(v, rs.part, rs.ticket + 0, sh)) return;
+    if (threadIdx.x >= 32) return;                      // the finishing block's first warp carries on
+    if (threadIdx.x == 0) {
         rs.sums[0] = v[0] * rp.pc; rs.sums[1] = v[1] * rp.pc; rs.sums[2] = v[2] * rp.pc;
         rs.sums[3] = (double)n;
+        __threadfence();
     }
+    if (rs.defer) return;
+    if (mb.world > 1) mailbox_exchange_warp(mb, 0, rs, mb_err);
+    if (threadIdx.x == 0) finish_momentum(rs, rp);
 }
 
 // ---------------------------------------------------------------------------
-// sweep 2: extents and charge centroid in the bunch frame (sc.py:172-173,181-182)
+// sweep 2: extents and charge centroid in the bunch frame (sc.py:172-173,181-182).  Every thread
+// remembers which particle gave each of its six extrema; the finishing block re-evaluates those
+// (at most six) particles in the reference's exact operation order before the mesh is derived.
 // ---------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 3) k_extent(const double* __restrict__ r, long long ld,
                                                        const double* __restrict__ q, long long n, KP kp,
-                                                       ReduceState rs) {
+                                                       ReduceState rs, MeshDims md, Mailbox mb, int* mb_err) {
     pdl_enter();
     const RefParams rp = kp_ref(kp);
     __shared__ double sh[10 * kWarps];
     __shared__ double pipe[kPipeDepth * 7 * kThreads];
     __shared__ Frame sf;
-    if (threadIdx.x == 0) derive_frame(rs.sums, rp.m_e_eV, sf);
-    __syncthreads();
+    __shared__ double shv[6];
+    __shared__ int shi[6];
+    {
+        constexpr int W = (int)(sizeof(Frame) / sizeof(double));
+        if (threadIdx.x < W) reinterpret_cast<double*>(&sf)[threadIdx.x] = __ldcg(reinterpret_cast<const double*>(&rs.geo->f) + threadIdx.x);
+        __syncthreads();
+    }
     const Frame f = sf;
     double v[10] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, 0.0, 0.0, 0.0, 0.0};
+    int ix[6] = {-1, -1, -1, -1, -1, -1};
     const double* const base[7] = {r, r + ld, r + 2 * ld, r + 3 * ld, r + 4 * ld, r + 5 * ld, q};
-    pipelined_sweep<7, kPipeDepth>(base, (int)n, pipe, [&](int, const double (&w)[7]) {
+    pipelined_sweep<7, kPipeDepth>(base, (int)n, pipe, [&](int i, const double (&w)[7]) {
         const Cart c = mad_to_cart(rp, w[0], w[1], w[2], w[3], w[4], w[5]);
         double a, b, g;
         rotate_stretch(f, c.x, c.y, c.z, a, b, g);
         const double qi = w[6];
-        v[0] = fmax(v[0], a); v[1] = fmax(v[1], b); v[2] = fmax(v[2], g);
-        v[3] = fmax(v[3], -a); v[4] = fmax(v[4], -b); v[5] = fmax(v[5], -g);
+        if (a > v[0]) { v[0] = a; ix[0] = i; }
+        if (b > v[1]) { v[1] = b; ix[1] = i; }
+        if (g > v[2]) { v[2] = g; ix[2] = i; }
+        if (-a > v[3]) { v[3] = -a; ix[3] = i; }
+        if (-b > v[4]) { v[4] = -b; ix[4] = i; }
+        if (-g > v[5]) { v[5] = -g; ix[5] = i; }
         v[6] += qi * a; v[7] += qi * b; v[8] += qi * g; v[9] += qi;
     });
     pdl_trigger();
-    if (grid_reduce<10, 6>(v, rs.part, rs.ticket + 1, sh) && threadIdx.x == 0) {
+    if (!grid_reduce_extent(v, ix, rs.part, rs.ticket + 1, sh, shv, shi)) return;
+    if (threadIdx.x >= 32) return;
+    // lanes 0..5: the particle behind extremum k, once more, exactly as the reference computes it
+    const int lane = threadIdx.x;
+    double exact = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const int who = __shfl_sync(0xffffffffu, ix[k], 0);
+        if (lane == k && who >= 0) {
+            double a, b, c;
+            exact_frame_position(rp, f, r[who], r[ld + who], r[2 * ld + who], r[3 * ld + who], r[4 * ld + who],
+                                 r[5 * ld + who], a, b, c);
+            const double p[3] = {a, b, c};
+            exact = k < 3 ? p[k] : -p[k - 3];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+        const double e = __shfl_sync(0xffffffffu, exact, k);
+        if (lane == 0 && e > -INFINITY) v[k] = e;
+    }
+    if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) rs.emax[k] = v[k];
 #pragma unroll
         for (int k = 0; k < 4; ++k) rs.esum[k] = v[6 + k];
+        __threadfence();
     }
+    if (rs.defer) return;
+    if (mb.world > 1) mailbox_exchange_warp(mb, 1, rs, mb_err);
+    if (threadIdx.x == 0) finish_extent(rs, md, kp_draws(kp));
+}
+
+// deferred tails (NCCL fallback of a sharded kick: the host all-reduces rs.sums / rs.emax,esum in between)
+__global__ void k_finish(int which, KP kp, ReduceState rs, MeshDims md) {
+    pdl_enter();
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (which == 0) finish_momentum(rs, kp_ref(kp));
+    else finish_extent(rs, md, kp_draws(kp));
 }
 
 // ---------------------------------------------------------------------------
@@ -111,25 +249,11 @@ __global__ void __launch_bounds__(kThreads, 3) k_deposit(const double* __restric
                                                         ReduceState rs, MeshDims md, double* __restrict__ rho) {
     pdl_enter();
     const RefParams rp = kp_ref(kp);
-    const Draws dr = kp_draws(kp);
     __shared__ double pipe[kPipeDepth * 7 * kThreads];
-    __shared__ Frame sf;
-    __shared__ Mesh sm;
-    if (threadIdx.x == 0) {
-        derive_frame(rs.sums, rp.m_e_eV, sf);
-        derive_mesh(rs.emax, rs.esum, md.nx, md.ny, md.nz, dr.scale, dr.shift, sm);
-        if (blockIdx.x == 0) {  // geometry tap
-            double* g = rs.geom;
-            for (int i = 0; i < 3; ++i)
-                for (int j = 0; j < 3; ++j) g[i * 3 + j] = sf.T[i][j];
-            g[9] = sf.pav; g[10] = sf.gamma0; g[11] = sf.beta0;
-            for (int c = 0; c < 3; ++c) { g[12 + c] = sm.steps[c]; g[15 + c] = sm.xoff[c]; }
-            g[18] = sm.sumq; g[19] = rs.sums[3];
-        }
-    }
-    __syncthreads();
-    const Frame f = sf;
-    const Mesh m = sm;
+    __shared__ Geo sg;
+    load_geo(rs.geo, &sg);
+    const Frame f = sg.f;
+    const Mesh m = sg.m;
     const double* const base[7] = {r, r + ld, r + 2 * ld, r + 3 * ld, r + 4 * ld, r + 5 * ld, q};
     pipelined_sweep<7, kPipeDepth>(base, (int)n, pipe, [&](int, const double (&w)[7]) {
         const Cart c = mad_to_cart(rp, w[0], w[1], w[2], w[3], w[4], w[5]);
@@ -166,27 +290,17 @@ struct StepSrc {
     double h[3];
 };
 
-__device__ __forceinline__ void resolve_steps(const StepSrc& src, const ReduceState& rs, const MeshDims& md,
-                                              const Draws& dr, double* h /* shared [3] */) {
-    if (threadIdx.x == 0) {
-        if (src.given) {
-            h[0] = src.h[0]; h[1] = src.h[1]; h[2] = src.h[2];
-        } else {
-            Mesh m;
-            derive_mesh(rs.emax, rs.esum, md.nx, md.ny, md.nz, dr.scale, dr.shift, m);
-            h[0] = m.steps[0]; h[1] = m.steps[1]; h[2] = m.steps[2];
-        }
-    }
+__device__ __forceinline__ void resolve_steps(const StepSrc& src, const ReduceState& rs, double* h /* shared [3] */) {
+    if (threadIdx.x < 3) h[threadIdx.x] = src.given ? src.h[threadIdx.x] : __ldcg(rs.geo->m.steps + threadIdx.x);
     __syncthreads();
 }
 
 // antiderivative on the (n+1)^3 half-offset points (sc.py:116-126)
-__global__ void __launch_bounds__(kThreads) k_green_table(StepSrc src, ReduceState rs, MeshDims md, KP kp,
+__global__ void __launch_bounds__(kThreads) k_green_table(StepSrc src, ReduceState rs, MeshDims md,
                                                          double* __restrict__ gtab, double* __restrict__ h3) {
     pdl_enter();
-    const Draws dr = kp_draws(kp);
     __shared__ double h[3];
-    resolve_steps(src, rs, md, dr, h);
+    resolve_steps(src, rs, h);
     if (blockIdx.x == 0 && threadIdx.x == 0) { h3[0] = h[0]; h3[1] = h[1]; h3[2] = h[2]; }   // for the solver
     const int gx = md.nx + 1, gy = md.ny + 1, gz = md.nz + 1;
     const long long total = (long long)gx * gy * gz;
@@ -282,11 +396,10 @@ __global__ void __launch_bounds__(kThreads) k_multiply(cufftDoubleComplex* __res
 
 // phi = conv[:n,:n,:n] / (4 pi eps0 hx hy hz)  (sc.py:167-168)
 __global__ void __launch_bounds__(kThreads) k_crop_phi(const double* __restrict__ conv, StepSrc src, ReduceState rs,
-                                                      MeshDims md, KP kp, double four_pi_eps0,
+                                                      MeshDims md, double four_pi_eps0,
                                                       double* __restrict__ phi) {
-    const Draws dr = kp_draws(kp);
     __shared__ double h[3];
-    resolve_steps(src, rs, md, dr, h);
+    resolve_steps(src, rs, h);
     const double denom = four_pi_eps0 * h[0] * h[1] * h[2];
     const long long total = (long long)md.nx * md.ny * md.nz;
     for (long long t = (long long)blockIdx.x * kThreads + threadIdx.x; t < total; t += (long long)gridDim.x * kThreads) {
@@ -313,12 +426,11 @@ __device__ __forceinline__ double field_value(const double* __restrict__ phi, co
 
 // grid = (ceil(nz*ny / threads), nx, 3): no integer division by runtime strides per thread
 __global__ void __launch_bounds__(kThreads) k_field(const double* __restrict__ phi, StepSrc src, ReduceState rs,
-                                                   MeshDims md, KP kp, EQuad* __restrict__ equad) {
+                                                   MeshDims md, EQuad* __restrict__ equad) {
     pdl_enter();
-    const Draws dr = kp_draws(kp);
     __shared__ double h[3];
     __shared__ double ih[3];
-    resolve_steps(src, rs, md, dr, h);
+    resolve_steps(src, rs, h);
     if (threadIdx.x < 3) ih[threadIdx.x] = 1.0 / h[threadIdx.x];
     __syncthreads();
     const int comp = blockIdx.z, i = blockIdx.y;
@@ -334,42 +446,90 @@ __global__ void __launch_bounds__(kThreads) k_field(const double* __restrict__ p
     equad[((size_t)comp * md.nx + i) * md.ny * md.nz + jk] = e;
 }
 
+// The same table stored x-fastest for the lane-pair gather (trilinear_pair): rec(comp, i, j, k) at
+// equad[comp*cells + (j*nz + k)*nx + i].  One block = one j and kFieldKT consecutive k: the phi values
+// it needs ((j..j+2) x (k..k+KT+1) for every i) are staged in shared memory with k-contiguous reads,
+// and the records leave with i fastest, i.e. fully coalesced 32-byte stores.
+constexpr int kFieldKT = 8;
+__global__ void __launch_bounds__(kThreads) k_field_xf(const double* __restrict__ phi, StepSrc src, ReduceState rs,
+                                                      MeshDims md, EQuad* __restrict__ equad) {
+    pdl_enter();
+    extern __shared__ double tile[];                      // [nx][3][KT + 2]
+    __shared__ double h[3];
+    __shared__ double ih[3];
+    resolve_steps(src, rs, h);
+    if (threadIdx.x < 3) ih[threadIdx.x] = 1.0 / h[threadIdx.x];
+    constexpr int KW = kFieldKT + 2;
+    const int j = blockIdx.y, k0 = blockIdx.x * kFieldKT;
+    const int nx = md.nx, ny = md.ny, nz = md.nz;
+    for (int t = threadIdx.x; t < nx * 3 * KW; t += kThreads) {
+        const int kk = t % KW, u = t / KW, jj = u % 3, i = u / 3;
+        const int js = min(j + jj, ny - 1), ks = min(k0 + kk, nz - 1);            // clamped: never used beyond the edge
+        tile[t] = __ldg(phi + ((size_t)i * ny + js) * nz + ks);
+    }
+    __syncthreads();
+    const size_t cells = (size_t)nx * ny * nz;
+    auto P = [&](int i, int jj, int kk) { return tile[(i * 3 + jj) * KW + kk]; };
+    // E at (i, j + dj, k0 + kk + dk) with the upper indices clamped like the z-fastest table
+    auto E = [&](int comp, int i, int jj, int kk) -> double {
+        const int jg = min(j + jj, ny - 1), kg = min(k0 + kk, nz - 1);
+        const int jl = jg - j, kl = kg - k0;                                       // local (clamped) tile coordinates
+        if (comp == 0) return (i < nx - 1) ? (P(i, jl, kl) - P(i + 1, jl, kl)) * ih[0] : 0.0;
+        if (comp == 1) return (jg < ny - 1) ? (P(i, jl, kl) - P(i, jl + 1, kl)) * ih[1] : 0.0;
+        return (kg < nz - 1) ? (P(i, jl, kl) - P(i, jl, kl + 1)) * ih[2] : 0.0;
+    };
+    const int kt = min(kFieldKT, nz - k0);
+    for (int t = threadIdx.x; t < 3 * kt * nx; t += kThreads) {
+        const int i = t % nx, u = t / nx, kk = u % kt, comp = u / kt;
+        EQuad e;
+        e.v00 = E(comp, i, 0, kk);
+        e.v01 = E(comp, i, 0, kk + 1);
+        e.v10 = E(comp, i, 1, kk);
+        e.v11 = E(comp, i, 1, kk + 1);
+        equad[comp * cells + ((size_t)j * nz + (k0 + kk)) * nx + i] = e;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // sweep 4: gather, kick, back-transform (sc.py:201-204, :244-251)
+//   LAYOUT 0: z-fastest quad table, six independent 256-bit gathers per particle
+//   LAYOUT 1: x-fastest quad table fetched by lane pairs (trilinear_pair)
 // ---------------------------------------------------------------------------
-template <bool KICK, bool TAP>
+template <bool KICK, bool TAP, int LAYOUT>
 __global__ void __launch_bounds__(kThreads, GK_BLOCKS) k_gather_kick(double* __restrict__ r, long long ld, long long n,
                                                             KP kp, ReduceState rs, MeshDims md,
                                                             const EQuad* __restrict__ equad,
                                                             double* __restrict__ exyz_out) {
     pdl_enter();
     const RefParams rp = kp_ref(kp);
-    const Draws dr = kp_draws(kp);
     const double cdT = kp_cdT(kp);
     __shared__ double pipe[kPipeDepth * 6 * kThreads];
-    __shared__ Frame sf;
-    __shared__ Mesh sm;
-    if (threadIdx.x == 0) {
-        derive_frame(rs.sums, rp.m_e_eV, sf);
-        derive_mesh(rs.emax, rs.esum, md.nx, md.ny, md.nz, dr.scale, dr.shift, sm);
-    }
-    __syncthreads();
-    const Frame f = sf;
-    const Mesh m = sm;
+    __shared__ Geo sg;
+    load_geo(rs.geo, &sg);
+    const Frame f = sg.f;
+    const Mesh m = sg.m;
     const double kt = cdT * (1.0 - f.beta0 * f.beta0);   // sc.py:246-247
     const size_t cells = (size_t)md.nx * md.ny * md.nz;
     const EQuad* __restrict__ ex = equad;
     const EQuad* __restrict__ ey = equad + cells;
     const EQuad* __restrict__ ez = equad + 2 * cells;
     const double* const base[6] = {r, r + ld, r + 2 * ld, r + 3 * ld, r + 4 * ld, r + 5 * ld};
-    pipelined_sweep<6, kPipeDepth>(base, (int)n, pipe, [&](int i, const double (&w)[6]) {
+    auto body = [&](int i, const double (&w)[6], bool valid) {
         Cart c = mad_to_cart(rp, w[0], w[1], w[2], w[3], w[4], w[5]);
         double a, b, g, g0, g1, g2;
         rotate_stretch(f, c.x, c.y, c.z, a, b, g);
         to_grid(m, a, b, g, g0, g1, g2);
-        const double e0 = trilinear(ex, md.nx, md.ny, md.nz, g0, g1 + 0.5, g2 + 0.5) * f.gamma0;   // :202
-        const double e1 = trilinear(ey, md.nx, md.ny, md.nz, g0 + 0.5, g1, g2 + 0.5) * f.gamma0;   // :203
-        const double e2 = trilinear(ez, md.nx, md.ny, md.nz, g0 + 0.5, g1 + 0.5, g2);              // :204
+        double e0, e1, e2;
+        if constexpr (LAYOUT == 1) {
+            e0 = trilinear_pair(ex, md.nx, md.ny, md.nz, g0, g1 + 0.5, g2 + 0.5) * f.gamma0;     // :202
+            e1 = trilinear_pair(ey, md.nx, md.ny, md.nz, g0 + 0.5, g1, g2 + 0.5) * f.gamma0;     // :203
+            e2 = trilinear_pair(ez, md.nx, md.ny, md.nz, g0 + 0.5, g1 + 0.5, g2);                // :204
+        } else {
+            e0 = trilinear(ex, md.nx, md.ny, md.nz, g0, g1 + 0.5, g2 + 0.5) * f.gamma0;
+            e1 = trilinear(ey, md.nx, md.ny, md.nz, g0 + 0.5, g1, g2 + 0.5) * f.gamma0;
+            e2 = trilinear(ez, md.nx, md.ny, md.nz, g0 + 0.5, g1 + 0.5, g2);
+        }
+        if (!valid) return;
         if (TAP) {
             exyz_out[3 * (size_t)i + 0] = e0; exyz_out[3 * (size_t)i + 1] = e1; exyz_out[3 * (size_t)i + 2] = e2;
         }
@@ -390,7 +550,13 @@ __global__ void __launch_bounds__(kThreads, GK_BLOCKS) k_gather_kick(double* __r
             r[i] = x; r[ld + i] = xs; r[2 * ld + i] = y; r[3 * ld + i] = ys; r[4 * ld + i] = tau;
             r[5 * ld + i] = delta;
         }
-    });
+    };
+    if constexpr (LAYOUT == 1) {
+        pipelined_sweep<6, kPipeDepth, true>(base, (int)n, pipe, body);
+    } else {
+        pipelined_sweep<6, kPipeDepth, false>(base, (int)n, pipe,
+                                              [&](int i, const double (&w)[6]) { body(i, w, true); });
+    }
 }
 
 // stand-alone transforms (known-answer tests)
@@ -432,57 +598,10 @@ __global__ void k_set_params(KickParams v, KickParams* dst) {
     pdl_enter();
     if (threadIdx.x == 0 && blockIdx.x == 0) *dst = v;
 }
-// ---------------------------------------------------------------------------
-// Fused exchange over NVLink peer memory (replaces an NCCL all-reduce / all-gather of a handful of
-// doubles): lane w stores this rank's values into rank w's mailbox, fences, raises its epoch flag
-// there; then waits for rank w's flag in the local mailbox; lane 0 folds the W slots in rank order
-// (bit-identical result on every rank) into the handle's reduced buffers.
-//   which 0: momentum {sum px, py, pz, count}        -> SUM
-//   which 1: extents  {max x6} MAX, {sum q x3, q} SUM
-// Slots are single-buffered: a rank can only push exchange e+1 after it has consumed everyone's
-// exchange e of the *other* kind, which in turn requires everyone to have consumed this kind's e.
-// ---------------------------------------------------------------------------
+// stand-alone exchange / barrier (which = 2), one warp
 __global__ void k_mailbox_exchange(Mailbox mb, int which, ReduceState rs, int* __restrict__ err_flag) {
     pdl_enter();
-    const int lane = threadIdx.x;
-    const int nv = which == 0 ? 4 : (which == 1 ? 10 : 0);      // which 2: barrier only ("rho ready")
-    const int vbase = which == 0 ? 0 : 32;
-    const int fbase = 128 + 8 * which;
-    const double* local_vals = which == 0 ? rs.sums : rs.emax;          // emax[6] and esum[4] are contiguous
-    const unsigned long long epoch = mb.epoch[which] + 1;
-    if (lane < mb.world) {
-        double* dst = mb.peer[lane] + vbase + mb.rank * nv;
-        for (int k = 0; k < nv; ++k) dst[k] = local_vals[k];
-        __threadfence_system();
-        volatile unsigned long long* flag = reinterpret_cast<unsigned long long*>(mb.peer[lane] + fbase) + mb.rank;
-        *flag = epoch;
-        // wait for rank `lane` to have delivered its values here
-        volatile unsigned long long* mine = reinterpret_cast<unsigned long long*>(mb.peer[mb.rank] + fbase) + lane;
-        const long long t0 = clock64();
-        while (*mine < epoch) {
-            if (clock64() - t0 > 8000000000LL) { atomicExch(err_flag, 1 + which); break; }   // ~4 s: a peer is gone
-        }
-        __threadfence_system();
-    }
-    __syncwarp();
-    if (lane == 0 && which == 2) mb.epoch[which] = epoch;
-    if (lane == 0 && which < 2) {
-        const volatile double* box = mb.peer[mb.rank] + vbase;
-        double v[10];
-        for (int k = 0; k < nv; ++k) v[k] = box[k];
-        for (int w = 1; w < mb.world; ++w)
-            for (int k = 0; k < nv; ++k) {
-                const double x = box[w * nv + k];
-                v[k] = (which == 1 && k < 6) ? fmax(v[k], x) : v[k] + x;
-            }
-        if (which == 0) {
-            for (int k = 0; k < 4; ++k) rs.sums[k] = v[k];
-        } else {
-            for (int k = 0; k < 6; ++k) rs.emax[k] = v[k];
-            for (int k = 0; k < 4; ++k) rs.esum[k] = v[6 + k];
-        }
-        mb.epoch[which] = epoch;
-    }
+    mailbox_exchange_warp(mb, which, rs, err_flag);
 }
 void launch_mailbox_exchange(Mailbox mb, int which, ReduceState rs, int* err_flag, cudaStream_t st) {
     launch_k(k_mailbox_exchange, dim3(1), dim3(32), 0, st, mb, which, rs, err_flag);
@@ -497,11 +616,45 @@ void launch_mailbox_exchange(Mailbox mb, int which, ReduceState rs, int* err_fla
 // by the switch, so all ranks end up with bit-identical grids.
 //   out == nullptr : all-reduce in place (redundant solve on every rank)
 //   out != nullptr : reduce-scatter: elements [lo, hi) of the sum go to out[0 .. hi-lo) (slab solve)
-// Ordering: the caller brackets the kernel with the mailbox barrier (k_mailbox_exchange which = 2).
+// ONE kernel including both cross-rank barriers (round 1: barrier kernel, reduce kernel, barrier kernel):
+//   entry: block 0 announces "my deposit is complete" in every peer's mailbox; every block waits until
+//          all peers have announced (their flags land in the LOCAL mailbox, so the poll is a local read);
+//   exit:  the block that draws the last ticket announces "my slice is reduced and broadcast" and waits for
+//          the same announcement of every peer, so the kernel completes only when the whole grid is final.
+// The exit wait is done by a single block after all others have finished: no co-residency is assumed.
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ void mailbox_signal(const Mailbox& mb, int fbase, unsigned long long epoch) {
+    const int lane = threadIdx.x & 31;
+    if (lane < mb.world) {
+        __threadfence_system();
+        volatile unsigned long long* flag = reinterpret_cast<unsigned long long*>(mb.peer[lane] + fbase) + mb.rank;
+        *flag = epoch;
+    }
+}
+__device__ __forceinline__ void mailbox_wait(const Mailbox& mb, int fbase, unsigned long long epoch, int* err_flag) {
+    const int lane = threadIdx.x & 31;
+    if (lane < mb.world) {
+        volatile unsigned long long* mine = reinterpret_cast<unsigned long long*>(mb.peer[mb.rank] + fbase) + lane;
+        const long long t0 = clock64();
+        while (*mine < epoch) {
+            if (clock64() - t0 > 8000000000LL) { atomicExch(err_flag, 3); break; }
+        }
+        __threadfence_system();
+    }
+    __syncwarp();
+}
+constexpr int kFlagRhoReady = 128 + 8 * 2;      // doubles [144,152): "deposit complete" epochs
+constexpr int kFlagRhoDone = 128 + 8 * 3;       // doubles [152,160): "slice reduced" epochs
 __global__ void __launch_bounds__(256) k_nvls_reduce(double* __restrict__ mc, long long lo, long long hi,
-                                                    double* __restrict__ out) {
+                                                    double* __restrict__ out, Mailbox mb, unsigned int* ticket,
+                                                    int* __restrict__ err_flag) {
     pdl_enter();
+    const unsigned long long epoch = mb.epoch[2] + 1;       // advanced by the last block, after everyone has read it
+    if (threadIdx.x < 32) {
+        if (blockIdx.x == 0) mailbox_signal(mb, kFlagRhoReady, epoch);
+        mailbox_wait(mb, kFlagRhoReady, epoch, err_flag);
+    }
+    __syncthreads();
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
         double v;
@@ -509,12 +662,23 @@ __global__ void __launch_bounds__(256) k_nvls_reduce(double* __restrict__ mc, lo
         if (out) out[i - lo] = v;
         else asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc + i), "d"(v) : "memory");
     }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!last || threadIdx.x >= 32) return;
+    // every block of this rank has issued (and fenced) its multimem stores
+    mailbox_signal(mb, kFlagRhoDone, epoch);
+    mailbox_wait(mb, kFlagRhoDone, epoch, err_flag);
+    if (threadIdx.x == 0) { mb.epoch[2] = epoch; *ticket = 0; __threadfence(); }
 }
-void launch_nvls_reduce(double* mc, long long lo, long long hi, double* out, cudaStream_t st) {
-    if (hi <= lo) return;
+void launch_nvls_reduce(double* mc, long long lo, long long hi, double* out, Mailbox mb, unsigned int* ticket,
+                        int* err_flag, cudaStream_t st) {
     long long blocks = (hi - lo + 255) / 256;
-    if (blocks > 148 * 8) blocks = 148 * 8;
-    launch_k(k_nvls_reduce, dim3((int)blocks), dim3(256), 0, st, mc, lo, hi, out);
+    if (blocks < 1) blocks = 1;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    launch_k(k_nvls_reduce, dim3((int)blocks), dim3(256), 0, st, mc, lo, hi, out, mb, ticket, err_flag);
 }
 
 // fold all-gathered extents: max over ranks of the first 6 doubles, sum of the last 4
@@ -537,30 +701,33 @@ void launch_combine_extents(const double* all, int world, ReduceState rs, cudaSt
 void launch_set_params(KickParams v, KickParams* dst, cudaStream_t st) { launch_k(k_set_params, dim3(1), dim3(32), 0, st, v, dst); }
 const void* set_params_kernel() { return (const void*)k_set_params; }
 
-void launch_momentum(const double* r, long long ld, long long n, KP kp, ReduceState rs, cudaStream_t st) {
-    launch_k(k_momentum, dim3(particle_grid(n, rs.max_blocks)), dim3(kThreads), 0, st, r, ld, n, kp, rs);
+void launch_momentum(const double* r, long long ld, long long n, KP kp, ReduceState rs, Mailbox mb, int* mb_err,
+                     cudaStream_t st) {
+    launch_k(k_momentum, dim3(particle_grid(n, rs.max_blocks)), dim3(kThreads), 0, st, r, ld, n, kp, rs, mb, mb_err);
 }
-void launch_extent(const double* r, long long ld, const double* q, long long n, KP kp, ReduceState rs,
-                   cudaStream_t st) {
-    launch_k(k_extent, dim3(particle_grid(n, 148 * 3)), dim3(kThreads), 0, st, r, ld, q, n, kp, rs);
+void launch_extent(const double* r, long long ld, const double* q, long long n, KP kp, ReduceState rs, MeshDims md,
+                   Mailbox mb, int* mb_err, cudaStream_t st) {
+    launch_k(k_extent, dim3(particle_grid(n, 148 * 3)), dim3(kThreads), 0, st, r, ld, q, n, kp, rs, md, mb, mb_err);
+}
+void launch_finish(int which, KP kp, ReduceState rs, MeshDims md, cudaStream_t st) {
+    launch_k(k_finish, dim3(1), dim3(32), 0, st, which, kp, rs, md);
 }
 void launch_deposit(const double* r, long long ld, const double* q, long long n, KP kp, ReduceState rs,
                     MeshDims md, double* rho, cudaStream_t st) {
     launch_k(k_deposit, dim3(grid_for(n, 148 * 3)), dim3(kThreads), 0, st, r, ld, q, n, kp, rs, md, rho);
 }
-void launch_green_table(ReduceState rs, MeshDims md, KP kp, double* gtab, double* h3, cudaStream_t st) {
+void launch_green_table(ReduceState rs, MeshDims md, double* gtab, double* h3, cudaStream_t st) {
     StepSrc src;
     src.given = 0; src.h[0] = src.h[1] = src.h[2] = 0.0;
     long long total = (long long)(md.nx + 1) * (md.ny + 1) * (md.nz + 1);
-    launch_k(k_green_table, dim3(grid_for(total, kGridCap)), dim3(kThreads), 0, st, src, rs, md, kp, gtab, h3);
+    launch_k(k_green_table, dim3(grid_for(total, kGridCap)), dim3(kThreads), 0, st, src, rs, md, gtab, h3);
 }
 void launch_green_table_steps(const double steps[3], MeshDims md, double* gtab, double* h3, cudaStream_t st) {
     StepSrc src;
     src.given = 1; src.h[0] = steps[0]; src.h[1] = steps[1]; src.h[2] = steps[2];
     ReduceState rs = {};
-    KP kp = {};
     long long total = (long long)(md.nx + 1) * (md.ny + 1) * (md.nz + 1);
-    launch_k(k_green_table, dim3(grid_for(total, kGridCap)), dim3(kThreads), 0, st, src, rs, md, kp, gtab, h3);
+    launch_k(k_green_table, dim3(grid_for(total, kGridCap)), dim3(kThreads), 0, st, src, rs, md, gtab, h3);
 }
 void launch_green_mirror(const double* gtab, MeshDims md, double* kpad, cudaStream_t st) {
     cudaMemsetAsync(kpad, 0, sizeof(double) * (size_t)md.mx * md.my * md.mz, st);
@@ -588,35 +755,49 @@ double four_pi_eps0_value() {
     const double eps0 = 1 / mu0 / (c * c);
     return 4 * pi * eps0;
 }
-void launch_crop_phi(const double* conv, ReduceState rs, MeshDims md, KP kp, double* phi, cudaStream_t st) {
+void launch_crop_phi(const double* conv, ReduceState rs, MeshDims md, double* phi, cudaStream_t st) {
     StepSrc src;
     src.given = 0; src.h[0] = src.h[1] = src.h[2] = 0.0;
     long long total = (long long)md.nx * md.ny * md.nz;
-    k_crop_phi<<<grid_for(total, kGridCap), kThreads, 0, st>>>(conv, src, rs, md, kp, four_pi_eps0(), phi);
+    k_crop_phi<<<grid_for(total, kGridCap), kThreads, 0, st>>>(conv, src, rs, md, four_pi_eps0(), phi);
 }
 void launch_crop_phi_steps(const double* conv, const double steps[3], MeshDims md, double* phi, cudaStream_t st) {
     StepSrc src;
     src.given = 1; src.h[0] = steps[0]; src.h[1] = steps[1]; src.h[2] = steps[2];
     ReduceState rs = {};
-    KP kp = {};
     long long total = (long long)md.nx * md.ny * md.nz;
-    k_crop_phi<<<grid_for(total, kGridCap), kThreads, 0, st>>>(conv, src, rs, md, kp, four_pi_eps0(), phi);
+    k_crop_phi<<<grid_for(total, kGridCap), kThreads, 0, st>>>(conv, src, rs, md, four_pi_eps0(), phi);
 }
-void launch_field(const double* phi, ReduceState rs, MeshDims md, KP kp, EQuad* equad, cudaStream_t st) {
+size_t field_tile_bytes(MeshDims md) { return sizeof(double) * (size_t)md.nx * 3 * (kFieldKT + 2); }
+void field_init_kernels() {
+    cudaFuncSetAttribute(k_field_xf, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+void launch_field(const double* phi, ReduceState rs, MeshDims md, EQuad* equad, int layout, cudaStream_t st) {
     StepSrc src;
     src.given = 0; src.h[0] = src.h[1] = src.h[2] = 0.0;
-    dim3 grid((md.ny * md.nz + kThreads - 1) / kThreads, md.nx, 3);
-    launch_k(k_field, dim3(grid), dim3(kThreads), 0, st, phi, src, rs, md, kp, equad);
+    if (layout == 1) {
+        dim3 grid((md.nz + kFieldKT - 1) / kFieldKT, md.ny, 1);
+        launch_k(k_field_xf, dim3(grid), dim3(kThreads), field_tile_bytes(md), st, phi, src, rs, md, equad);
+    } else {
+        dim3 grid((md.ny * md.nz + kThreads - 1) / kThreads, md.nx, 3);
+        launch_k(k_field, dim3(grid), dim3(kThreads), 0, st, phi, src, rs, md, equad);
+    }
 }
-void launch_gather_kick(double* r, long long ld, long long n, KP kp, ReduceState rs, MeshDims md,
-                        const EQuad* equad, double* exyz_out, int do_kick, cudaStream_t st) {
+template <int LAYOUT>
+static void launch_gather_kick_l(double* r, long long ld, long long n, KP kp, ReduceState rs, MeshDims md,
+                                 const EQuad* equad, double* exyz_out, int do_kick, cudaStream_t st) {
     int grid = grid_for(n, kGatherCap);
     if (do_kick && exyz_out)
-        launch_k(k_gather_kick<true, true>, dim3(grid), dim3(kThreads), 0, st, r, ld, n, kp, rs, md, equad, exyz_out);
+        launch_k(k_gather_kick<true, true, LAYOUT>, dim3(grid), dim3(kThreads), 0, st, r, ld, n, kp, rs, md, equad, exyz_out);
     else if (do_kick)
-        launch_k(k_gather_kick<true, false>, dim3(grid), dim3(kThreads), 0, st, r, ld, n, kp, rs, md, equad, nullptr);
+        launch_k(k_gather_kick<true, false, LAYOUT>, dim3(grid), dim3(kThreads), 0, st, r, ld, n, kp, rs, md, equad, nullptr);
     else
-        launch_k(k_gather_kick<false, true>, dim3(grid), dim3(kThreads), 0, st, r, ld, n, kp, rs, md, equad, exyz_out);
+        launch_k(k_gather_kick<false, true, LAYOUT>, dim3(grid), dim3(kThreads), 0, st, r, ld, n, kp, rs, md, equad, exyz_out);
+}
+void launch_gather_kick(double* r, long long ld, long long n, KP kp, ReduceState rs, MeshDims md,
+                        const EQuad* equad, double* exyz_out, int do_kick, int layout, cudaStream_t st) {
+    if (layout == 1) launch_gather_kick_l<1>(r, ld, n, kp, rs, md, equad, exyz_out, do_kick, st);
+    else launch_gather_kick_l<0>(r, ld, n, kp, rs, md, equad, exyz_out, do_kick, st);
 }
 void launch_mad_to_cart(const double* r, long long ld, long long n, RefParams rp, double* xp, long long ld_xp,
                         cudaStream_t st) {

@@ -8,13 +8,15 @@ namespace ocl {
 
 // device-resident reduction state shared by the particle sweeps
 struct ReduceState {
-    double* part;          // [max_blocks][10] per-block partials
+    double* part;          // [max_blocks][16] per-block partials
     unsigned int* ticket;  // [4] last-block tickets
     double* sums;          // [4]  OCL_SC_BUF_MOMENTUM
     double* emax;          // [6]  OCL_SC_BUF_EXTENT_MAX
     double* esum;          // [4]  OCL_SC_BUF_EXTENT_SUM
     double* geom;          // [24] geometry tap
+    Geo* geo;              // frame + mesh of the current kick, derived once on the device
     int max_blocks;
+    int defer;             // 1: the sweeps only reduce; the caller all-reduces and calls launch_finish (NCCL fallback)
 };
 
 struct MeshDims {
@@ -34,6 +36,7 @@ struct Mailbox {
     int rank, world;
 };
 //   doubles [144,152) "rho ready" flags (barrier before the fused rho reduction)
+//   doubles [152,160) "rho slice reduced" flags (exit barrier of k_nvls_reduce)
 constexpr int kMailboxDoubles = 256;
 // the charge grids of all ranks, as mapped in this rank's address space (world == 0: local rho only)
 struct PeerRho {
@@ -41,27 +44,32 @@ struct PeerRho {
     int world;
 };
 void launch_mailbox_exchange(Mailbox mb, int which, ReduceState rs, int* err_flag, cudaStream_t st);
-void launch_nvls_reduce(double* mc, long long lo, long long hi, double* out, cudaStream_t st);
+void launch_nvls_reduce(double* mc, long long lo, long long hi, double* out, Mailbox mb, unsigned int* ticket,
+                        int* err_flag, cudaStream_t st);
 
 int particle_grid(long long n, int max_blocks);
 
 void launch_set_params(KickParams v, KickParams* dst, cudaStream_t st);
 void launch_combine_extents(const double* all, int world, ReduceState rs, cudaStream_t st);
 const void* set_params_kernel();
-void launch_momentum(const double* r, long long ld, long long n, KP kp, ReduceState rs, cudaStream_t st);
-void launch_extent(const double* r, long long ld, const double* q, long long n, KP kp, ReduceState rs,
-                   cudaStream_t st);
+void launch_momentum(const double* r, long long ld, long long n, KP kp, ReduceState rs, Mailbox mb, int* mb_err,
+                     cudaStream_t st);
+void launch_extent(const double* r, long long ld, const double* q, long long n, KP kp, ReduceState rs, MeshDims md,
+                   Mailbox mb, int* mb_err, cudaStream_t st);
+void launch_finish(int which, KP kp, ReduceState rs, MeshDims md, cudaStream_t st);
 void launch_deposit(const double* r, long long ld, const double* q, long long n, KP kp, ReduceState rs,
                     MeshDims md, double* rho, cudaStream_t st);
-void launch_green_table(ReduceState rs, MeshDims md, KP kp, double* gtab, double* h3, cudaStream_t st);
+void launch_green_table(ReduceState rs, MeshDims md, double* gtab, double* h3, cudaStream_t st);
 void launch_green_mirror(const double* gtab, MeshDims md, double* kpad, cudaStream_t st);
 void launch_green_compact(const double* gtab, MeshDims md, double* k1, cudaStream_t st);
 void launch_pad_rho(const double* rho, MeshDims md, double* pad, cudaStream_t st);
 void launch_multiply(cufftDoubleComplex* rho_hat, const cufftDoubleComplex* k_hat, MeshDims md, cudaStream_t st);
-void launch_crop_phi(const double* conv, ReduceState rs, MeshDims md, KP kp, double* phi, cudaStream_t st);
-void launch_field(const double* phi, ReduceState rs, MeshDims md, KP kp, EQuad* equad, cudaStream_t st);
+void launch_crop_phi(const double* conv, ReduceState rs, MeshDims md, double* phi, cudaStream_t st);
+// layout 0: z-fastest quad table | 1: x-fastest quad table fetched by lane pairs
+void field_init_kernels();
+void launch_field(const double* phi, ReduceState rs, MeshDims md, EQuad* equad, int layout, cudaStream_t st);
 void launch_gather_kick(double* r, long long ld, long long n, KP kp, ReduceState rs, MeshDims md,
-                        const EQuad* equad, double* exyz_out, int do_kick, cudaStream_t st);
+                        const EQuad* equad, double* exyz_out, int do_kick, int layout, cudaStream_t st);
 void launch_mad_to_cart(const double* r, long long ld, long long n, RefParams rp, double* xp, long long ld_xp,
                         cudaStream_t st);
 void launch_cart_to_mad(const double* xp, long long ld_xp, long long n, RefParams rp, double* r, long long ld,

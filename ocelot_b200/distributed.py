@@ -3,10 +3,15 @@
 One process per GPU; rank r owns a contiguous range of the bunch's particles
 (SURVEY.md section 8e).  Per kick the ranks exchange only
 
-  1. sum of Cartesian momenta + particle count      4 doubles, all-reduce SUM   (sc.py:224)
-  2. extents of the rotated, stretched coordinates  6 doubles, MAX  }  one all-gather of 10
-     and the charge centroid                         4 doubles, SUM  }  doubles, folded on device
-  3. the deposited charge grid rho                   nx*ny*nz doubles, all-reduce SUM (sc.py:193)
+  1. sum of Cartesian momenta + particle count      4 doubles, SUM   (sc.py:224)
+  2. extents of the rotated, stretched coordinates  6 doubles, MAX
+     and the charge centroid                         4 doubles, SUM
+  3. the deposited charge grid rho                   nx*ny*nz doubles, SUM (sc.py:193)
+
+Exchanges 1 and 2 run INSIDE the sweep kernels over NVLink peer memory (the block that finishes the
+grid reduction pushes the rank's partials into every peer's mailbox, waits for theirs and folds them
+in rank order), exchange 3 is one kernel of in-switch multimem reductions bracketed by its own
+cross-rank barriers; NCCL (all-reduce / all-gather) is the fallback when no peer mapping exists.
 
 after which every rank holds the same rho and solves the Poisson problem
 redundantly ("small-mesh mode"); no particle ever crosses a link.  For large
@@ -64,6 +69,8 @@ class NativeStageEngine:
         self.mailbox = None
         self.peer_rho = None
         self.nvls = None
+        self._draws = None
+        self._E = None
 
     def setup_mailbox(self, dist, group, peer_rho=True, nvls=False):
         """Map one small symmetric buffer per rank into every rank (torch symmetric memory over
@@ -80,6 +87,7 @@ class NativeStageEngine:
         torch.cuda.synchronize()
         dist.barrier(group=group)
         self.solver.mailbox_init(rank, world, list(hdl.buffer_ptrs))
+        self.solver.defer_finish(False)        # the sweeps' finishing blocks now exchange over NVLink themselves
         self.mailbox = (box, hdl)              # keep the mapping alive
         # the charge grid itself also lives in symmetric memory: the first FFT pass then sums the
         # ranks' grids while loading them over NVLink (no all-reduce / reduce-scatter kernel)
@@ -115,7 +123,7 @@ class NativeStageEngine:
         """Slab-decomposed solve: rho (local partial sums, nx_pad planes) -> field table."""
         b, s = self.buffers, self.solver
         if self.nvls is not None:
-            s.nvls_reduce_rho()                # barrier + in-switch reduce-scatter into this rank's x-slab
+            s.nvls_reduce_rho()                # one kernel: barrier, in-switch reduce-scatter into this rank's x-slab, barrier
         elif self.peer_rho is not None:
             s.mailbox_exchange(2)              # barrier: every rank's deposit is complete
         else:
@@ -138,11 +146,24 @@ class NativeStageEngine:
         dist.all_gather_into_tensor(self._gathered, self.buffers["extent"], group=group)
         self.solver.combine_extents(self._gathered, world)
 
+    def begin_kick(self, draws, multi):
+        """Per-kick state: the mesh draws (the extent stage derives the mesh) and, for a sharded kick without
+        a peer-memory mailbox, the deferred form (the caller all-reduces, then ``finish_*``)."""
+        self._draws = draws
+        self.solver.defer_finish(bool(multi) and self.mailbox is None)
+
     def momentum(self, r, q, E):
-        self.solver.stage_momentum(r, E)
+        self._E = E
+        self.solver.stage_momentum(r, E)       # with a mailbox: exchange + frame inside the kernel's tail
+
+    def finish_momentum(self):
+        self.solver.stage_finish(0, self._E, self._draws)
 
     def extent(self, r, q, E):
-        self.solver.stage_extent(r, q, E)
+        self.solver.stage_extent(r, q, E, self._draws)
+
+    def finish_extent(self):
+        self.solver.stage_finish(1, self._E, self._draws)
 
     def deposit(self, r, q, E, draws):
         self.solver.stage_deposit(r, q, E, draws)
@@ -164,27 +185,31 @@ def sharded_kick(engine, r, q, E_GeV, dz, draws=None, group=None, dist=None):
     multi = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
     SUM, MAX = dist.ReduceOp.SUM, dist.ReduceOp.MAX
     b = engine.buffers
+    # with a peer-memory mailbox the two scalar exchanges happen inside the sweep kernels (the block that
+    # finishes the reduction pushes / folds over NVLink): no collective call and no extra launch here
     fused = multi and getattr(engine, "mailbox", None) is not None
+    if hasattr(engine, "begin_kick"):
+        engine.begin_kick(draws, multi)
     engine.momentum(r, q, E_GeV)
-    if fused:
-        engine.solver.mailbox_exchange(0)
-    elif multi:
+    if multi and not fused:
         dist.all_reduce(b["momentum"], op=SUM, group=group)
+        if hasattr(engine, "finish_momentum"):
+            engine.finish_momentum()
     engine.extent(r, q, E_GeV)
-    if fused:
-        engine.solver.mailbox_exchange(1)
-    elif multi:
+    if multi and not fused:
         if hasattr(engine, "combine_extents"):
             engine.combine_extents(dist, group)
         else:
             dist.all_reduce(b["extent_max"], op=MAX, group=group)
             dist.all_reduce(b["extent_sum"], op=SUM, group=group)
+        if hasattr(engine, "finish_extent"):
+            engine.finish_extent()
     engine.deposit(r, q, E_GeV, draws)
     if getattr(engine, "slab", None) is not None:
         engine.solve_slab(dist, group, draws)      # works for any world size >= 1
     else:
         if multi and getattr(engine, "nvls", None) is not None:
-            engine.solver.nvls_reduce_rho()        # barrier, in-switch all-reduce (multimem), barrier
+            engine.solver.nvls_reduce_rho()        # one kernel: barrier, in-switch all-reduce (multimem), barrier
         elif multi and getattr(engine, "peer_rho", None) is not None:
             engine.solver.mailbox_exchange(2)      # barrier; the solve's first pass sums the peers' grids
         elif multi:

@@ -253,10 +253,12 @@ class LSC(PhysProc):
 
 
 def install():
-    """Replace ``ocelot.cpbd.sc.LSC`` (and the re-export ``ocelot.LSC``) with this class."""
-    import ocelot
-    import ocelot.cpbd.sc as ref_sc
-    ref_sc.LSC = LSC
-    if hasattr(ocelot, "LSC"):
-        ocelot.LSC = LSC
-    return LSC
+    """Replace the reference ``LSC`` with this class in every module that already holds it."""
+    from ._install import swap
+    return swap("LSC", LSC)
+
+
+def uninstall():
+    """Undo ``install()``."""
+    from ._install import restore
+    restore("LSC")

@@ -51,7 +51,9 @@ _SIGNATURES = {
     "ocl_sc_use_device_params": (C.c_int, [_vp, C.c_int]),
     "ocl_sc_set_kick_params": (C.c_int, [_vp, C.c_double, C.c_double, _dp, _vp]),
     "ocl_sc_stage_momentum": (C.c_int, [_vp, _vp, _ll, _ll, C.c_double, _vp]),
-    "ocl_sc_stage_extent": (C.c_int, [_vp, _vp, _ll, _vp, _ll, C.c_double, _vp]),
+    "ocl_sc_stage_extent": (C.c_int, [_vp, _vp, _ll, _vp, _ll, C.c_double, _dp, _vp]),
+    "ocl_sc_defer_finish": (C.c_int, [_vp, C.c_int]),
+    "ocl_sc_stage_finish": (C.c_int, [_vp, C.c_int, C.c_double, _dp, _vp]),
     "ocl_sc_stage_deposit": (C.c_int, [_vp, _vp, _ll, _vp, _ll, C.c_double, _dp, _vp]),
     "ocl_sc_stage_solve": (C.c_int, [_vp, _dp, _vp]),
     "ocl_sc_stage_kick": (C.c_int, [_vp, _vp, _ll, _ll, C.c_double, C.c_double, _dp, _vp]),
@@ -259,10 +261,19 @@ class Solver:
         self._check(self._lib.ocl_sc_stage_momentum(self._h, ptr, ld, n, float(E_GeV), _stream_ptr(stream)),
                     "ocl_sc_stage_momentum")
 
-    def stage_extent(self, r, q, E_GeV, stream=None):
+    def stage_extent(self, r, q, E_GeV, mesh_draws=None, stream=None):
         ptr, ld, n = self._dev_rows(r, q)
         self._check(self._lib.ocl_sc_stage_extent(self._h, ptr, ld, q.data_ptr(), n, float(E_GeV),
-                                                  _stream_ptr(stream)), "ocl_sc_stage_extent")
+                                                  _draws(mesh_draws), _stream_ptr(stream)), "ocl_sc_stage_extent")
+
+    def defer_finish(self, on: bool):
+        """NCCL fallback of a sharded kick: the sweeps only reduce locally; the caller all-reduces the
+        collective buffers and calls ``stage_finish``."""
+        self._check(self._lib.ocl_sc_defer_finish(self._h, 1 if on else 0), "ocl_sc_defer_finish")
+
+    def stage_finish(self, which, E_GeV, mesh_draws=None, stream=None):
+        self._check(self._lib.ocl_sc_stage_finish(self._h, int(which), float(E_GeV), _draws(mesh_draws),
+                                                  _stream_ptr(stream)), "ocl_sc_stage_finish")
 
     def stage_deposit(self, r, q, E_GeV, mesh_draws=None, stream=None):
         ptr, ld, n = self._dev_rows(r, q)

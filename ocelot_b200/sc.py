@@ -116,10 +116,14 @@ class SpaceCharge(PhysProc):
 
 
 def install():
-    """Replace ``ocelot.cpbd.sc.SpaceCharge`` (and the re-export ``ocelot.SpaceCharge``)
-    with this class, so unmodified Ocelot scripts pick up the B200 kick."""
-    import ocelot
-    import ocelot.cpbd.sc as ref_sc
-    ref_sc.SpaceCharge = SpaceCharge
-    ocelot.SpaceCharge = SpaceCharge
-    return SpaceCharge
+    """Replace the reference ``SpaceCharge`` with this class in every module that already holds it
+    (``ocelot.cpbd.sc``, the ``ocelot`` re-export, and any module that star-imported it, e.g.
+    ``ocelot.utils.section_track``), so unmodified Ocelot scripts pick up the B200 kick."""
+    from ._install import swap
+    return swap("SpaceCharge", SpaceCharge)
+
+
+def uninstall():
+    """Undo ``install()``."""
+    from ._install import restore
+    restore("SpaceCharge")

@@ -26,7 +26,12 @@ def test_reference_arm_prints_one_contract_line():
     assert d["value"] > 0 and d["ms_per_step"] > 0 and d["vs_baseline"] is None
     assert d["config"]["workload"].startswith("BASELINE configs[0]")
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    staged = os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "ocelot", "cpbd", "sc.py"))
+    assert cb["kind"] == ("reference" if staged else "port")       # the unmodified reference when it is staged
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and cb["sample"]
+    assert d["cpu_port"]["kind"] == "port" and d["cpu_port"]["value"] > 0
+    if staged:
+        assert d["e2e_resident"]["kicks"] == 20 and d["e2e_resident"]["value"] > 0
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
 
 

@@ -21,6 +21,7 @@ def _emulated_slab_kick(native, W, r0, q0, E, dz, nmesh, draws=None):
         lo, hi = shard_bounds(n, W, w)
         s = native.Solver(0, nmesh)
         s.slab_init(w, W)
+        s.defer_finish(True)          # the emulated collectives run between the sweeps and the geometry derivation
         hs.append(s)
         rs.append(torch.from_numpy(np.ascontiguousarray(r0[:, lo:hi])).cuda())
         qs.append(torch.from_numpy(np.ascontiguousarray(q0[lo:hi])).cuda())
@@ -31,11 +32,13 @@ def _emulated_slab_kick(native, W, r0, q0, E, dz, nmesh, draws=None):
     tot = sum(buf(s, B.BUF_MOMENTUM) for s in hs)
     for s in hs:
         buf(s, B.BUF_MOMENTUM).copy_(tot)
+        s.stage_finish(0, E, draws)
     for s, r, q in zip(hs, rs, qs):
-        s.stage_extent(r, q, E)
+        s.stage_extent(r, q, E, draws)
     gathered = torch.cat([buf(s, B.BUF_EXTENT) for s in hs])
     for s in hs:
         s.combine_extents(gathered, W)
+        s.stage_finish(1, E, draws)
     for s, r, q in zip(hs, rs, qs):
         s.stage_deposit(r, q, E, draws)
     rho = sum(buf(s, B.BUF_RHO) for s in hs)                      # reduce ...

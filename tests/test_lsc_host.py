@@ -214,13 +214,17 @@ def test_install_swaps_both_reference_classes():
     import ocelot
     import ocelot.cpbd.sc as ref_sc
     import ocelot_b200
-    saved = (ref_sc.SpaceCharge, ref_sc.LSC, ocelot.SpaceCharge, getattr(ocelot, "LSC", None))
+    import ocelot.utils.section_track as st          # star-imported the classes before install
+    saved = (ref_sc.SpaceCharge, ref_sc.LSC)
+    assert st.SpaceCharge is saved[0] and st.LSC is saved[1]
     try:
         sc_cls, lsc_cls = ocelot_b200.install()
         assert ref_sc.SpaceCharge is ocelot_b200.SpaceCharge is sc_cls and ocelot.SpaceCharge is sc_cls
-        assert ref_sc.LSC is ocelot_b200.LSC is lsc_cls
+        assert ref_sc.LSC is ocelot_b200.LSC is lsc_cls and ocelot.LSC is lsc_cls
+        assert st.SpaceCharge is sc_cls and st.LSC is lsc_cls           # section_track.py:365,383 compare these
         assert ref_sc.SpaceCharge().nmesh_xyz == [63, 63, 63] and ref_sc.LSC().smooth_param == 0.1
+        ocelot_b200.install()                                           # idempotent
     finally:
-        ref_sc.SpaceCharge, ref_sc.LSC, ocelot.SpaceCharge = saved[:3]
-        if saved[3] is not None:
-            ocelot.LSC = saved[3]
+        ocelot_b200.uninstall()
+    assert (ref_sc.SpaceCharge, ref_sc.LSC) == saved and ocelot.SpaceCharge is saved[0] and ocelot.LSC is saved[1]
+    assert st.SpaceCharge is saved[0] and st.LSC is saved[1]
