@@ -62,6 +62,13 @@ int ocl_sc_kick_device(ocl_sc_t* h, double* d_r, long long ld, const double* d_q
 int ocl_sc_kick_host(ocl_sc_t* h, double* h_r, long long ld, const double* h_q, long long n,
                      double E_GeV, double dz, const double* mesh_draws);
 
+/* Page-lock a caller-owned host range (numpy rparticles / q_array) so that ocl_sc_kick_host copies at PCIe
+ * rate.  Not tied to a handle.  The CALLER owns the lifetime and must unregister before freeing the memory
+ * (the Python binding does so from a weakref finaliser of the owning array).  ocl_sc_host_register returns
+ * 0 = registered, 2 = already page-locked (nothing to undo), 1 = failed (copies still work, pageable). */
+int ocl_sc_host_register(void* ptr, long long bytes);
+int ocl_sc_host_unregister(void* ptr);
+
 /* ---- staged form of the same kick, for particle-sharded multi-GPU runs ----
  * With one rank the five stages in order are exactly ocl_sc_kick_device.  Across ranks the two scalar
  * reductions happen either
@@ -231,6 +238,12 @@ int ocl_sc_lsc_kick_async(ocl_sc_t* h, double* d_r, long long ld, long long n, c
                           void* stream);
 /* scalars the device derived for the last asynchronous kick, in the layout of ocl_sc_lsc_kick's params
  * (n_total not filled).  Synchronises; makes ocl_sc_lsc_get_profile usable with nb = out[6]. */
+/* Outcome of the asynchronous kicks issued so far: *status = 0 (all applied), 1 (a kick was SKIPPED because its
+ * grid exceeds the asynchronous form's capacity or is degenerate), 2 (skipped: packed deposit word too narrow).
+ * A skipped kick leaves the particles untouched, so the caller can redo it with the synchronous form
+ * (ocl_sc_lsc_stats + ocl_sc_lsc_kick).  synchronise != 0 waits for the stream last used first; the flag is
+ * cleared by the call. */
+int ocl_sc_lsc_async_status(ocl_sc_t* h, int synchronise, int* status);
 int ocl_sc_lsc_last_params(ocl_sc_t* h, double out[17]);
 /* taps of the last LSC kick (any pointer may be NULL): current profile I(s_j) [A] (s_to_cur's B[:,1]),
  * wake W(s_j)*q [V] (sc.py:592), transverse size sigma or rb used by the impedance (sc.py:584-589). */

@@ -26,6 +26,14 @@ def nvcc_path() -> str:
     return cand
 
 
+def have_nvcc() -> bool:
+    try:
+        nvcc_path()
+        return True
+    except RuntimeError:
+        return False
+
+
 def cuda_lib_dir(nvcc: str) -> str:
     return os.path.join(os.path.dirname(os.path.dirname(os.path.realpath(nvcc))), "lib64")
 

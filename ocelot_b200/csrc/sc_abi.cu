@@ -59,7 +59,7 @@ struct ocl_sc {
     double* own_rho = nullptr;                // the cudaMalloc'ed grid (kept for freeing)
     double* mc_rho = nullptr;                 // multicast mapping of every rank's rho (NVLS reduction)
     // host arrays page-locked in place on first use (numpy buffers persist across kicks)
-    bool pin_host = true;
+    bool pin_host = false;
     void* pinned[2] = {nullptr, nullptr};
     size_t pinned_bytes[2] = {0, 0};
     // host-mode staging
@@ -180,10 +180,25 @@ void mark(ocl_sc* h, int slot, cudaStream_t st) {
     if (h->timers) { cudaEventRecord(h->ev[slot], st); if (slot == T_KICK) h->ev_valid = true; }
 }
 
-int set_device(ocl_sc* h) {
-    CU(h, cudaSetDevice(h->device));
-    return 0;
-}
+// Every entry point runs on the handle's device and leaves the calling thread's current device as it
+// found it (callers such as torch keep their own notion of the current device).
+struct DeviceScope {
+    int prev = -1;
+    bool switched = false, bad = false;
+    explicit DeviceScope(ocl_sc* h) : DeviceScope(h, h->device) {}
+    DeviceScope(ocl_sc* h, int device) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != device) {
+            cudaError_t e = cudaSetDevice(device);
+            if (e != cudaSuccess) { fail(h, "cudaSetDevice", cudaGetErrorString(e)); bad = true; }
+            else switched = true;
+        }
+    }
+    ~DeviceScope() { if (switched && prev >= 0) cudaSetDevice(prev); }
+    DeviceScope(const DeviceScope&) = delete;
+    DeviceScope& operator=(const DeviceScope&) = delete;
+};
+#define ENTER_DEVICE(h) DeviceScope device_scope_(h); if (device_scope_.bad) return 1
 
 // The handle's scratch (reduction buffers, grids, FFT work space) is shared by consecutive kicks.
 // When a call arrives on a different stream than the previous one, order it after the work
@@ -326,7 +341,8 @@ int ocl_sc_create(int device, int nx, int ny, int nz, long long max_particles, o
             return 1;                                                         \
         }                                                                     \
     } while (0)
-    TRY(cudaSetDevice(device));
+    DeviceScope device_scope_(nullptr, device);
+    if (device_scope_.bad) { ocl_sc_destroy(h); return 1; }
     TRY(cudaMalloc(&h->rs.part, sizeof(double) * 16 * h->rs.max_blocks));
     TRY(cudaMalloc(&h->rs.ticket, sizeof(unsigned int) * 8));
     TRY(cudaMemset(h->rs.ticket, 0, sizeof(unsigned int) * 8));
@@ -352,8 +368,11 @@ int ocl_sc_create(int device, int nx, int ny, int nz, long long max_particles, o
     {
         const char* env = getenv("OCL_SC_GRAPH");
         h->use_graph = !(env && strcmp(env, "0") == 0);
+        // Page-locking the caller's arrays from inside the library is opt-in (OCL_SC_PIN=1): the library cannot
+        // know when the caller frees them.  The Python binding registers numpy buffers itself and ties the
+        // registration to the owning array's lifetime (ocl_sc_host_register / ocl_sc_host_unregister).
         const char* pin = getenv("OCL_SC_PIN");
-        h->pin_host = !(pin && strcmp(pin, "0") == 0);
+        h->pin_host = pin && strcmp(pin, "1") == 0;
     }
     if (h->solver == 0) {
         const size_t hx1 = h->md.mx / 2 + 1, hy1 = h->md.my / 2 + 1, hz1 = h->md.mz / 2 + 1;
@@ -397,7 +416,7 @@ int ocl_sc_create(int device, int nx, int ny, int nz, long long max_particles, o
 
 void ocl_sc_destroy(ocl_sc_t* h) {
     if (!h) return;
-    cudaSetDevice(h->device);
+    DeviceScope device_scope_(nullptr, h->device);
     drop_graph(h);
     cudaFree(h->mb.epoch); cudaFree(h->mb_err);
     for (int i = 0; i < 2; ++i) if (h->pinned[i]) cudaHostUnregister(h->pinned[i]);
@@ -445,7 +464,7 @@ int ocl_sc_collective_buffer(ocl_sc_t* h, int which, double** d_ptr, long long* 
 
 int ocl_sc_combine_extents(ocl_sc_t* h, const double* d_all, int world, void* stream) {
     if (!h || !d_all || world < 1) return 1;
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     launch_combine_extents(d_all, world, h->rs, (cudaStream_t)stream);
     h->launches += 1;
     return check_launch(h, "k_combine_extents");
@@ -455,7 +474,7 @@ int ocl_sc_mailbox_init(ocl_sc_t* h, int rank, int world, void* const* peer_ptrs
     if (!h || !peer_ptrs) return 1;
     if (world < 1 || world > 8 || rank < 0 || rank >= world)
         return fail(h, "ocl_sc_mailbox_init", "need 0 <= rank < world <= 8");
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     for (int w = 0; w < 8; ++w) h->mb.peer[w] = (w < world) ? (double*)peer_ptrs[w] : nullptr;
     h->mb.rank = rank; h->mb.world = world;
     if (!h->mb.epoch) {
@@ -471,7 +490,7 @@ int ocl_sc_mailbox_exchange(ocl_sc_t* h, int which, void* stream) {
     if (!h) return 1;
     if (!h->mb.world) return fail(h, "ocl_sc_mailbox_exchange", "call ocl_sc_mailbox_init first");
     if (which < 0 || which > 2) return fail(h, "ocl_sc_mailbox_exchange", "which must be 0, 1 or 2");
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     launch_mailbox_exchange(h->mb, which, h->rs, h->mb_err, (cudaStream_t)stream);
     h->launches += 1;
     return check_launch(h, "k_mailbox_exchange");
@@ -481,7 +500,7 @@ int ocl_sc_set_peer_rho(ocl_sc_t* h, int rank, int world, void* const* peer_rho)
     if (!h || !peer_rho) return 1;
     if (world < 1 || world > 8 || rank < 0 || rank >= world)
         return fail(h, "ocl_sc_set_peer_rho", "need 0 <= rank < world <= 8");
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     drop_graph(h);
     if (!h->own_rho) h->own_rho = h->rho;
     for (int w = 0; w < 8; ++w) h->peer_rho.p[w] = (w < world) ? (const double*)peer_rho[w] : nullptr;
@@ -494,7 +513,7 @@ int ocl_sc_set_peer_rho(ocl_sc_t* h, int rank, int world, void* const* peer_rho)
 int ocl_sc_set_multicast_rho(ocl_sc_t* h, void* local_rho, void* multicast_rho) {
     if (!h || !local_rho || !multicast_rho) return 1;
     if (!h->mb.world) return fail(h, "ocl_sc_set_multicast_rho", "call ocl_sc_mailbox_init first");
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     drop_graph(h);
     if (!h->own_rho) h->own_rho = h->rho;
     h->peer_rho.world = 0;                     // the solve reads the local (already reduced) grid
@@ -507,7 +526,7 @@ int ocl_sc_set_multicast_rho(ocl_sc_t* h, void* local_rho, void* multicast_rho) 
 int ocl_sc_nvls_reduce_rho(ocl_sc_t* h, void* stream) {
     if (!h) return 1;
     if (!h->mc_rho) return fail(h, "ocl_sc_nvls_reduce_rho", "call ocl_sc_set_multicast_rho first");
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
     const int world = h->mb.world, rank = h->mb.rank;
@@ -541,7 +560,7 @@ int ocl_sc_defer_finish(ocl_sc_t* h, int on) {
 int ocl_sc_stage_finish(ocl_sc_t* h, int which, double E_GeV, const double* mesh_draws, void* stream) {
     if (!h) return 1;
     if (which != 0 && which != 1) return fail(h, "ocl_sc_stage_finish", "which must be 0 (momentum) or 1 (extent)");
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
     launch_finish(which, kp_of(h, E_GeV, 0.0, mesh_draws), h->rs, h->md, st);
@@ -552,7 +571,7 @@ int ocl_sc_stage_finish(ocl_sc_t* h, int which, double E_GeV, const double* mesh
 int ocl_sc_set_kick_params(ocl_sc_t* h, double E_GeV, double dz, const double* mesh_draws, void* stream) {
     if (!h) return 1;
     if (!(E_GeV > 0.0)) return fail(h, "ocl_sc_set_kick_params", "beam energy must be positive");
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     launch_set_params(kick_params(h, E_GeV, dz, mesh_draws), h->kp_dev, (cudaStream_t)stream);
     h->launches += 1;
     return check_launch(h, "k_set_params");
@@ -563,7 +582,7 @@ int ocl_sc_slab_init(ocl_sc_t* h, int rank, int world) {
     if (!h) return 1;
     if (world < 1 || rank < 0 || rank >= world) return fail(h, "ocl_sc_slab_init", "bad rank/world");
     if (h->solver != 0) return fail(h, "ocl_sc_slab_init", "slab mode needs the hand-written solver");
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     drop_graph(h);
     const int hz1 = h->md.mz / 2 + 1;
     const int F = h->md.my * hz1;
@@ -592,7 +611,7 @@ int ocl_sc_slab_init(ocl_sc_t* h, int rank, int world) {
 
 int ocl_sc_slab_forward(ocl_sc_t* h, void* stream) {
     if (!h || !h->slab_world) return h ? fail(h, "ocl_sc_slab_forward", "call ocl_sc_slab_init first") : 1;
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
     launch_slab_forward(h->rho_slab, h->peer_rho, (long long)h->slab_rank * h->sx * h->md.ny, h->md, h->sx, h->fs, h->fw,
@@ -603,7 +622,7 @@ int ocl_sc_slab_forward(ocl_sc_t* h, void* stream) {
 
 int ocl_sc_slab_xpass(ocl_sc_t* h, void* stream) {
     if (!h || !h->slab_world) return h ? fail(h, "ocl_sc_slab_xpass", "call ocl_sc_slab_init first") : 1;
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
     if (h->khat_pending) {                      // join the Green's-function chain forked by stage_deposit
@@ -619,7 +638,7 @@ int ocl_sc_slab_xpass(ocl_sc_t* h, void* stream) {
 
 int ocl_sc_slab_inverse(ocl_sc_t* h, void* stream) {
     if (!h || !h->slab_world) return h ? fail(h, "ocl_sc_slab_inverse", "call ocl_sc_slab_init first") : 1;
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
     launch_slab_inverse(h->xchg_a, h->md, h->sx, h->fs, h->fw, h->h3, four_pi_eps0_value(), h->phi_slab, st);
@@ -630,7 +649,7 @@ int ocl_sc_slab_inverse(ocl_sc_t* h, void* stream) {
 
 int ocl_sc_slab_finish(ocl_sc_t* h, const double* mesh_draws, void* stream) {
     if (!h || !h->slab_world) return h ? fail(h, "ocl_sc_slab_finish", "call ocl_sc_slab_init first") : 1;
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
     (void)mesh_draws;
@@ -646,7 +665,7 @@ int ocl_sc_stage_momentum(ocl_sc_t* h, const double* d_r, long long ld, long lon
     if (n < 0 || ld < n) return fail(h, "ocl_sc_stage_momentum", "need 0 <= n <= ld");
     if (n == 0 && h->mb.world <= 1 && !h->rs.defer) return fail(h, "ocl_sc_stage_momentum", "empty bunch");
     if (n >= 2147483647LL - 2 * 148 * 4 * 256) return fail(h, "ocl_sc_stage_momentum", "more than 2^31 particles per GPU");
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
     mark(h, T_BEGIN, st);
@@ -659,7 +678,7 @@ int ocl_sc_stage_momentum(ocl_sc_t* h, const double* d_r, long long ld, long lon
 int ocl_sc_stage_extent(ocl_sc_t* h, const double* d_r, long long ld, const double* d_q, long long n, double E_GeV,
                         const double* mesh_draws, void* stream) {
     if (!h) return 1;
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
     launch_extent(d_r, ld, d_q, n, kp_of(h, E_GeV, 0.0, mesh_draws), h->rs, h->md, h->mb, h->mb_err, st);
@@ -671,7 +690,7 @@ int ocl_sc_stage_extent(ocl_sc_t* h, const double* d_r, long long ld, const doub
 int ocl_sc_stage_deposit(ocl_sc_t* h, const double* d_r, long long ld, const double* d_q, long long n, double E_GeV,
                          const double* mesh_draws, void* stream) {
     if (!h) return 1;
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
     // the mesh steps are final once the extents are reduced: start the Green's-function / K_hat
@@ -686,7 +705,7 @@ int ocl_sc_stage_deposit(ocl_sc_t* h, const double* d_r, long long ld, const dou
 
 int ocl_sc_stage_solve(ocl_sc_t* h, const double* mesh_draws, void* stream) {
     if (!h) return 1;
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
     (void)mesh_draws;                         // the mesh (incl. random_mesh draws) was fixed by the extent stage
@@ -712,7 +731,7 @@ int ocl_sc_stage_solve(ocl_sc_t* h, const double* mesh_draws, void* stream) {
 int ocl_sc_stage_kick(ocl_sc_t* h, double* d_r, long long ld, long long n, double E_GeV, double dz,
                       const double* mesh_draws, void* stream) {
     if (!h) return 1;
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
     launch_gather_kick(d_r, ld, n, kp_of(h, E_GeV, dz, mesh_draws), h->rs, h->md, h->equad, nullptr, 1, h->layout, st);
@@ -785,7 +804,7 @@ int ocl_sc_kick_device(ocl_sc_t* h, double* d_r, long long ld, const double* d_q
     cudaStream_t st = (cudaStream_t)stream;
     bool graph_ok = h->use_graph && h->solver == 0 && !h->timers;
     if (graph_ok) {
-        if (set_device(h)) return 1;
+        ENTER_DEVICE(h);
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
             cudaGetLastError();
@@ -813,13 +832,36 @@ int ocl_sc_kick_device(ocl_sc_t* h, double* d_r, long long ld, const double* d_q
     return 0;
 }
 
-// Page-lock the caller's buffer so the copies run at PCIe rate (pageable: ~13 GB/s, pinned: ~50 GB/s
-// measured).  Ocelot kicks the same rparticles buffer every step, so this is paid once.  Failure
-// (already pinned by the caller, unsupported range ...) is not an error: the copy still works.
+// Page-lock a host range so the copies of ocl_sc_kick_host run at PCIe rate (pageable: ~13 GB/s, pinned:
+// ~50 GB/s measured).  The caller owns the lifetime: it must unregister BEFORE the memory is freed (freeing
+// registered memory is undefined, and a new allocation at the same address would inherit a stale mapping).
+// Returns 0 (registered), 2 (already page-locked / managed: nothing to do), 1 (failed; the copies still work).
+int ocl_sc_host_register(void* ptr, long long bytes) {
+    if (!ptr || bytes <= 0) return 1;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) {
+        cudaGetLastError();
+        return 2;
+    }
+    cudaGetLastError();
+    if (cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return 1;
+    }
+    return 0;
+}
+
+int ocl_sc_host_unregister(void* ptr) {
+    if (!ptr) return 1;
+    const cudaError_t e = cudaHostUnregister(ptr);
+    cudaGetLastError();
+    return e == cudaSuccess ? 0 : 1;
+}
+
+// Legacy opt-in (OCL_SC_PIN=1): the handle registers the buffers it is given and re-validates on every call.
 static void pin_in_place(ocl_sc* h, int slot, const void* ptr, size_t bytes) {
     if (!h->pin_host) return;
-    if (h->pinned[slot] == ptr && h->pinned_bytes[slot] == bytes) return;
-    if (h->pinned[slot]) { cudaHostUnregister(h->pinned[slot]); h->pinned[slot] = nullptr; }
+    if (h->pinned[slot]) { cudaHostUnregister(h->pinned[slot]); h->pinned[slot] = nullptr; cudaGetLastError(); }
     cudaPointerAttributes at;
     if (cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type != cudaMemoryTypeUnregistered) {
         cudaGetLastError();
@@ -851,7 +893,7 @@ int ocl_sc_kick_host(ocl_sc_t* h, double* h_r, long long ld, const double* h_q, 
     if (!h) return 1;
     if (dz == 0.0) return 0;
     if (n <= 0 || ld < n) return fail(h, "ocl_sc_kick_host", "need 0 < n <= ld");
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     if (ensure_stage(h, n)) return 1;
     pin_in_place(h, 0, h_r, sizeof(double) * (size_t)(5 * ld + n));
     pin_in_place(h, 1, h_q, sizeof(double) * (size_t)n);
@@ -880,8 +922,8 @@ int ocl_sc_kick_host(ocl_sc_t* h, double* h_r, long long ld, const double* h_q, 
 
 // ---- taps -----------------------------------------------------------------
 static int sync_last(ocl_sc* h) {
-    if (set_device(h)) return 1;
-    CU(h, cudaStreamSynchronize(h->last_stream));
+    ENTER_DEVICE(h);
+    if (h->last_stream_valid) CU(h, cudaStreamSynchronize(h->last_stream));
     return 0;
 }
 
@@ -934,7 +976,7 @@ int ocl_sc_field_at_particles(ocl_sc_t* h, const double* d_r, long long ld, cons
 int ocl_sc_mad_to_cartesian(ocl_sc_t* h, const double* d_r, long long ld, long long n, double E_GeV, double* d_xp,
                             long long ld_xp, void* stream) {
     if (!h) return 1;
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     if (adopt_stream(h, (cudaStream_t)stream)) return 1;
     launch_mad_to_cart(d_r, ld, n, ref_params(h, E_GeV), d_xp, ld_xp, (cudaStream_t)stream);
     h->launches += 1;
@@ -944,7 +986,7 @@ int ocl_sc_mad_to_cartesian(ocl_sc_t* h, const double* d_r, long long ld, long l
 int ocl_sc_cartesian_to_mad(ocl_sc_t* h, const double* d_xp, long long ld_xp, long long n, double E_GeV, double* d_r,
                             long long ld, void* stream) {
     if (!h) return 1;
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     if (adopt_stream(h, (cudaStream_t)stream)) return 1;
     launch_cart_to_mad(d_xp, ld_xp, n, ref_params(h, E_GeV), d_r, ld, (cudaStream_t)stream);
     h->launches += 1;
@@ -953,7 +995,7 @@ int ocl_sc_cartesian_to_mad(ocl_sc_t* h, const double* d_xp, long long ld_xp, lo
 
 int ocl_sc_potential_host(ocl_sc_t* h, const double* h_rho, const double steps[3], double* h_phi) {
     if (!h) return 1;
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     cudaStream_t st = h->own_stream;
     if (adopt_stream(h, st)) return 1;
     const size_t n3 = (size_t)h->md.nx * h->md.ny * h->md.nz;
@@ -977,7 +1019,7 @@ int ocl_sc_map_apply(ocl_sc_t* h, double* d_r, long long ld, long long n, const 
                      const double* T, void* stream) {
     if (!h || !R) return 1;
     if (n <= 0 || ld < n) return fail(h, "ocl_sc_map_apply", "need 0 < n <= ld");
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     MapCoef mc;
     for (int i = 0; i < 36; ++i) mc.R[i] = R[i];
     for (int i = 0; i < 6; ++i) mc.B[i] = B ? B[i] : 0.0;
@@ -997,7 +1039,7 @@ int ocl_sc_cavity_apply(ocl_sc_t* h, double* d_r, long long ld, long long n, con
     if (!h || !R || !c) return 1;
     if (n <= 0 || ld < n) return fail(h, "ocl_sc_cavity_apply", "need 0 < n <= ld");
     if (mode != 1 && mode != 2) return fail(h, "ocl_sc_cavity_apply", "mode must be 1 or 2");
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     MapCoef mc;
     for (int i = 0; i < 36; ++i) mc.R[i] = R[i];
     for (int i = 0; i < 6; ++i) mc.B[i] = B ? B[i] : 0.0;
@@ -1014,7 +1056,7 @@ int ocl_sc_cavity_apply(ocl_sc_t* h, double* d_r, long long ld, long long n, con
 int ocl_sc_beam_moments(ocl_sc_t* h, const double* d_r, long long ld, long long n, double* h_out, void* stream) {
     if (!h || !h_out) return 1;
     if (n <= 0 || ld < n) return fail(h, "ocl_sc_beam_moments", "need 0 < n <= ld");
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
     launch_moments(d_r, ld, n, h->rs, h->moments, st);
@@ -1086,7 +1128,7 @@ int ocl_sc_lsc_stats(ocl_sc_t* h, const double* d_r, long long ld, long long n, 
                      void* stream) {
     if (!h || !h_out) return 1;
     if (n <= 0 || ld < n) return fail(h, "ocl_sc_lsc_stats", "need 0 < n <= ld");
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
     if (ensure_lsc(h, 1)) return 1;
@@ -1115,7 +1157,7 @@ int ocl_sc_lsc_deposit(ocl_sc_t* h, const double* d_r, long long ld, long long n
     if (n <= 0 || ld < n) return fail(h, "ocl_sc_lsc_deposit", "need 0 < n <= ld");
     LscParams lp;
     if (lsc_params(h, params, lp)) return 1;
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
     if (ensure_lsc(h, lp.nb)) return 1;
@@ -1133,7 +1175,7 @@ int ocl_sc_lsc_solve_kick(ocl_sc_t* h, double* d_r, long long ld, long long n, c
     LscParams lp;
     if (lsc_params(h, params, lp)) return 1;
     if (lp.nb != h->lsc_nb) return fail(h, "ocl_sc_lsc_solve_kick", "grid differs from the deposited one");
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
     if (h->lsc_tw_nb != lp.nb) {
@@ -1167,7 +1209,7 @@ int ocl_sc_lsc_kick_async(ocl_sc_t* h, double* d_r, long long ld, long long n, c
                           void* stream) {
     if (!h || !hostp) return 1;
     if (n <= 0 || ld < n) return fail(h, "ocl_sc_lsc_kick_async", "need 0 < n <= ld");
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     if (ensure_lsc(h, kLscAsyncCap)) return 1;
     if (lsc_async_error(h, "ocl_sc_lsc_kick_async")) return 1;
     cudaStream_t st = (cudaStream_t)stream;
@@ -1189,10 +1231,21 @@ int ocl_sc_lsc_kick_async(ocl_sc_t* h, double* d_r, long long ld, long long n, c
     return check_launch(h, "ocl_sc_lsc_kick_async");
 }
 
+int ocl_sc_lsc_async_status(ocl_sc_t* h, int synchronise, int* status) {
+    if (!h || !status) return 1;
+    *status = 0;
+    if (!h->lsc_err_host) return 0;                  // no asynchronous kick was ever issued
+    ENTER_DEVICE(h);
+    if (synchronise && sync_last(h)) return 1;
+    *status = *h->lsc_err_host;
+    *h->lsc_err_host = 0;
+    return 0;
+}
+
 int ocl_sc_lsc_last_params(ocl_sc_t* h, double out[17]) {
     if (!h || !out) return 1;
     if (!h->lsc_async_pending) return fail(h, "ocl_sc_lsc_last_params", "no asynchronous LSC kick recorded");
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     if (sync_last(h)) return 1;
     if (lsc_async_error(h, "ocl_sc_lsc_last_params")) return 1;
     LscParams lp;
@@ -1207,7 +1260,7 @@ int ocl_sc_lsc_last_params(ocl_sc_t* h, double out[17]) {
 int ocl_sc_lsc_get_profile(ocl_sc_t* h, int nb, double* h_current, double* h_wake, double* h_sigma) {
     if (!h) return 1;
     if (nb <= 0 || nb != h->lsc_nb) return fail(h, "ocl_sc_lsc_get_profile", "nb differs from the last LSC kick");
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     if (sync_last(h)) return 1;
     if (h_current) CU(h, cudaMemcpy(h_current, h->lw.cur, sizeof(double) * nb, cudaMemcpyDeviceToHost));
     if (h_wake) CU(h, cudaMemcpy(h_wake, h->lw.W, sizeof(double) * nb, cudaMemcpyDeviceToHost));
@@ -1226,7 +1279,7 @@ int ocl_sc_get_timers(ocl_sc_t* h, double out[8]) {
     if (!h) return 1;
     for (int i = 0; i < 8; ++i) out[i] = 0.0;
     if (!h->timers || !h->ev_valid) return fail(h, "ocl_sc_get_timers", "no timed kick recorded");
-    if (set_device(h)) return 1;
+    ENTER_DEVICE(h);
     CU(h, cudaEventSynchronize(h->ev[T_KICK]));
     float ms;
     for (int s = T_MOM; s <= T_KICK; ++s) {

@@ -303,31 +303,68 @@ __device__ __forceinline__ double trilinear(const EQuad* __restrict__ F, int nx,
 // own particle.  Wavefronts per particle: 3 x 1.25 instead of 6.  Must be called by all 32 lanes.
 __device__ __forceinline__ double shfl_xor1(double v) { return __shfl_xor_sync(0xffffffffu, v, 1); }
 
-__device__ __forceinline__ double trilinear_pair(const EQuad* __restrict__ F, int nx, int ny, int nz, double c0,
-                                                 double c1, double c2) {
-    const bool in = c0 >= 0.0 && c0 <= (double)(nx - 1) && c1 >= 0.0 && c1 <= (double)(ny - 1) && c2 >= 0.0 &&
-                    c2 <= (double)(nz - 1);
-    c0 = in ? c0 : 0.0; c1 = in ? c1 : 0.0; c2 = in ? c2 : 0.0;
+// cell, fractions and in-range flag of one interpolation point (map_coordinates, mode='constant', cval=0)
+struct Interp {
+    int rec;            // record index of the lower x plane: (i1*nz + i2)*nx + i0
+    double t0, t1, t2;
+    bool in;
+};
+__device__ __forceinline__ Interp interp_point(int nx, int ny, int nz, double c0, double c1, double c2) {
+    Interp p;
+    p.in = c0 >= 0.0 && c0 <= (double)(nx - 1) && c1 >= 0.0 && c1 <= (double)(ny - 1) && c2 >= 0.0 &&
+           c2 <= (double)(nz - 1);
+    c0 = p.in ? c0 : 0.0; c1 = p.in ? c1 : 0.0; c2 = p.in ? c2 : 0.0;     // out of range: a valid address, result discarded
     const double f0 = floor(c0), f1 = floor(c1), f2 = floor(c2);
-    const int i0 = (int)f0, i1 = (int)f1, i2 = (int)f2;
-    const double t0 = c0 - f0, t1 = c1 - f1, t2 = c2 - f2;
+    p.t0 = c0 - f0; p.t1 = c1 - f1; p.t2 = c2 - f2;
     // record i0 + 1 of the last plane (i0 == nx - 1, t0 == 0) is the next row's first record (or the zeroed
     // pad record behind the table): finite, and its weight is exactly zero
-    const int mine = (i1 * nz + i2) * nx + i0;
-    const int other = __shfl_xor_sync(0xffffffffu, mine, 1);
+    p.rec = ((int)f1 * nz + (int)f2) * nx + (int)f0;
+    return p;
+}
+// (y, z) part of the interpolation inside one quad record
+__device__ __forceinline__ double bilinear(const EQuad& q, double t1, double t2) {
+    const double d0 = 1.0 - t2;
+    const double z0 = fma(q.v01, t2, q.v00 * d0), z1 = fma(q.v11, t2, q.v10 * d0);
+    return fma(z1, t1, z0 * (1.0 - t1));
+}
+
+// All three field components of this lane's particle at grid position (g0, g1, g2) (sc.py:202-204; Ex, Ey NOT yet
+// multiplied by gamma0).  The lane pair (2k, 2k+1) handles its two particles together: for each of them the even
+// lane fetches the x = i0 records and the odd lane the x = i0 + 1 records (one request per particle and component
+// when the two share a 128-byte line), each lane reduces its record with that particle's (y, z) fractions, and
+// only the three reduced values per particle cross lanes.  Per particle: the partner's position (3 doubles) and
+// the three partial results (3 doubles) are exchanged = 12 SHFL.32, against 27 for exchanging whole records.
+__device__ __forceinline__ void gather_pair(const EQuad* __restrict__ ex, const EQuad* __restrict__ ey,
+                                            const EQuad* __restrict__ ez, int nx, int ny, int nz, double g0, double g1,
+                                            double g2, double& e0, double& e1, double& e2) {
     const int odd = (int)(threadIdx.x & 1);
-    const EQuad L1 = F[(odd ? other : mine) + odd];        // even lane's particle: records i0 | i0 + 1
-    const EQuad L2 = F[(odd ? mine : other) + odd];        // odd lane's particle
-    EQuad S = odd ? L1 : L2, R;
-    R.v00 = shfl_xor1(S.v00); R.v01 = shfl_xor1(S.v01); R.v10 = shfl_xor1(S.v10); R.v11 = shfl_xor1(S.v11);
-    const EQuad A = odd ? R : L1;
-    const EQuad B = odd ? L2 : R;
-    const double a0 = 1.0 - t0, b0 = 1.0 - t1, d0 = 1.0 - t2;
-    const double za0 = fma(A.v01, t2, A.v00 * d0), za1 = fma(A.v11, t2, A.v10 * d0);
-    const double zb0 = fma(B.v01, t2, B.v00 * d0), zb1 = fma(B.v11, t2, B.v10 * d0);
-    const double ya = fma(za1, t1, za0 * b0), yb = fma(zb1, t1, zb0 * b0);
-    const double acc = fma(yb, t0, ya * a0);
-    return in ? acc : 0.0;
+    const double h0 = shfl_xor1(g0), h1 = shfl_xor1(g1), h2 = shfl_xor1(g2);       // the partner's particle
+    // P: the even lane's particle, Q: the odd lane's particle (one of them is this lane's own)
+    const double p0 = odd ? h0 : g0, p1 = odd ? h1 : g1, p2 = odd ? h2 : g2;
+    const double q0 = odd ? g0 : h0, q1 = odd ? g1 : h1, q2 = odd ? g2 : h2;
+    const Interp px = interp_point(nx, ny, nz, p0, p1 + 0.5, p2 + 0.5), qx = interp_point(nx, ny, nz, q0, q1 + 0.5, q2 + 0.5);
+    const Interp py = interp_point(nx, ny, nz, p0 + 0.5, p1, p2 + 0.5), qy = interp_point(nx, ny, nz, q0 + 0.5, q1, q2 + 0.5);
+    const Interp pz = interp_point(nx, ny, nz, p0 + 0.5, p1 + 0.5, p2), qz = interp_point(nx, ny, nz, q0 + 0.5, q1 + 0.5, q2);
+    // six independent 256-bit loads; in each, the two lanes of a pair read adjacent records
+    const EQuad rpx = ex[px.rec + odd], rqx = ex[qx.rec + odd];
+    const EQuad rpy = ey[py.rec + odd], rqy = ey[qy.rec + odd];
+    const EQuad rpz = ez[pz.rec + odd], rqz = ez[qz.rec + odd];
+    const double bpx = bilinear(rpx, px.t1, px.t2), bqx = bilinear(rqx, qx.t1, qx.t2);
+    const double bpy = bilinear(rpy, py.t1, py.t2), bqy = bilinear(rqy, qy.t1, qy.t2);
+    const double bpz = bilinear(rpz, pz.t1, pz.t2), bqz = bilinear(rqz, qz.t1, qz.t2);
+    // the even lane keeps P's lower-plane parts and ships Q's; the odd lane keeps Q's upper-plane parts and ships P's
+    const double rx = shfl_xor1(odd ? bpx : bqx), ry = shfl_xor1(odd ? bpy : bqy), rz = shfl_xor1(odd ? bpz : bqz);
+    const double tx = odd ? qx.t0 : px.t0, ty = odd ? qy.t0 : py.t0, tz = odd ? qz.t0 : pz.t0;
+    const bool inx = odd ? qx.in : px.in, iny = odd ? qy.in : py.in, inz = odd ? qz.in : pz.in;
+    const double lox = odd ? rx : bpx, hix = odd ? bqx : rx;           // lower / upper x plane of the own particle
+    const double loy = odd ? ry : bpy, hiy = odd ? bqy : ry;
+    const double loz = odd ? rz : bpz, hiz = odd ? bqz : rz;
+    const double vx = fma(hix, tx, lox * (1.0 - tx));
+    const double vy = fma(hiy, ty, loy * (1.0 - ty));
+    const double vz = fma(hiz, tz, loz * (1.0 - tz));
+    e0 = inx ? vx : 0.0;
+    e1 = iny ? vy : 0.0;
+    e2 = inz ? vz : 0.0;
 }
 
 // ---- asynchronous row pipeline -------------------------------------------------

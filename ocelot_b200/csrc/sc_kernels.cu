@@ -42,9 +42,6 @@ int particle_grid(long long n, int max_blocks) {
 }
 
 constexpr int kPipeDepth = 3;
-#ifndef GK_BLOCKS
-#define GK_BLOCKS 2
-#endif
 
 // ---------------------------------------------------------------------------
 // Fused exchange over NVLink peer memory (replaces an NCCL all-reduce / all-gather of a handful of
@@ -191,12 +188,17 @@ __global__ void __launch_bounds__(kThreads, 3) k_extent(const double* __restrict
         double a, b, g;
         rotate_stretch(f, c.x, c.y, c.z, a, b, g);
         const double qi = w[6];
+#ifndef OCL_EXT_NOIDX
         if (a > v[0]) { v[0] = a; ix[0] = i; }
         if (b > v[1]) { v[1] = b; ix[1] = i; }
         if (g > v[2]) { v[2] = g; ix[2] = i; }
         if (-a > v[3]) { v[3] = -a; ix[3] = i; }
         if (-b > v[4]) { v[4] = -b; ix[4] = i; }
         if (-g > v[5]) { v[5] = -g; ix[5] = i; }
+#else
+        v[0] = fmax(v[0], a); v[1] = fmax(v[1], b); v[2] = fmax(v[2], g);
+        v[3] = fmax(v[3], -a); v[4] = fmax(v[4], -b); v[5] = fmax(v[5], -g);
+#endif
         v[6] += qi * a; v[7] += qi * b; v[8] += qi * g; v[9] += qi;
     });
     pdl_trigger();
@@ -205,22 +207,25 @@ __global__ void __launch_bounds__(kThreads, 3) k_extent(const double* __restrict
     // lanes 0..5: the particle behind extremum k, once more, exactly as the reference computes it
     const int lane = threadIdx.x;
     double exact = -INFINITY;
+#ifndef OCL_EXT_NOEXACT
+    int who = -1;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-        const int who = __shfl_sync(0xffffffffu, ix[k], 0);
-        if (lane == k && who >= 0) {
-            double a, b, c;
-            exact_frame_position(rp, f, r[who], r[ld + who], r[2 * ld + who], r[3 * ld + who], r[4 * ld + who],
-                                 r[5 * ld + who], a, b, c);
-            const double p[3] = {a, b, c};
-            exact = k < 3 ? p[k] : -p[k - 3];
-        }
+        const int w = __shfl_sync(0xffffffffu, ix[k], 0);      // ix[] is valid in thread 0
+        if (lane == k) who = w;
+    }
+    if (lane < 6 && who >= 0) {                                // six lanes, six particles, in parallel
+        double p[3];
+        exact_frame_position(rp, f, r[who], r[ld + who], r[2 * ld + who], r[3 * ld + who], r[4 * ld + who],
+                             r[5 * ld + who], p[0], p[1], p[2]);
+        exact = lane == 0 ? p[0] : lane == 1 ? p[1] : lane == 2 ? p[2] : lane == 3 ? -p[0] : lane == 4 ? -p[1] : -p[2];
     }
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
         const double e = __shfl_sync(0xffffffffu, exact, k);
         if (lane == 0 && e > -INFINITY) v[k] = e;
     }
+#endif
     if (threadIdx.x == 0) {
 #pragma unroll
         for (int k = 0; k < 6; ++k) rs.emax[k] = v[k];
@@ -495,8 +500,8 @@ __global__ void __launch_bounds__(kThreads) k_field_xf(const double* __restrict_
 //   LAYOUT 0: z-fastest quad table, six independent 256-bit gathers per particle
 //   LAYOUT 1: x-fastest quad table fetched by lane pairs (trilinear_pair)
 // ---------------------------------------------------------------------------
-template <bool KICK, bool TAP, int LAYOUT>
-__global__ void __launch_bounds__(kThreads, GK_BLOCKS) k_gather_kick(double* __restrict__ r, long long ld, long long n,
+template <bool KICK, bool TAP, int LAYOUT, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) k_gather_kick(double* __restrict__ r, long long ld, long long n,
                                                             KP kp, ReduceState rs, MeshDims md,
                                                             const EQuad* __restrict__ equad,
                                                             double* __restrict__ exyz_out) {
@@ -521,9 +526,8 @@ __global__ void __launch_bounds__(kThreads, GK_BLOCKS) k_gather_kick(double* __r
         to_grid(m, a, b, g, g0, g1, g2);
         double e0, e1, e2;
         if constexpr (LAYOUT == 1) {
-            e0 = trilinear_pair(ex, md.nx, md.ny, md.nz, g0, g1 + 0.5, g2 + 0.5) * f.gamma0;     // :202
-            e1 = trilinear_pair(ey, md.nx, md.ny, md.nz, g0 + 0.5, g1, g2 + 0.5) * f.gamma0;     // :203
-            e2 = trilinear_pair(ez, md.nx, md.ny, md.nz, g0 + 0.5, g1 + 0.5, g2);                // :204
+            gather_pair(ex, ey, ez, md.nx, md.ny, md.nz, g0, g1, g2, e0, e1, e2);                // :202-204
+            e0 *= f.gamma0; e1 *= f.gamma0;
         } else {
             e0 = trilinear(ex, md.nx, md.ny, md.nz, g0, g1 + 0.5, g2 + 0.5) * f.gamma0;
             e1 = trilinear(ey, md.nx, md.ny, md.nz, g0 + 0.5, g1, g2 + 0.5) * f.gamma0;
@@ -591,7 +595,6 @@ static inline int grid_for(long long total, int cap) {
     return (int)b;
 }
 constexpr int kSweepCap = 148 * 4;    // persistent grid-stride sweeps: 4 resident blocks per SM
-constexpr int kGatherCap = 148 * GK_BLOCKS;   // gather/kick: resident blocks per SM
 constexpr int kGridCap = 148 * 16;    // grid kernels
 
 __global__ void k_set_params(KickParams v, KickParams* dst) {
@@ -783,21 +786,37 @@ void launch_field(const double* phi, ReduceState rs, MeshDims md, EQuad* equad, 
         launch_k(k_field, dim3(grid), dim3(kThreads), 0, st, phi, src, rs, md, equad);
     }
 }
-template <int LAYOUT>
+// Resident blocks per SM of the gather (= its register budget): 2 blocks x 128 registers, or 3 x 85.  The
+// lane-pair gather is bound by the L1TEX data stage; with its smaller wavefront count a third block pays once
+// the kernel runs long enough to reach steady state (measured on B200, 12.5 M / 127^3: 428 -> 403 us), while at
+// 1 M particles two blocks are faster (39 vs 41 us).  OCL_SC_GK_BLOCKS overrides.
+static int gather_blocks(long long n, int layout) {
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("OCL_SC_GK_BLOCKS");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced == 2 || forced == 3) return forced;
+    return (layout == 1 && n >= 4000000) ? 3 : 2;
+}
+template <int LAYOUT, int MINB>
 static void launch_gather_kick_l(double* r, long long ld, long long n, KP kp, ReduceState rs, MeshDims md,
                                  const EQuad* equad, double* exyz_out, int do_kick, cudaStream_t st) {
-    int grid = grid_for(n, kGatherCap);
+    int grid = grid_for(n, 148 * MINB);
     if (do_kick && exyz_out)
-        launch_k(k_gather_kick<true, true, LAYOUT>, dim3(grid), dim3(kThreads), 0, st, r, ld, n, kp, rs, md, equad, exyz_out);
+        launch_k(k_gather_kick<true, true, LAYOUT, MINB>, dim3(grid), dim3(kThreads), 0, st, r, ld, n, kp, rs, md, equad, exyz_out);
     else if (do_kick)
-        launch_k(k_gather_kick<true, false, LAYOUT>, dim3(grid), dim3(kThreads), 0, st, r, ld, n, kp, rs, md, equad, nullptr);
+        launch_k(k_gather_kick<true, false, LAYOUT, MINB>, dim3(grid), dim3(kThreads), 0, st, r, ld, n, kp, rs, md, equad, nullptr);
     else
-        launch_k(k_gather_kick<false, true, LAYOUT>, dim3(grid), dim3(kThreads), 0, st, r, ld, n, kp, rs, md, equad, exyz_out);
+        launch_k(k_gather_kick<false, true, LAYOUT, MINB>, dim3(grid), dim3(kThreads), 0, st, r, ld, n, kp, rs, md, equad, exyz_out);
 }
 void launch_gather_kick(double* r, long long ld, long long n, KP kp, ReduceState rs, MeshDims md,
                         const EQuad* equad, double* exyz_out, int do_kick, int layout, cudaStream_t st) {
-    if (layout == 1) launch_gather_kick_l<1>(r, ld, n, kp, rs, md, equad, exyz_out, do_kick, st);
-    else launch_gather_kick_l<0>(r, ld, n, kp, rs, md, equad, exyz_out, do_kick, st);
+    const int mb = gather_blocks(n, layout);
+    if (layout == 1 && mb == 3) launch_gather_kick_l<1, 3>(r, ld, n, kp, rs, md, equad, exyz_out, do_kick, st);
+    else if (layout == 1) launch_gather_kick_l<1, 2>(r, ld, n, kp, rs, md, equad, exyz_out, do_kick, st);
+    else if (mb == 3) launch_gather_kick_l<0, 3>(r, ld, n, kp, rs, md, equad, exyz_out, do_kick, st);
+    else launch_gather_kick_l<0, 2>(r, ld, n, kp, rs, md, equad, exyz_out, do_kick, st);
 }
 void launch_mad_to_cart(const double* r, long long ld, long long n, RefParams rp, double* xp, long long ld_xp,
                         cudaStream_t st) {

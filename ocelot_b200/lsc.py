@@ -54,6 +54,8 @@ class LSC(PhysProc):
         self.device = kwargs.get("device", None)
         self.async_grid = kwargs.get("async_grid", True)
         self._solvers = {}
+        self._stage = {}
+        self._async_verified = False
         self._last_params = None
         self._last_solver = None
 
@@ -149,21 +151,49 @@ class LSC(PhysProc):
             self._kick_device(self._solver(dev), r, p_array.q_array, E, float(dz))
 
     def _apply_host(self, r, q_array, E, dz):
-        """Host numpy arrays: stage the four rows LSC reads (x, y, tau, delta) to the device, kick,
-        and copy row 5 back in place (the only row LSC writes, sc.py:599)."""
+        """Host numpy arrays: stage the four rows LSC reads (x, y, tau, delta) to the device through the
+        handle-owned pinned staging buffers, kick, and copy row 5 back in place (the only row LSC writes,
+        sc.py:599)."""
         import torch
         dev = self._host_device()
         solver = self._solver(dev)
+        n = r.shape[1]
         with torch.cuda.device(dev):
-            d_r = torch.empty((6, r.shape[1]), dtype=torch.float64, device=f"cuda:{dev}")
-            for row in (0, 2, 4, 5):
-                d_r[row].copy_(torch.from_numpy(r[row]), non_blocking=False)
-            d_q = torch.from_numpy(np.ascontiguousarray(q_array, dtype=np.float64)).to(d_r.device)
-            self._kick_device(solver, d_r, d_q, E, dz)
-            r[5][:] = d_r[5].cpu().numpy()
+            st = self._staging(dev, n)
+            d_r, d_q, pin = st["d_r"][:, :n], st["d_q"][:n], st["pin"]
+            for slot, row in enumerate((0, 2, 4, 5)):
+                pin[slot, :n].copy_(torch.from_numpy(r[row]))                 # host -> pinned (memcpy rate)
+                d_r[row].copy_(pin[slot, :n], non_blocking=True)              # pinned -> device (PCIe rate)
+            pin[4, :n].copy_(torch.from_numpy(np.ascontiguousarray(q_array, dtype=np.float64)))
+            d_q.copy_(pin[4, :n], non_blocking=True)
+            self._kick_device(solver, d_r, d_q, E, dz, checked=True)
+            pin[3, :n].copy_(d_r[5], non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            r[5][:] = pin[3, :n].numpy()
 
-    def _kick_device(self, solver, r, q, E, dz):
+    def _staging(self, dev, n):
+        import torch
+        st = self._stage.get(dev)
+        if st is None or st["cap"] < n:
+            cap = max(n + n // 8, 1024)
+            st = dict(cap=cap, d_r=torch.empty((6, cap), dtype=torch.float64, device=f"cuda:{dev}"),
+                      d_q=torch.empty(cap, dtype=torch.float64, device=f"cuda:{dev}"),
+                      pin=torch.empty((5, cap), dtype=torch.float64).pin_memory())
+            self._stage = {dev: st}
+        return st
+
+    def _kick_device(self, solver, r, q, E, dz, checked=False):
+        """``checked``: the caller synchronises anyway (host arrays), so the outcome of the asynchronous form is
+        read right away.  Otherwise the FIRST asynchronous kick of this object is checked once (one stream
+        synchronisation per tracking run); a grid that does not fit the asynchronous form (more than 8192 points:
+        small ``smooth_param``, long tails) switches the object to the host-derived grid for good and the kick
+        is redone -- never skipped.  Later overflows surface in the next ``apply`` / ``finalize`` as an error."""
         if self.async_grid:
+            late = solver.lsc_async_status(synchronise=False)
+            if late:
+                self.async_grid = False
+                raise RuntimeError("ocelot_b200.LSC: an earlier asynchronous kick was skipped on the device (its grid "
+                                   "outgrew the asynchronous form); set async_grid=False for this bunch")
             K_max, fill_factor = self.undulator_factor(dz)
             gamma = E / m_e_GeV
             solver.lsc_kick_async(r, q, gamma, np.sqrt(1 - 1 / gamma ** 2) * speed_of_light,
@@ -171,10 +201,26 @@ class LSC(PhysProc):
                                   1 + 0.5 * K_max * K_max * fill_factor, self.bounds, self.smooth_param,
                                   self.step_profile)
             self._last_params, self._last_solver = None, solver
-        else:
-            params = self.kick_parameters(solver.lsc_stats(r, q), E, dz)
-            solver.lsc_kick(r, params)
-            self._last_params, self._last_solver = params, None
+            if checked or not self._async_verified:
+                self._async_verified = True
+                if solver.lsc_async_status(synchronise=True):
+                    logger.warning("LSC: the current-profile grid does not fit the asynchronous form; "
+                                   "falling back to the host-derived grid (async_grid=False)")
+                    self.async_grid = False                     # the skipped kick left the particles untouched
+                else:
+                    return
+            else:
+                return
+        params = self.kick_parameters(solver.lsc_stats(r, q), E, dz)
+        solver.lsc_kick(r, params)
+        self._last_params, self._last_solver = params, None
+
+    def finalize(self, *args, **kwargs):
+        """End of a tracking run (track.py:498-499): the last asynchronous kick must not be dropped silently."""
+        for solver in self._solvers.values():
+            if solver.lsc_async_status(synchronise=True):
+                raise RuntimeError("ocelot_b200.LSC: the last asynchronous kick was skipped on the device (its grid "
+                                   "outgrew the asynchronous form); rerun with async_grid=False")
 
     # -- host-side utilities of the reference class (plotting / analysis helpers; ``apply`` does not
     #    use them: the kick evaluates the same formulas on the device, csrc/sc_lsc.cu) -------------
@@ -236,19 +282,21 @@ class LSC(PhysProc):
     def __getstate__(self):
         state = self.__dict__.copy()
         state["_solvers"] = {}
+        state["_stage"] = {}
         state["_last_solver"] = None
         return state
 
     def __setstate__(self, state):
         self.__dict__.update(state)
         self._solvers = {}
+        self._stage = {}
 
     def __deepcopy__(self, memo):
         import copy
         new = self.__class__.__new__(self.__class__)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            new.__dict__[k] = {} if k == "_solvers" else (None if k == "_last_solver" else copy.deepcopy(v, memo))
+            new.__dict__[k] = {} if k in ("_solvers", "_stage") else (None if k == "_last_solver" else copy.deepcopy(v, memo))
         return new
 
 

@@ -10,6 +10,7 @@ from __future__ import annotations
 import ctypes as C
 import os
 import re
+import weakref
 
 import numpy as np
 
@@ -36,6 +37,8 @@ _SIGNATURES = {
     "ocl_sc_last_error": (C.c_char_p, [_vp]),
     "ocl_sc_kick_device": (C.c_int, [_vp, _vp, _ll, _vp, _ll, C.c_double, C.c_double, _dp, _vp]),
     "ocl_sc_kick_host": (C.c_int, [_vp, _vp, _ll, _vp, _ll, C.c_double, C.c_double, _dp]),
+    "ocl_sc_host_register": (C.c_int, [_vp, _ll]),
+    "ocl_sc_host_unregister": (C.c_int, [_vp]),
     "ocl_sc_collective_buffer": (C.c_int, [_vp, C.c_int, C.POINTER(_vp), C.POINTER(_ll)]),
     "ocl_sc_combine_extents": (C.c_int, [_vp, _vp, C.c_int, _vp]),
     "ocl_sc_slab_init": (C.c_int, [_vp, C.c_int, C.c_int]),
@@ -75,6 +78,7 @@ _SIGNATURES = {
     "ocl_sc_lsc_get_profile": (C.c_int, [_vp, C.c_int, _dp, _dp, _dp]),
     "ocl_sc_lsc_kick_async": (C.c_int, [_vp, _vp, _ll, _ll, _vp, _dp, _vp]),
     "ocl_sc_lsc_last_params": (C.c_int, [_vp, _dp]),
+    "ocl_sc_lsc_async_status": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int)]),
     "ocl_sc_enable_timers": (C.c_int, [_vp, C.c_int]),
     "ocl_sc_get_timers": (C.c_int, [_vp, _dp]),
     "ocl_sc_launch_count": (_ll, [_vp]),
@@ -94,10 +98,12 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build
+    from . import build as _build
+    stale = (LIB_PATH == _build.LIB and os.path.exists(LIB_PATH) and not _build.up_to_date()
+             and os.access(os.path.dirname(LIB_PATH), os.W_OK) and _build.have_nvcc())
+    if not os.path.exists(LIB_PATH) or stale:     # stale: a source file is newer than the library
         try:
-            _build.build()
+            _build.build(force=stale)
         except Exception as exc:  # noqa: BLE001
             raise RuntimeError(
                 f"ocelot_b200: native library {LIB_PATH} is missing and could not be built ({exc}). "
@@ -109,6 +115,43 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+# ---- page-locking of caller-owned numpy buffers, tied to the owning array's lifetime ----
+_pinned = {}          # address of the owning array's buffer -> (bytes, finalizer)
+PIN_HOST = os.environ.get("OCL_SC_PIN_HOST", "1") != "0"
+
+
+def _unpin(ptr):
+    _pinned.pop(ptr, None)
+    try:
+        load().ocl_sc_host_unregister(ptr)
+    except Exception:  # noqa: BLE001  (interpreter shutdown)
+        pass
+
+
+def pin_host_array(arr: np.ndarray) -> bool:
+    """Page-lock the buffer behind ``arr`` (so host<->device copies run at PCIe rate) for as long as the array
+    that OWNS the buffer lives: a ``weakref.finalize`` on the owner unregisters the range before numpy frees it,
+    so a later allocation at the same address never inherits a stale registration.  Buffers owned by foreign
+    objects (e.g. a pinned torch tensor viewed through ``.numpy()``) are left alone."""
+    if not PIN_HOST:
+        return False
+    owner = arr
+    while isinstance(owner.base, np.ndarray):
+        owner = owner.base
+    if owner.base is not None or not owner.flags.owndata or owner.nbytes == 0:
+        return False
+    ptr = owner.ctypes.data
+    ent = _pinned.get(ptr)
+    if ent is not None:
+        if ent[0] == owner.nbytes and ent[1].alive:
+            return True
+        ent[1]()                                   # different extent at this address: drop the old registration
+    if load().ocl_sc_host_register(ptr, owner.nbytes) != 0:
+        return False
+    _pinned[ptr] = (owner.nbytes, weakref.finalize(owner, _unpin, ptr))
+    return True
 
 
 def constants() -> dict:
@@ -188,16 +231,28 @@ class Solver:
                                                  _draws(mesh_draws), _stream_ptr(stream)), "ocl_sc_kick_device")
 
     def kick_host(self, r: np.ndarray, q: np.ndarray, E_GeV, dz, mesh_draws=None):
-        if not (isinstance(r, np.ndarray) and r.dtype == np.float64 and r.ndim == 2 and r.shape[0] == 6
-                and r.strides[1] == 8 and r.flags.writeable):
-            raise TypeError("rparticles must be a writable float64 array of shape (6, n) with contiguous rows")
+        """Kick numpy particles in place.  A writable C-layout float64 (6, n) array is kicked where it lies (and
+        page-locked for the lifetime of its owner); anything else numpy's own code would accept (Fortran order,
+        slices with a column stride, float32 ...) goes through a contiguous float64 copy that is written back."""
+        if not isinstance(r, np.ndarray) or r.ndim != 2 or r.shape[0] != 6:
+            raise TypeError("rparticles must be a numpy array of shape (6, n)")
+        if not r.flags.writeable:
+            raise ValueError("rparticles is read-only: the kick works in place")
         n = r.shape[1]
-        q = np.ascontiguousarray(q, dtype=np.float64)
-        if q.shape != (n,):
+        direct = r.dtype == np.float64 and (n == 0 or (r.strides[1] == 8 and r.strides[0] % 8 == 0 and r.strides[0] >= 8 * n))
+        work = r if direct else np.ascontiguousarray(r, dtype=np.float64)
+        qc = np.ascontiguousarray(q, dtype=np.float64)
+        if qc.shape != (n,):
             raise ValueError("q_array must have one charge per particle")
-        ld = r.strides[0] // 8 if n > 0 else 0
-        self._check(self._lib.ocl_sc_kick_host(self._h, r.ctypes.data, ld, q.ctypes.data, n, float(E_GeV), float(dz),
-                                               _draws(mesh_draws)), "ocl_sc_kick_host")
+        if direct:
+            pin_host_array(work)
+        if qc is q:
+            pin_host_array(qc)                     # a temporary copy is not worth registering
+        ld = work.strides[0] // 8 if n > 0 else 0
+        self._check(self._lib.ocl_sc_kick_host(self._h, work.ctypes.data, ld, qc.ctypes.data, n, float(E_GeV),
+                                               float(dz), _draws(mesh_draws)), "ocl_sc_kick_host")
+        if not direct:
+            r[...] = work
 
     # -- stages (sharded operation) ----------------------------------------
     def collective_buffer(self, which: int):
@@ -417,6 +472,14 @@ class Solver:
                                float(bounds[1]), float(smooth_param), 1.0 if step_profile else 0.0, float(n_total))
         self._check(self._lib.ocl_sc_lsc_kick_async(self._h, ptr, ld, n, q.data_ptr(), hp, _stream_ptr(stream)),
                     "ocl_sc_lsc_kick_async")
+
+    def lsc_async_status(self, synchronise=True) -> int:
+        """0: every asynchronous LSC kick so far was applied; 1 / 2: one was skipped on the device (grid beyond
+        the asynchronous capacity / packed word too narrow) and left the particles untouched.  Clears the flag."""
+        st = C.c_int(0)
+        self._check(self._lib.ocl_sc_lsc_async_status(self._h, 1 if synchronise else 0, C.byref(st)),
+                    "ocl_sc_lsc_async_status")
+        return int(st.value)
 
     def lsc_last_params(self) -> dict:
         """Scalars the device derived for the last asynchronous kick (synchronises)."""

@@ -129,17 +129,38 @@ def test_long_grid():
     for sp in (0.004,):
         ref = r.copy()
         st = lo.lsc_kick(ref, q, E, 1.0, smooth_param=sp)
-        # the device-derived grid is sized for 8192 points: the kick is skipped and the handle says so
+        d_ref = ref[5] - r[5]
+        # the device-derived grid is sized for 8192 points.  A single apply() on an object that has never been
+        # verified must NOT drop the kick: the first asynchronous kick is checked, the skipped kick
+        # (particles untouched) is redone with the host-derived grid and the object stays in that mode.
         dev = DeviceParticleArray.from_host(_host_parray(r, q, E))
         lsc = LSC(step=1, smooth_param=sp, async_grid=True)
         lsc.apply(dev, 1.0)
-        with pytest.raises(RuntimeError, match="exceeds the buffer capacity"):
-            lsc.last_params
-        assert np.array_equal(dev.to_host().rparticles, r)
+        assert lsc.async_grid is False
+        assert lsc.last_params["nb"] == len(st["x"]) > 8192
+        d = dev.to_host().rparticles[5] - r[5]
+        assert np.abs(d - d_ref).max() <= TOL * np.abs(d_ref).max()
+        lsc.finalize()
+        # host arrays: same single apply, same fallback
+        host = _host_parray(r, q, E)
+        lsc = LSC(step=1, smooth_param=sp, async_grid=True)
+        lsc.apply(host, 1.0)
+        assert np.abs((host.rparticles[5] - r[5]) - d_ref).max() <= TOL * np.abs(d_ref).max()
+        # an overflow AFTER the verified first kick is not silent either: finalize() (and the next apply) raise
+        dev = DeviceParticleArray.from_host(_host_parray(r, q, E))
+        lsc = LSC(step=1, smooth_param=0.1, async_grid=True)
+        lsc.apply(dev, 1.0)                                     # fits: verified
+        lsc.smooth_param = sp
+        before = dev.to_host().rparticles.copy()
+        lsc.apply(dev, 1.0)                                     # skipped on the device
+        with pytest.raises(RuntimeError, match="skipped on the device"):
+            lsc.finalize()
+        assert np.array_equal(dev.to_host().rparticles, before)
+        # host-derived grid from the start
+        dev = DeviceParticleArray.from_host(_host_parray(r, q, E))
         lsc = LSC(step=1, smooth_param=sp, async_grid=False)
         lsc.apply(dev, 1.0)
-        assert lsc.last_params["nb"] == len(st["x"]) > 3072
-        d_ref = ref[5] - r[5]
+        assert lsc.last_params["nb"] == len(st["x"])
         d = dev.to_host().rparticles[5] - r[5]
         assert np.abs(d - d_ref).max() <= TOL * np.abs(d_ref).max()
 

@@ -270,8 +270,16 @@ def test_config2_vs_oracle_and_properties(native, monkeypatch):
     # step re-draws that noise; with bit-identical steps the agreement is ~7e-12)
     floor = _reference_floor(monkeypatch, r0, q0, E, nmesh, taps)
     err = field_err(Exyz.cpu().numpy(), taps["Exyz"])
-    print(f"config 2: device-vs-reference {err:.2e}, reference fp64-vs-80bit floor {floor:.2e}")
-    assert err < max(1e-10, 2 * floor)
+    steps = s.geometry()["steps"]
+    print(f"config 2: device-vs-reference {err:.2e}, reference fp64-vs-80bit floor {floor:.2e}, "
+          f"mesh steps bit-equal {[bool(a == b) for a, b in zip(steps, taps['steps'])]}")
+    # the extremal particles are re-evaluated in the reference's exact operation order (k_extent's tail), so the
+    # transverse steps are the reference's bits; the longitudinal one carries gamma0 = f(sum pz), whose last bits
+    # depend on the summation order (numpy: pairwise; device: fixed tree) and may differ by one ulp
+    assert steps[0] == taps["steps"][0] and steps[1] == taps["steps"][1]
+    assert abs(steps[2] / taps["steps"][2] - 1) < 3e-16
+    assert np.array_equal(steps, taps["steps"])          # this seed: all three bit-equal (B200, round 2)
+    assert err < 1e-10                                   # plain north-star bound, no floor escape
     s.kick_device(r, q, E, 0.1)
     got = r.cpu().numpy()
     assert row_err(got, r_ref) < 1e-10
@@ -298,18 +306,61 @@ def test_mesh_127_vs_oracle(native, monkeypatch):
     keeps the reference's operation order, so it must sit much closer to the reference
     than that floor (measured: 1.5e-10 vs 1.2e-9); bound = max(1e-10, 2*floor) as for config 2."""
     n, nmesh = 2_000_000, (127, 127, 127)
-    r0, q0, E = _bunch(n, 9)
+    for seed in (10, 9):
+        r0, q0, E = _bunch(n, seed)
+        s = native.Solver(0, nmesh)
+        r, q = dev(r0), dev(q0)
+        taps = {}
+        r_ref = r0.copy()
+        orc.sc_kick(r_ref, q0, E, 0.1, nmesh, fft="padded", workers=8, taps=taps)
+        Exyz = s.field_at_particles(r, q, E).cpu().numpy()
+        assert np.max(np.abs(s.rho() - taps["rho"])) < 1e-3 * q0[0]
+        err = field_err(Exyz, taps["Exyz"])
+        steps = s.geometry()["steps"]
+        same = np.array_equal(steps, taps["steps"])
+        assert steps[0] == taps["steps"][0] and steps[1] == taps["steps"][1]      # transverse steps: always the reference's bits
+        assert abs(steps[2] / taps["steps"][2] - 1) < 3e-16
+        if same:
+            print(f"127^3 seed {seed}: device-vs-reference {err:.2e}, mesh steps bit-equal")
+            assert err < 1e-10                      # plain north-star bound
+        else:
+            # hz differs by one ulp (gamma0 from a differently ordered sum): the reference's own cancellation
+            # noise is re-drawn; bound by twice its measured fp64-vs-80bit floor
+            floor = _reference_floor(monkeypatch, r0, q0, E, nmesh, taps)
+            print(f"127^3 seed {seed}: device-vs-reference {err:.2e}, hz one ulp apart, reference floor {floor:.2e}")
+            assert err < max(1e-10, 2 * floor)
+        s.kick_device(r, q, E, 0.1)
+        assert row_err(r.cpu().numpy(), r_ref) < 1e-10
+    assert seed == 9
+
+
+def test_mesh_255_vs_oracle(native, monkeypatch):
+    """BASELINE config 5's mesh (255^3, 512^3 box) against the oracle (padded real FFT on the host, threaded).
+    SURVEY 8c: "255^3 ... borderline; report it, don't hide it": sym_kernel's (r/h)^3 cancellation leaves the
+    REFERENCE's own field defined only to its fp64-vs-80bit floor, which is measured and printed here; the
+    device must agree with the reference to 1e-10 of max|E|, or to twice that floor where the floor is larger
+    (a mesh step one ulp apart re-draws the reference's noise)."""
+    n, nmesh = 2_000_000, (255, 255, 255)
+    r0, q0, E = _bunch(n, 12)
     s = native.Solver(0, nmesh)
     r, q = dev(r0), dev(q0)
     taps = {}
     r_ref = r0.copy()
-    orc.sc_kick(r_ref, q0, E, 0.1, nmesh, fft="padded", workers=8, taps=taps)
-    floor = _reference_floor(monkeypatch, r0, q0, E, nmesh, taps)
+    orc.sc_kick(r_ref, q0, E, 0.1, nmesh, fft="padded", workers=16, taps=taps)
     Exyz = s.field_at_particles(r, q, E).cpu().numpy()
-    assert np.max(np.abs(s.rho() - taps["rho"])) < 1e-3 * q0[0]
+    rho = s.rho()
+    assert abs(rho.sum() / q0.sum() - 1) < 1e-12
+    assert np.max(np.abs(rho - taps["rho"])) < 1e-3 * q0[0]                     # identical cell for every particle
+    phi = s.phi()
+    phi_err = np.max(np.abs(phi - taps["phi"])) / np.max(np.abs(taps["phi"]))
     err = field_err(Exyz, taps["Exyz"])
-    print(f"127^3: device-vs-reference {err:.2e}, reference fp64-vs-80bit floor {floor:.2e}")
-    assert err < max(1e-10, 2 * floor)
+    steps = s.geometry()["steps"]
+    same = np.array_equal(steps, taps["steps"])
+    floor = _reference_floor(monkeypatch, r0, q0, E, nmesh, taps)
+    print(f"255^3: field device-vs-reference {err:.2e}, potential {phi_err:.2e}, mesh steps bit-equal: {same}, "
+          f"reference fp64-vs-80bit floor {floor:.2e}")
+    assert steps[0] == taps["steps"][0] and steps[1] == taps["steps"][1]
+    assert err < (1e-10 if same and floor < 5e-11 else max(1e-10, 2 * floor))
     s.kick_device(r, q, E, 0.1)
     assert row_err(r.cpu().numpy(), r_ref) < 1e-10
 
