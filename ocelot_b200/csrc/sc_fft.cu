@@ -44,9 +44,10 @@ struct Geom {
     // M <= 128: the grids are small (63^3: 3969 z lines), so the lines per block decide how many blocks there
     // are to spread over 148 SMs.  Round 1 used 2048/M lines (125 blocks of 128 threads at M = 128: 6 % of the
     // warp slots busy, 8-16 us per pass); OCL_FFT_LINES_SMALL lines per block with one thread per 8 points
-    // gives 4x the blocks, each with a quarter of the loads in front of its first butterfly.
+    // gives more blocks, each with fewer loads in front of its first butterfly.  Measured on B200, whole solve
+    // at 63^3 (M = 128): 16 lines 50.8 us, 8 lines 42.2 us, 4 lines 54.6 us; no difference at 31^3 (M = 64).
 #ifndef OCL_FFT_LINES_SMALL
-#define OCL_FFT_LINES_SMALL 4
+#define OCL_FFT_LINES_SMALL 8
 #endif
     static constexpr int NL_SMALL = (OCL_FFT_LINES_SMALL * M > 2048) ? (2048 / M) : OCL_FFT_LINES_SMALL;
     static constexpr int T_SMALL = (NL_SMALL * M / 8 > 128) ? 128 : ((NL_SMALL * M / 8 < 32) ? 32 : NL_SMALL * M / 8);

@@ -362,7 +362,11 @@ def test_mesh_255_vs_oracle(native, monkeypatch):
     assert steps[0] == taps["steps"][0] and steps[1] == taps["steps"][1]
     assert err < (1e-10 if same and floor < 5e-11 else max(1e-10, 2 * floor))
     s.kick_device(r, q, E, 0.1)
-    assert row_err(r.cpu().numpy(), r_ref) < 1e-10
+    # rows: the kick moves a row by `moved` of its rms, so the field floor maps to floor * moved of the rms
+    moved = row_err(r_ref, r0)
+    rows = row_err(r.cpu().numpy(), r_ref)
+    print(f"255^3: rows device-vs-reference {rows:.2e} of rms (kick size {moved:.2e} of rms)")
+    assert rows < max(1e-10, 2 * floor * moved)
 
 
 def test_ragged_and_tiny_inputs(native, monkeypatch):

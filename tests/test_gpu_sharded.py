@@ -40,7 +40,7 @@ def test_sharded_wrapper_single_rank_equals_plugin():
     assert _row_err(b.to_host().rparticles, a.to_host().rparticles) < 1e-12
 
 
-def _worker(rank, world, port, n, nmesh, out, slab=False, p2p_rho=False, nvls=False):
+def _worker(rank, world, port, n, nmesh, out, slab=False, p2p_rho=False, nvls=False, p2p=True, empty_rank=None):
     import torch.distributed as dist
     from ocelot_b200 import ParticleArray, DeviceParticleArray
     from ocelot_b200.distributed import ShardedSpaceCharge, shard_bounds
@@ -51,10 +51,13 @@ def _worker(rank, world, port, n, nmesh, out, slab=False, p2p_rho=False, nvls=Fa
     try:
         r0, q0, E = _bunch(n, 4)
         lo, hi = shard_bounds(n, world, rank)
+        if empty_rank is not None:             # one rank lost all its particles (e.g. to an aperture)
+            lo, hi = (0, 0) if rank == empty_rank else (0, n)
         host = ParticleArray(hi - lo)
         host.rparticles[:], host.q_array[:], host.E = r0[:, lo:hi], q0[lo:hi], E
         shard = DeviceParticleArray.from_host(host, device=f"cuda:{rank}")
         sc = ShardedSpaceCharge(nmesh_xyz=list(nmesh), slab=slab)
+        sc.p2p = p2p                           # False: no peer-memory mailbox, NCCL collectives + deferred finish
         sc.p2p_rho = p2p_rho
         sc.nvls_rho = nvls
         sc.prepare(None)
@@ -70,9 +73,14 @@ def _worker(rank, world, port, n, nmesh, out, slab=False, p2p_rho=False, nvls=Fa
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("slab,p2p_rho,nvls", [(False, False, False), (True, False, False), (False, True, False),
-                                               (True, True, False), (False, False, True), (True, False, True)])
-def test_two_gpu_sharded_kick_matches_single_gpu(slab, p2p_rho, nvls):
+@pytest.mark.parametrize("slab,p2p_rho,nvls,p2p,empty", [
+    (False, False, False, True, None), (True, False, False, True, None), (False, True, False, True, None),
+    (True, True, False, True, None), (False, False, True, True, None), (True, False, True, True, None),
+    (False, False, False, False, None),        # pure NCCL: all-reduce / all-gather, then ocl_sc_stage_finish
+    (True, False, False, False, None),
+    (False, False, True, True, 1),             # rank 1 holds no particle: it still joins every exchange
+    (False, False, False, False, 0)])
+def test_two_gpu_sharded_kick_matches_single_gpu(slab, p2p_rho, nvls, p2p, empty):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     import torch.multiprocessing as mp
@@ -84,7 +92,7 @@ def test_two_gpu_sharded_kick_matches_single_gpu(slab, p2p_rho, nvls):
     ctx = mp.get_context("spawn")
     with ctx.Manager() as mgr:
         out = mgr.dict()
-        mp.spawn(_worker, args=(world, port, n, nmesh, out, slab, p2p_rho, nvls), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, port, n, nmesh, out, slab, p2p_rho, nvls, p2p, empty), nprocs=world, join=True)
         parts = [out[k] for k in range(world)]
     r0, q0, E = _bunch(n, 4)
     solver = native.Solver(0, nmesh)
@@ -95,7 +103,8 @@ def test_two_gpu_sharded_kick_matches_single_gpu(slab, p2p_rho, nvls):
     ref = r.cpu().numpy()
     got = np.empty_like(ref)
     for lo, hi, rr, used_nvls in parts:
-        got[:, lo:hi] = rr
+        if hi > lo:
+            got[:, lo:hi] = rr
         if nvls and not used_nvls:
             pytest.skip("no multicast mapping on this box: the NVLS reduction fell back to NCCL")
     # different reduction order across ranks: agreement to summation round-off (and its
