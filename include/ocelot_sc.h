@@ -199,6 +199,12 @@ int ocl_sc_potential_host(ocl_sc_t* h, const double* h_rho, const double steps[3
  * R[36] row-major; B[6] or NULL; T[216] (index a*36 + j*6 + k) or NULL for a first-order map. */
 int ocl_sc_map_apply(ocl_sc_t* h, double* d_r, long long ld, long long n, const double* R, const double* B,
                      const double* T, void* stream);
+/* The seven scalars ocl_sc_cavity_apply needs, from the cavity's voltage v [GV], phase phi [deg], frequency [Hz],
+ * the beam energy E [GeV] and the slice (delta_length of length; delta_length < 0 or NaN: the whole cavity):
+ * coef = {c1, c2, beta0*k, phi [rad], T566, T556, T555}, *mode = 1 (full map) or 2 (drift-like: non-physical final
+ * energy), *delta_e = V cos(phi).  Specification: CavityTM.map4cav, transformations/cavity.py:29-128. */
+int ocl_sc_cavity_coefficients(double v, double phi_deg, double freq, double E_GeV, double delta_length, double length,
+                               double coef[7], int* mode, double* delta_e);
 /* RF cavity body, CavityTM.map4cav (transformations/cavity.py:29-128): X <- R X + B, then
  *   delta <- delta0*c[0] + c[1]*(cos(c[3] - c[2]*tau0) - cos(c[3]))        (cavity.py:81-84)
  *   tau   += c[4]*delta0^2 + c[5]*tau0*delta0 + c[6]*tau0^2                 (cavity.py:126)

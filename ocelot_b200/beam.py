@@ -39,50 +39,12 @@ def apply_map(p_array, R, B=None, T=None, delta_e=0.0, length=0.0):
 
 
 def cavity_coefficients(v, phi_deg, freq, E, delta_length, length):
-    """Scalars of ``CavityTM.map4cav`` (transformations/cavity.py:29-128), restated expression by
-    expression.  Returns ``(mode, coef[7], delta_e)`` with coef = [E b0/(E1 b1), V b0/(E1 b1), b0 k,
-    phi, T566, T556, T555]; mode 2 is the drift-like branch for a non-physical final energy."""
-    m_e_GeV, c = _c.m_e_GeV, _c.speed_of_light
-    if delta_length is not None:                                   # :33-38
-        V = v * delta_length / length if length != 0 else v
-        z = delta_length
-    else:
-        V, z = v, length
-    beta0, igamma2, g0 = 1.0, 0.0, 1e10                            # :41-47
-    if E != 0.0:
-        g0 = E / m_e_GeV
-        igamma2 = 1.0 / (g0 * g0)
-        beta0 = np.sqrt(1.0 - igamma2)
-    phi = phi_deg * np.pi / 180.0                                  # :49
-    delta_e = V * np.cos(phi)                                      # :59
-    E1 = E + delta_e
-    T566 = 1.5 * z * igamma2 / (beta0 ** 3)                        # :63
-    T556 = T555 = 0.0
-    if E1 <= 0.0:                                                  # :67-69
-        return 2, [0.0, 0.0, 0.0, phi, T566, 0.0, 0.0], delta_e
-    k = 2.0 * np.pi * freq / c                                     # :72
-    g1 = E1 / m_e_GeV                                              # :75-76
-    beta1 = np.sqrt(1.0 - 1.0 / (g1 * g1))
-    c1 = E * beta0 / (E1 * beta1)                                  # :81-84
-    c2 = V * beta0 / (E1 * beta1)
-    dgamma = V / m_e_GeV                                           # :87-88
-    dg = g1 - g0
-    if abs(dg) < 1e-8 * abs(g0):                                   # :93-106
-        if abs(np.cos(phi)) < 1e-3:
-            T556 = 1.5 * z * k * dgamma / (beta0 ** 3 * g0 ** 3)
-            T555 = 0.5 * z * k * k * dgamma * dgamma / (beta0 ** 3 * g0 ** 4)
-    else:                                                          # :108-123
-        T566 = (z * (beta0 ** 3 * g0 ** 3 - beta1 ** 3 * g1 ** 3)
-                / (2.0 * beta0 * beta1 ** 3 * g0 * (g0 - g1) * g1 ** 3))
-        T556 = (beta0 * k * z * dgamma * g0 * (beta1 ** 3 * g1 ** 3 + beta0 * (g0 - g1 ** 3)) * np.sin(phi) /
-                (beta1 ** 3 * g1 ** 3 * (g0 - g1) ** 2))
-        T555 = (beta0 ** 2 * k ** 2 * z * dgamma / 2.0
-                * (dgamma * (2.0 * g0 * g1 ** 3 * (beta0 * beta1 ** 3 - 1.0)
-                             + g0 ** 2 + 3.0 * g1 ** 2 - 2.0) / (beta1 ** 3 * g1 ** 3 * (g0 - g1) ** 3) * np.sin(phi) ** 2
-                   - (g1 * g0 * (beta1 * beta0 - 1.0) + 1.0)
-                   / (beta1 * g1 * (g0 - g1) ** 2)
-                   * np.cos(phi)))
-    return 1, [c1, c2, beta0 * k, phi, T566, T556, T555], delta_e
+    """Scalars of the RF-cavity body map (specification: ``CavityTM.map4cav``, transformations/cavity.py:29-128),
+    derived inside the native library (``ocl_sc_cavity_coefficients``, csrc/sc_abi.cu).  Returns
+    ``(mode, coef[7], delta_e)`` with coef = [c1, c2, beta0*k, phi, T566, T556, T555]; mode 2 is the drift-like
+    branch for a non-physical final energy."""
+    from . import native
+    return native.cavity_coefficients(v, phi_deg, freq, E, delta_length, length)
 
 
 def apply_cavity(p_array, R, B, v, phi_deg, freq, delta_length, length, delta_e=None):

@@ -42,7 +42,12 @@ struct ocl_sc {
     cufftDoubleComplex* rho_hat = nullptr;    // M*M*(M/2+1)
     double* phi = nullptr;    // n^3
     EQuad* equad = nullptr;   // 3*n^3 (+1 pad) quads: the field table the gather reads
-    int layout = 1;           // 0: z-fastest table, independent gathers | 1: x-fastest table, lane-pair gathers
+    // 0: z-fastest table, independent gathers | 1: x-fastest table, lane-pair gathers, rows staged through shared
+    // memory (cp.async) | 2: same table, rows prefetched into registers.  Default (-1 -> resolved at create): 2 while
+    // the table stays near the L2 (the gather is then bound by the L1TEX data stage, which the staging also loads:
+    // 12.5 M / 127^3 368 -> 361 us, 1 M / 63^3 37.2 -> 34.8 us on B200), 1 for larger tables (DRAM-bound: the
+    // deeper shared-memory pipeline wins, 50 M / 255^3 2.70 vs 2.86 ms).  OCL_SC_GATHER overrides.
+    int layout = -1;
     cufftHandle plan_fwd = 0, plan_inv = 0;
     bool plans = false;
     // slab mode (multi-GPU solve)
@@ -392,7 +397,8 @@ int ocl_sc_create(int device, int nx, int ny, int nz, long long max_particles, o
     TRY(cudaMemset(h->equad + n3 * 3, 0, sizeof(EQuad)));          // pad record behind the x-fastest table
     {
         const char* env = getenv("OCL_SC_GATHER");
-        if (env) h->layout = atoi(env) ? 1 : 0;
+        if (env) h->layout = atoi(env);
+        if (h->layout < 0 || h->layout > 2) h->layout = (sizeof(EQuad) * n3 * 3 <= (size_t)400 << 20) ? 2 : 1;
         field_init_kernels();
     }
     TRY(cudaMemset(h->rho, 0, sizeof(double) * n3));
@@ -653,7 +659,7 @@ int ocl_sc_slab_finish(ocl_sc_t* h, const double* mesh_draws, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
     (void)mesh_draws;
-    launch_field(h->phi, h->rs, h->md, h->equad, h->layout, st);
+    launch_field(h->phi, h->rs, h->md, h->equad, h->layout ? 1 : 0, st);
     h->launches += 1;
     mark(h, T_FIELD, st);
     return check_launch(h, "slab_finish");
@@ -722,7 +728,7 @@ int ocl_sc_stage_solve(ocl_sc_t* h, const double* mesh_draws, void* stream) {
         launch_crop_phi(h->real_buf, h->rs, h->md, h->phi, st);
         h->launches += 1;
     }
-    launch_field(h->phi, h->rs, h->md, h->equad, h->layout, st);
+    launch_field(h->phi, h->rs, h->md, h->equad, h->layout ? 1 : 0, st);
     h->launches += 1;
     mark(h, T_FIELD, st);
     return check_launch(h, "stage_solve");
@@ -1051,6 +1057,59 @@ int ocl_sc_cavity_apply(ocl_sc_t* h, double* d_r, long long ld, long long n, con
     launch_map_apply(d_r, ld, n, mc, (cudaStream_t)stream);
     h->launches += 1;
     return check_launch(h, "k_map_apply(cavity)");
+}
+
+/* Scalars of the RF-cavity body map.  Specification: CavityTM.map4cav (transformations/cavity.py:29-128).
+ * Written in terms of the normalised momenta eta = beta*gamma before and after the cavity:
+ *   c1 = eta0/eta1, c2 = dgamma*beta0/eta1 (energy-deviation rescaling and RF curvature, cavity.py:81-84),
+ *   kb = beta0*k, and the path-length terms T566, T556, T555 (cavity.py:63, :93-123).
+ * delta_length < 0 or NaN means "whole cavity" (the reference's delta_length=None). */
+int ocl_sc_cavity_coefficients(double v, double phi_deg, double freq, double E_GeV, double delta_length, double length,
+                               double coef[7], int* mode, double* delta_e) {
+    if (!coef || !mode || !delta_e) return 1;
+    double m_e_eV, m_e_GeV, eps0, pi, c;
+    constants(m_e_eV, m_e_GeV, eps0, pi, c);
+    const bool partial = delta_length == delta_length && delta_length >= 0.0;
+    const double z = partial ? delta_length : length;
+    const double V = partial ? (length != 0.0 ? v * delta_length / length : v) : v;
+    const double phi = phi_deg * pi / 180.0;
+    const double sn = std::sin(phi), cs = std::cos(phi);
+    // entrance: a beam "at rest" (E == 0) is treated as ultra-relativistic by the reference (beta0 = 1, gamma0 = 1e10)
+    const double g0 = E_GeV != 0.0 ? E_GeV / m_e_GeV : 1e10;
+    const double inv_g0sq = E_GeV != 0.0 ? 1.0 / (g0 * g0) : 0.0;
+    const double b0 = E_GeV != 0.0 ? std::sqrt(1.0 - inv_g0sq) : 1.0;
+    const double b0cube = b0 * b0 * b0;
+    *delta_e = V * cs;
+    const double E1 = E_GeV + *delta_e;
+    for (int i = 0; i < 7; ++i) coef[i] = 0.0;
+    coef[3] = phi;
+    coef[4] = 1.5 * z * inv_g0sq / b0cube;                        // drift-like T566
+    if (E1 <= 0.0) { *mode = 2; return 0; }                       // non-physical final energy: drift only
+    *mode = 1;
+    const double k = 2.0 * pi * freq / c;
+    const double g1 = E1 / m_e_GeV;
+    const double b1 = std::sqrt(1.0 - 1.0 / (g1 * g1));
+    const double eta0 = b0 * g0, eta1 = b1 * g1;
+    const double eta0cube = b0cube * g0 * g0 * g0, eta1cube = b1 * b1 * b1 * g1 * g1 * g1;
+    const double dgam = V / m_e_GeV;                              // gamma gained at crest
+    coef[0] = E_GeV * b0 / (E1 * b1);
+    coef[1] = V * b0 / (E1 * b1);
+    coef[2] = b0 * k;
+    const double gap = g0 - g1;
+    if (std::fabs(g1 - g0) < 1e-8 * std::fabs(g0)) {              // zero crossing: the general forms are 0/0
+        if (std::fabs(cs) < 1e-3) {
+            coef[5] = 1.5 * z * k * dgam / eta0cube;
+            coef[6] = 0.5 * z * k * k * dgam * dgam / (eta0cube * g0);
+        }
+        return 0;
+    }
+    coef[4] = z * (eta0cube - eta1cube) / (2.0 * eta0 * eta1cube * gap);
+    coef[5] = b0 * k * z * dgam * g0 * (eta1cube + b0 * (g0 - g1 * g1 * g1)) * sn / (eta1cube * gap * gap);
+    const double curv = dgam * (2.0 * g0 * g1 * g1 * g1 * (b0 * b1 * b1 * b1 - 1.0) + g0 * g0 + 3.0 * g1 * g1 - 2.0)
+                        / (eta1cube * gap * gap * gap) * sn * sn;
+    const double lin = (g1 * g0 * (b1 * b0 - 1.0) + 1.0) / (eta1 * gap * gap) * cs;
+    coef[6] = b0 * b0 * k * k * z * dgam / 2.0 * (curv - lin);
+    return 0;
 }
 
 int ocl_sc_beam_moments(ocl_sc_t* h, const double* d_r, long long ld, long long n, double* h_out, void* stream) {

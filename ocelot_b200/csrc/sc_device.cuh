@@ -471,6 +471,29 @@ __device__ __forceinline__ void pipelined_sweep(const double* const (&base)[NR],
     cp_async_wait<0>();
 }
 
+// The same sweep without shared-memory staging: the next trip's rows are loaded straight into registers
+// (plain LDG) before the current particle's arithmetic, so they are in flight during it.  Costs NR more
+// registers per thread than the cp.async pipeline and saves its LDGSTS + LDS traffic through the L1TEX data
+// stage -- the unit that bounds the gather kernel.  Warp-uniform trip count; body(i, v, valid).
+template <int NR, typename F>
+__device__ __forceinline__ void prefetch_sweep(const double* const (&base)[NR], int n, F&& body) {
+    const int stride = (int)gridDim.x * kSweepThreads;
+    const int lane = (int)(threadIdx.x & 31);
+    int i = (int)blockIdx.x * kSweepThreads + (int)threadIdx.x;
+    double cur[NR], nxt[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) cur[k] = i < n ? __ldcs(base[k] + i) : 0.0;
+    while (i - lane < n) {
+        const int in = i + stride;
+#pragma unroll
+        for (int k = 0; k < NR; ++k) nxt[k] = in < n ? __ldcs(base[k] + in) : 0.0;
+        body(i, cur, i < n);
+#pragma unroll
+        for (int k = 0; k < NR; ++k) cur[k] = nxt[k];
+        i = in;
+    }
+}
+
 // ---- block reductions (fixed order => deterministic for a fixed launch shape) ----
 template <typename Op>
 __device__ __forceinline__ double warp_reduce(double v, Op op) {

@@ -508,7 +508,8 @@ __global__ void __launch_bounds__(kThreads, MINB) k_gather_kick(double* __restri
     pdl_enter();
     const RefParams rp = kp_ref(kp);
     const double cdT = kp_cdT(kp);
-    __shared__ double pipe[kPipeDepth * 6 * kThreads];
+    constexpr bool STAGED = LAYOUT < 2;                  // LAYOUT 2: pair gather with register prefetch of the rows
+    __shared__ double pipe[STAGED ? kPipeDepth * 6 * kThreads : 1];
     __shared__ Geo sg;
     load_geo(rs.geo, &sg);
     const Frame f = sg.f;
@@ -525,7 +526,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_gather_kick(double* __restri
         rotate_stretch(f, c.x, c.y, c.z, a, b, g);
         to_grid(m, a, b, g, g0, g1, g2);
         double e0, e1, e2;
-        if constexpr (LAYOUT == 1) {
+        if constexpr (LAYOUT >= 1) {
             gather_pair(ex, ey, ez, md.nx, md.ny, md.nz, g0, g1, g2, e0, e1, e2);                // :202-204
             e0 *= f.gamma0; e1 *= f.gamma0;
         } else {
@@ -555,7 +556,9 @@ __global__ void __launch_bounds__(kThreads, MINB) k_gather_kick(double* __restri
             r[5 * ld + i] = delta;
         }
     };
-    if constexpr (LAYOUT == 1) {
+    if constexpr (LAYOUT == 2) {
+        prefetch_sweep<6>(base, (int)n, body);
+    } else if constexpr (LAYOUT == 1) {
         pipelined_sweep<6, kPipeDepth, true>(base, (int)n, pipe, body);
     } else {
         pipelined_sweep<6, kPipeDepth, false>(base, (int)n, pipe,
@@ -796,8 +799,9 @@ static int gather_blocks(long long n, int layout) {
         const char* e = getenv("OCL_SC_GK_BLOCKS");
         forced = e ? atoi(e) : 0;
     }
-    if (forced == 2 || forced == 3) return forced;
-    return (layout == 1 && n >= 4000000) ? 3 : 2;
+    if (forced == 2 || forced == 3 || (forced == 4 && layout == 2)) return forced;
+    (void)n; (void)layout;
+    return 2;
 }
 template <int LAYOUT, int MINB>
 static void launch_gather_kick_l(double* r, long long ld, long long n, KP kp, ReduceState rs, MeshDims md,
@@ -813,7 +817,10 @@ static void launch_gather_kick_l(double* r, long long ld, long long n, KP kp, Re
 void launch_gather_kick(double* r, long long ld, long long n, KP kp, ReduceState rs, MeshDims md,
                         const EQuad* equad, double* exyz_out, int do_kick, int layout, cudaStream_t st) {
     const int mb = gather_blocks(n, layout);
-    if (layout == 1 && mb == 3) launch_gather_kick_l<1, 3>(r, ld, n, kp, rs, md, equad, exyz_out, do_kick, st);
+    if (layout == 2 && mb == 4) launch_gather_kick_l<2, 4>(r, ld, n, kp, rs, md, equad, exyz_out, do_kick, st);
+    else if (layout == 2 && mb == 3) launch_gather_kick_l<2, 3>(r, ld, n, kp, rs, md, equad, exyz_out, do_kick, st);
+    else if (layout == 2) launch_gather_kick_l<2, 2>(r, ld, n, kp, rs, md, equad, exyz_out, do_kick, st);
+    else if (layout == 1 && mb == 3) launch_gather_kick_l<1, 3>(r, ld, n, kp, rs, md, equad, exyz_out, do_kick, st);
     else if (layout == 1) launch_gather_kick_l<1, 2>(r, ld, n, kp, rs, md, equad, exyz_out, do_kick, st);
     else if (mb == 3) launch_gather_kick_l<0, 3>(r, ld, n, kp, rs, md, equad, exyz_out, do_kick, st);
     else launch_gather_kick_l<0, 2>(r, ld, n, kp, rs, md, equad, exyz_out, do_kick, st);

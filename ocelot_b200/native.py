@@ -71,6 +71,7 @@ _SIGNATURES = {
     "ocl_sc_map_apply": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _dp, _dp, _vp]),
     "ocl_sc_cavity_apply": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _dp, _dp, C.c_int, _vp]),
     "ocl_sc_beam_moments": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _vp]),
+    "ocl_sc_cavity_coefficients": (C.c_int, [C.c_double] * 6 + [_dp, C.POINTER(C.c_int), _dp]),
     "ocl_sc_lsc_stats": (C.c_int, [_vp, _vp, _ll, _ll, _vp, _dp, _vp]),
     "ocl_sc_lsc_kick": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _vp]),
     "ocl_sc_lsc_deposit": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _vp]),
@@ -158,6 +159,18 @@ def constants() -> dict:
     out = (C.c_double * 5)()
     load().ocl_sc_get_constants(out)
     return dict(m_e_eV=out[0], m_e_GeV=out[1], epsilon_0=out[2], pi=out[3], speed_of_light=out[4])
+
+
+def cavity_coefficients(v, phi_deg, freq, E, delta_length, length):
+    """(mode, coef[7], delta_e) of the RF-cavity body map (ocl_sc_cavity_coefficients)."""
+    coef = (C.c_double * 7)()
+    mode, de = C.c_int(0), C.c_double(0.0)
+    dl = float("nan") if delta_length is None else float(delta_length)
+    rc = load().ocl_sc_cavity_coefficients(float(v), float(phi_deg), float(freq), float(E), dl, float(length),
+                                           coef, C.byref(mode), C.byref(de))
+    if rc != 0:
+        raise RuntimeError("ocl_sc_cavity_coefficients failed")
+    return int(mode.value), list(coef), float(de.value)
 
 
 def fft_size(n: int) -> int:

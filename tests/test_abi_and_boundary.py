@@ -238,3 +238,29 @@ def test_resident_track_loop_drives_reference_navigator(monkeypatch):
         assert np.max(np.abs(dev.rparticles[row] - p_ref.rparticles[row])) <= 1e-13 * np.std(p_ref.rparticles[row])
     assert abs(tws[-1].xx / tws_ref[-1].xx - 1) < 1e-12 and abs(tws[-1].emit_x / tws_ref[-1].emit_x - 1) < 1e-9
     assert abs(tws[-1].s - tws_ref[-1].s) < 1e-12
+
+
+def test_cavity_coefficients_from_the_library_match_the_oracle_map():
+    """ocl_sc_cavity_coefficients (host arithmetic inside the C library, no GPU needed) against the oracle's
+    restatement of CavityTM.map4cav (cavity.py:29-128) over accelerating, decelerating, zero-crossing,
+    partial-length and non-physical cases: the longitudinal map built from the seven scalars must reproduce
+    the oracle's rows 4 and 5."""
+    from oracle import sc_oracle as orc
+    from ocelot_b200.beam import cavity_coefficients
+    rng = np.random.RandomState(2)
+    r0 = np.zeros((6, 200))
+    r0[4], r0[5] = rng.randn(200) * 1e-3, rng.randn(200) * 1e-3
+    cases = [(0.02, 18.0, 1.3e9, 0.005, None, 1.0), (0.02, 0.0, 1.3e9, 0.13, 0.25, 1.0), (0.04, 160.0, 3.9e9, 0.5, None, 0.35),
+             (0.01, 90.0, 1.3e9, 0.1, None, 1.0), (0.01, -90.0, 1.3e9, 0.1, 0.5, 1.0), (0.0, 30.0, 1.3e9, 0.2, None, 1.0),
+             (0.3, 180.0, 1.3e9, 0.1, None, 1.0), (0.02, 25.0, 1.3e9, 0.0, None, 1.0), (0.02, 45.0, 1.3e9, 0.05, 0.0, 0.0)]
+    for v, phi, f, E, dl, L in cases:
+        want = r0.copy()
+        de_ref = orc.cavity_map(want, np.eye(6), np.zeros(6), v, phi, f, E, dl, L)
+        mode, c, de = cavity_coefficients(v, phi, f, E, dl, L)
+        assert de == pytest.approx(de_ref, rel=1e-15, abs=1e-300)
+        x4, x5 = r0[4], r0[5]
+        y5 = x5 * c[0] + c[1] * (np.cos(-x4 * c[2] + c[3]) - np.cos(c[3])) if mode == 1 else x5
+        y4 = x4 + c[4] * x5 * x5 + c[5] * x4 * x5 + c[6] * x4 * x4
+        assert (mode == 2) == (E + de_ref <= 0)
+        assert np.max(np.abs(y5 - want[5])) <= 1e-13 * max(1e-30, np.max(np.abs(want[5]))), (v, phi, E)
+        assert np.max(np.abs(y4 - want[4])) <= 1e-13 * np.max(np.abs(want[4])), (v, phi, E)
