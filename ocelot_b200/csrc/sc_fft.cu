@@ -64,6 +64,9 @@ struct Geom {
 #endif
     static constexpr bool INPLACE = M >= OCL_FFT_INPLACE_MIN;
     static constexpr size_t SMEM = sizeof(double2) * ((INPLACE ? 1 : 2) * (size_t)ELEMS);
+    // direct-I/O transforms of at most two stages (every M <= 256) stage through ONE buffer: forward / inverse
+    // outer passes and the real-even passes ask for this much, which lets a fourth block share an SM at M = 256
+    static constexpr size_t SMEM_ONE = sizeof(double2) * (size_t)ELEMS;
 #ifndef OCL_FFT512_MINB
 #define OCL_FFT512_MINB 2
 #endif
@@ -266,6 +269,70 @@ __device__ __forceinline__ double2* block_fft(double2* x, double2* y, const doub
     return x;
 }
 
+// ---------------------------------------------------------------------------
+// Stages with pluggable source and sink.  The passes along an OUTER axis read and write global memory with the
+// line index fastest, which is exactly the (butterfly j, line l) work distribution of a stage: the first stage can
+// take its R inputs straight from global memory and the last stage can hand its R outputs straight to the
+// consumer (global store, or the K_hat multiply of the x pass), so a two-stage transform touches shared memory
+// once (one write, one read) instead of three times.  The FFT kernels are bound by the shared-memory / L1TEX data
+// stage (profiles/r1_all_kernels_c4_summary.csv: k_cplx_outer<256,2> 67 % L1TEX, 27 % fp64), so this is where
+// their time goes.  src(e, l) returns element e of line l; dst(e, l, v) consumes it.
+// ---------------------------------------------------------------------------
+template <int M>
+struct SmemIO {
+    double2* p;
+    __device__ __forceinline__ double2 operator()(int e, int l) const { return p[e * Geom<M>::NLP + l]; }
+    __device__ __forceinline__ void operator()(int e, int l, double2 v) const { p[e * Geom<M>::NLP + l] = v; }
+};
+
+template <bool INV, int M, int Ns, int R, typename Src, typename Dst>
+__device__ __forceinline__ void fft_stage_io(const Src& src, const Dst& dst, const double2* __restrict__ tw) {
+    constexpr int NL = Geom<M>::NL;
+    constexpr int nb = M / R;
+    constexpr int step = M / (Ns * R);
+    constexpr int total = nb * NL;
+    for (int t = threadIdx.x; t < total; t += Geom<M>::T) {
+        const int j = t / NL, l = t % NL;
+        const int k = j & (Ns - 1);
+        double2 v[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) v[r] = src(j + r * nb, l);
+        if (Ns > 1) {
+#pragma unroll
+            for (int r = 1; r < R; ++r) {
+                double2 w = __ldg(tw + r * k * step);
+                if (INV) w.y = -w.y;
+                v[r] = cmul(v[r], w);
+            }
+        }
+        dft<INV, R>(v);
+        const int base = (j - k) * R + k;
+#pragma unroll
+        for (int r = 0; r < R; ++r) dst(base + r * Ns, l, v[r]);
+    }
+}
+
+// whole transform: first stage from src, last stage into dst, shared memory (buffers a, b) in between.
+// Leaves a barrier-free exit: the caller synchronises before reusing the buffers.
+template <bool INV, int M, int Ns, typename Src, typename Dst>
+__device__ __forceinline__ void fft_io(const Src& src, const Dst& dst, double2* a, double2* b, const double2* tw) {
+    constexpr int R = radix_for(M / Ns);
+    constexpr bool last = Ns * R == M;
+    if constexpr (Ns == 1 && last) {
+        fft_stage_io<INV, M, Ns, R>(src, dst, tw);
+    } else if constexpr (Ns == 1) {
+        fft_stage_io<INV, M, Ns, R>(src, SmemIO<M>{a}, tw);
+        __syncthreads();
+        fft_io<INV, M, Ns * R>(src, dst, a, b, tw);
+    } else if constexpr (last) {
+        fft_stage_io<INV, M, Ns, R>(SmemIO<M>{a}, dst, tw);
+    } else {
+        fft_stage_io<INV, M, Ns, R>(SmemIO<M>{a}, SmemIO<M>{b}, tw);
+        __syncthreads();
+        fft_io<INV, M, Ns * R>(src, dst, b, a, tw);
+    }
+}
+
 __device__ __forceinline__ double green_entry_dev(const double* __restrict__ G, int gy, int gz, int i, int j, int k) {
     const size_t sx = (size_t)gy * gz, sy = gz;
     const double* lo = G + (size_t)i * sx + (size_t)j * sy + k;
@@ -335,6 +402,27 @@ __global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_real_even_outer(c
     const int pairs = min(NL, pairs_total - pair0);
     const double* src = in + (size_t)batch * n * inner;
     double* dst = out + (size_t)batch * (H + 1) * inner;
+    if constexpr (!Geom<M>::INPLACE) {
+        // direct-I/O path: the even extension is resolved in the source functor (element o and M - o are the same
+        // sample), the first H + 1 outputs go straight to global memory
+        auto gsrc = [&](int o, int p) -> double2 {
+            const int oo = o < n ? o : ((M - o) < n ? M - o : -1);
+            if (oo < 0 || p >= pairs) return make_double2(0.0, 0.0);
+            const int f = 2 * (pair0 + p);
+            const double e1 = __ldg(src + (size_t)oo * inner + f);
+            const double e2 = (f + 1 < inner) ? __ldg(src + (size_t)oo * inner + f + 1) : 0.0;
+            return make_double2(e1, e2);
+        };
+        auto gdst = [&](int ko, int p, double2 v) {
+            if (ko > H || p >= pairs) return;
+            const int f = 2 * (pair0 + p);
+            dst[(size_t)ko * inner + f] = v.x;
+            if (f + 1 < inner) dst[(size_t)ko * inner + f + 1] = v.y;
+        };
+        fft_io<false, M, 1>(gsrc, gdst, s.a, s.b, s.tw);
+        pdl_trigger();
+        return;
+    }
     for (int t = threadIdx.x; t < M * NLP; t += Geom<M>::T) s.a[t] = make_double2(0.0, 0.0);
     __syncthreads();
     {   // p fastest: adjacent inner indices; U independent load pairs in flight per thread
@@ -457,6 +545,51 @@ __global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_cplx_outer(const 
     double2* dst = out + (size_t)batch * n_out * inner + f0;
     // chunk-layout address of element (x plane = batch, line f)
     auto chunk = [&](int f) -> size_t { return ((size_t)(f / sm.fs) * sm.sx + batch) * sm.fs + f % sm.fs; };
+    if constexpr (!Geom<M>::INPLACE) {
+        // direct-I/O path (M <= 256): inputs from global memory into the first stage, outputs of the last stage
+        // straight to global memory (MODE 0/1) or through the K_hat multiply into the inverse transform (MODE 2)
+        auto gsrc = [&](int o, int l) -> double2 {
+            if (o >= n_in || l >= nl) return make_double2(0.0, 0.0);
+            if (sm.mode == 2) return in[chunk(o * inner + f0 + l)];
+            return src[(size_t)o * inner + l];
+        };
+        auto gdst = [&](int o, int l, double2 v) {
+            if (o >= n_out || l >= nl) return;
+            if (sm.mode == 1) out[chunk(o * inner + f0 + l)] = v;
+            else dst[(size_t)o * inner + l] = v;
+        };
+        __syncthreads();
+        if constexpr (MODE == 0) {
+            fft_io<false, M, 1>(gsrc, gdst, s.a, s.b, s.tw);
+            pdl_trigger();
+        } else if constexpr (MODE == 1) {
+            fft_io<true, M, 1>(gsrc, gdst, s.a, s.b, s.tw);
+            pdl_trigger();
+        } else {
+            const int hz1 = md.mz / 2 + 1, hy1 = md.my / 2 + 1;
+            const size_t kplane = (size_t)hy1 * hz1;
+            // spectrum element kx of line l, times the real even K_hat, lands in buffer b for the inverse transform
+            // every work item of this thread belongs to the same line (T is a multiple of NL): its (ky, kz) column
+            // of K_hat is located once
+            const int lt = threadIdx.x % Geom<M>::NL;
+            const double* kcol = nullptr;
+            if (lt < nl) {
+                const int f = f0 + lt + (sm.mode == 3 ? sm.f_base : 0);
+                const int ky = f / hz1, kz = f - ky * hz1;
+                kcol = khat + (size_t)min(ky, md.my - ky) * hz1 + kz;
+            }
+            auto mult = [&](int kx, int l, double2 v) {
+                const double g = kcol ? __ldg(kcol + (size_t)min(kx, M - kx) * kplane) : 0.0;
+                s.b[kx * Geom<M>::NLP + l] = make_double2(v.x * g, v.y * g);
+            };
+            fft_io<false, M, 1>(gsrc, mult, s.a, s.b, s.tw);
+            __syncthreads();
+            // inverse: source = buffer b; intermediate stages may use a (free again after the barrier above)
+            fft_io<true, M, 1>(SmemIO<M>{s.b}, gdst, s.a, s.b, s.tw);
+            pdl_trigger();
+        }
+        return;
+    }
     {   // global -> shared, U independent 16-byte loads in flight per thread
         constexpr int PER = NL * M / Geom<M>::T, U = PER < 8 ? PER : 8;
         static_assert(PER % U == 0, "load batching");
@@ -614,14 +747,14 @@ void launch_khat(const double* gtab, MeshDims md, FftWork w, cudaStream_t st) {
     OCL_FFT_DISPATCH(md.my,   // y: per a, in [ny][hz1] -> Q[a][hy1][hz1]
         const int pb = Geom<MM>::NL;
         const int blocks_per_batch = ((hz1 + 1) / 2 + pb - 1) / pb;
-        launch_k(k_real_even_outer<MM>, dim3(blocks_per_batch * md.nx), dim3(Geom<MM>::T), Geom<MM>::SMEM, st, w.P, w.Q, md.ny, hz1,
+        launch_k(k_real_even_outer<MM>, dim3(blocks_per_batch * md.nx), dim3(Geom<MM>::T), Geom<MM>::SMEM_ONE, st, w.P, w.Q, md.ny, hz1,
                                                                                            w.tw_y);
     )
     OCL_FFT_DISPATCH(md.mx,   // x: in [nx][hy1*hz1] -> khat[hx1][hy1*hz1]
         const int inner = hy1 * hz1;
         const int pb = Geom<MM>::NL;
         const int blocks = ((inner + 1) / 2 + pb - 1) / pb;
-        launch_k(k_real_even_outer<MM>, dim3(blocks), dim3(Geom<MM>::T), Geom<MM>::SMEM, st, w.Q, w.khat, md.nx, inner, w.tw_x);
+        launch_k(k_real_even_outer<MM>, dim3(blocks), dim3(Geom<MM>::T), Geom<MM>::SMEM_ONE, st, w.Q, w.khat, md.nx, inner, w.tw_x);
     )
 }
 
@@ -637,7 +770,7 @@ void launch_convolve_pre(const double* rho, PeerRho pr, MeshDims md, FftWork w, 
     OCL_FFT_DISPATCH(md.my,   // y forward: per i, [ny][hz1] -> [My][hz1]
         const int lb = Geom<MM>::NL;
         const int bpb = (hz1 + lb - 1) / lb;
-        launch_k(k_cplx_outer<MM, 0>, dim3(bpb * md.nx), dim3(Geom<MM>::T), Geom<MM>::SMEM, st, w.A, w.B, md.ny, md.my, hz1, w.tw_y,
+        launch_k(k_cplx_outer<MM, 0>, dim3(bpb * md.nx), dim3(Geom<MM>::T), Geom<MM>::SMEM_ONE, st, w.A, w.B, md.ny, md.my, hz1, w.tw_y,
                                                                              nullptr, md, SlabMap{});
     )
 }
@@ -655,7 +788,7 @@ void launch_convolve_post(MeshDims md, FftWork w, const double* h3, double four_
     OCL_FFT_DISPATCH(md.my,   // y inverse: per i, [My][hz1] -> [ny][hz1]
         const int lb = Geom<MM>::NL;
         const int bpb = (hz1 + lb - 1) / lb;
-        launch_k(k_cplx_outer<MM, 1>, dim3(bpb * md.nx), dim3(Geom<MM>::T), Geom<MM>::SMEM, st, w.B, w.A, md.my, md.ny, hz1, w.tw_y,
+        launch_k(k_cplx_outer<MM, 1>, dim3(bpb * md.nx), dim3(Geom<MM>::T), Geom<MM>::SMEM_ONE, st, w.B, w.A, md.my, md.ny, hz1, w.tw_y,
                                                                              nullptr, md, SlabMap{});
     )
     OCL_FFT_DISPATCH(md.mz,
@@ -683,7 +816,7 @@ void launch_slab_forward(const double* rho_slab, PeerRho pr, long long line_offs
     OCL_FFT_DISPATCH(md.my,   // y forward, stored in chunk layout for the all-to-all
         const int lb = Geom<MM>::NL;
         const int bpb = (hz1 + lb - 1) / lb;
-        launch_k(k_cplx_outer<MM, 0>, dim3(bpb * sx), dim3(Geom<MM>::T), Geom<MM>::SMEM, st, w.A, xchg, md.ny, md.my, hz1, w.tw_y,
+        launch_k(k_cplx_outer<MM, 0>, dim3(bpb * sx), dim3(Geom<MM>::T), Geom<MM>::SMEM_ONE, st, w.A, xchg, md.ny, md.my, hz1, w.tw_y,
                                                                           nullptr, md, sm);
     )
 }
@@ -708,7 +841,7 @@ void launch_slab_inverse(const double2* xchg, MeshDims md, int sx, int fs, FftWo
     OCL_FFT_DISPATCH(md.my,   // y inverse, read from chunk layout
         const int lb = Geom<MM>::NL;
         const int bpb = (hz1 + lb - 1) / lb;
-        launch_k(k_cplx_outer<MM, 1>, dim3(bpb * sx), dim3(Geom<MM>::T), Geom<MM>::SMEM, st, xchg, w.A, md.my, md.ny, hz1, w.tw_y,
+        launch_k(k_cplx_outer<MM, 1>, dim3(bpb * sx), dim3(Geom<MM>::T), Geom<MM>::SMEM_ONE, st, xchg, w.A, md.my, md.ny, hz1, w.tw_y,
                                                                           nullptr, md, sm);
     )
     OCL_FFT_DISPATCH(md.mz,

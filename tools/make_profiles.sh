@@ -23,7 +23,7 @@ has lsc && ncu --set full --clock-control none -k regex:"k_lsc_" -s 17 -c 8 \
     -o gpurun_out/${TAG}_lsc_kernels_c4 -f python tools/prof_lsc.py 12500000 >> gpurun_out/prof.log 2>&1
 # 255^3 mesh (512^3 box): launch list of one kick
 has c5 && ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/${TAG}_launches_c5.csv \
-    python tools/prof_kick.py 5000000 255 3 >> gpurun_out/prof.log 2>&1
+    python tools/prof_kick.py 50000000 255 3 >> gpurun_out/prof.log 2>&1
 tail -2 gpurun_out/prof.log
 # condense on the box, keep only the dominant kernel's full reports
 PROFILES_OUT=gpurun_out/profiles_${TAG} python tools/summarise_profiles.py ${TAG}
