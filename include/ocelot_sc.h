@@ -133,9 +133,9 @@ int ocl_sc_set_peer_rho(ocl_sc_t* h, int rank, int world, void* const* peer_rho)
 /* NVLS variant of the charge-grid reduction: `local_rho` is this rank's part of a symmetric allocation
  * of nx_pad*ny*nz doubles that is also mapped as one multicast range `multicast_rho` (e.g. torch
  * symmetric memory: buffer_ptrs[rank], multicast_ptr).  ocl_sc_nvls_reduce_rho then replaces the NCCL
- * all-reduce (redundant solve) or reduce-scatter (slab solve) of OCL_SC_BUF_RHO by ONE kernel: entry
- * barrier over the mailbox, multimem.ld_reduce / multimem.st (the NVSwitch sums each element once, so
- * every rank ends up with bit-identical sums), exit barrier.  Needs ocl_sc_mailbox_init. */
+ * all-reduce (redundant solve) or reduce-scatter (slab solve) of OCL_SC_BUF_RHO: barrier over the
+ * mailbox, one kernel of multimem.ld_reduce / multimem.st (the NVSwitch sums each element once, so
+ * every rank ends up with bit-identical sums), barrier.  Needs ocl_sc_mailbox_init. */
 int ocl_sc_set_multicast_rho(ocl_sc_t* h, void* local_rho, void* multicast_rho);
 int ocl_sc_nvls_reduce_rho(ocl_sc_t* h, void* stream);
 

@@ -63,6 +63,8 @@ struct ocl_sc {
     PeerRho peer_rho{};                       // world > 0: rho lives in caller-owned symmetric memory
     double* own_rho = nullptr;                // the cudaMalloc'ed grid (kept for freeing)
     double* mc_rho = nullptr;                 // multicast mapping of every rank's rho (NVLS reduction)
+    int debug_skip = 0;                       // timing experiments only (OCL_SC_DEBUG_SKIP): bit 0/1/2 = leave out the
+                                              // momentum exchange / extent exchange / rho reduction of a sharded kick
     // host arrays page-locked in place on first use (numpy buffers persist across kicks)
     bool pin_host = false;
     void* pinned[2] = {nullptr, nullptr};
@@ -396,6 +398,7 @@ int ocl_sc_create(int device, int nx, int ny, int nz, long long max_particles, o
     TRY(cudaMalloc(&h->equad, sizeof(EQuad) * (n3 * 3 + 1)));
     TRY(cudaMemset(h->equad + n3 * 3, 0, sizeof(EQuad)));          // pad record behind the x-fastest table
     {
+        if (const char* dbg = getenv("OCL_SC_DEBUG_SKIP")) h->debug_skip = atoi(dbg);
         const char* env = getenv("OCL_SC_GATHER");
         if (env) h->layout = atoi(env);
         if (h->layout < 0 || h->layout > 2) h->layout = (sizeof(EQuad) * n3 * 3 <= (size_t)400 << 20) ? 2 : 1;
@@ -535,19 +538,20 @@ int ocl_sc_nvls_reduce_rho(ocl_sc_t* h, void* stream) {
     ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
+    if (h->debug_skip & 4) return 0;
     const int world = h->mb.world, rank = h->mb.rank;
-    // one kernel: barrier ("every rank's deposit is complete"), in-switch reduction, barrier ("every slice final")
+    // barrier ("every rank's deposit is complete"), in-switch reduction, barrier ("every slice final")
     if (h->slab_world) {                                               // reduce-scatter into this rank's x-slab
         const long long plane = (long long)h->md.ny * h->md.nz;
         const long long lo = (long long)h->slab_rank * h->sx * plane;
-        launch_nvls_reduce(h->mc_rho, lo, lo + (long long)h->sx * plane, h->rho_slab, h->mb, h->rs.ticket + 4, h->mb_err, st);
+        launch_nvls_reduce(h->mc_rho, lo, lo + (long long)h->sx * plane, h->rho_slab, h->mb, h->rs, h->rs.ticket + 4, h->mb_err, st);
     } else {                                                           // all-reduce in place
         const long long n3 = (long long)h->rho_count;
         const long long chunk = (n3 + world - 1) / world;
         const long long lo = std::min(n3, (long long)rank * chunk), hi = std::min(n3, lo + chunk);
-        launch_nvls_reduce(h->mc_rho, lo, hi, nullptr, h->mb, h->rs.ticket + 4, h->mb_err, st);
+        launch_nvls_reduce(h->mc_rho, lo, hi, nullptr, h->mb, h->rs, h->rs.ticket + 4, h->mb_err, st);
     }
-    h->launches += 1;
+    h->launches += 3;
     return check_launch(h, "k_nvls_reduce");
 }
 
@@ -675,7 +679,9 @@ int ocl_sc_stage_momentum(ocl_sc_t* h, const double* d_r, long long ld, long lon
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
     mark(h, T_BEGIN, st);
-    launch_momentum(d_r, ld, n, kp_of(h, E_GeV, 0.0, nullptr), h->rs, h->mb, h->mb_err, st);
+    Mailbox mb = h->mb;
+    if (h->debug_skip & 1) mb.world = 1;
+    launch_momentum(d_r, ld, n, kp_of(h, E_GeV, 0.0, nullptr), h->rs, mb, h->mb_err, st);
     h->launches += 1;
     mark(h, T_MOM, st);
     return check_launch(h, "k_momentum");
@@ -687,7 +693,9 @@ int ocl_sc_stage_extent(ocl_sc_t* h, const double* d_r, long long ld, const doub
     ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
-    launch_extent(d_r, ld, d_q, n, kp_of(h, E_GeV, 0.0, mesh_draws), h->rs, h->md, h->mb, h->mb_err, st);
+    Mailbox mb = h->mb;
+    if (h->debug_skip & 2) mb.world = 1;
+    launch_extent(d_r, ld, d_q, n, kp_of(h, E_GeV, 0.0, mesh_draws), h->rs, h->md, mb, h->mb_err, st);
     h->launches += 1;
     mark(h, T_EXT, st);
     return check_launch(h, "k_extent");

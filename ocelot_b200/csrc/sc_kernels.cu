@@ -56,6 +56,32 @@ constexpr int kPipeDepth = 3;
 // Runs in ONE warp (all 32 lanes): either the warp that finishes a sweep's grid reduction (no extra
 // launch on the critical path) or the stand-alone k_mailbox_exchange.
 // ---------------------------------------------------------------------------
+// Flags cross NVLink with release / acquire accesses instead of plain accesses bracketed by full system fences:
+// a membar.sys per waiting warp is what made a many-block wait expensive (2 x B200: 17 us per kick when every block
+// of the reduction kernel fenced after its poll).
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// spin with relaxed loads, then one acquire load of the flag that was seen raised
+__device__ __forceinline__ bool wait_flag(const unsigned long long* p, unsigned long long epoch, bool backoff) {
+    const long long t0 = clock64();
+    while (ld_relaxed_sys(p) < epoch) {
+        if (clock64() - t0 > 8000000000LL) return false;            // ~4 s: a peer is gone
+        if (backoff) __nanosleep(64);      // many blocks may poll the same line: leave the L2 slice room for the remote write
+    }
+    return ld_acquire_sys(p) >= epoch;
+}
+
 __device__ __forceinline__ void mailbox_exchange_warp(const Mailbox& mb, int which, const ReduceState& rs,
                                                       int* __restrict__ err_flag) {
     const int lane = threadIdx.x & 31;
@@ -68,16 +94,11 @@ __device__ __forceinline__ void mailbox_exchange_warp(const Mailbox& mb, int whi
     if (lane < mb.world) {
         double* dst = mb.peer[lane] + vbase + mb.rank * nv;
         for (int k = 0; k < nv; ++k) dst[k] = __ldcg(local_vals + k);
-        __threadfence_system();
-        volatile unsigned long long* flag = reinterpret_cast<unsigned long long*>(mb.peer[lane] + fbase) + mb.rank;
-        *flag = epoch;
+        // the same thread wrote the values: a release store of the flag orders them before it
+        st_release_sys(reinterpret_cast<unsigned long long*>(mb.peer[lane] + fbase) + mb.rank, epoch);
         // wait for rank `lane` to have delivered its values here
-        volatile unsigned long long* mine = reinterpret_cast<unsigned long long*>(mb.peer[mb.rank] + fbase) + lane;
-        const long long t0 = clock64();
-        while (*mine < epoch) {
-            if (clock64() - t0 > 8000000000LL) { atomicExch(err_flag, 1 + which); break; }   // ~4 s: a peer is gone
-        }
-        __threadfence_system();
+        const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(mb.peer[mb.rank] + fbase) + lane;
+        if (!wait_flag(mine, epoch, false)) atomicExch(err_flag, 1 + which);
     }
     __syncwarp();
     if (lane == 0) {
@@ -246,6 +267,20 @@ __global__ void k_finish(int which, KP kp, ReduceState rs, MeshDims md) {
     else finish_extent(rs, md, kp_draws(kp));
 }
 
+__device__ __forceinline__ void mailbox_signal(const Mailbox& mb, int fbase, unsigned long long epoch) {
+    const int lane = threadIdx.x & 31;
+    if (lane < mb.world) st_release_sys(reinterpret_cast<unsigned long long*>(mb.peer[lane] + fbase) + mb.rank, epoch);
+}
+__device__ __forceinline__ void mailbox_wait(const Mailbox& mb, int fbase, unsigned long long epoch, int* err_flag) {
+    const int lane = threadIdx.x & 31;
+    if (lane < mb.world) {
+        const unsigned long long* mine = reinterpret_cast<const unsigned long long*>(mb.peer[mb.rank] + fbase) + lane;
+        if (!wait_flag(mine, epoch, true)) atomicExch(err_flag, 3);
+    }
+    __syncwarp();
+}
+constexpr int kFlagRhoReady = 128 + 8 * 2;      // doubles [144,152): "deposit complete" epochs
+constexpr int kFlagRhoDone = 128 + 8 * 3;       // doubles [152,160): "slice reduced" epochs
 // ---------------------------------------------------------------------------
 // sweep 3: nearest-grid-point deposit (sc.py:186-193)
 // ---------------------------------------------------------------------------
@@ -622,69 +657,102 @@ void launch_mailbox_exchange(Mailbox mb, int which, ReduceState rs, int* err_fla
 // by the switch, so all ranks end up with bit-identical grids.
 //   out == nullptr : all-reduce in place (redundant solve on every rank)
 //   out != nullptr : reduce-scatter: elements [lo, hi) of the sum go to out[0 .. hi-lo) (slab solve)
-// ONE kernel including both cross-rank barriers (round 1: barrier kernel, reduce kernel, barrier kernel):
-//   entry: block 0 announces "my deposit is complete" in every peer's mailbox; every block waits until
-//          all peers have announced (their flags land in the LOCAL mailbox, so the poll is a local read);
-//   exit:  the block that draws the last ticket announces "my slice is reduced and broadcast" and waits for
-//          the same announcement of every peer, so the kernel completes only when the whole grid is final.
-// The exit wait is done by a single block after all others have finished: no co-residency is assumed.
+// Default form: a one-warp barrier kernel ("every rank's deposit is complete"), the reduction, a one-warp barrier
+// kernel ("every slice is final"), all three launched programmatically (PDL).  A single-kernel form with both
+// barriers inside exists (k_nvls_reduce, OCL_SC_NVLS_FUSED=1) and measured slower, see there.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ void mailbox_signal(const Mailbox& mb, int fbase, unsigned long long epoch) {
-    const int lane = threadIdx.x & 31;
-    if (lane < mb.world) {
-        __threadfence_system();
-        volatile unsigned long long* flag = reinterpret_cast<unsigned long long*>(mb.peer[lane] + fbase) + mb.rank;
-        *flag = epoch;
-    }
-}
-__device__ __forceinline__ void mailbox_wait(const Mailbox& mb, int fbase, unsigned long long epoch, int* err_flag) {
-    const int lane = threadIdx.x & 31;
-    if (lane < mb.world) {
-        volatile unsigned long long* mine = reinterpret_cast<unsigned long long*>(mb.peer[mb.rank] + fbase) + lane;
-        const long long t0 = clock64();
-        while (*mine < epoch) {
-            if (clock64() - t0 > 8000000000LL) { atomicExch(err_flag, 3); break; }
+// elements [lo, hi) of the multicast range: in-switch sum, then broadcast (out == nullptr) or local store.
+// kNvlsUnroll reductions are in flight per thread before the first store: the kernel runs on a SMALL grid (it
+// may have to wait for the peers with all its blocks resident, and the K_hat chain shares the GPU with it:
+// 592 waiting blocks cost 11 us per kick on 2 x B200), so each thread carries several elements.
+constexpr int kNvlsUnroll = 4;
+__device__ __forceinline__ void nvls_reduce_range(double* __restrict__ mc, long long lo, long long hi,
+                                                  double* __restrict__ out) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i0 = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += stride * kNvlsUnroll) {
+        double v[kNvlsUnroll];
+#pragma unroll
+        for (int u = 0; u < kNvlsUnroll; ++u) {
+            const long long i = i0 + u * stride;
+            if (i < hi) asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(v[u]) : "l"(mc + i) : "memory");
         }
-        __threadfence_system();
+#pragma unroll
+        for (int u = 0; u < kNvlsUnroll; ++u) {
+            const long long i = i0 + u * stride;
+            if (i < hi) {
+                if (out) out[i - lo] = v[u];
+                else asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc + i), "d"(v[u]) : "memory");
+            }
+        }
     }
-    __syncwarp();
 }
-constexpr int kFlagRhoReady = 128 + 8 * 2;      // doubles [144,152): "deposit complete" epochs
-constexpr int kFlagRhoDone = 128 + 8 * 3;       // doubles [152,160): "slice reduced" epochs
+
+// Single-kernel form (OCL_SC_NVLS_FUSED=1; NOT the default): entry barrier, reduction and exit barrier in one
+// launch.  Measured on 2 x B200 (1 M / 63^3 per GPU, tools/r2_comm_probe.py): 176.9 us per kick against 173.9 us
+// for the three launches below -- waiting for the peers inside a wide grid costs more than the two extra
+// launches of one-warp barrier kernels save (and 193.7 us while every waiting block still issued a membar.sys).
+// mode bits (timing experiments): 1 = leave out the entry barrier, 2 = leave out the exit barrier (both unsafe),
+// 4 = one system fence per block instead of one per thread
 __global__ void __launch_bounds__(256) k_nvls_reduce(double* __restrict__ mc, long long lo, long long hi,
                                                     double* __restrict__ out, Mailbox mb, unsigned int* ticket,
-                                                    int* __restrict__ err_flag) {
+                                                    int* __restrict__ err_flag, int mode) {
     pdl_enter();
     const unsigned long long epoch = mb.epoch[2] + 1;       // advanced by the last block, after everyone has read it
-    if (threadIdx.x < 32) {
-        if (blockIdx.x == 0) mailbox_signal(mb, kFlagRhoReady, epoch);
-        mailbox_wait(mb, kFlagRhoReady, epoch, err_flag);
+    if (!(mode & 1)) {
+        if (threadIdx.x < 32) {
+            if (blockIdx.x == 0) mailbox_signal(mb, kFlagRhoReady, epoch);
+            mailbox_wait(mb, kFlagRhoReady, epoch, err_flag);
+        }
+        __syncthreads();
     }
-    __syncthreads();
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = lo + (long long)blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += stride) {
-        double v;
-        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f64 %0, [%1];" : "=d"(v) : "l"(mc + i) : "memory");
-        if (out) out[i - lo] = v;
-        else asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(mc + i), "d"(v) : "memory");
+    nvls_reduce_range(mc, lo, hi, out);
+    if (mode & 4) {
+        __syncthreads();
+        if (threadIdx.x == 0) __threadfence_system();
+    } else {
+        __threadfence_system();
+        __syncthreads();
     }
-    __threadfence_system();
-    __syncthreads();
     __shared__ bool last;
     if (threadIdx.x == 0) last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
     __syncthreads();
     if (!last || threadIdx.x >= 32) return;
     // every block of this rank has issued (and fenced) its multimem stores
-    mailbox_signal(mb, kFlagRhoDone, epoch);
-    mailbox_wait(mb, kFlagRhoDone, epoch, err_flag);
+    if (!(mode & 2)) {
+        mailbox_signal(mb, kFlagRhoDone, epoch);
+        mailbox_wait(mb, kFlagRhoDone, epoch, err_flag);
+    }
     if (threadIdx.x == 0) { mb.epoch[2] = epoch; *ticket = 0; __threadfence(); }
 }
-void launch_nvls_reduce(double* mc, long long lo, long long hi, double* out, Mailbox mb, unsigned int* ticket,
+// the reduction proper; launch_nvls_reduce brackets it with two one-warp barrier kernels (the default form)
+__global__ void __launch_bounds__(256) k_nvls_reduce_plain(double* __restrict__ mc, long long lo, long long hi,
+                                                          double* __restrict__ out) {
+    pdl_enter();
+    nvls_reduce_range(mc, lo, hi, out);
+}
+static int nvls_mode() {      // -1: three launches (default); >= 0: the single-kernel form with these mode bits
+    static int m = -2;
+    if (m == -2) {
+        const char* f = getenv("OCL_SC_NVLS_FUSED");
+        const char* e = getenv("OCL_SC_NVLS_MODE");
+        m = (f && atoi(f)) ? (e ? atoi(e) : 0) : -1;
+    }
+    return m;
+}
+void launch_nvls_reduce(double* mc, long long lo, long long hi, double* out, Mailbox mb, ReduceState rs, unsigned int* ticket,
                         int* err_flag, cudaStream_t st) {
-    long long blocks = (hi - lo + 255) / 256;
+    const int mode = nvls_mode();
+    // one block per kNvlsUnroll * 256 elements: 123 blocks for the 63^3 grid on two ranks, at most 4 per SM
+    long long blocks = (hi - lo + 256 * kNvlsUnroll - 1) / (256 * kNvlsUnroll);
     if (blocks < 1) blocks = 1;
     if (blocks > 148 * 4) blocks = 148 * 4;
-    launch_k(k_nvls_reduce, dim3((int)blocks), dim3(256), 0, st, mc, lo, hi, out, mb, ticket, err_flag);
+    if (mode < 0) {
+        launch_mailbox_exchange(mb, 2, rs, err_flag, st);
+        launch_k(k_nvls_reduce_plain, dim3((int)blocks), dim3(256), 0, st, mc, lo, hi, out);
+        launch_mailbox_exchange(mb, 2, rs, err_flag, st);
+        return;
+    }
+    launch_k(k_nvls_reduce, dim3((int)blocks), dim3(256), 0, st, mc, lo, hi, out, mb, ticket, err_flag, mode);
 }
 
 // fold all-gathered extents: max over ranks of the first 6 doubles, sum of the last 4

@@ -44,7 +44,7 @@ struct PeerRho {
     int world;
 };
 void launch_mailbox_exchange(Mailbox mb, int which, ReduceState rs, int* err_flag, cudaStream_t st);
-void launch_nvls_reduce(double* mc, long long lo, long long hi, double* out, Mailbox mb, unsigned int* ticket,
+void launch_nvls_reduce(double* mc, long long lo, long long hi, double* out, Mailbox mb, ReduceState rs, unsigned int* ticket,
                         int* err_flag, cudaStream_t st);
 
 int particle_grid(long long n, int max_blocks);

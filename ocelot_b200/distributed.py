@@ -10,8 +10,8 @@ One process per GPU; rank r owns a contiguous range of the bunch's particles
 
 Exchanges 1 and 2 run INSIDE the sweep kernels over NVLink peer memory (the block that finishes the
 grid reduction pushes the rank's partials into every peer's mailbox, waits for theirs and folds them
-in rank order), exchange 3 is one kernel of in-switch multimem reductions bracketed by its own
-cross-rank barriers; NCCL (all-reduce / all-gather) is the fallback when no peer mapping exists.
+in rank order), exchange 3 is a kernel of in-switch multimem reductions bracketed by two one-warp
+barrier kernels; NCCL (all-reduce / all-gather) is the fallback when no peer mapping exists.
 
 after which every rank holds the same rho and solves the Poisson problem
 redundantly ("small-mesh mode"); no particle ever crosses a link.  For large
@@ -123,7 +123,7 @@ class NativeStageEngine:
         """Slab-decomposed solve: rho (local partial sums, nx_pad planes) -> field table."""
         b, s = self.buffers, self.solver
         if self.nvls is not None:
-            s.nvls_reduce_rho()                # one kernel: barrier, in-switch reduce-scatter into this rank's x-slab, barrier
+            s.nvls_reduce_rho()                # barrier, in-switch reduce-scatter into this rank's x-slab, barrier
         elif self.peer_rho is not None:
             s.mailbox_exchange(2)              # barrier: every rank's deposit is complete
         else:
@@ -209,7 +209,7 @@ def sharded_kick(engine, r, q, E_GeV, dz, draws=None, group=None, dist=None):
         engine.solve_slab(dist, group, draws)      # works for any world size >= 1
     else:
         if multi and getattr(engine, "nvls", None) is not None:
-            engine.solver.nvls_reduce_rho()        # one kernel: barrier, in-switch all-reduce (multimem), barrier
+            engine.solver.nvls_reduce_rho()        # barrier, in-switch all-reduce (multimem), barrier
         elif multi and getattr(engine, "peer_rho", None) is not None:
             engine.solver.mailbox_exchange(2)      # barrier; the solve's first pass sums the peers' grids
         elif multi:
