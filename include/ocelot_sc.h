@@ -212,6 +212,16 @@ int ocl_sc_cavity_coefficients(double v, double phi_deg, double freq, double E_G
  * reference's scalar formulas; mode 1 = full, mode 2 = drift-like branch (cavity.py:67-69). */
 int ocl_sc_cavity_apply(ocl_sc_t* h, double* d_r, long long ld, long long n, const double* R, const double* B,
                         const double* c, int mode, void* stream);
+/* Aperture cut on a resident bunch with ordered stream compaction (RectAperture / EllipticalAperture,
+ * physics_proc.py:341-390; ParticleArray.delete_particles, beam/particle.py:323-333).  kind 0: a particle is lost if
+ * row `row` is outside [params[0], params[1]]; kind 1: if ((x-params[2])/params[0])^2 + ((y-params[3])/params[1])^2 > 1.
+ * Survivors (six rows, charge, id) are written in order to the *_out buffers (distinct from the inputs), the ids of
+ * the lost particles in order to d_lost_out (n entries; may be NULL; d_ids NULL = ids are the indices).  Synchronises
+ * `stream` and returns the survivor count in *n_out. */
+int ocl_sc_aperture_cut(ocl_sc_t* h, const double* d_r, long long ld, const double* d_q, const long long* d_ids,
+                        long long n, int kind, int row, const double* params, double* d_r_out, long long ld_out,
+                        double* d_q_out, long long* d_ids_out, long long* d_lost_out, long long* n_out, void* stream);
+
 /* First and centred second moments of get_envelope's default path (beam/analysis.py:72-76,
  * :121-166): h_out[18] = {x, px, y, py, tau, p, xx, xpx, pxpx, yy, ypy, pypy, tautau, pp, xy, pxpy,
  * xpy, ypx} with the reference's px, py correction factor applied.  Synchronous. */

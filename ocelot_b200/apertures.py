@@ -25,6 +25,10 @@ class RectAperture(PhysProc):
         self.xmin, self.xmax, self.ymin, self.ymax = xmin, xmax, ymin, ymax
 
     def apply(self, p_array, dz):
+        if hasattr(p_array, "cut"):                       # device-resident: predicate + ordered compaction kernels
+            p_array.cut(0, 0, (self.xmin, self.xmax, 0.0, 0.0))                                # :362-365
+            p_array.cut(0, 2, (self.ymin, self.ymax, 0.0, 0.0))                                # :367-370
+            return
         x = p_array.x()
         lib = _lib(x)
         p_array.delete_particles(_where(lib, lib.logical_or(x < self.xmin, x > self.xmax)))   # :362-365
@@ -43,6 +47,9 @@ class EllipticalAperture(PhysProc):
         self.dx, self.dy = dx, dy
 
     def apply(self, p_array, dz):
+        if hasattr(p_array, "cut"):                       # device-resident: predicate + ordered compaction kernels
+            p_array.cut(1, 0, (self.xmax, self.ymax, self.dx, self.dy))
+            return
         x, y = p_array.x(), p_array.y()
         lib = _lib(x)
         out = (x - self.dx) ** 2 / self.xmax ** 2 + (y - self.dy) ** 2 / self.ymax ** 2 > 1.0   # :388

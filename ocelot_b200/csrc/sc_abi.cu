@@ -37,6 +37,9 @@ struct ocl_sc {
     double2* tw[3] = {nullptr, nullptr, nullptr};
     double* h3 = nullptr;                     // mesh steps of the current kick
     double* moments = nullptr;                // 18 doubles: beam moments (ocl_sc_beam_moments)
+    int* cut_counts = nullptr;                // aperture compaction: per-tile survivor counts / offsets
+    long long cut_tiles = 0;
+    long long* cut_n = nullptr;               // mapped host word: survivors of the last cut
     double* real_buf = nullptr;               // M^3 real: K, then padded rho, then the convolution
     cufftDoubleComplex* k_hat = nullptr;      // M*M*(M/2+1)
     cufftDoubleComplex* rho_hat = nullptr;    // M*M*(M/2+1)
@@ -437,7 +440,8 @@ void ocl_sc_destroy(ocl_sc_t* h) {
     cudaFree(h->k_hat); cudaFree(h->rho_hat); cudaFree(h->phi); cudaFree(h->equad);
     cudaFree(h->fw.P); cudaFree(h->fw.Q); cudaFree(h->fw.khat); cudaFree(h->fw.A); cudaFree(h->fw.B);
     cudaFree(h->tw[0]); cudaFree(h->tw[1]); cudaFree(h->tw[2]); cudaFree(h->h3); cudaFree(h->moments);
-    cudaFree(h->stage_r); cudaFree(h->stage_q);
+    cudaFree(h->stage_r); cudaFree(h->stage_q); cudaFree(h->cut_counts);
+    if (h->cut_n) cudaFreeHost(h->cut_n);
     cudaFree(h->lw.ticket); cudaFree(h->lw.stats); cudaFree(h->lw.bins); cudaFree(h->lw.cnt); cudaFree(h->lw.Z);
     cudaFree(h->lw.spread);
     cudaFree(h->lw.tw);
@@ -1117,6 +1121,38 @@ int ocl_sc_cavity_coefficients(double v, double phi_deg, double freq, double E_G
                         / (eta1cube * gap * gap * gap) * sn * sn;
     const double lin = (g1 * g0 * (b1 * b0 - 1.0) + 1.0) / (eta1 * gap * gap) * cs;
     coef[6] = b0 * b0 * k * k * z * dgam / 2.0 * (curv - lin);
+    return 0;
+}
+
+int ocl_sc_aperture_cut(ocl_sc_t* h, const double* d_r, long long ld, const double* d_q, const long long* d_ids,
+                        long long n, int kind, int row, const double* params, double* d_r_out, long long ld_out,
+                        double* d_q_out, long long* d_ids_out, long long* d_lost_out, long long* n_out, void* stream) {
+    if (!h || !params || !n_out || !d_r_out || !d_q_out) return 1;
+    if (n < 0 || ld < n || ld_out < n) return fail(h, "ocl_sc_aperture_cut", "need 0 <= n <= ld, ld_out");
+    if (kind != 0 && kind != 1) return fail(h, "ocl_sc_aperture_cut", "kind must be 0 (row against [lo, hi]) or 1 (ellipse)");
+    if (kind == 0 && (row < 0 || row > 5)) return fail(h, "ocl_sc_aperture_cut", "row must be 0..5");
+    *n_out = 0;
+    if (n == 0) return 0;
+    ENTER_DEVICE(h);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (adopt_stream(h, st)) return 1;
+    const long long tiles = (n + 1023) / 1024;
+    if (tiles + 1 > h->cut_tiles) {
+        cudaFree(h->cut_counts);
+        h->cut_counts = nullptr; h->cut_tiles = 0;
+        CU(h, cudaMalloc(&h->cut_counts, sizeof(int) * (size_t)(tiles + 1 + tiles / 4)));
+        h->cut_tiles = tiles + 1 + tiles / 4;
+    }
+    if (!h->cut_n) CU(h, cudaHostAlloc(&h->cut_n, sizeof(long long), cudaHostAllocMapped));
+    long long* d_n = nullptr;
+    CU(h, cudaHostGetDevicePointer((void**)&d_n, h->cut_n, 0));
+    CutSpec c;
+    c.kind = kind; c.row = row; c.a = params[0]; c.b = params[1]; c.c = params[2]; c.d = params[3];
+    launch_cut(d_r, ld, d_q, d_ids, n, c, h->cut_counts, d_n, d_r_out, ld_out, d_q_out, d_ids_out, d_lost_out, st);
+    h->launches += 3;
+    if (check_launch(h, "k_cut")) return 1;
+    CU(h, cudaStreamSynchronize(st));                    // the new particle count shapes everything that follows
+    *n_out = *h->cut_n;
     return 0;
 }
 

@@ -163,4 +163,113 @@ void launch_moments(const double* r, long long ld, long long n, ReduceState rs, 
     k_moments_2<<<sweep_grid(n, 148 * 3), kBThreads, 0, st>>>(r, ld, n, rs, out18);
 }
 
+// ---- f4: aperture cut + stream compaction ---------------------------------------------------
+// RectAperture / EllipticalAperture (physics_proc.py:341-390) on a resident bunch: particles outside the aperture
+// are removed and the survivors keep their order (ParticleArray.delete_particles, beam/particle.py:323-333).
+// Three small kernels: per-tile survivor counts, one-block exclusive scan, ordered scatter of the six rows, the
+// charges and the particle ids into a second buffer (in-place compaction would let one tile overwrite rows another
+// tile has not read yet); the ids of the lost particles are written in order as well (lost-particle recorder).
+//   kind 0: lost if v < lo || v > hi with v = row `row`            (RectAperture, one plane per call)
+//   kind 1: lost if (x-dx)^2/ax^2 + (y-dy)^2/ay^2 > 1              (EllipticalAperture)
+constexpr int kCutTile = 1024;
+__device__ __forceinline__ bool cut_lost(const double* __restrict__ r, long long ld, long long i, CutSpec c) {
+    if (c.kind == 0) {
+        const double v = r[c.row * ld + i];
+        return v < c.a || v > c.b;
+    }
+    const double x = r[i] - c.c, y = r[2 * ld + i] - c.d;
+    return (x * x) / (c.a * c.a) + (y * y) / (c.b * c.b) > 1.0;                  // physics_proc.py:388
+}
+__global__ void __launch_bounds__(256) k_cut_count(const double* __restrict__ r, long long ld, long long n, CutSpec c,
+                                                  int* __restrict__ counts) {
+    __shared__ int sh[8];
+    const long long base = (long long)blockIdx.x * kCutTile;
+    int keep = 0;
+#pragma unroll
+    for (int u = 0; u < kCutTile / 256; ++u) {
+        const long long i = base + u * 256 + threadIdx.x;
+        if (i < n && !cut_lost(r, ld, i, c)) ++keep;
+    }
+    for (int o = 16; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = keep;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < 8; ++w) t += sh[w];
+        counts[blockIdx.x] = t;
+    }
+}
+// exclusive scan of the tile counts in place; counts[tiles] = total survivors
+__global__ void __launch_bounds__(1024) k_cut_scan(int* __restrict__ counts, int tiles, long long* __restrict__ n_out) {
+    __shared__ int sh[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < tiles; b0 += 1024) {
+        const int b = b0 + threadIdx.x;
+        const int v = b < tiles ? counts[b] : 0;
+        int x = v;
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if ((threadIdx.x & 31) >= o) x += y; }
+        if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = x;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = sh[threadIdx.x];
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, w, o); if (threadIdx.x >= o) w += y; }
+            sh[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const int warp_off = (threadIdx.x >> 5) ? sh[(threadIdx.x >> 5) - 1] : 0;
+        if (b < tiles) counts[b] = carry + warp_off + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += warp_off + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { counts[tiles] = carry; *n_out = carry; }
+}
+__global__ void __launch_bounds__(256) k_cut_scatter(const double* __restrict__ r, long long ld, const double* __restrict__ q,
+                                                    const long long* __restrict__ ids, long long n, CutSpec c,
+                                                    const int* __restrict__ offsets, double* __restrict__ r_out,
+                                                    long long ld_out, double* __restrict__ q_out,
+                                                    long long* __restrict__ ids_out, long long* __restrict__ lost_out) {
+    __shared__ int sh[8];
+    const long long base = (long long)blockIdx.x * kCutTile;
+    long long keep_pos = offsets[blockIdx.x];
+    long long lost_pos = base - keep_pos;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int u = 0; u < kCutTile / 256; ++u) {
+        const long long i = base + u * 256 + threadIdx.x;
+        const bool in = i < n;
+        const bool keep = in && !cut_lost(r, ld, i, c);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0) sh[warp] = __popc(m);
+        __syncthreads();
+        int before = 0, total = 0;
+        for (int w = 0; w < 8; ++w) { if (w < warp) before += sh[w]; total += sh[w]; }
+        const int rank_in = before + __popc(m & ((1u << lane) - 1));       // survivors ahead of this one in the chunk
+        const int idx_in = u * 256 + threadIdx.x;                          // position in the tile
+        if (keep) {
+            const long long o = keep_pos + rank_in;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) r_out[k * ld_out + o] = r[k * ld + i];
+            q_out[o] = q[i];
+            if (ids_out) ids_out[o] = ids[i];
+        } else if (in && lost_out) {
+            lost_out[lost_pos + (idx_in - u * 256) - rank_in] = ids ? ids[i] : i;
+        }
+        const long long chunk = (n - (base + u * 256)) < 256 ? (n - (base + u * 256)) : 256;
+        keep_pos += total;
+        lost_pos += (chunk > 0 ? chunk : 0) - total;
+        __syncthreads();
+    }
+}
+void launch_cut(const double* r, long long ld, const double* q, const long long* ids, long long n, CutSpec c, int* counts,
+                long long* n_out, double* r_out, long long ld_out, double* q_out, long long* ids_out, long long* lost_out,
+                cudaStream_t st) {
+    const int tiles = (int)((n + kCutTile - 1) / kCutTile);
+    k_cut_count<<<tiles, 256, 0, st>>>(r, ld, n, c, counts);
+    k_cut_scan<<<1, 1024, 0, st>>>(counts, tiles, n_out);
+    k_cut_scatter<<<tiles, 256, 0, st>>>(r, ld, q, ids, n, c, counts, r_out, ld_out, q_out, ids_out, lost_out);
+}
+
 }  // namespace ocl

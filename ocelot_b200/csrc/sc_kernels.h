@@ -88,6 +88,15 @@ struct MapCoef {
 };
 void launch_map_apply(double* r, long long ld, long long n, const MapCoef& mc, cudaStream_t st);
 void launch_moments(const double* r, long long ld, long long n, ReduceState rs, double* out18, cudaStream_t st);
+// aperture cut + ordered stream compaction (sc_beam.cu); counts holds ceil(n/1024) + 1 ints
+struct CutSpec {
+    int kind;          // 0: one coordinate row against [a, b] | 1: ellipse with semi-axes (a, b) centred at (c, d)
+    int row;
+    double a, b, c, d;
+};
+void launch_cut(const double* r, long long ld, const double* q, const long long* ids, long long n, CutSpec c, int* counts,
+                long long* n_out, double* r_out, long long ld_out, double* q_out, long long* ids_out, long long* lost_out,
+                cudaStream_t st);
 
 // ---- longitudinal space charge (sc_lsc.cu) ----
 // physical constants of ocelot/common/globals.py:13-36 (same expressions as the host code)

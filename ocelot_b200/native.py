@@ -71,6 +71,8 @@ _SIGNATURES = {
     "ocl_sc_map_apply": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _dp, _dp, _vp]),
     "ocl_sc_cavity_apply": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _dp, _dp, C.c_int, _vp]),
     "ocl_sc_beam_moments": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _vp]),
+    "ocl_sc_aperture_cut": (C.c_int, [_vp, _vp, _ll, _vp, _vp, _ll, C.c_int, C.c_int, _dp, _vp, _ll, _vp, _vp, _vp,
+                                      C.POINTER(_ll), _vp]),
     "ocl_sc_cavity_coefficients": (C.c_int, [C.c_double] * 6 + [_dp, C.POINTER(C.c_int), _dp]),
     "ocl_sc_lsc_stats": (C.c_int, [_vp, _vp, _ll, _ll, _vp, _dp, _vp]),
     "ocl_sc_lsc_kick": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _vp]),
@@ -434,6 +436,17 @@ class Solver:
         self._check(self._lib.ocl_sc_cavity_apply(self._h, ptr, ld, n, Rc.ctypes.data_as(_dp), Bc.ctypes.data_as(_dp),
                                                   cc.ctypes.data_as(_dp), int(mode), _stream_ptr(stream)),
                     "ocl_sc_cavity_apply")
+
+    def aperture_cut(self, r, q, ids, kind, row, params, r_out, q_out, ids_out, lost_out, stream=None) -> int:
+        """Ordered compaction of the particles inside the aperture into the *_out tensors; returns the survivor count."""
+        ptr, ld, n = self._dev_rows(r, q)
+        prm = (C.c_double * 4)(*[float(v) for v in params])
+        n_out = _ll(0)
+        self._check(self._lib.ocl_sc_aperture_cut(self._h, ptr, ld, q.data_ptr(), ids.data_ptr(), n, int(kind), int(row), prm,
+                                                  r_out.data_ptr(), r_out.stride(0), q_out.data_ptr(), ids_out.data_ptr(),
+                                                  lost_out.data_ptr(), C.byref(n_out), _stream_ptr(stream)),
+                    "ocl_sc_aperture_cut")
+        return int(n_out.value)
 
     MOMENT_KEYS = ("x", "px", "y", "py", "tau", "p", "xx", "xpx", "pxpx", "yy", "ypy", "pypy", "tautau", "pp",
                    "xy", "pxpy", "xpy", "ypx")

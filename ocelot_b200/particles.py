@@ -135,6 +135,35 @@ class DeviceParticleArray:
         self._q[:m] = self._q[:self._n][keep]
         self._n = m
 
+    def cut(self, kind, row, params, record=True):
+        """Aperture cut with ordered compaction on the device (``ocl_sc_aperture_cut``: three small kernels, survivors
+        keep their order like ``ParticleArray.delete_particles``, beam/particle.py:323-333).  kind 0: lose particles whose
+        row ``row`` is outside [params[0], params[1]]; kind 1: outside the ellipse (ax, ay, dx, dy) in (x, y).  One
+        host synchronisation, for the new particle count.  Returns the number of lost particles."""
+        import torch
+        from .beam import _scratch_solver
+        if self._n == 0:
+            return 0
+        ld = self._buf.shape[1]
+        new_buf = torch.zeros_like(self._buf)
+        new_q = torch.zeros_like(self._q)
+        ids = self._current_particle
+        if ids.dtype != torch.int64 or not ids.is_contiguous():
+            ids = ids.to(torch.int64).contiguous()
+        new_ids = torch.empty(self._n, dtype=torch.int64, device=self.device)
+        lost = torch.empty(self._n, dtype=torch.int64, device=self.device)
+        m = _scratch_solver(self.device.index or 0).aperture_cut(self.rparticles, self.q_array, ids, kind, row, params,
+                                                                 new_buf, new_q, new_ids, lost)
+        n_lost = self._n - m
+        if n_lost == 0:
+            return 0
+        if record:
+            self.lost_particles += lost[:n_lost].tolist()
+            self.lp_to_pos_hist.append((self.s, n_lost))
+            self._current_particle = new_ids[:m]
+        self._buf, self._q, self._n = new_buf, new_q, m
+        return n_lost
+
     @classmethod
     def from_host(cls, p_array, device=None):
         """Copy any object with rparticles/q_array/E/s (e.g. Ocelot's ParticleArray) to the device."""
