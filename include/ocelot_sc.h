@@ -136,6 +136,9 @@ int ocl_sc_set_peer_rho(ocl_sc_t* h, int rank, int world, void* const* peer_rho)
  * all-reduce (redundant solve) or reduce-scatter (slab solve) of OCL_SC_BUF_RHO: barrier over the
  * mailbox, one kernel of multimem.ld_reduce / multimem.st (the NVSwitch sums each element once, so
  * every rank ends up with bit-identical sums), barrier.  Needs ocl_sc_mailbox_init. */
+/* Once the mailbox and the multicast mapping are set and the handle is not in slab mode, ocl_sc_kick_device on every
+ * rank's shard IS the complete sharded kick (both scalar exchanges inside the sweeps, rho summed in the switch, redundant
+ * solve), captured in the library's own CUDA graph. */
 int ocl_sc_set_multicast_rho(ocl_sc_t* h, void* local_rho, void* multicast_rho);
 int ocl_sc_nvls_reduce_rho(ocl_sc_t* h, void* stream);
 

@@ -763,6 +763,11 @@ static int run_stages(ocl_sc_t* h, double* d_r, long long ld, const double* d_q,
     if (ocl_sc_stage_momentum(h, d_r, ld, n, E_GeV, stream)) return 1;
     if (ocl_sc_stage_extent(h, d_r, ld, d_q, n, E_GeV, mesh_draws, stream)) return 1;
     if (ocl_sc_stage_deposit(h, d_r, ld, d_q, n, E_GeV, mesh_draws, stream)) return 1;
+    // particle-sharded handle whose exchanges are all the library's own kernels (peer-memory mailbox for the two
+    // scalar exchanges, multicast mapping for rho, redundant solve): the WHOLE sharded kick is this one call, so it
+    // is captured into the library's own graph with its parameter node (no caller-side capture, no separate
+    // parameter kernel per kick)
+    if (h->mc_rho && h->mb.world > 1 && !h->slab_world && ocl_sc_nvls_reduce_rho(h, stream)) return 1;
     if (ocl_sc_stage_solve(h, mesh_draws, stream)) return 1;
     return ocl_sc_stage_kick(h, d_r, ld, n, E_GeV, dz, mesh_draws, stream);
 }

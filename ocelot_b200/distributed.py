@@ -278,6 +278,13 @@ class ShardedSpaceCharge:
         if not self.use_graph:
             sharded_kick(self._engine, r, q, E, float(dz), draws, self.group)
             return
+        eng = self._engine
+        if eng.mailbox is not None and eng.nvls is not None and eng.slab is None and r.shape[1] > 0:
+            # every exchange of this kick is one of the library's own kernels (mailbox + in-switch rho reduction,
+            # redundant solve): the handle's kick_device IS the sharded kick, in the library's own CUDA graph
+            eng.solver.defer_finish(False)
+            eng.solver.kick_device(r, q, E, float(dz), draws)
+            return
         # The staged kick *and* its NCCL collectives are captured once per particle buffer into a
         # CUDA graph; E, dz and the mesh draws live in a device block refreshed before each replay.
         solver = self._engine.solver
