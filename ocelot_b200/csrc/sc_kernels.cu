@@ -82,8 +82,10 @@ __device__ __forceinline__ bool wait_flag(const unsigned long long* p, unsigned 
     return ld_acquire_sys(p) >= epoch;
 }
 
+// vio (optional): lane 0 holds this rank's values in registers on entry (else they are read from the handle's
+// buffers) and receives the folded values on exit, so the caller need not read them back from memory.
 __device__ __forceinline__ void mailbox_exchange_warp(const Mailbox& mb, int which, const ReduceState& rs,
-                                                      int* __restrict__ err_flag) {
+                                                      int* __restrict__ err_flag, double* vio = nullptr) {
     const int lane = threadIdx.x & 31;
     const int nv = which == 0 ? 4 : (which == 1 ? 10 : 0);
     const int vbase = which == 0 ? 0 : 32;
@@ -91,9 +93,14 @@ __device__ __forceinline__ void mailbox_exchange_warp(const Mailbox& mb, int whi
     const double* local_vals = which == 0 ? rs.sums : rs.emax;          // emax[6] and esum[4] are contiguous
     const unsigned long long epoch = mb.epoch[which] + 1;
     __syncwarp();
+    double mine_v[10];
+    for (int k = 0; k < nv; ++k) {
+        const double x = vio ? vio[k] : 0.0;                              // meaningful in lane 0 only
+        mine_v[k] = vio ? __shfl_sync(0xffffffffu, x, 0) : __ldcg(local_vals + k);
+    }
     if (lane < mb.world) {
         double* dst = mb.peer[lane] + vbase + mb.rank * nv;
-        for (int k = 0; k < nv; ++k) dst[k] = __ldcg(local_vals + k);
+        for (int k = 0; k < nv; ++k) dst[k] = mine_v[k];
         // the same thread wrote the values: a release store of the flag orders them before it
         st_release_sys(reinterpret_cast<unsigned long long*>(mb.peer[lane] + fbase) + mb.rank, epoch);
         // wait for rank `lane` to have delivered its values here
@@ -117,6 +124,7 @@ __device__ __forceinline__ void mailbox_exchange_warp(const Mailbox& mb, int whi
                 for (int k = 0; k < 6; ++k) rs.emax[k] = v[k];
                 for (int k = 0; k < 4; ++k) rs.esum[k] = v[6 + k];
             }
+            if (vio) for (int k = 0; k < nv; ++k) vio[k] = v[k];
         }
         mb.epoch[which] = epoch;
         __threadfence();
@@ -125,28 +133,47 @@ __device__ __forceinline__ void mailbox_exchange_warp(const Mailbox& mb, int whi
 }
 
 // frame of the kick from the (globally) reduced momentum sums -> rs.geo->f        (one thread)
-__device__ __forceinline__ void finish_momentum(const ReduceState& rs, const RefParams& rp) {
+// sums_reg: the four reduced values in registers, or nullptr = read the handle's buffer
+__device__ __forceinline__ void finish_momentum(const ReduceState& rs, const RefParams& rp, const double* sums_reg = nullptr) {
     Frame f;
     double sums[4];
-    for (int k = 0; k < 4; ++k) sums[k] = __ldcg(rs.sums + k);
+    for (int k = 0; k < 4; ++k) sums[k] = sums_reg ? sums_reg[k] : __ldcg(rs.sums + k);
     derive_frame(sums, rp.m_e_eV, f);
     rs.geo->f = f;
 }
 
-// mesh of the kick from the (globally) reduced extents -> rs.geo->m, geometry tap   (one thread)
-__device__ __forceinline__ void finish_extent(const ReduceState& rs, const MeshDims& md, const Draws& dr) {
-    Mesh m;
+// mesh of the kick from the (globally) reduced extents -> rs.geo->m, geometry tap.  Called by a whole warp:
+// lanes 0..2 each derive one axis (the IEEE divisions of an axis are the long pole of this tail; same operations as
+// derive_mesh), lane 0 holds the ten reduced values in e_reg (or nullptr = read the handle's buffer).
+__device__ __forceinline__ void finish_extent_warp(const ReduceState& rs, const MeshDims& md, const Draws& dr, const Frame& f,
+                                                   const double* e_reg = nullptr) {
+    const int lane = threadIdx.x & 31;
     double e[10];
-    for (int k = 0; k < 10; ++k) e[k] = __ldcg(rs.emax + k);              // emax[6] and esum[4] are contiguous
-    derive_mesh(e, e + 6, md.nx, md.ny, md.nz, dr.scale, dr.shift, m);
-    rs.geo->m = m;
-    const Frame f = rs.geo->f;
+    for (int k = 0; k < 10; ++k) {
+        const double x = e_reg ? e_reg[k] : 0.0;
+        e[k] = e_reg ? __shfl_sync(0xffffffffu, x, 0) : __ldcg(rs.emax + k);      // emax[6] and esum[4] are contiguous
+    }
     double* g = rs.geom;
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) g[i * 3 + j] = f.T[i][j];
-    g[9] = f.pav; g[10] = f.gamma0; g[11] = f.beta0;
-    for (int c = 0; c < 3; ++c) { g[12 + c] = m.steps[c]; g[15 + c] = m.xoff[c]; }
-    g[18] = m.sumq; g[19] = __ldcg(rs.sums + 3);
+    if (lane < 3) {
+        const int c = lane;
+        const int n = c == 0 ? md.nx : (c == 1 ? md.ny : md.nz);
+        const double lo = -e[3 + c];
+        double extent = e[c] - lo;                                     // sc.py:173
+        if (dr.scale > 0.0) extent = extent * dr.scale;                // :175
+        const double h = extent / (double)(n - 3);                     // :179
+        const double xmin = lo / h;                                    // :181 (min commutes with /h)
+        const double xmid = (e[6 + c] / h) / e[9];                     // :182
+        double off = floor(xmin - xmid) + xmid;                        // :183
+        if (dr.scale > 0.0) off = off + dr.shift;                      // :185
+        Mesh* m = &rs.geo->m;
+        m->steps[c] = h; m->inv_steps[c] = 1.0 / h; m->xoff[c] = off; m->n[c] = n;
+        g[12 + c] = h; g[15 + c] = off;
+        for (int j = 0; j < 3; ++j) g[c * 3 + j] = f.T[c][j];
+    } else if (lane == 3) {
+        rs.geo->m.sumq = e[9];
+        g[9] = f.pav; g[10] = f.gamma0; g[11] = f.beta0;
+        g[18] = e[9]; g[19] = __ldcg(rs.sums + 3);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -176,8 +203,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_momentum(const double* __restri
         __threadfence();
     }
     if (rs.defer) return;
-    if (mb.world > 1) mailbox_exchange_warp(mb, 0, rs, mb_err);
-    if (threadIdx.x == 0) finish_momentum(rs, rp);
+    double sums[4] = {v[0] * rp.pc, v[1] * rp.pc, v[2] * rp.pc, (double)n};     // valid in thread 0
+    if (mb.world > 1) mailbox_exchange_warp(mb, 0, rs, mb_err, sums);
+    if (threadIdx.x == 0) finish_momentum(rs, rp, sums);
 }
 
 // ---------------------------------------------------------------------------
@@ -255,16 +283,22 @@ __global__ void __launch_bounds__(kThreads, 3) k_extent(const double* __restrict
         __threadfence();
     }
     if (rs.defer) return;
-    if (mb.world > 1) mailbox_exchange_warp(mb, 1, rs, mb_err);
-    if (threadIdx.x == 0) finish_extent(rs, md, kp_draws(kp));
+    if (mb.world > 1) mailbox_exchange_warp(mb, 1, rs, mb_err, v);
+    finish_extent_warp(rs, md, kp_draws(kp), f, v);
 }
 
 // deferred tails (NCCL fallback of a sharded kick: the host all-reduces rs.sums / rs.emax,esum in between)
 __global__ void k_finish(int which, KP kp, ReduceState rs, MeshDims md) {
     pdl_enter();
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (which == 0) finish_momentum(rs, kp_ref(kp));
-    else finish_extent(rs, md, kp_draws(kp));
+    if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+    if (which == 0) {
+        if (threadIdx.x == 0) finish_momentum(rs, kp_ref(kp));
+    } else {
+        Frame f;
+        constexpr int W = (int)(sizeof(Frame) / sizeof(double));
+        for (int k = 0; k < W; ++k) reinterpret_cast<double*>(&f)[k] = __ldcg(reinterpret_cast<const double*>(&rs.geo->f) + k);
+        finish_extent_warp(rs, md, kp_draws(kp), f);
+    }
 }
 
 __device__ __forceinline__ void mailbox_signal(const Mailbox& mb, int fbase, unsigned long long epoch) {

@@ -5,6 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 os.environ.setdefault("OCL_SC_GRAPH", "0")
 from ocelot_b200 import native, SpaceCharge, ParticleArray, DeviceParticleArray, apply_map, get_envelope
 from ocelot_b200.beam import apply_cavity
+from ocelot_b200 import RectAperture, EllipticalAperture, LSC
 rng = np.random.RandomState(0)
 for n, nm in ((3001, (9, 12, 7)), (20000, (31, 31, 31)), (5000, (20, 33, 64))):
     host = ParticleArray(n)
@@ -27,4 +28,21 @@ for n, nm in ((3001, (9, 12, 7)), (20000, (31, 31, 31)), (5000, (20, 33, 64))):
     s.collective_buffer(native.BUF_PHI).copy_(s.collective_buffer(native.BUF_PHI_SLAB)[:s.collective_buffer(native.BUF_PHI).numel()]) if s.collective_buffer(native.BUF_PHI).numel() <= s.collective_buffer(native.BUF_PHI_SLAB).numel() else None
     s.slab_finish(); s.stage_kick(r, dev.E, 0.1)
     torch.cuda.synchronize()
-    print("ok", n, nm, t)
+    # round 2: every gather mode (z-fastest / lane pairs staged / lane pairs with register prefetch), the deferred
+    # finish form, the aperture compaction kernels, LSC in both grid modes
+    for mode in ("0", "1", "2"):
+        os.environ["OCL_SC_GATHER"] = mode
+        sg = native.Solver(0, nm)
+        sg.kick_device(r, q, dev.E, 0.1)
+        sg.field_at_particles(r, q, dev.E)
+    os.environ.pop("OCL_SC_GATHER")
+    sd = native.Solver(0, nm)
+    sd.defer_finish(True)
+    sd.stage_momentum(r, dev.E); sd.stage_finish(0, dev.E); sd.stage_extent(r, q, dev.E); sd.stage_finish(1, dev.E)
+    sd.stage_deposit(r, q, dev.E); sd.stage_solve(); sd.stage_kick(r, dev.E, 0.1)
+    RectAperture(xmin=-1.5e-4, xmax=2e-4, ymax=1e-4).apply(dev, 0.0)
+    EllipticalAperture(xmax=1.8e-4, ymax=0.9e-4, dx=1e-5).apply(dev, 0.0)
+    LSC(async_grid=True).apply(dev, 0.1); LSC(async_grid=False).apply(dev, 0.1)
+    sc.apply(dev, 0.1)
+    torch.cuda.synchronize()
+    print("ok", n, dev.n, nm, t)
