@@ -68,7 +68,7 @@ struct Cart {
 
 // Frame and mesh of the current kick, derived ONCE per kick on the device (by the block that finishes the
 // momentum / extent reduction, after the cross-rank exchange in a sharded kick) and read by every
-// later kernel: no kernel repeats the serial fp64 divisions / square roots of derive_frame / derive_mesh
+// later kernel: no kernel repeats the serial fp64 divisions / square roots of derive_frame / the mesh derivation
 // in its prologue, and all of them see bit-identical geometry.
 struct Geo {
     Frame f;
@@ -169,28 +169,8 @@ __device__ __forceinline__ void derive_frame(const double* sums, double m_e_eV, 
     f.beta0 = sqrt(1.0 - 1.0 / (f.gamma0 * f.gamma0));                 // :238-239
 }
 
-// ---- sc.py:173-186 -----------------------------------------------------------
-// emax = {max x, max y, max z, -min x, -min y, -min z}; esum = {sum q*x, q*y, q*z, sum q}
-// draws = {scale, shift} of random_mesh, or scale <= 0 for "off"
-__device__ __forceinline__ void derive_mesh(const double* emax, const double* esum, int nx, int ny, int nz,
-                                            double scale, double shift, Mesh& m) {
-    m.n[0] = nx; m.n[1] = ny; m.n[2] = nz;
-    m.sumq = esum[3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-        double lo = -emax[3 + c];
-        double extent = emax[c] - lo;                                  // :173
-        if (scale > 0.0) extent = extent * scale;                      // :175
-        double h = extent / (double)(m.n[c] - 3);                      // :179
-        double xmin = lo / h;                                          // :181 (min commutes with /h)
-        double xmid = (esum[c] / h) / esum[3];                         // :182
-        double off = floor(xmin - xmid) + xmid;                        // :183
-        if (scale > 0.0) off = off + shift;                            // :185
-        m.steps[c] = h;
-        m.inv_steps[c] = 1.0 / h;
-        m.xoff[c] = off;
-    }
-}
+// sc.py:173-186 (mesh steps and origin from the reduced extents) lives in finish_extent_warp (sc_kernels.cu): one lane
+// per axis, emax = {max x, max y, max z, -min x, -min y, -min z}, esum = {sum q*x, q*y, q*z, sum q}.
 
 // block-wide copy of the kick geometry into shared memory (ends with a barrier)
 __device__ __forceinline__ void load_geo(const Geo* __restrict__ g, Geo* s) {

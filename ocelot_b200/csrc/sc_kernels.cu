@@ -520,7 +520,7 @@ __global__ void __launch_bounds__(kThreads) k_field(const double* __restrict__ p
     equad[((size_t)comp * md.nx + i) * md.ny * md.nz + jk] = e;
 }
 
-// The same table stored x-fastest for the lane-pair gather (trilinear_pair): rec(comp, i, j, k) at
+// The same table stored x-fastest for the lane-pair gather (gather_pair): rec(comp, i, j, k) at
 // equad[comp*cells + (j*nz + k)*nx + i].  One block = one j and kFieldKT consecutive k: the phi values
 // it needs ((j..j+2) x (k..k+KT+1) for every i) are staged in shared memory with k-contiguous reads,
 // and the records leave with i fastest, i.e. fully coalesced 32-byte stores.
@@ -567,7 +567,8 @@ __global__ void __launch_bounds__(kThreads) k_field_xf(const double* __restrict_
 // ---------------------------------------------------------------------------
 // sweep 4: gather, kick, back-transform (sc.py:201-204, :244-251)
 //   LAYOUT 0: z-fastest quad table, six independent 256-bit gathers per particle
-//   LAYOUT 1: x-fastest quad table fetched by lane pairs (trilinear_pair)
+//   LAYOUT 1: x-fastest quad table fetched by lane pairs (gather_pair), rows staged through shared memory
+//   LAYOUT 2: the same with the rows prefetched into registers (prefetch_sweep)
 // ---------------------------------------------------------------------------
 template <bool KICK, bool TAP, int LAYOUT, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB) k_gather_kick(double* __restrict__ r, long long ld, long long n,
