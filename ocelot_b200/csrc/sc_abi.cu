@@ -92,6 +92,10 @@ struct ocl_sc {
     const void* g_r = nullptr; const void* g_q = nullptr; long long g_ld = 0, g_n = 0;
     long long graph_launches_per_kick = 0;
     const KickParams* cur_pp = nullptr;       // non-null while stages are being captured
+    bool publish_params = false;              // capture of the library's own graph: k_momentum is the parameter node
+    cudaKernelNodeParams param_np = {};       // its launch shape, as captured
+    Mailbox g_mb{};                           // arguments the parameter node was captured with
+    ReduceState g_rs{};
     // longitudinal space charge (sc_lsc.cu): 1-D work space, grown on demand
     LscWork lw{};
     int lsc_cap = 0;                          // grid points the buffers hold
@@ -685,7 +689,14 @@ int ocl_sc_stage_momentum(ocl_sc_t* h, const double* d_r, long long ld, long lon
     mark(h, T_BEGIN, st);
     Mailbox mb = h->mb;
     if (h->debug_skip & 1) mb.world = 1;
-    launch_momentum(d_r, ld, n, kp_of(h, E_GeV, 0.0, nullptr), h->rs, mb, h->mb_err, st);
+    KP kp = kp_of(h, E_GeV, 0.0, nullptr);
+    KickParams* publish = nullptr;
+    if (h->publish_params) {                  // the graph's parameter node: scalars by value, published for the rest
+        kp.p = nullptr;
+        publish = h->kp_dev;
+        h->g_mb = mb; h->g_rs = h->rs;
+    }
+    launch_momentum(d_r, ld, n, kp, h->rs, mb, h->mb_err, publish, st);
     h->launches += 1;
     mark(h, T_MOM, st);
     return check_launch(h, "k_momentum");
@@ -778,20 +789,22 @@ static void drop_graph(ocl_sc* h) {
     h->graph_exec = nullptr; h->graph = nullptr; h->param_node = nullptr;
 }
 
-// Capture the whole kick (parameter node + ~19 kernels + the side-stream fork/join) once.
+// Capture the whole kick (15 kernels, the first of which doubles as the parameter node, + memset + the
+// side-stream fork/join) once.
 static int capture_kick(ocl_sc* h, double* d_r, long long ld, const double* d_q, long long n, double E_GeV,
                         double dz, const double* mesh_draws) {
     drop_graph(h);
     cudaStream_t cs = h->own_stream;
     CU(h, cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-    launch_set_params(kick_params(h, E_GeV, dz, mesh_draws), h->kp_dev, cs);
     h->cur_pp = h->kp_dev;
+    h->publish_params = true;                 // k_momentum carries the scalars by value and stores them in kp_dev
     const long long before = h->launches;
     int rc = run_stages(h, d_r, ld, d_q, n, E_GeV, dz, mesh_draws, cs);
     h->cur_pp = nullptr;
+    h->publish_params = false;
     cudaGraph_t g = nullptr;
     cudaError_t e = cudaStreamEndCapture(cs, &g);
-    h->graph_launches_per_kick = h->launches - before + 1;
+    h->graph_launches_per_kick = h->launches - before;
     h->launches = before;
     if (rc || e != cudaSuccess || !g) {
         if (g) cudaGraphDestroy(g);
@@ -808,8 +821,9 @@ static int capture_kick(ocl_sc* h, double* d_r, long long ld, const double* d_q,
         cudaGraphNodeType t;
         if (cudaGraphNodeGetType(nodes[i], &t) != cudaSuccess || t != cudaGraphNodeTypeKernel) continue;
         cudaKernelNodeParams kp;
-        if (cudaGraphKernelNodeGetParams(nodes[i], &kp) == cudaSuccess && kp.func == set_params_kernel()) {
+        if (cudaGraphKernelNodeGetParams(nodes[i], &kp) == cudaSuccess && kp.func == momentum_kernel()) {
             h->param_node = nodes[i];
+            h->param_np = kp;
             break;
         }
     }
@@ -843,11 +857,14 @@ int ocl_sc_kick_device(ocl_sc_t* h, double* d_r, long long ld, const double* d_q
         if (rc) return 1;
     }
     if (adopt_stream(h, st)) return 1;
-    KickParams kp = kick_params(h, E_GeV, dz, mesh_draws);
-    void* args[2] = {&kp, &h->kp_dev};
-    cudaKernelNodeParams np = {};
-    np.func = const_cast<void*>(set_params_kernel());
-    np.gridDim = dim3(1); np.blockDim = dim3(32); np.sharedMemBytes = 0;
+    // refresh the parameter node (k_momentum): same launch shape and pointers as captured, this kick's scalars
+    KP kp;
+    kp.v = kick_params(h, E_GeV, dz, mesh_draws);
+    kp.p = nullptr;
+    const double* a_r = d_r;
+    long long a_ld = ld, a_n = n;
+    void* args[8] = {&a_r, &a_ld, &a_n, &kp, &h->g_rs, &h->g_mb, &h->mb_err, &h->kp_dev};
+    cudaKernelNodeParams np = h->param_np;
     np.kernelParams = args; np.extra = nullptr;
     CU(h, cudaGraphExecKernelNodeSetParams(h->graph_exec, h->param_node, &np));
     CU(h, cudaGraphLaunch(h->graph_exec, st));

@@ -181,9 +181,14 @@ __device__ __forceinline__ void finish_extent_warp(const ReduceState& rs, const 
 // cross-rank exchange (sharded kick) and derives the frame, unless the caller defers that
 // (NCCL fallback: all-reduce of rs.sums, then k_finish).
 // ---------------------------------------------------------------------------
+// publish != nullptr (whole-kick graph): this kernel is the graph's parameter node -- it receives the kick's
+// scalars by value (refreshed per launch with cudaGraphExecKernelNodeSetParams) and stores them for the kernels
+// downstream, which read the device block; no separate one-block parameter kernel in front of the kick.
 __global__ void __launch_bounds__(kThreads, 4) k_momentum(const double* __restrict__ r, long long ld, long long n,
-                                                         KP kp, ReduceState rs, Mailbox mb, int* mb_err) {
+                                                         KP kp, ReduceState rs, Mailbox mb, int* mb_err,
+                                                         KickParams* publish) {
     pdl_enter();
+    if (publish && blockIdx.x == 0 && threadIdx.x == 0) *publish = kp.v;
     const RefParams rp = kp_ref(kp);
     __shared__ double sh[3 * kWarps];
     __shared__ double pipe[kPipeDepth * 3 * kThreads];
@@ -811,9 +816,11 @@ void launch_set_params(KickParams v, KickParams* dst, cudaStream_t st) { launch_
 const void* set_params_kernel() { return (const void*)k_set_params; }
 
 void launch_momentum(const double* r, long long ld, long long n, KP kp, ReduceState rs, Mailbox mb, int* mb_err,
-                     cudaStream_t st) {
-    launch_k(k_momentum, dim3(particle_grid(n, rs.max_blocks)), dim3(kThreads), 0, st, r, ld, n, kp, rs, mb, mb_err);
+                     KickParams* publish, cudaStream_t st) {
+    launch_k(k_momentum, dim3(particle_grid(n, rs.max_blocks)), dim3(kThreads), 0, st, r, ld, n, kp, rs, mb, mb_err,
+             publish);
 }
+const void* momentum_kernel() { return (const void*)k_momentum; }
 void launch_extent(const double* r, long long ld, const double* q, long long n, KP kp, ReduceState rs, MeshDims md,
                    Mailbox mb, int* mb_err, cudaStream_t st) {
     launch_k(k_extent, dim3(particle_grid(n, 148 * 3)), dim3(kThreads), 0, st, r, ld, q, n, kp, rs, md, mb, mb_err);

@@ -53,7 +53,8 @@ void launch_set_params(KickParams v, KickParams* dst, cudaStream_t st);
 void launch_combine_extents(const double* all, int world, ReduceState rs, cudaStream_t st);
 const void* set_params_kernel();
 void launch_momentum(const double* r, long long ld, long long n, KP kp, ReduceState rs, Mailbox mb, int* mb_err,
-                     cudaStream_t st);
+                     KickParams* publish, cudaStream_t st);
+const void* momentum_kernel();
 void launch_extent(const double* r, long long ld, const double* q, long long n, KP kp, ReduceState rs, MeshDims md,
                    Mailbox mb, int* mb_err, cudaStream_t st);
 void launch_finish(int which, KP kp, ReduceState rs, MeshDims md, cudaStream_t st);
