@@ -821,7 +821,8 @@ static int capture_kick(ocl_sc* h, double* d_r, long long ld, const double* d_q,
         cudaGraphNodeType t;
         if (cudaGraphNodeGetType(nodes[i], &t) != cudaSuccess || t != cudaGraphNodeTypeKernel) continue;
         cudaKernelNodeParams kp;
-        if (cudaGraphKernelNodeGetParams(nodes[i], &kp) == cudaSuccess && kp.func == momentum_kernel()) {
+        if (cudaGraphKernelNodeGetParams(nodes[i], &kp) == cudaSuccess &&
+            (kp.func == momentum_kernel(0) || kp.func == momentum_kernel(1))) {
             h->param_node = nodes[i];
             h->param_np = kp;
             break;

@@ -451,6 +451,92 @@ __device__ __forceinline__ void pipelined_sweep(const double* const (&base)[NR],
     cp_async_wait<0>();
 }
 
+// ---- TMA row pipeline ------------------------------------------------------------------------------------------
+// The same sweep with the rows moved by the bulk-copy engine (cp.async.bulk = 1-D TMA, UBLKCP in the SASS) instead of
+// one 8-byte LDGSTS per thread and row: one thread per block posts NR copies of 2 KB (256 particles of one row) per
+// stage against an mbarrier, the block consumes the stage when the barrier's transaction count completes.  Tiles are
+// block-strided; D stages are in flight per block.  Requirements (checked by the launchers): every row base and the
+// shared buffer are 16-byte aligned.  The last, partial tile (n % 256 particles) is read with plain loads -- a bulk
+// copy may not run past the end of the caller's arrays.
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gmem_src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+// sm: [D][NR][kSweepThreads] doubles, 16-byte aligned; bars: [D].  body(i, v) once per particle.
+template <int NR, int D, typename F>
+__device__ __forceinline__ void bulk_sweep(const double* const (&base)[NR], int n, double* sm, unsigned long long* bars,
+                                           F&& body) {
+    constexpr int T = kSweepThreads;
+    constexpr unsigned kRowBytes = T * sizeof(double);
+    const int tiles = (n + T - 1) / T, full = n / T;           // tiles [0, full) are complete
+    const int grid = (int)gridDim.x;
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) mbar_init(bars + d, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    auto post = [&](int it) {                                   // tile of iteration `it` into stage it % D
+        const int ti = (int)blockIdx.x + it * grid;
+        if (threadIdx.x == 0 && ti < full) {
+            unsigned long long* bar = bars + it % D;
+            mbar_expect_tx(bar, NR * kRowBytes);
+            double* dst = sm + (size_t)(it % D) * NR * T;
+#pragma unroll
+            for (int k = 0; k < NR; ++k) bulk_load(dst + k * T, base[k] + (size_t)ti * T, kRowBytes, bar);
+        }
+    };
+#pragma unroll
+    for (int d = 0; d < D; ++d) post(d);
+    for (int it = 0;; ++it) {
+        const int ti = (int)blockIdx.x + it * grid;
+        if (ti >= tiles) break;
+        const int i = ti * T + (int)threadIdx.x;
+        double v[NR];
+        bool valid = true;
+        if (ti < full) {
+            mbar_wait(bars + it % D, (unsigned)((it / D) & 1));
+            const double* src = sm + (size_t)(it % D) * NR * T + threadIdx.x;
+#pragma unroll
+            for (int k = 0; k < NR; ++k) v[k] = src[k * T];
+        } else {                                                // the ragged tail, at most one tile per sweep
+            valid = i < n;
+#pragma unroll
+            for (int k = 0; k < NR; ++k) v[k] = valid ? __ldcs(base[k] + i) : 0.0;
+        }
+        // The refill is written by the async proxy (TMA engine), which is not ordered behind this thread's LDS queue:
+        // order the generic-proxy reads of the stage before it, then meet the other threads.  (Without the proxy
+        // fence ~1 in 10^4 particles of k_deposit saw the NEXT tile's values: measured on B200.)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();                                        // every thread has taken its values out of this stage
+        post(it + D);
+        if (valid) body(i, v);
+    }
+}
+
 // The same sweep without shared-memory staging: the next trip's rows are loaded straight into registers
 // (plain LDG) before the current particle's arithmetic, so they are in flight during it.  Costs NR more
 // registers per thread than the cp.async pipeline and saves its LDGSTS + LDS traffic through the L1TEX data

@@ -16,6 +16,7 @@
 // No kernel needs a host round trip: the scalar state (frame, mesh) is
 // re-derived on the device by every block from the tiny reduced buffers, which
 // is also what lets a multi-GPU caller all-reduce those buffers in between.
+#include <cstdint>
 #include <cstdlib>
 
 #include "sc_kernels.h"
@@ -184,6 +185,7 @@ __device__ __forceinline__ void finish_extent_warp(const ReduceState& rs, const 
 // publish != nullptr (whole-kick graph): this kernel is the graph's parameter node -- it receives the kick's
 // scalars by value (refreshed per launch with cudaGraphExecKernelNodeSetParams) and stores them for the kernels
 // downstream, which read the device block; no separate one-block parameter kernel in front of the kick.
+template <bool TMA>
 __global__ void __launch_bounds__(kThreads, 4) k_momentum(const double* __restrict__ r, long long ld, long long n,
                                                          KP kp, ReduceState rs, Mailbox mb, int* mb_err,
                                                          KickParams* publish) {
@@ -191,14 +193,17 @@ __global__ void __launch_bounds__(kThreads, 4) k_momentum(const double* __restri
     if (publish && blockIdx.x == 0 && threadIdx.x == 0) *publish = kp.v;
     const RefParams rp = kp_ref(kp);
     __shared__ double sh[3 * kWarps];
-    __shared__ double pipe[kPipeDepth * 3 * kThreads];
+    __shared__ __align__(128) double pipe[kPipeDepth * 3 * kThreads];
+    __shared__ unsigned long long bars[kPipeDepth];
     double v[3] = {0.0, 0.0, 0.0};
     const double* const base[3] = {r + ld, r + 3 * ld, r + 5 * ld};
-    pipelined_sweep<3, kPipeDepth>(base, (int)n, pipe, [&](int, const double (&w)[3]) {
+    auto body = [&](int, const double (&w)[3]) {
         double gam;
         const double pzr = mad_pz_rel(rp, w[0], w[1], w[2], gam);
         v[0] += w[0]; v[1] += w[1]; v[2] += pzr;       // p = (x', y', pz_rel) * pc: scaled once at the end
-    });
+    };
+    if constexpr (TMA) bulk_sweep<3, kPipeDepth>(base, (int)n, pipe, bars, body);
+    else pipelined_sweep<3, kPipeDepth>(base, (int)n, pipe, body);
     pdl_trigger();
     if (!grid_reduce<3, 0>(v, rs.part, rs.ticket + 0, sh)) return;
     if (threadIdx.x >= 32) return;                      // the finishing block's first warp carries on
@@ -218,13 +223,15 @@ __global__ void __launch_bounds__(kThreads, 4) k_momentum(const double* __restri
 // remembers which particle gave each of its six extrema; the finishing block re-evaluates those
 // (at most six) particles in the reference's exact operation order before the mesh is derived.
 // ---------------------------------------------------------------------------
+template <bool TMA>
 __global__ void __launch_bounds__(kThreads, 3) k_extent(const double* __restrict__ r, long long ld,
                                                        const double* __restrict__ q, long long n, KP kp,
                                                        ReduceState rs, MeshDims md, Mailbox mb, int* mb_err) {
     pdl_enter();
     const RefParams rp = kp_ref(kp);
     __shared__ double sh[10 * kWarps];
-    __shared__ double pipe[kPipeDepth * 7 * kThreads];
+    __shared__ __align__(128) double pipe[kPipeDepth * 7 * kThreads];
+    __shared__ unsigned long long bars[kPipeDepth];
     __shared__ Frame sf;
     __shared__ double shv[6];
     __shared__ int shi[6];
@@ -237,7 +244,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_extent(const double* __restrict
     double v[10] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY, 0.0, 0.0, 0.0, 0.0};
     int ix[6] = {-1, -1, -1, -1, -1, -1};
     const double* const base[7] = {r, r + ld, r + 2 * ld, r + 3 * ld, r + 4 * ld, r + 5 * ld, q};
-    pipelined_sweep<7, kPipeDepth>(base, (int)n, pipe, [&](int i, const double (&w)[7]) {
+    auto body = [&](int i, const double (&w)[7]) {
         const Cart c = mad_to_cart(rp, w[0], w[1], w[2], w[3], w[4], w[5]);
         double a, b, g;
         rotate_stretch(f, c.x, c.y, c.z, a, b, g);
@@ -254,7 +261,9 @@ __global__ void __launch_bounds__(kThreads, 3) k_extent(const double* __restrict
         v[3] = fmax(v[3], -a); v[4] = fmax(v[4], -b); v[5] = fmax(v[5], -g);
 #endif
         v[6] += qi * a; v[7] += qi * b; v[8] += qi * g; v[9] += qi;
-    });
+    };
+    if constexpr (TMA) bulk_sweep<7, kPipeDepth>(base, (int)n, pipe, bars, body);
+    else pipelined_sweep<7, kPipeDepth>(base, (int)n, pipe, body);
     pdl_trigger();
     if (!grid_reduce_extent(v, ix, rs.part, rs.ticket + 1, sh, shv, shi)) return;
     if (threadIdx.x >= 32) return;
@@ -323,18 +332,20 @@ constexpr int kFlagRhoDone = 128 + 8 * 3;       // doubles [152,160): "slice red
 // ---------------------------------------------------------------------------
 // sweep 3: nearest-grid-point deposit (sc.py:186-193)
 // ---------------------------------------------------------------------------
+template <bool TMA>
 __global__ void __launch_bounds__(kThreads, 3) k_deposit(const double* __restrict__ r, long long ld,
                                                         const double* __restrict__ q, long long n, KP kp,
                                                         ReduceState rs, MeshDims md, double* __restrict__ rho) {
     pdl_enter();
     const RefParams rp = kp_ref(kp);
-    __shared__ double pipe[kPipeDepth * 7 * kThreads];
+    __shared__ __align__(128) double pipe[kPipeDepth * 7 * kThreads];
+    __shared__ unsigned long long bars[kPipeDepth];
     __shared__ Geo sg;
     load_geo(rs.geo, &sg);
     const Frame f = sg.f;
     const Mesh m = sg.m;
     const double* const base[7] = {r, r + ld, r + 2 * ld, r + 3 * ld, r + 4 * ld, r + 5 * ld, q};
-    pipelined_sweep<7, kPipeDepth>(base, (int)n, pipe, [&](int, const double (&w)[7]) {
+    auto body = [&](int, const double (&w)[7]) {
         const Cart c = mad_to_cart(rp, w[0], w[1], w[2], w[3], w[4], w[5]);
         double a, b, g, g0, g1, g2;
         rotate_stretch(f, c.x, c.y, c.z, a, b, g);
@@ -342,7 +353,9 @@ __global__ void __launch_bounds__(kThreads, 3) k_deposit(const double* __restric
         const int c0 = (int)floor(g0) + 1, c1 = (int)floor(g1) + 1, c2 = (int)floor(g2) + 1;   // sc.py:191
         if ((unsigned)c0 < (unsigned)md.nx && (unsigned)c1 < (unsigned)md.ny && (unsigned)c2 < (unsigned)md.nz)
             atomicAdd(rho + ((size_t)c0 * md.ny + c1) * md.nz + c2, w[6]);                     // sc.py:192-193
-    });
+    };
+    if constexpr (TMA) bulk_sweep<7, kPipeDepth>(base, (int)n, pipe, bars, body);
+    else pipelined_sweep<7, kPipeDepth>(base, (int)n, pipe, body);
 }
 
 // ---------------------------------------------------------------------------
@@ -815,22 +828,43 @@ void launch_combine_extents(const double* all, int world, ReduceState rs, cudaSt
 void launch_set_params(KickParams v, KickParams* dst, cudaStream_t st) { launch_k(k_set_params, dim3(1), dim3(32), 0, st, v, dst); }
 const void* set_params_kernel() { return (const void*)k_set_params; }
 
+// Rows go through the bulk-copy engine (bulk_sweep: cp.async.bulk + mbarrier) when every row base is 16-byte aligned
+// and the sweep is long enough for it to pay.  Measured on B200, whole kick: 12.5 M / 127^3 996.6 -> 992.1 us, 50 M /
+// 255^3 6626 -> 6565 us (k_momentum 205 -> 189 us, k_extent 445 -> 425 us), but 1 M / 63^3 133.7 -> 136.6 us (the
+// per-tile block barrier costs more than the per-thread cp.async pipeline when a block sees only 9 tiles).
+// OCL_SC_TMA=0 / 1 forces one path.
+static bool tma_rows(const double* r, long long ld, const double* q, long long n) {
+    static int mode = -2;
+    if (mode == -2) { const char* e = getenv("OCL_SC_TMA"); mode = e ? atoi(e) : -1; }
+    if (mode == 0) return false;
+    if (mode < 0 && n < 4000000) return false;
+    return ((uintptr_t)r % 16 == 0) && (ld % 2 == 0) && ((uintptr_t)q % 16 == 0);
+}
 void launch_momentum(const double* r, long long ld, long long n, KP kp, ReduceState rs, Mailbox mb, int* mb_err,
                      KickParams* publish, cudaStream_t st) {
-    launch_k(k_momentum, dim3(particle_grid(n, rs.max_blocks)), dim3(kThreads), 0, st, r, ld, n, kp, rs, mb, mb_err,
-             publish);
+    const dim3 grid(particle_grid(n, rs.max_blocks));
+    if (tma_rows(r, ld, nullptr, n))
+        launch_k(k_momentum<true>, grid, dim3(kThreads), 0, st, r, ld, n, kp, rs, mb, mb_err, publish);
+    else
+        launch_k(k_momentum<false>, grid, dim3(kThreads), 0, st, r, ld, n, kp, rs, mb, mb_err, publish);
 }
-const void* momentum_kernel() { return (const void*)k_momentum; }
+const void* momentum_kernel(int tma) { return tma ? (const void*)k_momentum<true> : (const void*)k_momentum<false>; }
 void launch_extent(const double* r, long long ld, const double* q, long long n, KP kp, ReduceState rs, MeshDims md,
                    Mailbox mb, int* mb_err, cudaStream_t st) {
-    launch_k(k_extent, dim3(particle_grid(n, 148 * 3)), dim3(kThreads), 0, st, r, ld, q, n, kp, rs, md, mb, mb_err);
+    if (tma_rows(r, ld, q, n))
+        launch_k(k_extent<true>, dim3(particle_grid(n, 148 * 3)), dim3(kThreads), 0, st, r, ld, q, n, kp, rs, md, mb, mb_err);
+    else
+        launch_k(k_extent<false>, dim3(particle_grid(n, 148 * 3)), dim3(kThreads), 0, st, r, ld, q, n, kp, rs, md, mb, mb_err);
 }
 void launch_finish(int which, KP kp, ReduceState rs, MeshDims md, cudaStream_t st) {
     launch_k(k_finish, dim3(1), dim3(32), 0, st, which, kp, rs, md);
 }
 void launch_deposit(const double* r, long long ld, const double* q, long long n, KP kp, ReduceState rs,
                     MeshDims md, double* rho, cudaStream_t st) {
-    launch_k(k_deposit, dim3(grid_for(n, 148 * 3)), dim3(kThreads), 0, st, r, ld, q, n, kp, rs, md, rho);
+    if (tma_rows(r, ld, q, n))
+        launch_k(k_deposit<true>, dim3(grid_for(n, 148 * 3)), dim3(kThreads), 0, st, r, ld, q, n, kp, rs, md, rho);
+    else
+        launch_k(k_deposit<false>, dim3(grid_for(n, 148 * 3)), dim3(kThreads), 0, st, r, ld, q, n, kp, rs, md, rho);
 }
 void launch_green_table(ReduceState rs, MeshDims md, double* gtab, double* h3, cudaStream_t st) {
     StepSrc src;

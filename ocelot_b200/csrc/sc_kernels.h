@@ -54,7 +54,7 @@ void launch_combine_extents(const double* all, int world, ReduceState rs, cudaSt
 const void* set_params_kernel();
 void launch_momentum(const double* r, long long ld, long long n, KP kp, ReduceState rs, Mailbox mb, int* mb_err,
                      KickParams* publish, cudaStream_t st);
-const void* momentum_kernel();
+const void* momentum_kernel(int tma);
 void launch_extent(const double* r, long long ld, const double* q, long long n, KP kp, ReduceState rs, MeshDims md,
                    Mailbox mb, int* mb_err, cudaStream_t st);
 void launch_finish(int which, KP kp, ReduceState rs, MeshDims md, cudaStream_t st);
