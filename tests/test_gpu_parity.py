@@ -11,6 +11,7 @@ bound); post-kick coordinates per row relative to the row rms (<= 1e-10);
 cell indices / rho must agree exactly up to fp64 summation order; geometry
 scalars to 1e-14 relative.
 """
+import os
 import numpy as np
 import pytest
 
@@ -488,3 +489,43 @@ def test_fft_512_box_matches_cufft(native, monkeypatch):
     phi_lib = native.Solver(0, shape).potential_host(rho, steps)
     monkeypatch.delenv("OCL_SC_SOLVER", raising=False)
     assert rel_to_max(phi_own, phi_lib) < 1e-13
+
+
+def test_tma_row_pipeline_is_bit_identical_to_cp_async():
+    """The bulk-copy (TMA) row pipeline that large bunches use (>= 4 M particles by default) against the per-thread
+    cp.async pipeline, forced with OCL_SC_TMA in two fresh processes on the same 1 000 037-particle bunch (ragged last
+    tile, padded rows): both assign particles to threads identically, so reductions, mesh, charge grid and kicked
+    particles must agree bit for bit.  (This is the test that caught the cross-proxy write-after-read hazard of the
+    stage refill: without the proxy fence ~1e-4 of the particles were deposited with the next tile's coordinates.)"""
+    import json
+    import subprocess
+    import sys
+    worker = r'''
+import json, sys, numpy as np, torch
+sys.path.insert(0, %r)
+from ocelot_b200 import native, DeviceParticleArray, ParticleArray
+rng = np.random.RandomState(11)
+n = 1_000_037
+host = ParticleArray(n)
+host.rparticles[:] = rng.randn(6, n) * np.array([1e-4, 2e-5, 1e-4, 2e-5, 1e-3, 1e-4])[:, None]
+host.q_array[:] = 2.5e-16          # equal charges: the atomic sums of the deposit do not depend on their order
+host.E = 0.13
+dev = DeviceParticleArray.from_host(host)
+s = native.Solver(0, (31, 63, 47))
+s.kick_device(dev.rparticles, dev.q_array, 0.13, 0.1)
+torch.cuda.synchronize()
+rho, g, r = s.rho(), s.geometry(), dev.rparticles.cpu().numpy()
+w = np.arange(rho.size, dtype=np.float64).reshape(rho.shape)
+print(json.dumps(dict(mom=s.collective_buffer(native.BUF_MOMENTUM).cpu().numpy().tolist(),
+                      ext=s.collective_buffer(native.BUF_EXTENT).cpu().numpy().tolist(),
+                      steps=g["steps"].tolist(), xoff=g["X_off"].tolist(),
+                      rho=[float(rho.sum()), float((rho * w).sum()), float((rho * w * w).sum())],
+                      rows=[float(x) for x in (r.sum(axis=1).tolist() + (r * r).sum(axis=1).tolist())])))
+''' % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for mode in ("0", "1"):
+        res = subprocess.run([sys.executable, "-c", worker], env=dict(os.environ, OCL_SC_TMA=mode), capture_output=True,
+                             text=True, timeout=600)
+        assert res.returncode == 0, res.stderr[-2000:]
+        out[mode] = json.loads(res.stdout.strip().splitlines()[-1])
+    assert out["0"] == out["1"]
