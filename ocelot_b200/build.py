@@ -55,9 +55,28 @@ def command(verbose: bool = False) -> list[str]:
     return cmd
 
 
+STAMP = LIB + ".srchash"
+
+
+def source_hash() -> str:
+    """Content hash of everything the library is built from (sources, headers, this recipe)."""
+    import hashlib
+    h = hashlib.sha256()
+    for d in [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]:
+        with open(d, "rb") as f:
+            h.update(os.path.basename(d).encode() + b"\0" + f.read())
+    return h.hexdigest()
+
+
 def up_to_date() -> bool:
+    """True when the library was built from the sources as they are now.  Decided by content (a stamp file written
+    next to the library), not by modification times: a snapshot copied to another machine keeps the contents, not
+    necessarily the mtimes.  Without a stamp, fall back to comparing mtimes."""
     if not os.path.exists(LIB):
         return False
+    if os.path.exists(STAMP):
+        with open(STAMP) as f:
+            return f.read().strip() == source_hash()
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
     return all(os.path.getmtime(d) <= t for d in deps)
@@ -72,6 +91,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         sys.stderr.write(res.stdout + res.stderr)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    with open(STAMP, "w") as f:
+        f.write(source_hash() + "\n")
     return LIB
 
 

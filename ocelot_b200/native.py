@@ -102,15 +102,21 @@ def load():
     if _lib is not None:
         return _lib
     from . import build as _build
-    stale = (LIB_PATH == _build.LIB and os.path.exists(LIB_PATH) and not _build.up_to_date()
+    exists = os.path.exists(LIB_PATH)
+    stale = (exists and LIB_PATH == _build.LIB and not _build.up_to_date()
              and os.access(os.path.dirname(LIB_PATH), os.W_OK) and _build.have_nvcc())
-    if not os.path.exists(LIB_PATH) or stale:     # stale: a source file is newer than the library
+    if not exists or stale:                        # stale: the sources differ from what the library was built from
         try:
             _build.build(force=stale)
         except Exception as exc:  # noqa: BLE001
-            raise RuntimeError(
-                f"ocelot_b200: native library {LIB_PATH} is missing and could not be built ({exc}). "
-                "There is no CPU fallback for the space-charge kick.") from exc
+            if exists:                             # keep running on the library that is there; say so
+                import warnings
+                warnings.warn(f"ocelot_b200: {LIB_PATH} is older than its sources and could not be rebuilt ({exc}); "
+                              "using the existing library")
+            else:
+                raise RuntimeError(
+                    f"ocelot_b200: native library {LIB_PATH} is missing and could not be built ({exc}). "
+                    "There is no CPU fallback for the space-charge kick.") from exc
     lib = C.CDLL(LIB_PATH)
     for name, (res, args) in _SIGNATURES.items():
         fn = getattr(lib, name)
