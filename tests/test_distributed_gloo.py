@@ -137,6 +137,68 @@ def test_two_rank_sharded_kick_matches_single_process(draws):
         assert np.max(np.abs(got[row] - ref[row])) / np.std(ref[row]) < 1e-10
 
 
+class DeferredOracleEngine(OracleStageEngine):
+    """The same double with the hooks of the native engine's NCCL-fallback form (begin_kick, finish_momentum,
+    finish_extent: geometry derived only AFTER the caller's all-reduce), recording the order of the calls."""
+
+    def __init__(self, nmesh):
+        super().__init__(nmesh)
+        self.log = []
+
+    def begin_kick(self, draws, multi):
+        self.log.append(("begin", multi))
+
+    def momentum(self, r, q, E):
+        self.log.append("momentum")
+        super().momentum(r, q, E)
+        self.local_count = float(self.buffers["momentum"][3])
+
+    def finish_momentum(self):
+        # must run after the all-reduce: the count is now the whole bunch's
+        assert float(self.buffers["momentum"][3]) > self.local_count
+        self.log.append("finish_momentum")
+
+    def extent(self, r, q, E):
+        self.log.append("extent")
+        super().extent(r, q, E)
+        self.local_sumq = float(self.buffers["extent_sum"][3])
+
+    def finish_extent(self):
+        assert float(self.buffers["extent_sum"][3]) > self.local_sumq
+        self.log.append("finish_extent")
+
+    def deposit(self, r, q, E, draws):
+        self.log.append("deposit")
+        super().deposit(r, q, E, draws)
+
+
+def _deferred_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        np.random.seed(3)
+        r0, q0, E = orc.gaussian_bunch(4000, energy=0.05, charge=1e-10)
+        lo, hi = shard_bounds(4000, world, rank)
+        eng = DeferredOracleEngine((9, 9, 9))
+        sharded_kick(eng, torch.from_numpy(r0[:, lo:hi].copy()), torch.from_numpy(q0[lo:hi].copy()), E, 0.05, None)
+        out[rank] = list(eng.log)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_deferred_finish_hooks_run_after_the_collectives():
+    """Without a peer-memory mailbox the sweeps only reduce locally; the engine's finish hooks (ocl_sc_stage_finish in
+    the native engine) must be called after each all-reduce and before the next stage."""
+    port = _free_port()
+    with mp.Manager() as mgr:
+        out = mgr.dict()
+        mp.spawn(_deferred_worker, args=(2, port, out), nprocs=2, join=True)
+        logs = [out[k] for k in range(2)]
+    for log in logs:
+        assert log == [("begin", True), "momentum", "finish_momentum", "extent", "finish_extent", "deposit"]
+
+
 def test_shard_bounds_cover_everything():
     for n in (0, 1, 7, 1000, 1001):
         for w in (1, 2, 3, 8):
