@@ -421,8 +421,7 @@ __global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_real_even_outer(c
         };
         fft_io<false, M, 1>(gsrc, gdst, s.a, s.b, s.tw);
         pdl_trigger();
-        return;
-    }
+    } else {
     for (int t = threadIdx.x; t < M * NLP; t += Geom<M>::T) s.a[t] = make_double2(0.0, 0.0);
     __syncthreads();
     {   // p fastest: adjacent inner indices; U independent load pairs in flight per thread
@@ -459,6 +458,7 @@ __global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_real_even_outer(c
         const double2 v = X[ko * NLP + p];
         dst[(size_t)ko * inner + f] = v.x;
         if (f + 1 < inner) dst[(size_t)ko * inner + f + 1] = v.y;
+    }
     }
 }
 
@@ -588,8 +588,7 @@ __global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_cplx_outer(const 
             fft_io<true, M, 1>(SmemIO<M>{s.b}, gdst, s.a, s.b, s.tw);
             pdl_trigger();
         }
-        return;
-    }
+    } else {
     {   // global -> shared, U independent 16-byte loads in flight per thread
         constexpr int PER = NL * M / Geom<M>::T, U = PER < 8 ? PER : 8;
         static_assert(PER % U == 0, "load batching");
@@ -648,6 +647,7 @@ __global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_cplx_outer(const 
             if (sm.mode == 1) out[chunk(o * inner + f0 + l)] = X[o * NLP + l];
             else dst[(size_t)o * inner + l] = X[o * NLP + l];
         }
+    }
     }
 }
 

@@ -542,7 +542,10 @@ __global__ void __launch_bounds__(kThreads) k_field(const double* __restrict__ p
 // equad[comp*cells + (j*nz + k)*nx + i].  One block = one j and kFieldKT consecutive k: the phi values
 // it needs ((j..j+2) x (k..k+KT+1) for every i) are staged in shared memory with k-contiguous reads,
 // and the records leave with i fastest, i.e. fully coalesced 32-byte stores.
-constexpr int kFieldKT = 8;
+#ifndef OCL_FIELD_KT
+#define OCL_FIELD_KT 8
+#endif
+constexpr int kFieldKT = OCL_FIELD_KT;
 __global__ void __launch_bounds__(kThreads) k_field_xf(const double* __restrict__ phi, StepSrc src, ReduceState rs,
                                                       MeshDims md, EQuad* __restrict__ equad) {
     pdl_enter();
