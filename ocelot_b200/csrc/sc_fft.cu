@@ -333,6 +333,72 @@ __device__ __forceinline__ void fft_io(const Src& src, const Dst& dst, double2* 
     }
 }
 
+// The in-place geometry (M = 512: one shared buffer, every thread holds all its butterflies in registers across the
+// barrier) with the same pluggable source / sink.  A stage whose source AND sink are the shared buffer needs the barrier
+// between its reads and its writes; a stage that reads global memory or writes to the consumer does not.
+template <bool INV, int M, int Ns, int R, bool SYNC, typename Src, typename Dst>
+__device__ __forceinline__ void fft_stage_inplace_io(const Src& src, const Dst& dst, const double2* __restrict__ tw) {
+    constexpr int NL = Geom<M>::NL, T = Geom<M>::T;
+    constexpr int nb = M / R;
+    constexpr int step = M / (Ns * R);
+    constexpr int total = nb * NL;
+    constexpr int ITEMS = (total + T - 1) / T;
+    double2 v[ITEMS][R];
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        const int t = threadIdx.x + it * T;
+        if (total % T == 0 || t < total) {
+            const int j = t / NL, l = t % NL;
+            const int k = j & (Ns - 1);
+#pragma unroll
+            for (int r = 0; r < R; ++r) v[it][r] = src(j + r * nb, l);
+            if (Ns > 1) {
+#pragma unroll
+                for (int r = 1; r < R; ++r) {
+                    double2 w = __ldg(tw + r * k * step);
+                    if (INV) w.y = -w.y;
+                    v[it][r] = cmul(v[it][r], w);
+                }
+            }
+            dft<INV, R>(v[it]);
+        }
+    }
+    if (SYNC) __syncthreads();
+#pragma unroll
+    for (int it = 0; it < ITEMS; ++it) {
+        const int t = threadIdx.x + it * T;
+        if (total % T == 0 || t < total) {
+            const int j = t / NL, l = t % NL;
+            const int k = j & (Ns - 1);
+            const int base = (j - k) * R + k;
+#pragma unroll
+            for (int r = 0; r < R; ++r) dst(base + r * Ns, l, v[it][r]);
+        }
+    }
+}
+
+// SRC_BUF / DST_BUF: the caller's source / sink is the shared buffer `buf` itself
+template <bool INV, int M, int Ns, bool SRC_BUF, bool DST_BUF, typename Src, typename Dst>
+__device__ __forceinline__ void fft_io_inplace(const Src& src, const Dst& dst, double2* buf, const double2* tw) {
+    constexpr int R = radix_inplace(M / Ns);
+    constexpr bool first = Ns == 1, last = Ns * R == M;
+    constexpr bool src_buf = first ? SRC_BUF : true, dst_buf = last ? DST_BUF : true;
+    constexpr bool SYNC = src_buf && dst_buf;
+    if constexpr (first && last) {
+        fft_stage_inplace_io<INV, M, Ns, R, SYNC>(src, dst, tw);
+    } else if constexpr (first) {
+        fft_stage_inplace_io<INV, M, Ns, R, SYNC>(src, SmemIO<M>{buf}, tw);
+        __syncthreads();
+        fft_io_inplace<INV, M, Ns * R, SRC_BUF, DST_BUF>(src, dst, buf, tw);
+    } else if constexpr (last) {
+        fft_stage_inplace_io<INV, M, Ns, R, SYNC>(SmemIO<M>{buf}, dst, tw);
+    } else {
+        fft_stage_inplace_io<INV, M, Ns, R, SYNC>(SmemIO<M>{buf}, SmemIO<M>{buf}, tw);
+        __syncthreads();
+        fft_io_inplace<INV, M, Ns * R, SRC_BUF, DST_BUF>(src, dst, buf, tw);
+    }
+}
+
 __device__ __forceinline__ double green_entry_dev(const double* __restrict__ G, int gy, int gz, int i, int j, int k) {
     const size_t sx = (size_t)gy * gz, sy = gz;
     const double* lo = G + (size_t)i * sx + (size_t)j * sy + k;
@@ -402,64 +468,25 @@ __global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_real_even_outer(c
     const int pairs = min(NL, pairs_total - pair0);
     const double* src = in + (size_t)batch * n * inner;
     double* dst = out + (size_t)batch * (H + 1) * inner;
-    if constexpr (!Geom<M>::INPLACE) {
-        // direct-I/O path: the even extension is resolved in the source functor (element o and M - o are the same
-        // sample), the first H + 1 outputs go straight to global memory
-        auto gsrc = [&](int o, int p) -> double2 {
-            const int oo = o < n ? o : ((M - o) < n ? M - o : -1);
-            if (oo < 0 || p >= pairs) return make_double2(0.0, 0.0);
-            const int f = 2 * (pair0 + p);
-            const double e1 = __ldg(src + (size_t)oo * inner + f);
-            const double e2 = (f + 1 < inner) ? __ldg(src + (size_t)oo * inner + f + 1) : 0.0;
-            return make_double2(e1, e2);
-        };
-        auto gdst = [&](int ko, int p, double2 v) {
-            if (ko > H || p >= pairs) return;
-            const int f = 2 * (pair0 + p);
-            dst[(size_t)ko * inner + f] = v.x;
-            if (f + 1 < inner) dst[(size_t)ko * inner + f + 1] = v.y;
-        };
-        fft_io<false, M, 1>(gsrc, gdst, s.a, s.b, s.tw);
-        pdl_trigger();
-    } else {
-    for (int t = threadIdx.x; t < M * NLP; t += Geom<M>::T) s.a[t] = make_double2(0.0, 0.0);
-    __syncthreads();
-    {   // p fastest: adjacent inner indices; U independent load pairs in flight per thread
-        constexpr int U = 4;
-        const int p = threadIdx.x % NL, o0 = threadIdx.x / NL;
-        constexpr int OSTEP = Geom<M>::T / NL;
+    // direct I/O: the even extension is resolved in the source functor (element o and M - o are the same sample),
+    // the first H + 1 outputs go straight to global memory
+    auto gsrc = [&](int o, int p) -> double2 {
+        const int oo = o < n ? o : ((M - o) < n ? M - o : -1);
+        if (oo < 0 || p >= pairs) return make_double2(0.0, 0.0);
         const int f = 2 * (pair0 + p);
-        const bool live = p < pairs, two = f + 1 < inner;
-        for (int ob = o0; ob < n; ob += U * OSTEP) {
-            double e1[U], e2[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int o = ob + u * OSTEP;
-                const bool ok = live && o < n;
-                e1[u] = ok ? __ldg(src + (size_t)o * inner + f) : 0.0;
-                e2[u] = (ok && two) ? __ldg(src + (size_t)o * inner + f + 1) : 0.0;
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int o = ob + u * OSTEP;
-                if (live && o < n) {
-                    s.a[o * NLP + p] = make_double2(e1[u], e2[u]);
-                    if (o) s.a[(M - o) * NLP + p] = make_double2(e1[u], e2[u]);
-                }
-            }
-        }
-    }
-    double2* X = block_fft<false, M>(s.a, s.b, s.tw);
-    pdl_trigger();
-    for (int t = threadIdx.x; t < NL * (H + 1); t += Geom<M>::T) {
-        const int ko = t / NL, p = t % NL;
-        if (p >= pairs) continue;
+        const double e1 = __ldg(src + (size_t)oo * inner + f);
+        const double e2 = (f + 1 < inner) ? __ldg(src + (size_t)oo * inner + f + 1) : 0.0;
+        return make_double2(e1, e2);
+    };
+    auto gdst = [&](int ko, int p, double2 v) {
+        if (ko > H || p >= pairs) return;
         const int f = 2 * (pair0 + p);
-        const double2 v = X[ko * NLP + p];
         dst[(size_t)ko * inner + f] = v.x;
         if (f + 1 < inner) dst[(size_t)ko * inner + f + 1] = v.y;
-    }
-    }
+    };
+    if constexpr (Geom<M>::INPLACE) fft_io_inplace<false, M, 1, false, false>(gsrc, gdst, s.a, s.tw);
+    else fft_io<false, M, 1>(gsrc, gdst, s.a, s.b, s.tw);
+    pdl_trigger();
 }
 
 // ---------------------------------------------------------------------------
@@ -545,110 +572,57 @@ __global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_cplx_outer(const 
     double2* dst = out + (size_t)batch * n_out * inner + f0;
     // chunk-layout address of element (x plane = batch, line f)
     auto chunk = [&](int f) -> size_t { return ((size_t)(f / sm.fs) * sm.sx + batch) * sm.fs + f % sm.fs; };
-    if constexpr (!Geom<M>::INPLACE) {
-        // direct-I/O path (M <= 256): inputs from global memory into the first stage, outputs of the last stage
-        // straight to global memory (MODE 0/1) or through the K_hat multiply into the inverse transform (MODE 2)
-        auto gsrc = [&](int o, int l) -> double2 {
-            if (o >= n_in || l >= nl) return make_double2(0.0, 0.0);
-            if (sm.mode == 2) return in[chunk(o * inner + f0 + l)];
-            return src[(size_t)o * inner + l];
+    // direct I/O: inputs from global memory into the first stage, outputs of the last stage straight to global memory
+    // (MODE 0/1) or through the K_hat multiply into the inverse transform (MODE 2)
+    auto gsrc = [&](int o, int l) -> double2 {
+        if (o >= n_in || l >= nl) return make_double2(0.0, 0.0);
+        if (sm.mode == 2) return in[chunk(o * inner + f0 + l)];
+        return src[(size_t)o * inner + l];
+    };
+    auto gdst = [&](int o, int l, double2 v) {
+        if (o >= n_out || l >= nl) return;
+        if (sm.mode == 1) out[chunk(o * inner + f0 + l)] = v;
+        else dst[(size_t)o * inner + l] = v;
+    };
+    constexpr bool IP = Geom<M>::INPLACE;
+    __syncthreads();
+    if constexpr (MODE == 0) {
+        if constexpr (IP) fft_io_inplace<false, M, 1, false, false>(gsrc, gdst, s.a, s.tw);
+        else fft_io<false, M, 1>(gsrc, gdst, s.a, s.b, s.tw);
+    } else if constexpr (MODE == 1) {
+        if constexpr (IP) fft_io_inplace<true, M, 1, false, false>(gsrc, gdst, s.a, s.tw);
+        else fft_io<true, M, 1>(gsrc, gdst, s.a, s.b, s.tw);
+    } else {
+        const int hz1 = md.mz / 2 + 1, hy1 = md.my / 2 + 1;
+        const size_t kplane = (size_t)hy1 * hz1;
+        // every work item of this thread belongs to the same line (T is a multiple of NL): its (ky, kz) column
+        // of K_hat is located once
+        const int lt = threadIdx.x % Geom<M>::NL;
+        const double* kcol = nullptr;
+        if (lt < nl) {
+            const int f = f0 + lt + (sm.mode == 3 ? sm.f_base : 0);
+            const int ky = f / hz1, kz = f - ky * hz1;
+            kcol = khat + (size_t)min(ky, md.my - ky) * hz1 + kz;
+        }
+        // spectrum element kx of line l, times the real even K_hat, is the input of the inverse transform: it lands
+        // in buffer b (two-buffer geometry) or back in the one buffer (in-place geometry)
+        double2* spec = IP ? s.a : s.b;
+        auto mult = [&](int kx, int l, double2 v) {
+            const double g = kcol ? __ldg(kcol + (size_t)min(kx, M - kx) * kplane) : 0.0;
+            spec[kx * Geom<M>::NLP + l] = make_double2(v.x * g, v.y * g);
         };
-        auto gdst = [&](int o, int l, double2 v) {
-            if (o >= n_out || l >= nl) return;
-            if (sm.mode == 1) out[chunk(o * inner + f0 + l)] = v;
-            else dst[(size_t)o * inner + l] = v;
-        };
-        __syncthreads();
-        if constexpr (MODE == 0) {
-            fft_io<false, M, 1>(gsrc, gdst, s.a, s.b, s.tw);
-            pdl_trigger();
-        } else if constexpr (MODE == 1) {
-            fft_io<true, M, 1>(gsrc, gdst, s.a, s.b, s.tw);
-            pdl_trigger();
+        if constexpr (IP) {
+            fft_io_inplace<false, M, 1, false, true>(gsrc, mult, s.a, s.tw);
+            __syncthreads();
+            fft_io_inplace<true, M, 1, true, false>(SmemIO<M>{s.a}, gdst, s.a, s.tw);
         } else {
-            const int hz1 = md.mz / 2 + 1, hy1 = md.my / 2 + 1;
-            const size_t kplane = (size_t)hy1 * hz1;
-            // spectrum element kx of line l, times the real even K_hat, lands in buffer b for the inverse transform
-            // every work item of this thread belongs to the same line (T is a multiple of NL): its (ky, kz) column
-            // of K_hat is located once
-            const int lt = threadIdx.x % Geom<M>::NL;
-            const double* kcol = nullptr;
-            if (lt < nl) {
-                const int f = f0 + lt + (sm.mode == 3 ? sm.f_base : 0);
-                const int ky = f / hz1, kz = f - ky * hz1;
-                kcol = khat + (size_t)min(ky, md.my - ky) * hz1 + kz;
-            }
-            auto mult = [&](int kx, int l, double2 v) {
-                const double g = kcol ? __ldg(kcol + (size_t)min(kx, M - kx) * kplane) : 0.0;
-                s.b[kx * Geom<M>::NLP + l] = make_double2(v.x * g, v.y * g);
-            };
             fft_io<false, M, 1>(gsrc, mult, s.a, s.b, s.tw);
             __syncthreads();
-            // inverse: source = buffer b; intermediate stages may use a (free again after the barrier above)
+            // inverse: source = buffer b; the intermediate stage uses a (free again after the barrier above)
             fft_io<true, M, 1>(SmemIO<M>{s.b}, gdst, s.a, s.b, s.tw);
-            pdl_trigger();
         }
-    } else {
-    {   // global -> shared, U independent 16-byte loads in flight per thread
-        constexpr int PER = NL * M / Geom<M>::T, U = PER < 8 ? PER : 8;
-        static_assert(PER % U == 0, "load batching");
-        const int l = threadIdx.x % NL, o0 = threadIdx.x / NL;          // l fastest: adjacent inner indices
-        constexpr int OSTEP = Geom<M>::T / NL;
-        const double2* col = src + l;
-        for (int c = 0; c < PER; c += U) {
-            double2 v[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const int o = o0 + (c + u) * OSTEP;
-                if (sm.mode == 2)
-                    v[u] = (o < n_in && l < nl) ? in[chunk(o * inner + f0 + l)] : make_double2(0.0, 0.0);
-                else
-                    v[u] = (o < n_in && l < nl) ? col[(size_t)o * inner] : make_double2(0.0, 0.0);
-            }
-#pragma unroll
-            for (int u = 0; u < U; ++u) s.a[(o0 + (c + u) * OSTEP) * NLP + l] = v[u];
-        }
-    }
-    double2* X = (MODE == 1) ? block_fft<true, M>(s.a, s.b, s.tw) : block_fft<false, M>(s.a, s.b, s.tw);
-    if (MODE == 2) {
-        const int hz1 = md.mz / 2 + 1, hy1 = md.my / 2 + 1;
-        // each thread owns one line l for the multiply: its (ky, kz) is computed once
-        const int l = threadIdx.x % NL;
-        if (l < nl) {
-            const int f = f0 + l + (sm.mode == 3 ? sm.f_base : 0);
-            const int ky = f / hz1, kz = f - ky * hz1;
-            const int sy = min(ky, md.my - ky);
-            const double* kcol = khat + (size_t)sy * hz1 + kz;
-            const size_t kplane = (size_t)hy1 * hz1;
-            constexpr int KSTEP = Geom<M>::T / NL, KPER = M / KSTEP, KU = KPER < 8 ? KPER : 8;
-            const int kx0 = threadIdx.x / NL;
-            for (int c = 0; c < KPER; c += KU) {
-                double gk[KU];
-#pragma unroll
-                for (int u = 0; u < KU; ++u) {
-                    const int kx = kx0 + (c + u) * KSTEP;
-                    gk[u] = __ldg(kcol + (size_t)min(kx, M - kx) * kplane);
-                }
-#pragma unroll
-                for (int u = 0; u < KU; ++u) {
-                    const int kx = kx0 + (c + u) * KSTEP;
-                    double2 v = X[kx * NLP + l];
-                    X[kx * NLP + l] = make_double2(v.x * gk[u], v.y * gk[u]);
-                }
-            }
-        }
-        double2* Y = (X == s.a) ? s.b : s.a;
-        X = block_fft<true, M>(X, Y, s.tw);
     }
     pdl_trigger();
-    for (int t = threadIdx.x; t < NL * n_out; t += Geom<M>::T) {
-        const int o = t / NL, l = t % NL;
-        if (l < nl) {
-            if (sm.mode == 1) out[chunk(o * inner + f0 + l)] = X[o * NLP + l];
-            else dst[(size_t)o * inner + l] = X[o * NLP + l];
-        }
-    }
-    }
 }
 
 // ---------------------------------------------------------------------------
