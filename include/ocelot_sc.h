@@ -159,6 +159,12 @@ int ocl_sc_set_kick_params(ocl_sc_t* h, double E_GeV, double dz, const double* m
  *     all-gather PHI_SLAB -> PHI      ; ocl_sc_slab_finish    (staggered field table)
  * replaces sc.py:135-168 + :195-200 exactly as the single-GPU solve does. */
 int ocl_sc_slab_init(ocl_sc_t* h, int rank, int world);
+/* Fused transposes: peer_a[w] / peer_b[w] = rank w's XCHG_A / XCHG_B buffers (2*nx_pad*fs doubles each, symmetric /
+ * IPC-mapped memory) as mapped in THIS rank's address space.  ocl_sc_slab_forward then stores the y pass's output
+ * straight into the peers' XCHG_B over NVLink and ocl_sc_slab_xpass its output into the peers' XCHG_A, each followed by
+ * a mailbox barrier: the two all-to-alls of the sequence above disappear (the transfer overlaps the transform tile by
+ * tile).  Needs ocl_sc_slab_init and ocl_sc_mailbox_init; world <= 8. */
+int ocl_sc_set_peer_xchg(ocl_sc_t* h, int rank, int world, void* const* peer_a, void* const* peer_b);
 int ocl_sc_slab_forward(ocl_sc_t* h, void* stream);
 int ocl_sc_slab_xpass(ocl_sc_t* h, void* stream);
 int ocl_sc_slab_inverse(ocl_sc_t* h, void* stream);

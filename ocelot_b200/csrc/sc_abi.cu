@@ -60,6 +60,9 @@ struct ocl_sc {
     double* phi_slab = nullptr;
     double2* xchg_a = nullptr;
     double2* xchg_b = nullptr;
+    double2* own_xchg_a = nullptr;            // the cudaMalloc'ed buffers (kept for freeing when xchg_* are symmetric)
+    double2* own_xchg_b = nullptr;
+    PeerXchg peer_xchg{};                     // world > 0: the passes store straight into the peers' exchange buffers
     // peer-memory mailbox (multi-GPU scalar exchanges)
     Mailbox mb{};
     int* mb_err = nullptr;
@@ -449,7 +452,8 @@ void ocl_sc_destroy(ocl_sc_t* h) {
     cudaFree(h->lw.ticket); cudaFree(h->lw.stats); cudaFree(h->lw.bins); cudaFree(h->lw.cnt); cudaFree(h->lw.Z);
     cudaFree(h->lw.spread);
     cudaFree(h->lw.tw);
-    cudaFree(h->rho_slab); cudaFree(h->phi_slab); cudaFree(h->xchg_a); cudaFree(h->xchg_b);
+    cudaFree(h->rho_slab); cudaFree(h->phi_slab);
+    cudaFree(h->own_xchg_a ? h->own_xchg_a : h->xchg_a); cudaFree(h->own_xchg_b ? h->own_xchg_b : h->xchg_b);
     for (int i = 0; i < T_COUNT; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->side_stream) cudaStreamDestroy(h->side_stream);
@@ -611,7 +615,9 @@ int ocl_sc_slab_init(ocl_sc_t* h, int rank, int world) {
     const size_t plane = (size_t)h->md.ny * h->md.nz;
     cudaFree(h->own_rho ? h->own_rho : h->rho); cudaFree(h->phi);
     h->own_rho = nullptr; h->peer_rho.world = 0;
-    cudaFree(h->rho_slab); cudaFree(h->phi_slab); cudaFree(h->xchg_a); cudaFree(h->xchg_b);
+    cudaFree(h->rho_slab); cudaFree(h->phi_slab);
+    cudaFree(h->own_xchg_a ? h->own_xchg_a : h->xchg_a); cudaFree(h->own_xchg_b ? h->own_xchg_b : h->xchg_b);
+    h->own_xchg_a = h->own_xchg_b = nullptr; h->peer_xchg = PeerXchg{};
     h->rho = h->phi = h->rho_slab = h->phi_slab = nullptr; h->xchg_a = h->xchg_b = nullptr;
     h->rho_count = (size_t)h->nx_pad * plane;
     CU(h, cudaMalloc(&h->rho, sizeof(double) * h->rho_count));
@@ -627,14 +633,40 @@ int ocl_sc_slab_init(ocl_sc_t* h, int rank, int world) {
     return 0;
 }
 
+int ocl_sc_set_peer_xchg(ocl_sc_t* h, int rank, int world, void* const* peer_a, void* const* peer_b) {
+    if (!h || !peer_a || !peer_b) return 1;
+    if (!h->slab_world) return fail(h, "ocl_sc_set_peer_xchg", "call ocl_sc_slab_init first");
+    if (!h->mb.world) return fail(h, "ocl_sc_set_peer_xchg", "call ocl_sc_mailbox_init first");
+    if (world != h->slab_world || rank != h->slab_rank || world > 8)
+        return fail(h, "ocl_sc_set_peer_xchg", "rank / world differ from ocl_sc_slab_init (world <= 8)");
+    ENTER_DEVICE(h);
+    drop_graph(h);
+    if (!h->own_xchg_a) { h->own_xchg_a = h->xchg_a; h->own_xchg_b = h->xchg_b; }
+    for (int w = 0; w < 8; ++w) {
+        h->peer_xchg.a[w] = w < world ? (double2*)peer_a[w] : nullptr;
+        h->peer_xchg.b[w] = w < world ? (double2*)peer_b[w] : nullptr;
+    }
+    h->peer_xchg.rank = rank; h->peer_xchg.world = world;
+    h->xchg_a = (double2*)peer_a[rank];
+    h->xchg_b = (double2*)peer_b[rank];
+    const size_t bytes = sizeof(double2) * (size_t)h->nx_pad * h->fs;
+    CU(h, cudaMemset(h->xchg_a, 0, bytes));          // padding planes / lines are never written: they must read as zero
+    CU(h, cudaMemset(h->xchg_b, 0, bytes));
+    return 0;
+}
+
 int ocl_sc_slab_forward(ocl_sc_t* h, void* stream) {
     if (!h || !h->slab_world) return h ? fail(h, "ocl_sc_slab_forward", "call ocl_sc_slab_init first") : 1;
     ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
     launch_slab_forward(h->rho_slab, h->peer_rho, (long long)h->slab_rank * h->sx * h->md.ny, h->md, h->sx, h->fs, h->fw,
-                        h->xchg_a, st);
+                        h->xchg_a, h->peer_xchg, st);
     h->launches += 2;
+    if (h->peer_xchg.world > 0) {            // every rank's y output has landed in this rank's x-pass input
+        launch_mailbox_exchange(h->mb, 2, h->rs, h->mb_err, st);
+        h->launches += 1;
+    }
     return check_launch(h, "slab_forward");
 }
 
@@ -649,8 +681,12 @@ int ocl_sc_slab_xpass(ocl_sc_t* h, void* stream) {
     } else {
         return fail(h, "ocl_sc_slab_xpass", "K_hat not available: ocl_sc_stage_deposit must precede the solve");
     }
-    launch_slab_xpass(h->xchg_b, h->md, h->fs, h->slab_rank * h->fs, h->fw, st);
+    launch_slab_xpass(h->xchg_b, h->md, h->sx, h->fs, h->slab_rank * h->fs, h->fw, h->peer_xchg, st);
     h->launches += 1;
+    if (h->peer_xchg.world > 0) {            // every rank's x output has landed in this rank's inverse-y input
+        launch_mailbox_exchange(h->mb, 2, h->rs, h->mb_err, st);
+        h->launches += 1;
+    }
     return check_launch(h, "slab_xpass");
 }
 

@@ -581,8 +581,15 @@ __global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_cplx_outer(const 
     };
     auto gdst = [&](int o, int l, double2 v) {
         if (o >= n_out || l >= nl) return;
-        if (sm.mode == 1) out[chunk(o * inner + f0 + l)] = v;
-        else dst[(size_t)o * inner + l] = v;
+        if (sm.mode == 1) {
+            const int f = o * inner + f0 + l;
+            if (sm.peer[0]) sm.peer[f / sm.fs][((size_t)sm.rank * sm.sx + batch) * sm.fs + f % sm.fs] = v;   // NVLink store
+            else out[chunk(f)] = v;
+        } else if (sm.mode == 3 && sm.peer[0]) {
+            sm.peer[o / sm.sx][((size_t)sm.rank * sm.sx + o % sm.sx) * sm.fs + f0 + l] = v;                    // NVLink store
+        } else {
+            dst[(size_t)o * inner + l] = v;
+        }
     };
     constexpr bool IP = Geom<M>::INPLACE;
     __syncthreads();
@@ -777,7 +784,7 @@ void launch_convolve_post(MeshDims md, FftWork w, const double* h3, double four_
 // lines of the x pass; the caller exchanges `xchg` between the calls (all-to-all).
 // ---------------------------------------------------------------------------
 void launch_slab_forward(const double* rho_slab, PeerRho pr, long long line_offset, MeshDims md, int sx, int fs,
-                         FftWork w, double2* xchg, cudaStream_t st) {
+                         FftWork w, double2* xchg, PeerXchg px, cudaStream_t st) {
     MeshDims ms = md;
     ms.nx = sx;
     const int hz1 = md.mz / 2 + 1;
@@ -786,7 +793,8 @@ void launch_slab_forward(const double* rho_slab, PeerRho pr, long long line_offs
         const int zblocks = (sx * md.ny + lbz - 1) / lbz;
         launch_k(k_rho_z<MM>, dim3(zblocks), dim3(Geom<MM>::T), Geom<MM>::SMEM, st, rho_slab, pr, line_offset, ms, w.tw_z, w.A);
     )
-    SlabMap sm{1, fs, sx, 0, 0};
+    SlabMap sm{1, fs, sx, 0, 0, {}, px.rank};
+    for (int w_ = 0; w_ < 8; ++w_) sm.peer[w_] = px.world > 0 ? px.b[w_] : nullptr;     // y output = the peers' x-pass input
     OCL_FFT_DISPATCH(md.my,   // y forward, stored in chunk layout for the all-to-all
         const int lb = Geom<MM>::NL;
         const int bpb = (hz1 + lb - 1) / lb;
@@ -795,9 +803,10 @@ void launch_slab_forward(const double* rho_slab, PeerRho pr, long long line_offs
     )
 }
 
-void launch_slab_xpass(double2* xchg, MeshDims md, int fs, int f_base, FftWork w, cudaStream_t st) {
+void launch_slab_xpass(double2* xchg, MeshDims md, int sx, int fs, int f_base, FftWork w, PeerXchg px, cudaStream_t st) {
     const int hz1 = md.mz / 2 + 1;
-    SlabMap sm{3, fs, 0, f_base, md.my * hz1};
+    SlabMap sm{3, fs, sx, f_base, md.my * hz1, {}, px.rank};
+    for (int w_ = 0; w_ < 8; ++w_) sm.peer[w_] = px.world > 0 ? px.a[w_] : nullptr;     // x output = the peers' inverse-y input
     OCL_FFT_DISPATCH(md.mx,   // x: forward, * K_hat, inverse on this rank's chunk of lines, [nx_pad][fs] in place
         const int lb = Geom<MM>::NL;
         const int blocks = (fs + lb - 1) / lb;
@@ -811,7 +820,7 @@ void launch_slab_inverse(const double2* xchg, MeshDims md, int sx, int fs, FftWo
     MeshDims ms = md;
     ms.nx = sx;
     const int hz1 = md.mz / 2 + 1;
-    SlabMap sm{2, fs, sx, 0, 0};
+    SlabMap sm{2, fs, sx, 0, 0, {}, 0};
     OCL_FFT_DISPATCH(md.my,   // y inverse, read from chunk layout
         const int lb = Geom<MM>::NL;
         const int bpb = (hz1 + lb - 1) / lb;

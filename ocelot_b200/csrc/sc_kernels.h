@@ -194,6 +194,18 @@ struct SlabMap {
     int sx;        // x planes per rank
     int f_base;    // mode 3: global index of this rank's first line
     int f_total;   // mode 3: number of real lines (My * H); beyond it the chunk is padding
+    // Fused transpose (peer[0] != nullptr): the pass stores its output straight into the exchange buffer of the rank
+    // that consumes it, over NVLink peer mappings, instead of into a local buffer that an all-to-all then moves.
+    //   mode 1: element (plane i of this rank, line f) -> peer[f / fs] [(rank*sx + i)*fs + f % fs]      (the x-pass input)
+    //   mode 3: element (plane o, local line fl)       -> peer[o / sx] [(rank*sx + o % sx)*fs + fl]     (the inverse-y input)
+    double2* peer[8];
+    int rank;
+};
+// the exchange buffers of every rank as mapped here (world == 0: no peer mappings, NCCL all-to-all)
+struct PeerXchg {
+    double2* a[8];
+    double2* b[8];
+    int rank, world;
 };
 void fft_init_kernels();
 int fft_max_length();
@@ -203,8 +215,8 @@ void launch_convolve_post(MeshDims md, FftWork w, const double* h3, double four_
                           cudaStream_t st);
 // slab-decomposed variants (this rank owns sx x-planes and one chunk of fs (ky,kz) lines)
 void launch_slab_forward(const double* rho_slab, PeerRho pr, long long line_offset, MeshDims md, int sx, int fs,
-                         FftWork w, double2* xchg, cudaStream_t st);
-void launch_slab_xpass(double2* xchg, MeshDims md, int fs, int f_base, FftWork w, cudaStream_t st);
+                         FftWork w, double2* xchg, PeerXchg px, cudaStream_t st);
+void launch_slab_xpass(double2* xchg, MeshDims md, int sx, int fs, int f_base, FftWork w, PeerXchg px, cudaStream_t st);
 void launch_slab_inverse(const double2* xchg, MeshDims md, int sx, int fs, FftWork w, const double* h3,
                          double four_pi_eps0, double* phi_slab, cudaStream_t st);
 double four_pi_eps0_value();

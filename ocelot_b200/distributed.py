@@ -19,8 +19,10 @@ meshes ("slab mode") step 3 becomes a reduce-scatter of rho into
 x-slabs, the FFT passes are split across ranks with two all-to-all transposes
 around the x pass, and the potential is all-gathered:
 
-  3'. reduce-scatter rho -> x-slab ; z,y passes ; all-to-all ; x pass (FFT * K_hat * IFFT) ;
-      all-to-all ; inverse y,z passes ; all-gather phi
+  3'. reduce-scatter rho -> x-slab ; z,y passes ; transpose ; x pass (FFT * K_hat * IFFT) ;
+      transpose ; inverse y,z passes ; all-gather phi
+      (the transposes are fused into the y and x passes: their output is stored straight into the
+      consumer rank's buffer over NVLink peer mappings; NCCL all-to-all without peer mappings)
 
 The
 collectives run in place on the native handle's device buffers, stream-ordered
@@ -44,6 +46,8 @@ def shard_bounds(n_total: int, world_size: int, rank: int):
 
 class NativeStageEngine:
     """The five stages of the kick on one GPU (include/ocelot_sc.h, ocl_sc_stage_*)."""
+
+    fused_transposes = True     # slab mode: transposes as NVLink stores of the FFT passes (False: NCCL all-to-all)
 
     def __init__(self, device: int, nmesh_xyz, slab=None):
         """``slab`` = (rank, world) switches the Poisson solve to the slab-decomposed form."""
@@ -69,6 +73,7 @@ class NativeStageEngine:
         self.mailbox = None
         self.peer_rho = None
         self.nvls = None
+        self.peer_xchg = None
         self._draws = None
         self._E = None
 
@@ -89,6 +94,22 @@ class NativeStageEngine:
         self.solver.mailbox_init(rank, world, list(hdl.buffer_ptrs))
         self.solver.defer_finish(False)        # the sweeps' finishing blocks now exchange over NVLink themselves
         self.mailbox = (box, hdl)              # keep the mapping alive
+        if self.slab is not None and self.fused_transposes:
+            # slab mode: the exchange buffers of the two transposes live in symmetric memory, and the y / x passes
+            # store their output straight into the consumer rank's buffer over NVLink (no all-to-all)
+            grp = group if group is not None else dist.group.WORLD
+            ta = symm.empty(self.buffers["xchg_a"].numel(), dtype=torch.float64, device=box.device)
+            tb = symm.empty(self.buffers["xchg_b"].numel(), dtype=torch.float64, device=box.device)
+            ha, hb = symm.rendezvous(ta, group=grp), symm.rendezvous(tb, group=grp)
+            torch.cuda.synchronize()
+            dist.barrier(group=group)
+            self.solver.set_peer_xchg(rank, world, list(ha.buffer_ptrs), list(hb.buffer_ptrs))
+            torch.cuda.synchronize()
+            dist.barrier(group=group)          # every rank has zeroed its buffers before anyone stores into them
+            native = self._native
+            self.buffers["xchg_a"] = self.solver.collective_buffer(native.BUF_XCHG_A)
+            self.buffers["xchg_b"] = self.solver.collective_buffer(native.BUF_XCHG_B)
+            self.peer_xchg = (ta, ha, tb, hb)
         # the charge grid itself also lives in symmetric memory: the first FFT pass then sums the
         # ranks' grids while loading them over NVLink (no all-reduce / reduce-scatter kernel)
         if nvls:
@@ -128,10 +149,14 @@ class NativeStageEngine:
             s.mailbox_exchange(2)              # barrier: every rank's deposit is complete
         else:
             dist.reduce_scatter_tensor(b["rho_slab"], b["rho"], op=dist.ReduceOp.SUM, group=group)
-        s.slab_forward()
-        dist.all_to_all_single(b["xchg_b"], b["xchg_a"], group=group)
-        s.slab_xpass()
-        dist.all_to_all_single(b["xchg_a"], b["xchg_b"], group=group)
+        if self.peer_xchg is not None:
+            s.slab_forward()                   # z, y passes; y output stored into the peers' x-pass input; barrier
+            s.slab_xpass()                     # x pass; output stored into the peers' inverse-y input; barrier
+        else:
+            s.slab_forward()
+            dist.all_to_all_single(b["xchg_b"], b["xchg_a"], group=group)
+            s.slab_xpass()
+            dist.all_to_all_single(b["xchg_a"], b["xchg_b"], group=group)
         s.slab_inverse()
         dist.all_gather_into_tensor(b["phi"], b["phi_slab"], group=group)
         s.slab_finish(draws)

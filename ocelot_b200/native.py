@@ -49,6 +49,7 @@ _SIGNATURES = {
     "ocl_sc_mailbox_init": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
     "ocl_sc_mailbox_exchange": (C.c_int, [_vp, C.c_int, _vp]),
     "ocl_sc_set_peer_rho": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "ocl_sc_set_peer_xchg": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp)]),
     "ocl_sc_set_multicast_rho": (C.c_int, [_vp, _vp, _vp]),
     "ocl_sc_nvls_reduce_rho": (C.c_int, [_vp, _vp]),
     "ocl_sc_use_device_params": (C.c_int, [_vp, C.c_int]),
@@ -313,6 +314,12 @@ class Solver:
     def set_peer_rho(self, rank, world, peer_ptrs):
         arr = (_vp * int(world))(*[int(p) for p in peer_ptrs])
         self._check(self._lib.ocl_sc_set_peer_rho(self._h, int(rank), int(world), arr), "ocl_sc_set_peer_rho")
+
+    def set_peer_xchg(self, rank, world, peer_a, peer_b):
+        """Slab mode: the y and x passes store straight into the peers' exchange buffers (no all-to-all)."""
+        a = (_vp * int(world))(*[int(p) for p in peer_a])
+        b = (_vp * int(world))(*[int(p) for p in peer_b])
+        self._check(self._lib.ocl_sc_set_peer_xchg(self._h, int(rank), int(world), a, b), "ocl_sc_set_peer_xchg")
 
     def set_multicast_rho(self, local_ptr, multicast_ptr):
         self._check(self._lib.ocl_sc_set_multicast_rho(self._h, int(local_ptr), int(multicast_ptr)),
