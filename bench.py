@@ -412,8 +412,9 @@ def north_star_leg(ctx, name, n_total, mesh, slab, steps):
     alg = 104 * (hi - lo) + grid_bytes(mesh, m, ctx.world if eng.slab else 1)
     peak = load_peak()[0]
     out = {"particles_total": n_total, "particles_per_gpu": hi - lo, "nmesh": [mesh] * 3, "fft_box": [m] * 3,
-           "poisson": ("slab-decomposed FFT (reduce-scatter, 2 transposes fused into the FFT passes as NVLink peer stores, "
-                       "all-gather)" if getattr(eng, "peer_xchg", None) is not None else
+           "poisson": ("slab-decomposed FFT (in-switch reduce-scatter, 2 transposes fused into the FFT passes as NVLink peer "
+                       "stores, phi " + ("broadcast through the switch by the inverse z pass" if getattr(eng, "mc_phi", None)
+                                         is not None else "all-gather") + ")" if getattr(eng, "peer_xchg", None) is not None else
                        "slab-decomposed FFT (reduce-scatter, 2 all-to-all, all-gather)") if eng.slab
                       else "redundant per rank after the in-switch all-reduce of rho",
            "rho_reduce": "in-switch multimem kernel (NVLS)" if eng.nvls is not None else "NCCL",

@@ -165,6 +165,11 @@ int ocl_sc_slab_init(ocl_sc_t* h, int rank, int world);
  * a mailbox barrier: the two all-to-alls of the sequence above disappear (the transfer overlaps the transform tile by
  * tile).  Needs ocl_sc_slab_init and ocl_sc_mailbox_init; world <= 8. */
 int ocl_sc_set_peer_xchg(ocl_sc_t* h, int rank, int world, void* const* peer_a, void* const* peer_b);
+/* Slab mode, fused all-gather: `local_phi` is this rank's part of a symmetric allocation of nx_pad*ny*nz doubles that is
+ * also mapped as one multicast range `multicast_phi`.  ocl_sc_slab_inverse then writes its x-slab of the potential
+ * through the multicast mapping (multimem.st: the NVSwitch replicates every store into all ranks' grids) and ends with
+ * a mailbox barrier: the all-gather of PHI disappears. */
+int ocl_sc_set_multicast_phi(ocl_sc_t* h, void* local_phi, void* multicast_phi);
 int ocl_sc_slab_forward(ocl_sc_t* h, void* stream);
 int ocl_sc_slab_xpass(ocl_sc_t* h, void* stream);
 int ocl_sc_slab_inverse(ocl_sc_t* h, void* stream);

@@ -69,6 +69,8 @@ struct ocl_sc {
     PeerRho peer_rho{};                       // world > 0: rho lives in caller-owned symmetric memory
     double* own_rho = nullptr;                // the cudaMalloc'ed grid (kept for freeing)
     double* mc_rho = nullptr;                 // multicast mapping of every rank's rho (NVLS reduction)
+    double* mc_phi = nullptr;                 // slab mode: multicast mapping of every rank's phi (the inverse z pass
+    double* own_phi = nullptr;                // broadcasts its slab through the switch); own_phi: the cudaMalloc'ed grid
     int debug_skip = 0;                       // timing experiments only (OCL_SC_DEBUG_SKIP): bit 0/1/2 = leave out the
                                               // momentum exchange / extent exchange / rho reduction of a sharded kick
     // host arrays page-locked in place on first use (numpy buffers persist across kicks)
@@ -444,7 +446,7 @@ void ocl_sc_destroy(ocl_sc_t* h) {
     if (h->plans) { cufftDestroy(h->plan_fwd); cufftDestroy(h->plan_inv); }
     cudaFree(h->rs.part); cudaFree(h->rs.ticket); cudaFree(h->rs.sums); cudaFree(h->rs.geo);
     cudaFree(h->own_rho ? h->own_rho : h->rho); cudaFree(h->gtab); cudaFree(h->k1); cudaFree(h->real_buf);
-    cudaFree(h->k_hat); cudaFree(h->rho_hat); cudaFree(h->phi); cudaFree(h->equad);
+    cudaFree(h->k_hat); cudaFree(h->rho_hat); cudaFree(h->own_phi ? h->own_phi : h->phi); cudaFree(h->equad);
     cudaFree(h->fw.P); cudaFree(h->fw.Q); cudaFree(h->fw.khat); cudaFree(h->fw.A); cudaFree(h->fw.B);
     cudaFree(h->tw[0]); cudaFree(h->tw[1]); cudaFree(h->tw[2]); cudaFree(h->h3); cudaFree(h->moments);
     cudaFree(h->stage_r); cudaFree(h->stage_q); cudaFree(h->cut_counts);
@@ -544,6 +546,19 @@ int ocl_sc_set_multicast_rho(ocl_sc_t* h, void* local_rho, void* multicast_rho) 
     return 0;
 }
 
+int ocl_sc_set_multicast_phi(ocl_sc_t* h, void* local_phi, void* multicast_phi) {
+    if (!h || !local_phi || !multicast_phi) return 1;
+    if (!h->slab_world) return fail(h, "ocl_sc_set_multicast_phi", "call ocl_sc_slab_init first");
+    if (!h->mb.world) return fail(h, "ocl_sc_set_multicast_phi", "call ocl_sc_mailbox_init first");
+    ENTER_DEVICE(h);
+    drop_graph(h);
+    if (!h->own_phi) h->own_phi = h->phi;
+    h->phi = (double*)local_phi;
+    h->mc_phi = (double*)multicast_phi;
+    CU(h, cudaMemset(h->phi, 0, sizeof(double) * h->rho_count));
+    return 0;
+}
+
 int ocl_sc_nvls_reduce_rho(ocl_sc_t* h, void* stream) {
     if (!h) return 1;
     if (!h->mc_rho) return fail(h, "ocl_sc_nvls_reduce_rho", "call ocl_sc_set_multicast_rho first");
@@ -613,8 +628,8 @@ int ocl_sc_slab_init(ocl_sc_t* h, int rank, int world) {
     h->nx_pad = h->sx * world;
     h->fs = (F + world - 1) / world;
     const size_t plane = (size_t)h->md.ny * h->md.nz;
-    cudaFree(h->own_rho ? h->own_rho : h->rho); cudaFree(h->phi);
-    h->own_rho = nullptr; h->peer_rho.world = 0;
+    cudaFree(h->own_rho ? h->own_rho : h->rho); cudaFree(h->own_phi ? h->own_phi : h->phi);
+    h->own_rho = nullptr; h->peer_rho.world = 0; h->own_phi = nullptr; h->mc_phi = nullptr;
     cudaFree(h->rho_slab); cudaFree(h->phi_slab);
     cudaFree(h->own_xchg_a ? h->own_xchg_a : h->xchg_a); cudaFree(h->own_xchg_b ? h->own_xchg_b : h->xchg_b);
     h->own_xchg_a = h->own_xchg_b = nullptr; h->peer_xchg = PeerXchg{};
@@ -695,7 +710,14 @@ int ocl_sc_slab_inverse(ocl_sc_t* h, void* stream) {
     ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
-    launch_slab_inverse(h->xchg_a, h->md, h->sx, h->fs, h->fw, h->h3, four_pi_eps0_value(), h->phi_slab, st);
+    if (h->mc_phi) {     // phi slab broadcast through the NVSwitch by the inverse z pass itself, then "every slab has landed"
+        const size_t off = (size_t)h->slab_rank * h->sx * h->md.ny * h->md.nz;
+        launch_slab_inverse(h->xchg_a, h->md, h->sx, h->fs, h->fw, h->h3, four_pi_eps0_value(), h->mc_phi + off, 1, st);
+        launch_mailbox_exchange(h->mb, 2, h->rs, h->mb_err, st);
+        h->launches += 1;
+    } else {
+        launch_slab_inverse(h->xchg_a, h->md, h->sx, h->fs, h->fw, h->h3, four_pi_eps0_value(), h->phi_slab, 0, st);
+    }
     h->launches += 2;
     mark(h, T_SOLVE, st);
     return check_launch(h, "slab_inverse");

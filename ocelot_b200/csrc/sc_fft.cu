@@ -637,9 +637,11 @@ __global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_cplx_outer(const 
 // phi[l][k<nz] = value / (Mx My Mz) / (4 pi eps0 hx hy hz)   (sc.py:164,167)
 // ---------------------------------------------------------------------------
 template <int M>
+// mc != 0: phi is a multicast address (every rank's potential grid mapped as one range); the stores go through the
+// NVSwitch, which replicates them into all ranks' grids (multimem.st): the all-gather of phi is this kernel's epilogue.
 __global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_inv_z(const double2* __restrict__ D, MeshDims md,
                                                       const double2* __restrict__ tw_g, const double* __restrict__ hsrc,
-                                                      double four_pi_eps0, double* __restrict__ phi) {
+                                                      double four_pi_eps0, double* __restrict__ phi, int mc) {
     pdl_enter();
     constexpr int NL = Geom<M>::NL, NLP = Geom<M>::NLP, H = M / 2;
     const int n = md.nz;
@@ -678,8 +680,15 @@ __global__ void __launch_bounds__(Geom<M>::T, Geom<M>::MINB) k_inv_z(const doubl
         const int l1 = line0 + 2 * p, l2 = l1 + 1;
         if (l1 >= nlines) continue;
         const double2 v = X[k * NLP + p];
-        phi[(size_t)l1 * n + k] = (v.x * inv_m3) / denom;
-        if (l2 < nlines) phi[(size_t)l2 * n + k] = (v.y * inv_m3) / denom;
+        const double p1 = (v.x * inv_m3) / denom, p2 = (v.y * inv_m3) / denom;
+        if (mc) {
+            asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(phi + (size_t)l1 * n + k), "d"(p1) : "memory");
+            if (l2 < nlines)
+                asm volatile("multimem.st.relaxed.sys.global.f64 [%0], %1;" ::"l"(phi + (size_t)l2 * n + k), "d"(p2) : "memory");
+        } else {
+            phi[(size_t)l1 * n + k] = p1;
+            if (l2 < nlines) phi[(size_t)l2 * n + k] = p2;
+        }
     }
 }
 
@@ -775,7 +784,7 @@ void launch_convolve_post(MeshDims md, FftWork w, const double* h3, double four_
     OCL_FFT_DISPATCH(md.mz,
         const int lbz = 2 * Geom<MM>::NL;
         const int zblocks = (md.nx * md.ny + lbz - 1) / lbz;
-        launch_k(k_inv_z<MM>, dim3(zblocks), dim3(Geom<MM>::T), Geom<MM>::SMEM, st, w.A, md, w.tw_z, h3, four_pi_eps0, phi);
+        launch_k(k_inv_z<MM>, dim3(zblocks), dim3(Geom<MM>::T), Geom<MM>::SMEM, st, w.A, md, w.tw_z, h3, four_pi_eps0, phi, 0);
     )
 }
 
@@ -816,7 +825,7 @@ void launch_slab_xpass(double2* xchg, MeshDims md, int sx, int fs, int f_base, F
 }
 
 void launch_slab_inverse(const double2* xchg, MeshDims md, int sx, int fs, FftWork w, const double* h3,
-                         double four_pi_eps0, double* phi_slab, cudaStream_t st) {
+                         double four_pi_eps0, double* phi_slab, int multicast, cudaStream_t st) {
     MeshDims ms = md;
     ms.nx = sx;
     const int hz1 = md.mz / 2 + 1;
@@ -830,7 +839,8 @@ void launch_slab_inverse(const double2* xchg, MeshDims md, int sx, int fs, FftWo
     OCL_FFT_DISPATCH(md.mz,
         const int lbz = 2 * Geom<MM>::NL;
         const int zblocks = (sx * md.ny + lbz - 1) / lbz;
-        launch_k(k_inv_z<MM>, dim3(zblocks), dim3(Geom<MM>::T), Geom<MM>::SMEM, st, w.A, ms, w.tw_z, h3, four_pi_eps0, phi_slab);
+        launch_k(k_inv_z<MM>, dim3(zblocks), dim3(Geom<MM>::T), Geom<MM>::SMEM, st, w.A, ms, w.tw_z, h3, four_pi_eps0, phi_slab,
+                 multicast);
     )
 }
 

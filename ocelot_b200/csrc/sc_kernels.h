@@ -218,7 +218,7 @@ void launch_slab_forward(const double* rho_slab, PeerRho pr, long long line_offs
                          FftWork w, double2* xchg, PeerXchg px, cudaStream_t st);
 void launch_slab_xpass(double2* xchg, MeshDims md, int sx, int fs, int f_base, FftWork w, PeerXchg px, cudaStream_t st);
 void launch_slab_inverse(const double2* xchg, MeshDims md, int sx, int fs, FftWork w, const double* h3,
-                         double four_pi_eps0, double* phi_slab, cudaStream_t st);
+                         double four_pi_eps0, double* phi_slab, int multicast, cudaStream_t st);
 double four_pi_eps0_value();
 
 // potential KAT helpers: steps given explicitly instead of derived from particles

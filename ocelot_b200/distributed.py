@@ -74,6 +74,7 @@ class NativeStageEngine:
         self.peer_rho = None
         self.nvls = None
         self.peer_xchg = None
+        self.mc_phi = None
         self._draws = None
         self._E = None
 
@@ -110,6 +111,19 @@ class NativeStageEngine:
             self.buffers["xchg_a"] = self.solver.collective_buffer(native.BUF_XCHG_A)
             self.buffers["xchg_b"] = self.solver.collective_buffer(native.BUF_XCHG_B)
             self.peer_xchg = (ta, ha, tb, hb)
+            # ... and the potential grid in symmetric memory with a multicast mapping: the inverse z pass broadcasts
+            # its slab through the switch (multimem.st), which replaces the all-gather of phi
+            tp = symm.empty(self.buffers["phi"].numel(), dtype=torch.float64, device=box.device)
+            hp = symm.rendezvous(tp, group=grp)
+            mcp = int(getattr(hp, "multicast_ptr", 0) or 0)
+            torch.cuda.synchronize()
+            dist.barrier(group=group)
+            if mcp:
+                self.solver.set_multicast_phi(hp.buffer_ptrs[rank], mcp)
+                torch.cuda.synchronize()
+                dist.barrier(group=group)
+                self.buffers["phi"] = self.solver.collective_buffer(native.BUF_PHI)
+                self.mc_phi = (tp, hp)
         # the charge grid itself also lives in symmetric memory: the first FFT pass then sums the
         # ranks' grids while loading them over NVLink (no all-reduce / reduce-scatter kernel)
         if nvls:
@@ -157,8 +171,9 @@ class NativeStageEngine:
             dist.all_to_all_single(b["xchg_b"], b["xchg_a"], group=group)
             s.slab_xpass()
             dist.all_to_all_single(b["xchg_a"], b["xchg_b"], group=group)
-        s.slab_inverse()
-        dist.all_gather_into_tensor(b["phi"], b["phi_slab"], group=group)
+        s.slab_inverse()                       # with a multicast phi: broadcasts the slab through the switch + barrier
+        if self.mc_phi is None:
+            dist.all_gather_into_tensor(b["phi"], b["phi_slab"], group=group)
         s.slab_finish(draws)
 
     def combine_extents(self, dist, group):

@@ -51,6 +51,7 @@ _SIGNATURES = {
     "ocl_sc_set_peer_rho": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
     "ocl_sc_set_peer_xchg": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp)]),
     "ocl_sc_set_multicast_rho": (C.c_int, [_vp, _vp, _vp]),
+    "ocl_sc_set_multicast_phi": (C.c_int, [_vp, _vp, _vp]),
     "ocl_sc_nvls_reduce_rho": (C.c_int, [_vp, _vp]),
     "ocl_sc_use_device_params": (C.c_int, [_vp, C.c_int]),
     "ocl_sc_set_kick_params": (C.c_int, [_vp, C.c_double, C.c_double, _dp, _vp]),
@@ -324,6 +325,10 @@ class Solver:
     def set_multicast_rho(self, local_ptr, multicast_ptr):
         self._check(self._lib.ocl_sc_set_multicast_rho(self._h, int(local_ptr), int(multicast_ptr)),
                     "ocl_sc_set_multicast_rho")
+
+    def set_multicast_phi(self, local_ptr, multicast_ptr):
+        self._check(self._lib.ocl_sc_set_multicast_phi(self._h, int(local_ptr), int(multicast_ptr)),
+                    "ocl_sc_set_multicast_phi")
 
     def nvls_reduce_rho(self, stream=None):
         self._check(self._lib.ocl_sc_nvls_reduce_rho(self._h, _stream_ptr(stream)), "ocl_sc_nvls_reduce_rho")
