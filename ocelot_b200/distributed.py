@@ -13,20 +13,20 @@ grid reduction pushes the rank's partials into every peer's mailbox, waits for t
 in rank order), exchange 3 is a kernel of in-switch multimem reductions bracketed by two one-warp
 barrier kernels; NCCL (all-reduce / all-gather) is the fallback when no peer mapping exists.
 
-after which every rank holds the same rho and solves the Poisson problem
-redundantly ("small-mesh mode"); no particle ever crosses a link.  For large
-meshes ("slab mode") step 3 becomes a reduce-scatter of rho into
-x-slabs, the FFT passes are split across ranks with two all-to-all transposes
-around the x pass, and the potential is all-gathered:
+After step 3 every rank holds the same rho and solves the Poisson problem redundantly ("small-mesh
+mode"); no particle ever crosses a link.  For large meshes ("slab mode") step 3 becomes
+a reduce-scatter of rho into x-slabs and the FFT passes are split across ranks:
 
   3'. reduce-scatter rho -> x-slab ; z,y passes ; transpose ; x pass (FFT * K_hat * IFFT) ;
       transpose ; inverse y,z passes ; all-gather phi
-      (the transposes are fused into the y and x passes: their output is stored straight into the
-      consumer rank's buffer over NVLink peer mappings; NCCL all-to-all without peer mappings)
 
-The
-collectives run in place on the native handle's device buffers, stream-ordered
-with the kernels, so a kick involves no host synchronisation.
+With peer / multicast mappings none of these is a collective call: the transposes are the store side of
+the y and x passes (output written straight into the consumer rank's buffer over NVLink), the inverse z
+pass broadcasts its phi slab through the switch (multimem.st); without the mappings NCCL's all-to-all /
+all-gather do the same job.
+
+Every exchange runs in place on the native handle's device buffers, stream-ordered with the kernels, so
+a kick involves no host synchronisation.
 
 ``StageEngine`` is the seam used by the CPU (gloo) tests: the product engine is
 the native CUDA solver; tests substitute an engine backed by the oracle to check
@@ -124,8 +124,6 @@ class NativeStageEngine:
                 dist.barrier(group=group)
                 self.buffers["phi"] = self.solver.collective_buffer(native.BUF_PHI)
                 self.mc_phi = (tp, hp)
-        # the charge grid itself also lives in symmetric memory: the first FFT pass then sums the
-        # ranks' grids while loading them over NVLink (no all-reduce / reduce-scatter kernel)
         if nvls:
             # rho in symmetric memory that is also mapped as one multicast range: the NVSwitch sums the
             # ranks' grids (multimem.ld_reduce) inside ocl_sc_nvls_reduce_rho -- no NCCL on the grid
@@ -143,6 +141,8 @@ class NativeStageEngine:
                 return True
             peer_rho = False                   # no multicast mapping on this system: stay on NCCL for rho
         if peer_rho:
+            # opt-in: rho in plain symmetric memory; the first FFT pass sums the ranks' grids while loading them
+            # over NVLink (no all-reduce / reduce-scatter kernel)
             native = self._native
             grid = symm.empty(self.buffers["rho"].numel(), dtype=torch.float64, device=box.device)
             grid.zero_()
@@ -262,7 +262,10 @@ class ShardedSpaceCharge:
     """PhysProc-style wrapper for a particle-sharded bunch: same attributes as
     ``SpaceCharge``; ``apply`` takes this rank's ``DeviceParticleArray`` shard."""
 
-    SLAB_MIN_MESH = 200      # meshes with any axis >= this use the slab-decomposed solve by default
+    # Meshes with any axis >= this use the slab-decomposed solve by default.  Measured [B200]: with the exchanges
+    # fused into the FFT passes the slab form wins from 127^3 up (100 M / 127^3 on 2 / 4 / 8 GPUs: 3.06 / 1.69 /
+    # 1.008 ms against 3.17 / 1.74 / 1.075 ms redundant); at 63^3 the redundant solve is one library graph.
+    SLAB_MIN_MESH = 100
 
     def __init__(self, step=1, nmesh_xyz=(63, 63, 63), random_mesh=False, group=None, slab=None):
         self.step = step
@@ -273,9 +276,9 @@ class ShardedSpaceCharge:
         self.slab = slab          # None: automatic (by mesh size); True / False: forced
         self.p2p = True           # scalar exchanges through NVLink peer memory instead of NCCL
         # Opt-in: fuse the charge-grid reduction into the first FFT pass (peer loads of every rank's
-        # grid).  Correct (bit-identical to the NCCL path at W = 2) but measured 40 us SLOWER than the
-        # NCCL all-reduce at 1M / 63^3 on 2 x B200 (8-byte peer loads in a latency-bound 125-block
-        # kernel), so the default keeps NCCL (NVLS) for rho.
+        # grid).  Correct (bit-identical to the NCCL path at W = 2) but measured 40 us SLOWER than an
+        # all-reduce at 1M / 63^3 on 2 x B200 (8-byte peer loads in a latency-bound 125-block
+        # kernel), so the default is the in-switch reduction below.
         self.p2p_rho = False
         # Default: the charge grid is summed inside the NVSwitch by the library's own kernel
         # (multimem.ld_reduce / multimem.st on a multicast mapping of the ranks' grids); falls back to the
