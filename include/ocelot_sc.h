@@ -186,6 +186,14 @@ int ocl_sc_stage_solve(ocl_sc_t* h, const double* mesh_draws, void* stream);
 int ocl_sc_stage_kick(ocl_sc_t* h, double* d_r, long long ld, long long n, double E_GeV, double dz,
                       const double* mesh_draws, void* stream);
 
+/* Ordered deposit on / off (also OCL_SC_DETERMINISTIC=1 at create).  The default deposit adds each particle's
+ * charge to its cell with an fp64 L2 atomic, i.e. in arrival order: rho jitters by ~1e-16 relative from run to
+ * run.  With this switch the charges of a cell are added one after the other in ascending particle order
+ * starting from 0.0 -- the order of np.bincount (sc.py:193) -- so rho is bit-identical from run to run and,
+ * whenever every particle lands in the reference's cell, bit-identical to the reference's grid.  A debugging
+ * aid (no reference equivalent; the reference is sequential): ~3x the deposit's time, kick not graph-captured. */
+int ocl_sc_set_deterministic(ocl_sc_t* h, int on);
+
 /* ---- stage taps (tests / diagnostics); each synchronises the stream last used ----
  * geometry out[24] = {T row-major [9], pav, gamma0, beta0, steps[3], X_off[3],
  *                     sum q, count, reserved[4]}  (sc.py:224-239, :179-185) */

@@ -7,8 +7,24 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "../../include/ocelot_sc.h"
 #include "sc_kernels.h"
+
+// NVTX range per entry point (tracing).  Header-only NVTX v3: without a profiler attached a
+// push/pop pair is two calls through a no-op function pointer.  ncu / nsys show the kick as
+// ocl_sc_kick_device > momentum / extent / deposit / rho reduce / solve / kick; under graph replay the stage ranges
+// appear once, around the capture.
+namespace {
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
+}  // namespace
+#define OCL_RANGE(name) NvtxRange nvtx_range_(name)
 
 using namespace ocl;
 
@@ -71,6 +87,11 @@ struct ocl_sc {
     double* mc_rho = nullptr;                 // multicast mapping of every rank's rho (NVLS reduction)
     double* mc_phi = nullptr;                 // slab mode: multicast mapping of every rank's phi (the inverse z pass
     double* own_phi = nullptr;                // broadcasts its slab through the switch); own_phi: the cudaMalloc'ed grid
+    // ordered deposit (ocl_sc_set_deterministic / OCL_SC_DETERMINISTIC=1): np.bincount's summation order, bit-identical
+    // rho from run to run; runs the stages directly (no kick graph), scratch sized for the largest bunch seen
+    bool ordered = false;
+    void* ordered_buf = nullptr;
+    size_t ordered_bytes = 0;
     int debug_skip = 0;                       // timing experiments only (OCL_SC_DEBUG_SKIP): bit 0/1/2 = leave out the
                                               // momentum exchange / extent exchange / rho reduction of a sharded kick
     // host arrays page-locked in place on first use (numpy buffers persist across kicks)
@@ -411,6 +432,7 @@ int ocl_sc_create(int device, int nx, int ny, int nz, long long max_particles, o
     TRY(cudaMemset(h->equad + n3 * 3, 0, sizeof(EQuad)));          // pad record behind the x-fastest table
     {
         if (const char* dbg = getenv("OCL_SC_DEBUG_SKIP")) h->debug_skip = atoi(dbg);
+        if (const char* det = getenv("OCL_SC_DETERMINISTIC")) h->ordered = atoi(det) != 0;
         const char* env = getenv("OCL_SC_GATHER");
         if (env) h->layout = atoi(env);
         if (h->layout < 0 || h->layout > 2) h->layout = (sizeof(EQuad) * n3 * 3 <= (size_t)400 << 20) ? 2 : 1;
@@ -449,7 +471,7 @@ void ocl_sc_destroy(ocl_sc_t* h) {
     cudaFree(h->k_hat); cudaFree(h->rho_hat); cudaFree(h->own_phi ? h->own_phi : h->phi); cudaFree(h->equad);
     cudaFree(h->fw.P); cudaFree(h->fw.Q); cudaFree(h->fw.khat); cudaFree(h->fw.A); cudaFree(h->fw.B);
     cudaFree(h->tw[0]); cudaFree(h->tw[1]); cudaFree(h->tw[2]); cudaFree(h->h3); cudaFree(h->moments);
-    cudaFree(h->stage_r); cudaFree(h->stage_q); cudaFree(h->cut_counts);
+    cudaFree(h->stage_r); cudaFree(h->stage_q); cudaFree(h->cut_counts); cudaFree(h->ordered_buf);
     if (h->cut_n) cudaFreeHost(h->cut_n);
     cudaFree(h->lw.ticket); cudaFree(h->lw.stats); cudaFree(h->lw.bins); cudaFree(h->lw.cnt); cudaFree(h->lw.Z);
     cudaFree(h->lw.spread);
@@ -560,6 +582,7 @@ int ocl_sc_set_multicast_phi(ocl_sc_t* h, void* local_phi, void* multicast_phi) 
 }
 
 int ocl_sc_nvls_reduce_rho(ocl_sc_t* h, void* stream) {
+    OCL_RANGE("ocl_sc_nvls_reduce_rho");
     if (!h) return 1;
     if (!h->mc_rho) return fail(h, "ocl_sc_nvls_reduce_rho", "call ocl_sc_set_multicast_rho first");
     ENTER_DEVICE(h);
@@ -585,6 +608,15 @@ int ocl_sc_nvls_reduce_rho(ocl_sc_t* h, void* stream) {
 int ocl_sc_use_device_params(ocl_sc_t* h, int on) {
     if (!h) return 1;
     h->cur_pp = on ? h->kp_dev : nullptr;
+    return 0;
+}
+
+// Ordered deposit on / off (SURVEY section 8e "Determinism"): every cell's charges are added in ascending particle
+// order, as np.bincount does (sc.py:193), instead of by L2 atomics in arrival order.  For debugging cell-flip /
+// reproducibility questions: about 3x the deposit's time, and the kick runs stage by stage instead of as one graph.
+int ocl_sc_set_deterministic(ocl_sc_t* h, int on) {
+    if (!h) return 1;
+    h->ordered = on != 0;
     return 0;
 }
 
@@ -671,6 +703,7 @@ int ocl_sc_set_peer_xchg(ocl_sc_t* h, int rank, int world, void* const* peer_a, 
 }
 
 int ocl_sc_slab_forward(ocl_sc_t* h, void* stream) {
+    OCL_RANGE("ocl_sc_slab_forward");
     if (!h || !h->slab_world) return h ? fail(h, "ocl_sc_slab_forward", "call ocl_sc_slab_init first") : 1;
     ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
@@ -686,6 +719,7 @@ int ocl_sc_slab_forward(ocl_sc_t* h, void* stream) {
 }
 
 int ocl_sc_slab_xpass(ocl_sc_t* h, void* stream) {
+    OCL_RANGE("ocl_sc_slab_xpass");
     if (!h || !h->slab_world) return h ? fail(h, "ocl_sc_slab_xpass", "call ocl_sc_slab_init first") : 1;
     ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
@@ -706,6 +740,7 @@ int ocl_sc_slab_xpass(ocl_sc_t* h, void* stream) {
 }
 
 int ocl_sc_slab_inverse(ocl_sc_t* h, void* stream) {
+    OCL_RANGE("ocl_sc_slab_inverse");
     if (!h || !h->slab_world) return h ? fail(h, "ocl_sc_slab_inverse", "call ocl_sc_slab_init first") : 1;
     ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
@@ -724,6 +759,7 @@ int ocl_sc_slab_inverse(ocl_sc_t* h, void* stream) {
 }
 
 int ocl_sc_slab_finish(ocl_sc_t* h, const double* mesh_draws, void* stream) {
+    OCL_RANGE("ocl_sc_slab_finish");
     if (!h || !h->slab_world) return h ? fail(h, "ocl_sc_slab_finish", "call ocl_sc_slab_init first") : 1;
     ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
@@ -737,6 +773,7 @@ int ocl_sc_slab_finish(ocl_sc_t* h, const double* mesh_draws, void* stream) {
 
 // ---- stages ---------------------------------------------------------------
 int ocl_sc_stage_momentum(ocl_sc_t* h, const double* d_r, long long ld, long long n, double E_GeV, void* stream) {
+    OCL_RANGE("ocl_sc_stage_momentum");
     if (!h) return 1;
     if (n < 0 || ld < n) return fail(h, "ocl_sc_stage_momentum", "need 0 <= n <= ld");
     if (n == 0 && h->mb.world <= 1 && !h->rs.defer) return fail(h, "ocl_sc_stage_momentum", "empty bunch");
@@ -762,6 +799,7 @@ int ocl_sc_stage_momentum(ocl_sc_t* h, const double* d_r, long long ld, long lon
 
 int ocl_sc_stage_extent(ocl_sc_t* h, const double* d_r, long long ld, const double* d_q, long long n, double E_GeV,
                         const double* mesh_draws, void* stream) {
+    OCL_RANGE("ocl_sc_stage_extent");
     if (!h) return 1;
     ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
@@ -776,6 +814,7 @@ int ocl_sc_stage_extent(ocl_sc_t* h, const double* d_r, long long ld, const doub
 
 int ocl_sc_stage_deposit(ocl_sc_t* h, const double* d_r, long long ld, const double* d_q, long long n, double E_GeV,
                          const double* mesh_draws, void* stream) {
+    OCL_RANGE("ocl_sc_stage_deposit");
     if (!h) return 1;
     ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
@@ -784,13 +823,28 @@ int ocl_sc_stage_deposit(ocl_sc_t* h, const double* d_r, long long ld, const dou
     // chain now, concurrently with the deposit and the first two rho passes
     if (h->solver == 0 && fork_khat(h, st)) return 1;
     CU(h, cudaMemsetAsync(h->rho, 0, sizeof(double) * h->rho_count, st));
-    launch_deposit(d_r, ld, d_q, n, kp_of(h, E_GeV, 0.0, mesh_draws), h->rs, h->md, h->rho, st);
-    h->launches += 2;
+    if (h->ordered && n > 0) {
+        const size_t need = deposit_ordered_scratch_bytes(n, h->md);
+        if (need > h->ordered_bytes) {
+            CU(h, cudaStreamSynchronize(st));                       // an earlier kick may still be using the old scratch
+            cudaFree(h->ordered_buf); h->ordered_buf = nullptr; h->ordered_bytes = 0;
+            CU(h, cudaMalloc(&h->ordered_buf, need + need / 8));
+            h->ordered_bytes = need + need / 8;
+        }
+        if (launch_deposit_ordered(d_r, ld, d_q, n, kp_of(h, E_GeV, 0.0, mesh_draws), h->rs, h->md, h->rho,
+                                   h->ordered_buf, h->ordered_bytes, st))
+            return fail(h, "ocl_sc_stage_deposit", "ordered deposit: radix sort failed");
+        h->launches += 3;                                           // + the sort's own kernels (library code, not counted)
+    } else {
+        launch_deposit(d_r, ld, d_q, n, kp_of(h, E_GeV, 0.0, mesh_draws), h->rs, h->md, h->rho, st);
+        h->launches += 2;
+    }
     mark(h, T_DEP, st);
     return check_launch(h, "k_deposit");
 }
 
 int ocl_sc_stage_solve(ocl_sc_t* h, const double* mesh_draws, void* stream) {
+    OCL_RANGE("ocl_sc_stage_solve");
     if (!h) return 1;
     ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
@@ -817,6 +871,7 @@ int ocl_sc_stage_solve(ocl_sc_t* h, const double* mesh_draws, void* stream) {
 
 int ocl_sc_stage_kick(ocl_sc_t* h, double* d_r, long long ld, long long n, double E_GeV, double dz,
                       const double* mesh_draws, void* stream) {
+    OCL_RANGE("ocl_sc_stage_kick");
     if (!h) return 1;
     ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
@@ -893,12 +948,13 @@ static int capture_kick(ocl_sc* h, double* d_r, long long ld, const double* d_q,
 
 int ocl_sc_kick_device(ocl_sc_t* h, double* d_r, long long ld, const double* d_q, long long n, double E_GeV,
                        double dz, const double* mesh_draws, void* stream) {
+    OCL_RANGE("ocl_sc_kick_device");
     if (!h) return 1;
     if (dz == 0.0) return 0;   // sc.py:210-212
     if (!(E_GeV > 0.0)) return fail(h, "ocl_sc_kick_device", "beam energy must be positive");
     if (n <= 0 || ld < n) return fail(h, "ocl_sc_kick_device", "need 0 < n <= ld");
     cudaStream_t st = (cudaStream_t)stream;
-    bool graph_ok = h->use_graph && h->solver == 0 && !h->timers;
+    bool graph_ok = h->use_graph && h->solver == 0 && !h->timers && !h->ordered;
     if (graph_ok) {
         ENTER_DEVICE(h);
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
@@ -989,6 +1045,7 @@ static int ensure_stage(ocl_sc* h, long long n) {
 
 int ocl_sc_kick_host(ocl_sc_t* h, double* h_r, long long ld, const double* h_q, long long n, double E_GeV, double dz,
                      const double* mesh_draws) {
+    OCL_RANGE("ocl_sc_kick_host");
     if (!h) return 1;
     if (dz == 0.0) return 0;
     if (n <= 0 || ld < n) return fail(h, "ocl_sc_kick_host", "need 0 < n <= ld");
@@ -1116,6 +1173,7 @@ int ocl_sc_potential_host(ocl_sc_t* h, const double* h_rho, const double steps[3
 
 int ocl_sc_map_apply(ocl_sc_t* h, double* d_r, long long ld, long long n, const double* R, const double* B,
                      const double* T, void* stream) {
+    OCL_RANGE("ocl_sc_map_apply");
     if (!h || !R) return 1;
     if (n <= 0 || ld < n) return fail(h, "ocl_sc_map_apply", "need 0 < n <= ld");
     ENTER_DEVICE(h);
@@ -1135,6 +1193,7 @@ int ocl_sc_map_apply(ocl_sc_t* h, double* d_r, long long ld, long long n, const 
 
 int ocl_sc_cavity_apply(ocl_sc_t* h, double* d_r, long long ld, long long n, const double* R, const double* B,
                         const double* c, int mode, void* stream) {
+    OCL_RANGE("ocl_sc_cavity_apply");
     if (!h || !R || !c) return 1;
     if (n <= 0 || ld < n) return fail(h, "ocl_sc_cavity_apply", "need 0 < n <= ld");
     if (mode != 1 && mode != 2) return fail(h, "ocl_sc_cavity_apply", "mode must be 1 or 2");
@@ -1208,6 +1267,7 @@ int ocl_sc_cavity_coefficients(double v, double phi_deg, double freq, double E_G
 int ocl_sc_aperture_cut(ocl_sc_t* h, const double* d_r, long long ld, const double* d_q, const long long* d_ids,
                         long long n, int kind, int row, const double* params, double* d_r_out, long long ld_out,
                         double* d_q_out, long long* d_ids_out, long long* d_lost_out, long long* n_out, void* stream) {
+    OCL_RANGE("ocl_sc_aperture_cut");
     if (!h || !params || !n_out || !d_r_out || !d_q_out) return 1;
     if (n < 0 || ld < n || ld_out < n) return fail(h, "ocl_sc_aperture_cut", "need 0 <= n <= ld, ld_out");
     if (kind != 0 && kind != 1) return fail(h, "ocl_sc_aperture_cut", "kind must be 0 (row against [lo, hi]) or 1 (ellipse)");
@@ -1238,6 +1298,7 @@ int ocl_sc_aperture_cut(ocl_sc_t* h, const double* d_r, long long ld, const doub
 }
 
 int ocl_sc_beam_moments(ocl_sc_t* h, const double* d_r, long long ld, long long n, double* h_out, void* stream) {
+    OCL_RANGE("ocl_sc_beam_moments");
     if (!h || !h_out) return 1;
     if (n <= 0 || ld < n) return fail(h, "ocl_sc_beam_moments", "need 0 < n <= ld");
     ENTER_DEVICE(h);
@@ -1310,6 +1371,7 @@ static int lsc_params(ocl_sc* h, const double* p, LscParams& lp) {
 
 int ocl_sc_lsc_stats(ocl_sc_t* h, const double* d_r, long long ld, long long n, const double* d_q, double h_out[8],
                      void* stream) {
+    OCL_RANGE("ocl_sc_lsc_stats");
     if (!h || !h_out) return 1;
     if (n <= 0 || ld < n) return fail(h, "ocl_sc_lsc_stats", "need 0 < n <= ld");
     ENTER_DEVICE(h);
@@ -1337,6 +1399,7 @@ int ocl_sc_lsc_stats(ocl_sc_t* h, const double* d_r, long long ld, long long n, 
 }
 
 int ocl_sc_lsc_deposit(ocl_sc_t* h, const double* d_r, long long ld, long long n, const double* params, void* stream) {
+    OCL_RANGE("ocl_sc_lsc_deposit");
     if (!h) return 1;
     if (n <= 0 || ld < n) return fail(h, "ocl_sc_lsc_deposit", "need 0 < n <= ld");
     LscParams lp;
@@ -1354,6 +1417,7 @@ int ocl_sc_lsc_deposit(ocl_sc_t* h, const double* d_r, long long ld, long long n
 }
 
 int ocl_sc_lsc_solve_kick(ocl_sc_t* h, double* d_r, long long ld, long long n, const double* params, void* stream) {
+    OCL_RANGE("ocl_sc_lsc_solve_kick");
     if (!h) return 1;
     if (n <= 0 || ld < n) return fail(h, "ocl_sc_lsc_solve_kick", "need 0 < n <= ld");
     LscParams lp;
@@ -1374,6 +1438,7 @@ int ocl_sc_lsc_solve_kick(ocl_sc_t* h, double* d_r, long long ld, long long n, c
 }
 
 int ocl_sc_lsc_kick(ocl_sc_t* h, double* d_r, long long ld, long long n, const double* params, void* stream) {
+    OCL_RANGE("ocl_sc_lsc_kick");
     if (ocl_sc_lsc_deposit(h, d_r, ld, n, params, stream)) return 1;
     return ocl_sc_lsc_solve_kick(h, d_r, ld, n, params, stream);
 }
@@ -1391,6 +1456,7 @@ static int lsc_async_error(ocl_sc* h, const char* who) {
 
 int ocl_sc_lsc_kick_async(ocl_sc_t* h, double* d_r, long long ld, long long n, const double* d_q, const double* hostp,
                           void* stream) {
+    OCL_RANGE("ocl_sc_lsc_kick_async");
     if (!h || !hostp) return 1;
     if (n <= 0 || ld < n) return fail(h, "ocl_sc_lsc_kick_async", "need 0 < n <= ld");
     ENTER_DEVICE(h);

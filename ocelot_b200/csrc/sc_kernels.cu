@@ -19,6 +19,8 @@
 #include <cstdint>
 #include <cstdlib>
 
+#include <cub/device/device_radix_sort.cuh>
+
 #include "sc_kernels.h"
 
 namespace ocl {
@@ -356,6 +358,51 @@ __global__ void __launch_bounds__(kThreads, 3) k_deposit(const double* __restric
     };
     if constexpr (TMA) bulk_sweep<7, kPipeDepth>(base, (int)n, pipe, bars, body);
     else pipelined_sweep<7, kPipeDepth>(base, (int)n, pipe, body);
+}
+
+// ---------------------------------------------------------------------------
+// Ordered deposit (debugging mode, SURVEY section 8e "Determinism"): the same cells, but every cell's charges are
+// added one after the other in ascending particle order starting from 0.0 -- the order np.bincount uses
+// (sc.py:193) -- so rho is bit-identical from run to run and, for identical cell indices, to the reference's grid.
+//   k_cell_index   sweep 3': 6 rows -> (cell, particle) pairs; particles outside the mesh get the key 0xffffffff
+//   stable radix sort of the pairs by cell (cub::DeviceRadixSort: equal keys keep their particle order)
+//   k_ordered_sum  the thread at the head of each run of equal cells adds that run sequentially
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 3) k_cell_index(const double* __restrict__ r, long long ld, long long n,
+                                                           KP kp, ReduceState rs, MeshDims md,
+                                                           unsigned* __restrict__ key, unsigned* __restrict__ val) {
+    pdl_enter();
+    const RefParams rp = kp_ref(kp);
+    __shared__ __align__(128) double pipe[kPipeDepth * 6 * kThreads];
+    __shared__ Geo sg;
+    load_geo(rs.geo, &sg);
+    const Frame f = sg.f;
+    const Mesh m = sg.m;
+    const double* const base[6] = {r, r + ld, r + 2 * ld, r + 3 * ld, r + 4 * ld, r + 5 * ld};
+    auto body = [&](int i, const double (&w)[6]) {
+        const Cart c = mad_to_cart(rp, w[0], w[1], w[2], w[3], w[4], w[5]);
+        double a, b, g, g0, g1, g2;
+        rotate_stretch(f, c.x, c.y, c.z, a, b, g);
+        to_grid(m, a, b, g, g0, g1, g2);
+        const int c0 = (int)floor(g0) + 1, c1 = (int)floor(g1) + 1, c2 = (int)floor(g2) + 1;   // sc.py:191
+        const bool in = (unsigned)c0 < (unsigned)md.nx && (unsigned)c1 < (unsigned)md.ny && (unsigned)c2 < (unsigned)md.nz;
+        key[i] = in ? (unsigned)(((size_t)c0 * md.ny + c1) * md.nz + c2) : 0xffffffffu;
+        val[i] = (unsigned)i;
+    };
+    pipelined_sweep<6, kPipeDepth>(base, (int)n, pipe, body);
+}
+
+__global__ void __launch_bounds__(kThreads) k_ordered_sum(const unsigned* __restrict__ key, const unsigned* __restrict__ val,
+                                                         const double* __restrict__ q, long long n, unsigned cells,
+                                                         double* __restrict__ rho) {
+    pdl_enter();
+    for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x) {
+        const unsigned c = key[j];
+        if (c >= cells || (j > 0 && key[j - 1] == c)) continue;          // not the head of a run
+        double s = 0.0;
+        for (long long k = j; k < n && key[k] == c; ++k) s = __dadd_rn(s, q[val[k]]);
+        rho[c] = s;
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -868,6 +915,35 @@ void launch_deposit(const double* r, long long ld, const double* q, long long n,
         launch_k(k_deposit<true>, dim3(grid_for(n, 148 * 3)), dim3(kThreads), 0, st, r, ld, q, n, kp, rs, md, rho);
     else
         launch_k(k_deposit<false>, dim3(grid_for(n, 148 * 3)), dim3(kThreads), 0, st, r, ld, q, n, kp, rs, md, rho);
+}
+// scratch layout: key_in | val_in | key_out | val_out (n unsigned each, 256-byte aligned) | cub temporary storage
+static size_t ordered_pad(long long n) { return ((size_t)n * sizeof(unsigned) + 255) / 256 * 256; }
+size_t deposit_ordered_scratch_bytes(long long n, MeshDims md) {
+    size_t tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tmp, (const unsigned*)nullptr, (unsigned*)nullptr, (const unsigned*)nullptr,
+                                    (unsigned*)nullptr, (int)n, 0, 32);
+    (void)md;
+    return 4 * ordered_pad(n) + tmp + 256;
+}
+int launch_deposit_ordered(const double* r, long long ld, const double* q, long long n, KP kp, ReduceState rs,
+                           MeshDims md, double* rho, void* scratch, size_t scratch_bytes, cudaStream_t st) {
+    const size_t pad = ordered_pad(n);
+    if (scratch_bytes < 4 * pad) return 1;
+    char* base = static_cast<char*>(scratch);
+    unsigned* key_in = reinterpret_cast<unsigned*>(base);
+    unsigned* val_in = reinterpret_cast<unsigned*>(base + pad);
+    unsigned* key_out = reinterpret_cast<unsigned*>(base + 2 * pad);
+    unsigned* val_out = reinterpret_cast<unsigned*>(base + 3 * pad);
+    void* tmp = base + 4 * pad;
+    size_t tmp_bytes = scratch_bytes - 4 * pad;
+    launch_k(k_cell_index, dim3(grid_for(n, 148 * 3)), dim3(kThreads), 0, st, r, ld, n, kp, rs, md, key_in, val_in);
+    // all 32 key bits: particles outside the mesh carry the key 0xffffffff and must sort behind every cell
+    if (cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, key_in, key_out, val_in, val_out, (int)n, 0, 32, st) != cudaSuccess)
+        return 1;
+    const unsigned cells = (unsigned)((size_t)md.nx * md.ny * md.nz);
+    launch_k(k_ordered_sum, dim3(grid_for(n, 148 * 8)), dim3(kThreads), 0, st, (const unsigned*)key_out,
+             (const unsigned*)val_out, q, n, cells, rho);
+    return 0;
 }
 void launch_green_table(ReduceState rs, MeshDims md, double* gtab, double* h3, cudaStream_t st) {
     StepSrc src;

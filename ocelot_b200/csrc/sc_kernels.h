@@ -60,6 +60,10 @@ void launch_extent(const double* r, long long ld, const double* q, long long n, 
 void launch_finish(int which, KP kp, ReduceState rs, MeshDims md, cudaStream_t st);
 void launch_deposit(const double* r, long long ld, const double* q, long long n, KP kp, ReduceState rs,
                     MeshDims md, double* rho, cudaStream_t st);
+// ordered (run-to-run bit-identical, np.bincount order) deposit; scratch from deposit_ordered_scratch_bytes
+size_t deposit_ordered_scratch_bytes(long long n, MeshDims md);
+int launch_deposit_ordered(const double* r, long long ld, const double* q, long long n, KP kp, ReduceState rs,
+                           MeshDims md, double* rho, void* scratch, size_t scratch_bytes, cudaStream_t st);
 void launch_green_table(ReduceState rs, MeshDims md, double* gtab, double* h3, cudaStream_t st);
 void launch_green_mirror(const double* gtab, MeshDims md, double* kpad, cudaStream_t st);
 void launch_green_compact(const double* gtab, MeshDims md, double* k1, cudaStream_t st);

@@ -58,6 +58,7 @@ _SIGNATURES = {
     "ocl_sc_stage_momentum": (C.c_int, [_vp, _vp, _ll, _ll, C.c_double, _vp]),
     "ocl_sc_stage_extent": (C.c_int, [_vp, _vp, _ll, _vp, _ll, C.c_double, _dp, _vp]),
     "ocl_sc_defer_finish": (C.c_int, [_vp, C.c_int]),
+    "ocl_sc_set_deterministic": (C.c_int, [_vp, C.c_int]),
     "ocl_sc_stage_finish": (C.c_int, [_vp, C.c_int, C.c_double, _dp, _vp]),
     "ocl_sc_stage_deposit": (C.c_int, [_vp, _vp, _ll, _vp, _ll, C.c_double, _dp, _vp]),
     "ocl_sc_stage_solve": (C.c_int, [_vp, _dp, _vp]),
@@ -358,6 +359,10 @@ class Solver:
         """NCCL fallback of a sharded kick: the sweeps only reduce locally; the caller all-reduces the
         collective buffers and calls ``stage_finish``."""
         self._check(self._lib.ocl_sc_defer_finish(self._h, 1 if on else 0), "ocl_sc_defer_finish")
+
+    def set_deterministic(self, on: bool):
+        """Ordered deposit (np.bincount's summation order; bit-identical rho from run to run) on / off."""
+        self._check(self._lib.ocl_sc_set_deterministic(self._h, 1 if on else 0), "ocl_sc_set_deterministic")
 
     def stage_finish(self, which, E_GeV, mesh_draws=None, stream=None):
         self._check(self._lib.ocl_sc_stage_finish(self._h, int(which), float(E_GeV), _draws(mesh_draws),

@@ -28,6 +28,8 @@ class SpaceCharge(PhysProc):
                       after construction, space_charge_test.py:71-77)
         random_mesh, random_seed, low_order_kick, debug -- as in the reference
         device     -- CUDA device index used for host-array kicks (default: current)
+        deterministic -- extension (default False): deposit the charge in np.bincount's order (sc.py:193) instead
+                      of with atomics, so the grid is bit-identical from run to run (a debugging aid, slower)
     """
 
     def __init__(self, step=1, **kwargs):
@@ -41,6 +43,7 @@ class SpaceCharge(PhysProc):
         self.random_mesh = kwargs.get("random_mesh", False)
         self.random_seed = 10
         self.device = kwargs.get("device", None)
+        self.deterministic = kwargs.get("deterministic", False)    # ordered deposit (debugging aid), see class doc
         self._solvers = {}
         # unknown kwargs are ignored, as in the reference (sc.py:92-102)
 
@@ -86,6 +89,9 @@ class SpaceCharge(PhysProc):
         if s is None:
             s = native.Solver(int(device), nmesh)
             self._solvers = {key: s}               # one live handle; a mesh change re-plans
+        if getattr(self, "deterministic", False) != getattr(s, "_ordered", False):
+            s.set_deterministic(bool(self.deterministic))
+            s._ordered = bool(self.deterministic)
         return s
 
     # Navigator deep-copies the process table (navi.py:189) and ParameterScanner

@@ -118,6 +118,10 @@ def test_stage_taps_vs_reference(native, golden, name):
     geo = s.geometry()
     assert np.max(np.abs(geo["steps"] / g["steps"] - 1)) < 1e-14
     assert abs(geo["gamma0"] / float(g["gamma0"]) - 1) < 1e-14
+    # the rotation into the mean-momentum frame itself (sc.py:224-231): columns t1, t2, t3
+    T, pav, _, beta0 = orc.bunch_frame(orc.mad_to_cartesian(g["r_in"], float(g["E"]) / orc.M_E_GEV)[3:6])
+    assert np.max(np.abs(geo["T"] - T)) < 1e-14
+    assert abs(geo["pav"] / pav - 1) < 1e-14 and abs(geo["beta0"] / beta0 - 1) < 1e-14
     rho = s.rho()
     # identical cell for every particle: any flip would change rho by a whole charge
     assert np.max(np.abs(rho - g["rho"])) < 1e-3 * np.min(g["q"])
@@ -489,6 +493,36 @@ def test_fft_512_box_matches_cufft(native, monkeypatch):
     phi_lib = native.Solver(0, shape).potential_host(rho, steps)
     monkeypatch.delenv("OCL_SC_SOLVER", raising=False)
     assert rel_to_max(phi_own, phi_lib) < 1e-13
+
+
+def test_ordered_deposit_is_bit_identical_to_bincount(native, golden):
+    """SURVEY 8e "Determinism": with ocl_sc_set_deterministic the charges of a cell are added in ascending particle
+    order from 0.0, the order of np.bincount (sc.py:193), so the grid equals the reference's BIT FOR BIT (non-uniform
+    charges, so that the order of the additions matters) and a kick is bit-identical from run to run."""
+    g = golden("kat_c1_31.npz")
+    rng = np.random.RandomState(5)
+    q = g["q"] * (0.5 + rng.rand(g["q"].size))
+    E, dz = float(g["E"]), float(g["dz"])
+    taps = {}
+    ref = g["r_in"].copy()
+    orc.sc_kick(ref, q, E, dz, g["nmesh"], taps=taps)
+    s = native.Solver(0, g["nmesh"])
+    s.set_deterministic(True)
+    outs = []
+    for _ in range(2):
+        r = dev(g["r_in"])
+        s.kick_device(r, dev(q), E, dz)
+        outs.append(r.cpu().numpy())
+        rho = s.rho()
+        assert np.array_equal(rho, taps["rho"])                       # every bit of every cell
+    assert np.array_equal(outs[0], outs[1])
+    for row in range(6):
+        assert np.max(np.abs(outs[0][row] - ref[row])) < 1e-10 * np.sqrt(np.mean(ref[row] ** 2))
+    # the default (atomic) deposit agrees to rounding, in whatever order the additions arrived
+    s.set_deterministic(False)
+    r = dev(g["r_in"])
+    s.kick_device(r, dev(q), E, dz)
+    assert rel_to_max(s.rho(), taps["rho"]) < 1e-13
 
 
 def test_tma_row_pipeline_is_bit_identical_to_cp_async():

@@ -36,6 +36,9 @@ for n, nm in ((3001, (9, 12, 7)), (20000, (31, 31, 31)), (5000, (20, 33, 64))):
         sg.kick_device(r, q, dev.E, 0.1)
         sg.field_at_particles(r, q, dev.E)
     os.environ.pop("OCL_SC_GATHER")
+    so = native.Solver(0, nm)                 # ordered (deterministic) deposit: cell index sweep, radix sort, ordered sums
+    so.set_deterministic(True)
+    so.kick_device(r, q, dev.E, 0.1)
     sd = native.Solver(0, nm)
     sd.defer_finish(True)
     sd.stage_momentum(r, dev.E); sd.stage_finish(0, dev.E); sd.stage_extent(r, q, dev.E); sd.stage_finish(1, dev.E)
