@@ -491,7 +491,7 @@ def resident_track_leg(ctx, n, mesh=31):
     the ones the reference's Navigator produced for this lattice (tests/golden/track_c1.npz, recorded by
     oracle/make_golden.py), applied by the device map kernel."""
     torch = ctx.torch
-    from ocelot_b200 import SpaceCharge, DeviceParticleArray, get_envelope
+    from ocelot_b200 import SpaceCharge, DeviceParticleArray, EnvelopeRecorder
     from ocelot_b200.track import replay_track
     path = os.path.join(ROOT, "tests", "golden", "track_c1.npz")
     with np.load(path) as z:
@@ -509,10 +509,13 @@ def resident_track_leg(ctx, n, mesh=31):
         p.rparticles.copy_(hr, non_blocking=True)
         p.q_array.copy_(hq, non_blocking=True)
         p.E = E_GEV
-        moments.clear()
-        moments.append(get_envelope(p))
-        replay_track(p, R, B, map_step, kick_dz, sc, after_step=lambda step, pa: moments.append(get_envelope(pa)))
+        # as ocelot_b200.track.track does: the moments of every step are recorded on the device (two moment passes per
+        # step, no host synchronisation) and read back once, after the loop
+        rec = EnvelopeRecorder(ctx.device)
+        rec.record(p)
+        replay_track(p, R, B, map_step, kick_dz, sc, after_step=lambda step, pa: rec.record(pa))
         out_r.copy_(p.rparticles, non_blocking=True)
+        moments[:] = rec.collect()
         torch.cuda.synchronize()
         return p
 
@@ -525,7 +528,7 @@ def resident_track_leg(ctx, n, mesh=31):
     kicks = int(np.count_nonzero(kick_dz))
     return {"particles": n, "nmesh": [mesh] * 3, "kicks": kicks, "maps": int(len(R)), "seconds": best,
             "value": n * kicks / best, "unit": UNIT, "ms_per_step": best / kicks * 1e3,
-            "h2d_bytes": 56 * n, "d2h_bytes": 48 * n + 18 * 8 * (kicks + 1),
+            "h2d_bytes": 56 * n, "d2h_bytes": 48 * n + 24 * 8 * 128 * ((kicks + 1 + 127) // 128),
             "final_sigma_x": float(np.sqrt(moments[-1].xx))}
 
 
@@ -680,9 +683,11 @@ def run_native(args):
         if not args.no_e2e:
             try:
                 line["e2e_resident"] = {
-                    "call": "ocelot_b200.track.replay_track + get_envelope per step: BASELINE config-1 lattice (10 m FODO, "
-                            "100 kicks, 31^3), bunch H2D once at the start and D2H once at the end inside the timed "
-                            "region, device transfer maps and device beam moments; best of 3 runs",
+                    "call": "ocelot_b200.track.replay_track + beam moments every step (EnvelopeRecorder, as "
+                            "ocelot_b200.track.track does: moments kept on the device, read back once after the loop): "
+                            "BASELINE config-1 lattice (10 m FODO, 100 kicks, 31^3), bunch H2D once at the start, bunch "
+                            "and moments D2H once at the end, all inside the timed region; device transfer maps; "
+                            "best of 3 runs",
                     "runs": [resident_track_leg(ctx, 200_000), resident_track_leg(ctx, 1_000_000)]}
             except Exception as exc:  # noqa: BLE001
                 line["e2e_resident"] = {"error": repr(exc)}

@@ -248,6 +248,12 @@ int ocl_sc_aperture_cut(ocl_sc_t* h, const double* d_r, long long ld, const doub
  * :121-166): h_out[18] = {x, px, y, py, tau, p, xx, xpx, pxpx, yy, ypy, pypy, tautau, pp, xy, pxpy,
  * xpy, ypx} with the reference's px, py correction factor applied.  Synchronous. */
 int ocl_sc_beam_moments(ocl_sc_t* h, const double* d_r, long long ld, long long n, double* h_out, void* stream);
+/* The same with the result left in DEVICE memory d_out and no host synchronisation (a resident tracking loop records
+ * every step's moments on the device and reads them back once at the end; the reference's track() also only returns
+ * them when tracking is over, track.py:482,504).  d_out[0..17] as above; d_q != NULL adds d_out[18] = sum q
+ * (Twiss.q, analysis.py:81). */
+int ocl_sc_beam_moments_device(ocl_sc_t* h, const double* d_r, long long ld, long long n, const double* d_q,
+                               double* d_out, void* stream);
 
 /* ---- longitudinal space charge: class LSC (ocelot/cpbd/sc.py:261-599), the 1-D sibling of the
  * kick.  One LSC.apply = ocl_sc_lsc_stats (sweep A, synchronous) -> the host derives the 1-D grid like

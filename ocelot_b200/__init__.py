@@ -5,13 +5,13 @@ from .sc import SpaceCharge
 from .sc import install as install_space_charge, uninstall as uninstall_space_charge
 from .lsc import LSC
 from .lsc import install as install_lsc, uninstall as uninstall_lsc
-from .beam import apply_map, get_envelope, Moments
+from .beam import apply_map, get_envelope, Moments, EnvelopeRecorder
 from .track import track, replay_track
 from .apertures import RectAperture, EllipticalAperture
 from .io import save_particle_array2npz, load_particle_array_from_npz
 
 __all__ = ["PhysProc", "ParticleArray", "DeviceParticleArray", "SpaceCharge", "LSC", "install", "uninstall", "install_space_charge", "install_lsc",
-           "apply_map", "get_envelope", "Moments", "track", "replay_track",
+           "apply_map", "get_envelope", "Moments", "EnvelopeRecorder", "track", "replay_track",
            "RectAperture", "EllipticalAperture", "save_particle_array2npz", "load_particle_array_from_npz"]
 
 

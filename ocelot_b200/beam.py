@@ -92,14 +92,63 @@ def moments_from_sums(m: dict, E=0.0, q=0.0) -> Moments:
     return t
 
 
+class EnvelopeRecorder:
+    """Beam moments of many steps of a resident tracking run, kept ON THE DEVICE until ``collect()``.
+
+    The reference computes ``get_envelope`` after every step (track.py:482) but hands the list back only when
+    tracking is over (track.py:504); reading 19 doubles back per step would put a host synchronisation into every
+    step of an otherwise asynchronous loop (kick graph, map kernel, moment kernels).  ``record`` launches the two
+    moment passes into the next slot of a device buffer; ``collect`` does one device->host copy and the scalar
+    post-processing (analysis.py:179-220) for all recorded steps."""
+
+    SLOT = 24                       # doubles per record (19 used), keeps slots 64-byte aligned
+    CHUNK = 128                     # records per device buffer; buffers are never reallocated while writes are pending
+
+    def __init__(self, device):
+        self.device = device
+        self._chunks = []
+        self._meta = []             # (slot or None, E, s)
+        self._slots = 0
+
+    def __len__(self):
+        return len(self._meta)
+
+    def record(self, p_array, s=0.0):
+        """Queue the moments of ``p_array`` as it is now.  ``s`` is what the record's ``.s`` will report: the
+        reference's get_envelope leaves Twiss.s at 0 and track() adds the tracked length (track.py:482-484)."""
+        import torch
+        r = p_array.rparticles
+        E, s = float(p_array.E), float(s)
+        if r.shape[1] < 3:                       # analysis.py:86-88: an empty Twiss carrying only the energy
+            self._meta.append((None, E, 0.0))
+            return
+        k = self._slots
+        self._slots += 1
+        if k // self.CHUNK >= len(self._chunks):
+            self._chunks.append(torch.zeros(self.CHUNK, self.SLOT, dtype=torch.float64, device=r.device))
+        out = self._chunks[k // self.CHUNK][k % self.CHUNK]
+        _scratch_solver(r.device.index or 0).beam_moments_device(r, p_array.q_array, out)
+        self._meta.append((k, E, s))
+
+    def collect(self):
+        """One synchronising device->host copy per buffer; returns the list of ``Moments`` in recording order."""
+        from . import native
+        host = [c.cpu().numpy() for c in self._chunks]
+        res = []
+        for slot, E, s in self._meta:
+            if slot is None:
+                t = Moments()
+                t.E = E
+            else:
+                row = host[slot // self.CHUNK][slot % self.CHUNK]
+                t = moments_from_sums(dict(zip(native.Solver.MOMENT_KEYS, row[:18])), E=E, q=float(row[18]))
+                t.s = s
+            res.append(t)
+        return res
+
+
 def get_envelope(p_array) -> Moments:
-    """Beam moments of a DeviceParticleArray (two streaming passes on the GPU, 18 doubles back)."""
-    r = p_array.rparticles
-    if r.shape[1] < 3:                       # analysis.py:86-88
-        t = Moments()
-        t.E = float(p_array.E)
-        return t
-    m = _scratch_solver(r.device.index or 0).beam_moments(r)
-    t = moments_from_sums(m, E=p_array.E, q=float(p_array.q_array.sum().item()))
-    t.s = float(getattr(p_array, "s", 0.0))
-    return t
+    """Beam moments of a DeviceParticleArray (two streaming passes on the GPU, 19 doubles back)."""
+    rec = EnvelopeRecorder(p_array.rparticles.device)
+    rec.record(p_array)
+    return rec.collect()[0]

@@ -1304,12 +1304,29 @@ int ocl_sc_beam_moments(ocl_sc_t* h, const double* d_r, long long ld, long long 
     ENTER_DEVICE(h);
     cudaStream_t st = (cudaStream_t)stream;
     if (adopt_stream(h, st)) return 1;
-    launch_moments(d_r, ld, n, h->rs, h->moments, st);
+    launch_moments(d_r, ld, n, nullptr, h->rs, h->moments, st);
     h->launches += 2;
     if (check_launch(h, "k_moments")) return 1;
     CU(h, cudaMemcpyAsync(h_out, h->moments, sizeof(double) * 18, cudaMemcpyDeviceToHost, st));
     CU(h, cudaStreamSynchronize(st));
     return 0;
+}
+
+// The same two passes with the result left in DEVICE memory and no host synchronisation: a resident tracking loop
+// records the moments of every step into its own device buffer and reads them back once at the end (track.py:482
+// computes them per step but only returns them when tracking is over).  d_out[0..17] as ocl_sc_beam_moments;
+// d_q != NULL adds d_out[18] = sum q.
+int ocl_sc_beam_moments_device(ocl_sc_t* h, const double* d_r, long long ld, long long n, const double* d_q,
+                               double* d_out, void* stream) {
+    OCL_RANGE("ocl_sc_beam_moments_device");
+    if (!h || !d_out) return 1;
+    if (n <= 0 || ld < n) return fail(h, "ocl_sc_beam_moments_device", "need 0 < n <= ld");
+    ENTER_DEVICE(h);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (adopt_stream(h, st)) return 1;
+    launch_moments(d_r, ld, n, d_q, h->rs, d_out, st);
+    h->launches += 2;
+    return check_launch(h, "k_moments");
 }
 
 /* ---- longitudinal space charge (LSC, sc.py:261-599) ---- */

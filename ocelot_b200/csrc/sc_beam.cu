@@ -101,21 +101,31 @@ __global__ void __launch_bounds__(kBThreads, 3) k_map_apply(double* __restrict__
 
 // ---- f2: beam moments ----------------------------------------------------------------------
 // pass 1: sums of x, px*f, y, py*f, tau, p with f = 1 - p - p^2/2 + px^2/2 + py^2/2 (analysis.py:121-123)
+// NR = 7: the charges are a seventh row and out[18] = sum q (the bunch charge that get_envelope reports, analysis.py:81)
+template <int NR>
 __global__ void __launch_bounds__(kBThreads, 4) k_moments_1(const double* __restrict__ r, long long ld, long long n,
-                                                           ReduceState rs, double* __restrict__ out) {
-    __shared__ double sh[6 * kBWarps];
-    __shared__ double pipe[kBDepth * 6 * kBThreads];
-    double v[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
-    const double* const base[6] = {r, r + ld, r + 2 * ld, r + 3 * ld, r + 4 * ld, r + 5 * ld};
-    pipelined_sweep<6, kBDepth>(base, (int)n, pipe, [&](int, const double (&x)[6]) {
+                                                           const double* __restrict__ q, ReduceState rs,
+                                                           double* __restrict__ out) {
+    __shared__ double sh[NR * kBWarps];
+    __shared__ double pipe[kBDepth * NR * kBThreads];
+    double v[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) v[k] = 0.0;
+    const double* base[NR];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) base[k] = r + k * ld;
+    if constexpr (NR == 7) base[6] = q;
+    pipelined_sweep<NR, kBDepth>(base, (int)n, pipe, [&](int, const double (&x)[NR]) {
         const double p = x[5];
         const double f = 1. - p - 0.5 * p * p + 0.5 * x[1] * x[1] + 0.5 * x[3] * x[3];
         v[0] += x[0]; v[1] += x[1] * f; v[2] += x[2]; v[3] += x[3] * f; v[4] += x[4]; v[5] += p;
+        if constexpr (NR == 7) v[6] += x[6];
     });
-    if (grid_sum<6>(v, rs.part, rs.ticket + 2, sh) && threadIdx.x == 0) {
+    if (grid_sum<NR>(v, rs.part, rs.ticket + 2, sh) && threadIdx.x == 0) {
         const double inv = 1.0 / (double)n;
 #pragma unroll
         for (int k = 0; k < 6; ++k) out[k] = v[k] * inv;        // np.mean
+        if constexpr (NR == 7) out[18] = v[6];
     }
 }
 
@@ -158,9 +168,12 @@ void launch_map_apply(double* r, long long ld, long long n, const MapCoef& mc, c
     k_map_apply<<<sweep_grid(n, 148 * 3), kBThreads, 0, st>>>(r, ld, n, mc);
 }
 
-void launch_moments(const double* r, long long ld, long long n, ReduceState rs, double* out18, cudaStream_t st) {
-    k_moments_1<<<sweep_grid(n, rs.max_blocks), kBThreads, 0, st>>>(r, ld, n, rs, out18);
-    k_moments_2<<<sweep_grid(n, 148 * 3), kBThreads, 0, st>>>(r, ld, n, rs, out18);
+// out: 18 doubles (q == nullptr) or 19 (q given: out[18] = sum q), device memory
+void launch_moments(const double* r, long long ld, long long n, const double* q, ReduceState rs, double* out,
+                    cudaStream_t st) {
+    if (q) k_moments_1<7><<<sweep_grid(n, rs.max_blocks), kBThreads, 0, st>>>(r, ld, n, q, rs, out);
+    else k_moments_1<6><<<sweep_grid(n, rs.max_blocks), kBThreads, 0, st>>>(r, ld, n, q, rs, out);
+    k_moments_2<<<sweep_grid(n, 148 * 3), kBThreads, 0, st>>>(r, ld, n, rs, out);
 }
 
 // ---- f4: aperture cut + stream compaction ---------------------------------------------------

@@ -92,7 +92,8 @@ struct MapCoef {
     double c1, c2, kb, phi, cosphi, t566, t556, t555;
 };
 void launch_map_apply(double* r, long long ld, long long n, const MapCoef& mc, cudaStream_t st);
-void launch_moments(const double* r, long long ld, long long n, ReduceState rs, double* out18, cudaStream_t st);
+void launch_moments(const double* r, long long ld, long long n, const double* q, ReduceState rs, double* out,
+                    cudaStream_t st);
 // aperture cut + ordered stream compaction (sc_beam.cu); counts holds ceil(n/1024) + 1 ints
 struct CutSpec {
     int kind;          // 0: one coordinate row against [a, b] | 1: ellipse with semi-axes (a, b) centred at (c, d)

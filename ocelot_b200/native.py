@@ -74,6 +74,7 @@ _SIGNATURES = {
     "ocl_sc_map_apply": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _dp, _dp, _vp]),
     "ocl_sc_cavity_apply": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _dp, _dp, C.c_int, _vp]),
     "ocl_sc_beam_moments": (C.c_int, [_vp, _vp, _ll, _ll, _dp, _vp]),
+    "ocl_sc_beam_moments_device": (C.c_int, [_vp, _vp, _ll, _ll, _vp, _vp, _vp]),
     "ocl_sc_aperture_cut": (C.c_int, [_vp, _vp, _ll, _vp, _vp, _ll, C.c_int, C.c_int, _dp, _vp, _ll, _vp, _vp, _vp,
                                       C.POINTER(_ll), _vp]),
     "ocl_sc_cavity_coefficients": (C.c_int, [C.c_double] * 6 + [_dp, C.POINTER(C.c_int), _dp]),
@@ -480,6 +481,15 @@ class Solver:
         self._check(self._lib.ocl_sc_beam_moments(self._h, ptr, ld, n, out, _stream_ptr(stream)),
                     "ocl_sc_beam_moments")
         return dict(zip(self.MOMENT_KEYS, out[:]))
+
+    def beam_moments_device(self, r, q, out, stream=None):
+        """The same two passes, result left on the device: ``out`` is a contiguous CUDA float64 tensor of at least
+        19 elements (18 moments in MOMENT_KEYS order, then sum q); no host synchronisation."""
+        ptr, ld, n = self._dev_rows(r, q)
+        if not (out.is_cuda and out.dtype == r.dtype and out.is_contiguous() and out.numel() >= 19):
+            raise TypeError("out must be a contiguous CUDA float64 tensor with at least 19 elements")
+        self._check(self._lib.ocl_sc_beam_moments_device(self._h, ptr, ld, n, q.data_ptr(), out.data_ptr(),
+                                                         _stream_ptr(stream)), "ocl_sc_beam_moments_device")
 
     # -- longitudinal space charge (sc.py:261-599) ----------------------------------
     LSC_STAT_KEYS = ("n", "mean_tau", "m2_tau", "min_tau", "max_tau", "sum_q", "sum_x", "sum_y")

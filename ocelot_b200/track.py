@@ -13,7 +13,7 @@ import logging
 
 import numpy as np
 
-from .beam import apply_map, apply_cavity, get_envelope
+from .beam import apply_map, apply_cavity, EnvelopeRecorder
 from .particles import DeviceParticleArray, ParticleArray
 
 logger = logging.getLogger(__name__)
@@ -64,7 +64,10 @@ def track(lattice, p_array, navi, calc_tws=True, print_progress=False):
     Returns ``(tws_track, p_array)`` like track.py:431-504."""
     if not isinstance(p_array, DeviceParticleArray):
         raise TypeError("p_array must be an ocelot_b200.DeviceParticleArray (use DeviceParticleArray.from_host)")
-    tws_track = [get_envelope(p_array)] if calc_tws else []
+    # the moments of every step stay on the device until the loop is over: no host synchronisation per step
+    rec = EnvelopeRecorder(getattr(p_array.rparticles, "device", None)) if calc_tws else None
+    if calc_tws:
+        rec.record(p_array)
     L = 0.0
     for t_maps, dz, proc_list, phys_steps in navi.get_next_step():                  # track.py:470
         for tm in t_maps:
@@ -76,17 +79,15 @@ def track(lattice, p_array, navi, calc_tws=True, print_progress=False):
             else:
                 _host_round_trip(p_array, lambda host, p=p, z=z_step: p.apply(host, z))
         if p_array.n == 0:
-            return tws_track, p_array
+            return (rec.collect() if calc_tws else []), p_array
         L += dz
         if calc_tws:
-            tw = get_envelope(p_array)                                               # track.py:482
-            tw.s += L
-            tws_track.append(tw)
+            rec.record(p_array, s=L)                                                 # track.py:482-484
         if print_progress:
             print(f"\rz = {navi.z0} / {lattice.totalLen}", end="")
     for p in navi.get_phys_procs():                                                  # track.py:498-499
         p.finalize()
-    return tws_track, p_array
+    return (rec.collect() if calc_tws else []), p_array
 
 
 def replay_track(p_array, R, B, map_step, kick_dz, sc, T=None, after_step=None):

@@ -203,7 +203,19 @@ def test_resident_track_loop_drives_reference_navigator(monkeypatch):
         m = orc.beam_moments(p.rparticles)
         return moments_from_sums({k: v for k, v in m.items() if not k.startswith("emit")}, E=p.E)
 
-    monkeypatch.setattr(T, "get_envelope", envelope)
+    class HostRecorder:                      # stands in for beam.EnvelopeRecorder (device moment kernels)
+        def __init__(self, device):
+            self.items = []
+
+        def record(self, p, s=0.0):
+            t = envelope(p)
+            t.s = s
+            self.items.append(t)
+
+        def collect(self):
+            return self.items
+
+    monkeypatch.setattr(T, "EnvelopeRecorder", HostRecorder)
     monkeypatch.setattr(T, "DeviceParticleArray", HostDev)
     monkeypatch.setattr(SpaceCharge, "_host_device", lambda self: 0)
     monkeypatch.setattr(native, "Solver", OracleSolver)

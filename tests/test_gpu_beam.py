@@ -64,6 +64,29 @@ def test_beam_moments_vs_oracle():
         assert abs(t.q / q0.sum() - 1) < 1e-12 and t.E == E
 
 
+def test_envelope_recorder_defers_the_readback():
+    """EnvelopeRecorder (what track() uses): the moments of every step are computed when recorded but read back once;
+    each record equals the synchronous get_envelope of the bunch at that moment bit for bit, across buffer chunks
+    (more records than one chunk holds), with the caller's s and the bunch's E at recording time."""
+    from ocelot_b200 import get_envelope, EnvelopeRecorder, apply_map
+    r0, q0, E, dev = _device_bunch(20_000, 11)
+    rec = EnvelopeRecorder(dev.rparticles.device)
+    rng = np.random.RandomState(1)
+    direct = []
+    steps = EnvelopeRecorder.CHUNK + 9
+    for k in range(steps):
+        apply_map(dev, np.eye(6) + 1e-3 * rng.randn(6, 6), 1e-7 * rng.randn(6), None, delta_e=1e-4, length=0.1)
+        rec.record(dev, s=0.1 * (k + 1))
+        if k % 17 == 0 or k == steps - 1:
+            direct.append((k, get_envelope(dev)))
+    got = rec.collect()
+    assert len(got) == steps == len(rec)
+    for k, t in direct:
+        for key in ("x", "px", "tau", "p", "xx", "xpx", "pxpx", "yy", "tautau", "pp", "xpy", "emit_x", "beta_y", "q", "E"):
+            assert getattr(got[k], key) == getattr(t, key), (k, key)
+        assert got[k].s == 0.1 * (k + 1) and t.s == 0.0            # get_envelope leaves s at 0 (beam/core.py:51)
+
+
 @pytest.mark.parametrize("fixture,second", [("track_c1.npz", False), ("track_second_order.npz", True)])
 def test_resident_tracking_moments(golden, fixture, second):
     """Maps, kicks and moments all on the device; only 18 doubles per step come back.
