@@ -92,6 +92,13 @@ struct ocl_sc {
     bool ordered = false;
     void* ordered_buf = nullptr;
     size_t ordered_bytes = 0;
+    // ... and the momentum sum follows numpy's pairwise tree over exactly rounded momenta (plan per bunch size)
+    long long pw_n = -1;
+    int pw_leaves = 0, pw_levels = 0;
+    uint2* pw_leaf_dev = nullptr;
+    uint2* pw_node_dev = nullptr;
+    int* pw_level_dev = nullptr;
+    double* pw_values = nullptr;
     int debug_skip = 0;                       // timing experiments only (OCL_SC_DEBUG_SKIP): bit 0/1/2 = leave out the
                                               // momentum exchange / extent exchange / rho reduction of a sharded kick
     // host arrays page-locked in place on first use (numpy buffers persist across kicks)
@@ -472,6 +479,7 @@ void ocl_sc_destroy(ocl_sc_t* h) {
     cudaFree(h->fw.P); cudaFree(h->fw.Q); cudaFree(h->fw.khat); cudaFree(h->fw.A); cudaFree(h->fw.B);
     cudaFree(h->tw[0]); cudaFree(h->tw[1]); cudaFree(h->tw[2]); cudaFree(h->h3); cudaFree(h->moments);
     cudaFree(h->stage_r); cudaFree(h->stage_q); cudaFree(h->cut_counts); cudaFree(h->ordered_buf);
+    cudaFree(h->pw_leaf_dev); cudaFree(h->pw_node_dev); cudaFree(h->pw_level_dev); cudaFree(h->pw_values);
     if (h->cut_n) cudaFreeHost(h->cut_n);
     cudaFree(h->lw.ticket); cudaFree(h->lw.stats); cudaFree(h->lw.bins); cudaFree(h->lw.cnt); cudaFree(h->lw.Z);
     cudaFree(h->lw.spread);
@@ -772,6 +780,63 @@ int ocl_sc_slab_finish(ocl_sc_t* h, const double* mesh_draws, void* stream) {
 }
 
 // ---- stages ---------------------------------------------------------------
+// numpy's pairwise summation of a row of n elements as a tree (numpy/_core/src/umath/loops_utils.h.src,
+// pairwise_sum: n > 128 splits at n/2 rounded down to a multiple of 8; shorter ranges are leaves).  Leaves are
+// (offset, length); internal nodes are (left, right) value indices, sorted by height so that one block can combine
+// them level by level; value index = leaf index, or leaf count + position in the sorted node list.
+static int ensure_pairwise_plan(ocl_sc* h, long long n, cudaStream_t st) {
+    if (h->pw_n == n) return 0;
+    struct Node { unsigned l, r; int height; };
+    std::vector<uint2> leaves;
+    std::vector<Node> nodes;                                   // post order: children before parents
+    struct Ref { unsigned id; int height; bool leaf; };
+    // explicit recursion (depth <= ~24)
+    struct Builder {
+        std::vector<uint2>& leaves; std::vector<Node>& nodes;
+        Ref build(long long off, long long len) {
+            if (len <= 128) {
+                leaves.push_back(make_uint2((unsigned)off, (unsigned)len));
+                return Ref{(unsigned)(leaves.size() - 1), 0, true};
+            }
+            long long n2 = len / 2;
+            n2 -= n2 % 8;
+            const Ref a = build(off, n2), b = build(off + n2, len - n2);
+            // leaf ids are final; internal ids are post-order positions tagged with the top bit until the sort below
+            nodes.push_back(Node{a.leaf ? a.id : (a.id | 0x80000000u), b.leaf ? b.id : (b.id | 0x80000000u),
+                                 std::max(a.height, b.height) + 1});
+            return Ref{(unsigned)(nodes.size() - 1), nodes.back().height, false};
+        }
+    } builder{leaves, nodes};
+    builder.build(0, n);
+    const int nleaves = (int)leaves.size(), nnodes = (int)nodes.size();
+    int levels = 0;
+    for (const Node& nd : nodes) levels = std::max(levels, nd.height);
+    // stable counting sort by height; remap the tagged post-order ids to sorted positions
+    std::vector<int> level_start(levels + 1, 0), pos(nnodes);
+    for (const Node& nd : nodes) level_start[nd.height]++;                  // counts at [height], heights are 1-based
+    { int acc = 0; for (int l = 1; l <= levels; ++l) { const int c = level_start[l]; level_start[l - 1] = acc; acc += c; }
+      level_start[levels] = acc; }
+    { std::vector<int> cur(level_start.begin(), level_start.end());
+      for (int k = 0; k < nnodes; ++k) pos[k] = cur[nodes[k].height - 1]++; }
+    std::vector<uint2> sorted(nnodes);
+    for (int k = 0; k < nnodes; ++k) {
+        auto remap = [&](unsigned id) { return (id & 0x80000000u) ? (unsigned)(nleaves + pos[id & 0x7fffffffu]) : id; };
+        sorted[pos[k]] = make_uint2(remap(nodes[k].l), remap(nodes[k].r));
+    }
+    CU(h, cudaStreamSynchronize(st));                                       // an earlier kick may still read the old plan
+    cudaFree(h->pw_leaf_dev); cudaFree(h->pw_node_dev); cudaFree(h->pw_level_dev); cudaFree(h->pw_values);
+    h->pw_leaf_dev = h->pw_node_dev = nullptr; h->pw_level_dev = nullptr; h->pw_values = nullptr; h->pw_n = -1;
+    CU(h, cudaMalloc(&h->pw_leaf_dev, sizeof(uint2) * nleaves));
+    CU(h, cudaMalloc(&h->pw_node_dev, sizeof(uint2) * std::max(nnodes, 1)));
+    CU(h, cudaMalloc(&h->pw_level_dev, sizeof(int) * (levels + 1)));
+    CU(h, cudaMalloc(&h->pw_values, sizeof(double) * 3 * (size_t)(nleaves + nnodes)));
+    CU(h, cudaMemcpy(h->pw_leaf_dev, leaves.data(), sizeof(uint2) * nleaves, cudaMemcpyHostToDevice));
+    if (nnodes) CU(h, cudaMemcpy(h->pw_node_dev, sorted.data(), sizeof(uint2) * nnodes, cudaMemcpyHostToDevice));
+    CU(h, cudaMemcpy(h->pw_level_dev, level_start.data(), sizeof(int) * (levels + 1), cudaMemcpyHostToDevice));
+    h->pw_n = n; h->pw_leaves = nleaves; h->pw_levels = levels;
+    return 0;
+}
+
 int ocl_sc_stage_momentum(ocl_sc_t* h, const double* d_r, long long ld, long long n, double E_GeV, void* stream) {
     OCL_RANGE("ocl_sc_stage_momentum");
     if (!h) return 1;
@@ -790,6 +855,19 @@ int ocl_sc_stage_momentum(ocl_sc_t* h, const double* d_r, long long ld, long lon
         kp.p = nullptr;
         publish = h->kp_dev;
         h->g_mb = mb; h->g_rs = h->rs;
+    }
+    if (h->ordered && mb.world <= 1 && n > 0 && !publish) {
+        // ordered mode: np.mean's own summation tree over momenta rounded exactly as the reference rounds them
+        if (ensure_pairwise_plan(h, n, st)) return 1;
+        launch_momentum_exact(d_r, ld, n, kp, h->pw_leaf_dev, h->pw_leaves, h->pw_node_dev, h->pw_level_dev,
+                              h->pw_levels, h->pw_values, h->rs.sums, st);
+        h->launches += 2;
+        if (!h->rs.defer) {
+            launch_finish(0, kp, h->rs, h->md, st);
+            h->launches += 1;
+        }
+        mark(h, T_MOM, st);
+        return check_launch(h, "k_momentum_exact");
     }
     launch_momentum(d_r, ld, n, kp, h->rs, mb, h->mb_err, publish, st);
     h->launches += 1;

@@ -146,27 +146,41 @@ __device__ __forceinline__ void cart_to_mad(const RefParams& rp, const Cart& c, 
     ys = c.py * rp.inv_pref;                                      // :53
 }
 
+// 1 / g^2 rounded to nearest: numpy evaluates `gamma ** -2` (coord_transform.py:69) with libm / SVML pow,
+// which is (nearly always) the correctly rounded value; a plain 1/(g*g) carries two roundings.
+__device__ __forceinline__ double inv_square_rn(double g) {
+    const double g2 = __dmul_rn(g, g);
+    const double e = __fma_rn(g, g, -g2);                 // g*g = g2 + e exactly
+    const double r0 = __ddiv_rn(1.0, g2);
+    const double res = __fma_rn(-g2, r0, 1.0) - e * r0;   // 1 - (g2 + e) r0
+    return __fma_rn(res, r0, r0);
+}
+
 // ---- sc.py:224-239 -----------------------------------------------------------
 // sums = {sum px, sum py, sum pz, particle count}
 __device__ __forceinline__ void derive_frame(const double* sums, double m_e_eV, Frame& f) {
-    double cnt = sums[3];
-    double a = sums[0] / cnt, b = sums[1] / cnt, c = sums[2] / cnt;   // np.mean(xp[3:6], axis=1)
-    double pav = sqrt(a * a + b * b + c * c);                          // np.linalg.norm(t3)
-    a = a / pav; b = b / pav; c = c / pav;
+    // Every operation is rounded on its own, as numpy does -- except the two norms, which numpy takes as
+    // sqrt(dot(x, x)) with the BLAS dot kernel's k-sequential FMAs (checked against numpy bit for bit on 3000 random
+    // frames, round 2): an FMA-contracted gamma0 or a separately rounded c*c would move pav / gamma0 by one ulp in
+    // ~0.03 % / ~14 % of kicks, and one ulp of gamma0 is one ulp of h_z.
+    const double cnt = sums[3];
+    double a = __ddiv_rn(sums[0], cnt), b = __ddiv_rn(sums[1], cnt), c = __ddiv_rn(sums[2], cnt);   // np.mean(xp[3:6], axis=1)
+    const double pav = __dsqrt_rn(__fma_rn(c, c, __fma_rn(b, b, __dmul_rn(a, a))));                // np.linalg.norm(t3)
+    a = __ddiv_rn(a, pav); b = __ddiv_rn(b, pav); c = __ddiv_rn(c, pav);
     // t1 = cross(ey, t3) = (c, 0, -a), normalised
-    double n1 = sqrt(c * c + 0.0 + a * a);
-    double t1x = c / n1, t1y = 0.0 / n1, t1z = -a / n1;
-    // t2 = cross(t3, t1)
-    double t2x = b * t1z - c * t1y;
-    double t2y = c * t1x - a * t1z;
-    double t2z = a * t1y - b * t1x;
+    const double n1 = __dsqrt_rn(__fma_rn(a, a, __dmul_rn(c, c)));
+    const double t1x = __ddiv_rn(c, n1), t1y = __ddiv_rn(0.0, n1), t1z = __ddiv_rn(-a, n1);
+    // t2 = cross(t3, t1): np.cross rounds both products, then subtracts
+    const double t2x = __dsub_rn(__dmul_rn(b, t1z), __dmul_rn(c, t1y));
+    const double t2y = __dsub_rn(__dmul_rn(c, t1x), __dmul_rn(a, t1z));
+    const double t2z = __dsub_rn(__dmul_rn(a, t1y), __dmul_rn(b, t1x));
     f.T[0][0] = t1x; f.T[0][1] = t2x; f.T[0][2] = a;
     f.T[1][0] = t1y; f.T[1][1] = t2y; f.T[1][2] = b;
     f.T[2][0] = t1z; f.T[2][1] = t2z; f.T[2][2] = c;
     f.pav = pav;
-    double g = pav / m_e_eV;
-    f.gamma0 = sqrt(g * g + 1.0);                                      // :237
-    f.beta0 = sqrt(1.0 - 1.0 / (f.gamma0 * f.gamma0));                 // :238-239
+    const double g = __ddiv_rn(pav, m_e_eV);
+    f.gamma0 = __dsqrt_rn(__dadd_rn(__dmul_rn(g, g), 1.0));                                         // :237
+    f.beta0 = __dsqrt_rn(__dsub_rn(1.0, inv_square_rn(f.gamma0)));                                  // :238-239
 }
 
 // sc.py:173-186 (mesh steps and origin from the reduced extents) lives in finish_extent_warp (sc_kernels.cu): one lane
@@ -180,16 +194,6 @@ __device__ __forceinline__ void load_geo(const Geo* __restrict__ g, Geo* s) {
     __syncthreads();
 }
 
-// 1 / g^2 rounded to nearest: numpy evaluates `gamma ** -2` (coord_transform.py:69) with libm / SVML pow,
-// which is (nearly always) the correctly rounded value; a plain 1/(g*g) carries two roundings.
-__device__ __forceinline__ double inv_square_rn(double g) {
-    const double g2 = __dmul_rn(g, g);
-    const double e = __fma_rn(g, g, -g2);                 // g*g = g2 + e exactly
-    const double r0 = __ddiv_rn(1.0, g2);
-    const double res = __fma_rn(-g2, r0, 1.0) - e * r0;   // 1 - (g2 + e) r0
-    return __fma_rn(res, r0, r0);
-}
-
 // ---- coord_transform.py:68-92 + sc.py:233,172 in the REFERENCE's operation order ------------------------
 // Position of one particle in the bunch frame (z stretched by gamma0), every operation rounded separately
 // as numpy does; the 3x3 rotation accumulates like the BLAS kernel behind np.dot (k-sequential FMAs).
@@ -197,23 +201,40 @@ __device__ __forceinline__ double inv_square_rn(double g) {
 // the integrated Green's function, whose 8-corner cancellation amplifies a one-ulp change of h to ~1e-10
 // of the field, so the extremal coordinates are re-evaluated exactly like the reference does
 // (DESIGN.md section 5).  All other per-particle work uses the reduced forms above.
-__device__ __forceinline__ void exact_frame_position(const RefParams& rp, const Frame& f, double x, double xs, double y,
-                                                     double ys, double tau, double delta, double& a, double& b,
-                                                     double& c) {
-    const double gam = __dmul_rn(__dadd_rn(__dmul_rn(rp.betaref, delta), 1.0), rp.gamref);            // :68
-    const double bet = __dsqrt_rn(__dsub_rn(1.0, inv_square_rn(gam)));                                 // :69
-    const double t = __ddiv_rn(__dmul_rn(gam, bet), rp.gb_ref);
+struct ExactDir {
+    double gam, bet, u0, u1, u2;
+};
+__device__ __forceinline__ ExactDir exact_direction(const RefParams& rp, double xs, double ys, double delta) {
+    ExactDir d;
+    d.gam = __dmul_rn(__dadd_rn(__dmul_rn(rp.betaref, delta), 1.0), rp.gamref);                       // :68
+    d.bet = __dsqrt_rn(__dsub_rn(1.0, inv_square_rn(d.gam)));                                          // :69
+    const double t = __ddiv_rn(__dmul_rn(d.gam, d.bet), rp.gb_ref);
     const double pz = __dsqrt_rn(__dsub_rn(__dsub_rn(__dmul_rn(t, t), __dmul_rn(xs, xs)), __dmul_rn(ys, ys)));   // :70
     const double d0 = __ddiv_rn(xs, pz), d1 = __ddiv_rn(ys, pz);                                       // :72
     const double nrm = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(d0, d0), __dmul_rn(d1, d1)), 1.0));    // :74
-    const double u0 = __ddiv_rn(d0, nrm), u1 = __ddiv_rn(d1, nrm), u2 = __ddiv_rn(1.0, nrm);           // :77
-    const double X = __dsub_rn(x, __dmul_rn(__dmul_rn(u0, bet), tau));                                 // :90
-    const double Y = __dsub_rn(y, __dmul_rn(__dmul_rn(u1, bet), tau));                                 // :91
-    const double Z = __dmul_rn(__dmul_rn(-u2, bet), tau);                                              // :92
+    d.u0 = __ddiv_rn(d0, nrm); d.u1 = __ddiv_rn(d1, nrm); d.u2 = __ddiv_rn(1.0, nrm);                  // :77
+    return d;
+}
+__device__ __forceinline__ void exact_frame_position(const RefParams& rp, const Frame& f, double x, double xs, double y,
+                                                     double ys, double tau, double delta, double& a, double& b,
+                                                     double& c) {
+    const ExactDir d = exact_direction(rp, xs, ys, delta);
+    const double X = __dsub_rn(x, __dmul_rn(__dmul_rn(d.u0, d.bet), tau));                             // :90
+    const double Y = __dsub_rn(y, __dmul_rn(__dmul_rn(d.u1, d.bet), tau));                             // :91
+    const double Z = __dmul_rn(__dmul_rn(-d.u2, d.bet), tau);                                          // :92
     a = __fma_rn(Z, f.T[2][0], __fma_rn(Y, f.T[1][0], __dmul_rn(X, f.T[0][0])));                       // sc.py:233
     b = __fma_rn(Z, f.T[2][1], __fma_rn(Y, f.T[1][1], __dmul_rn(X, f.T[0][1])));
     c = __fma_rn(Z, f.T[2][2], __fma_rn(Y, f.T[1][2], __dmul_rn(X, f.T[0][2])));
     c = __dmul_rn(c, f.gamma0);                                                                        // sc.py:172
+}
+// Cartesian momentum of one particle exactly as the reference rounds it (coord_transform.py:93-95:
+// u * gamma * beta * m_e_eV, left to right); used by the ordered mode's pairwise momentum sum.
+__device__ __forceinline__ void exact_momentum(const RefParams& rp, double xs, double ys, double delta, double& px,
+                                               double& py, double& pz) {
+    const ExactDir d = exact_direction(rp, xs, ys, delta);
+    px = __dmul_rn(__dmul_rn(__dmul_rn(d.u0, d.gam), d.bet), rp.m_e_eV);
+    py = __dmul_rn(__dmul_rn(__dmul_rn(d.u1, d.gam), d.bet), rp.m_e_eV);
+    pz = __dmul_rn(__dmul_rn(__dmul_rn(d.u2, d.gam), d.bet), rp.m_e_eV);
 }
 
 // rotate into the bunch frame and stretch z (sc.py:233, :172)

@@ -361,6 +361,80 @@ __global__ void __launch_bounds__(kThreads, 3) k_deposit(const double* __restric
 }
 
 // ---------------------------------------------------------------------------
+// Ordered momentum sum (debugging mode, with the ordered deposit): np.mean(xp[3:6], axis=1) (sc.py:224) bit for
+// bit.  numpy adds a contiguous row with its pairwise scheme: ranges longer than 128 are split at n/2 rounded down
+// to a multiple of 8, ranges of 8..128 elements are summed with eight interleaved accumulators r[j] += a[i + j],
+// combined as ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then the last n % 8 elements are added one by one
+// (checked against np.add.reduce bit for bit for n = 1 .. 10^6, round 2).  The host lists the leaves and the
+// combination tree for a given n once (PairwisePlan, sc_abi.cu); here
+//   k_momentum_exact_leaves  one warp per leaf: the momenta of its <= 128 particles exactly as the reference rounds
+//                            them (exact_momentum), the leaf's three sums in numpy's order
+//   k_pairwise_combine       one block walks the tree level by level -> rs.sums
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_momentum_exact_leaves(const double* __restrict__ r, long long ld, KP kp,
+                                                              const uint2* __restrict__ leaves, int nleaves,
+                                                              double* __restrict__ V) {
+    pdl_enter();
+    const RefParams rp = kp_ref(kp);
+    __shared__ double sh[8][3][128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int leaf = blockIdx.x * 8 + warp;
+    if (leaf >= nleaves) return;
+    const uint2 lf = leaves[leaf];
+    const long long off = lf.x;
+    const int len = (int)lf.y;
+    for (int i = lane; i < len; i += 32) {
+        const long long p = off + i;
+        double px, py, pz;
+        exact_momentum(rp, r[ld + p], r[3 * ld + p], r[5 * ld + p], px, py, pz);
+        sh[warp][0][i] = px; sh[warp][1][i] = py; sh[warp][2][i] = pz;
+    }
+    __syncwarp();
+    if (lane < 24) {                                    // lane = component * 8 + accumulator
+        const unsigned mask = 0x00ffffffu;
+        const int comp = lane >> 3, j = lane & 7;
+        const double* a = sh[warp][comp];
+        double res = 0.0;
+        if (len < 8) {                                  // only a bunch of fewer than 8 particles: 0 + a0 + a1 + ...
+            if (j == 0) for (int i = 0; i < len; ++i) res = __dadd_rn(res, a[i]);
+        } else {
+            double rj = a[j];
+            const int nb = len - (len % 8);
+            for (int i = 8; i < nb; i += 8) rj = __dadd_rn(rj, a[i + j]);
+            double t = __dadd_rn(rj, __shfl_down_sync(mask, rj, 1, 8));     // j even: r_j + r_j+1
+            t = __dadd_rn(t, __shfl_down_sync(mask, t, 2, 8));              // j % 4 == 0: (r_j + r_j+1) + (r_j+2 + r_j+3)
+            t = __dadd_rn(t, __shfl_down_sync(mask, t, 4, 8));              // j == 0: the eight
+            res = t;
+            if (j == 0) for (int i = nb; i < len; ++i) res = __dadd_rn(res, a[i]);
+        }
+        if (j == 0) V[(size_t)leaf * 3 + comp] = res;
+    }
+}
+
+// nodes[k] = (left, right) value indices of internal node nleaves + k; nodes are sorted by height and
+// level_start[l] .. level_start[l + 1] are the nodes of height l + 1.  The root is the last value.
+__global__ void __launch_bounds__(1024) k_pairwise_combine(double* __restrict__ V, const uint2* __restrict__ nodes,
+                                                          const int* __restrict__ level_start, int nlevels, int nleaves,
+                                                          long long n, double* __restrict__ sums) {
+    pdl_enter();
+    for (int l = 0; l < nlevels; ++l) {
+        const int lo = level_start[l], hi = level_start[l + 1];
+        for (int k = lo + (int)threadIdx.x; k < hi; k += (int)blockDim.x) {
+            const uint2 c = nodes[k];
+            double* out = V + (size_t)(nleaves + k) * 3;
+#pragma unroll
+            for (int m = 0; m < 3; ++m) out[m] = __dadd_rn(V[(size_t)c.x * 3 + m], V[(size_t)c.y * 3 + m]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 3) {
+        const size_t root = (size_t)nleaves + (size_t)level_start[nlevels] - 1;
+        sums[threadIdx.x] = V[root * 3 + threadIdx.x];
+    }
+    if (threadIdx.x == 3) sums[3] = (double)n;
+}
+
+// ---------------------------------------------------------------------------
 // Ordered deposit (debugging mode, SURVEY section 8e "Determinism"): the same cells, but every cell's charges are
 // added one after the other in ascending particle order starting from 0.0 -- the order np.bincount uses
 // (sc.py:193) -- so rho is bit-identical from run to run and, for identical cell indices, to the reference's grid.
@@ -915,6 +989,12 @@ void launch_deposit(const double* r, long long ld, const double* q, long long n,
         launch_k(k_deposit<true>, dim3(grid_for(n, 148 * 3)), dim3(kThreads), 0, st, r, ld, q, n, kp, rs, md, rho);
     else
         launch_k(k_deposit<false>, dim3(grid_for(n, 148 * 3)), dim3(kThreads), 0, st, r, ld, q, n, kp, rs, md, rho);
+}
+void launch_momentum_exact(const double* r, long long ld, long long n, KP kp, const uint2* leaves, int nleaves,
+                           const uint2* nodes, const int* level_start, int nlevels, double* V, double* sums,
+                           cudaStream_t st) {
+    launch_k(k_momentum_exact_leaves, dim3((nleaves + 7) / 8), dim3(256), 0, st, r, ld, kp, leaves, nleaves, V);
+    launch_k(k_pairwise_combine, dim3(1), dim3(1024), 0, st, V, nodes, level_start, nlevels, nleaves, n, sums);
 }
 // scratch layout: key_in | val_in | key_out | val_out (n unsigned each, 256-byte aligned) | cub temporary storage
 static size_t ordered_pad(long long n) { return ((size_t)n * sizeof(unsigned) + 255) / 256 * 256; }

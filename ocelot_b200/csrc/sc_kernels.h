@@ -60,6 +60,10 @@ void launch_extent(const double* r, long long ld, const double* q, long long n, 
 void launch_finish(int which, KP kp, ReduceState rs, MeshDims md, cudaStream_t st);
 void launch_deposit(const double* r, long long ld, const double* q, long long n, KP kp, ReduceState rs,
                     MeshDims md, double* rho, cudaStream_t st);
+// ordered momentum sum: numpy's pairwise tree over exactly rounded momenta (plan built by the host, sc_abi.cu)
+void launch_momentum_exact(const double* r, long long ld, long long n, KP kp, const uint2* leaves, int nleaves,
+                           const uint2* nodes, const int* level_start, int nlevels, double* V, double* sums,
+                           cudaStream_t st);
 // ordered (run-to-run bit-identical, np.bincount order) deposit; scratch from deposit_ordered_scratch_bytes
 size_t deposit_ordered_scratch_bytes(long long n, MeshDims md);
 int launch_deposit_ordered(const double* r, long long ld, const double* q, long long n, KP kp, ReduceState rs,
