@@ -422,6 +422,8 @@ def north_star_leg(ctx, name, n_total, mesh, slab, steps):
            "device_memory_gib_max_over_ranks": round(mem, 2),
            "whole_kick_roofline": {"algorithmic_bytes_per_gpu": alg, "achieved_gbs": alg / (ms * 1e-3) / 1e9,
                                    "frac": alg / (ms * 1e-3) / 1e9 / peak}}
+    # failure detection of the exchanges that run inside the kernels: 0 = none of them ever timed out on any rank
+    out["exchange_status"] = int(ctx.max_over_ranks(float(s.exchange_status())))
     drop_sharded(ctx, s)
     del p
     gc.collect()
@@ -466,7 +468,9 @@ def sharded_parity(ctx, n_total=10_000_000, mesh=63):
         out[label] = {"row_error": err, "kick_size": ctx.max_over_ranks(moved),
                       "charge_conservation": abs(rho_sum / CHARGE - 1.0),
                       "solve": "slab-decomposed" if eng.slab else "redundant"}
-        worst = max(worst, err, abs(rho_sum / CHARGE - 1.0))
+        status = int(ctx.max_over_ranks(float(s.exchange_status())))
+        out[label]["exchange_status"] = status
+        worst = max(worst, err, abs(rho_sum / CHARGE - 1.0), float(status))
         drop_sharded(ctx, s)
         del shard
     out["ok"] = bool(worst < 1e-10)

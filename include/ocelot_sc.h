@@ -124,6 +124,10 @@ int ocl_sc_combine_extents(ocl_sc_t* h, const double* d_all, int world, void* st
 #define OCL_SC_MAILBOX_DOUBLES 256
 int ocl_sc_mailbox_init(ocl_sc_t* h, int rank, int world, void* const* peer_ptrs);
 int ocl_sc_mailbox_exchange(ocl_sc_t* h, int which, void* stream);
+/* Failure detection: an exchange whose peer does not answer within ~4 s gives up (the kernels must terminate) and
+ * raises a device flag; *status = 0 ok, 1 / 2 / 3 = a momentum / extent / barrier-type exchange timed out and the
+ * results since then are invalid.  synchronise != 0 waits for the stream last used first. */
+int ocl_sc_mailbox_status(ocl_sc_t* h, int synchronise, int* status);
 /* Fused reduction of the charge grid: the handle deposits into peer_rho[rank] (caller-owned symmetric
  * memory of at least the RHO buffer's size, mapped on every rank) and, after
  * ocl_sc_mailbox_exchange(h, 2, stream) -- a barrier: every rank's deposit is complete -- the first FFT

@@ -549,6 +549,21 @@ int ocl_sc_mailbox_exchange(ocl_sc_t* h, int which, void* stream) {
     return check_launch(h, "k_mailbox_exchange");
 }
 
+// Failure detection of the fused exchanges: a rank that waits ~4 s for a peer's flag gives up, raises a device
+// flag and carries on with whatever the mailbox holds (the kernels must terminate: a hung peer would otherwise hang
+// every GPU of the job).  *status = 0: every exchange so far completed; 1 / 2 / 3: a momentum / extent /
+// barrier-type exchange (rho reduction, slab transposes, phi broadcast) timed out -- the results since then are
+// invalid.  synchronise != 0 waits for the stream last used first.
+int ocl_sc_mailbox_status(ocl_sc_t* h, int synchronise, int* status) {
+    if (!h || !status) return 1;
+    *status = 0;
+    if (!h->mb_err) return 0;                                  // no mailbox: nothing can have timed out
+    ENTER_DEVICE(h);
+    if (synchronise && h->last_stream_valid) CU(h, cudaStreamSynchronize(h->last_stream));
+    CU(h, cudaMemcpy(status, h->mb_err, sizeof(int), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
 int ocl_sc_set_peer_rho(ocl_sc_t* h, int rank, int world, void* const* peer_rho) {
     if (!h || !peer_rho) return 1;
     if (world < 1 || world > 8 || rank < 0 || rank >= world)

@@ -348,6 +348,27 @@ class ShardedSpaceCharge:
         solver.set_kick_params(E, float(dz), draws)
         self._graph.replay()
 
+    def exchange_status(self) -> int:
+        """0: every exchange that runs inside the library's kernels has completed so far; 1 / 2 / 3: a momentum /
+        extent / barrier-type exchange (rho reduction, slab transposes, phi broadcast) gave up after its ~4 s time-out
+        -- the kernels terminate rather than hang the job when a peer is gone, and every result since is invalid.
+        Synchronises the device."""
+        if self._engine is None:
+            return 0
+        import torch
+        torch.cuda.synchronize()
+        return self._engine.solver.mailbox_status(True)
+
+    def check(self):
+        """Raise if a fused exchange timed out (see ``exchange_status``).  Call it before results are consumed on
+        the host; ``finalize`` logs the same condition as an error."""
+        code = self.exchange_status()
+        if code:
+            raise RuntimeError("sharded space-charge kick: " + self._STATUS.get(code, "exchange") + " timed out "
+                               "waiting for a peer rank; the particle data of this rank is invalid since that kick")
+
+    _STATUS = {1: "momentum exchange", 2: "extent exchange", 3: "barrier (rho reduction / slab exchange)"}
+
     def release(self):
         """Drop the captured graph.  NCCL requires graphs that captured its collectives to be
         destroyed before the communicator: call this (or finalize) before destroy_process_group."""
@@ -355,6 +376,12 @@ class ShardedSpaceCharge:
 
     def finalize(self, *a, **k):
         self.release()
+        code = self.exchange_status()
+        if code:
+            import logging
+            logging.getLogger(__name__).error("sharded space-charge kick: %s timed out waiting for a peer rank; the "
+                                              "particle data of this rank is invalid since that kick",
+                                              self._STATUS.get(code, "exchange"))
 
     def __del__(self):
         try:

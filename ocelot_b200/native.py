@@ -48,6 +48,7 @@ _SIGNATURES = {
     "ocl_sc_slab_finish": (C.c_int, [_vp, _dp, _vp]),
     "ocl_sc_mailbox_init": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
     "ocl_sc_mailbox_exchange": (C.c_int, [_vp, C.c_int, _vp]),
+    "ocl_sc_mailbox_status": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int)]),
     "ocl_sc_set_peer_rho": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp)]),
     "ocl_sc_set_peer_xchg": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(_vp), C.POINTER(_vp)]),
     "ocl_sc_set_multicast_rho": (C.c_int, [_vp, _vp, _vp]),
@@ -334,6 +335,13 @@ class Solver:
 
     def nvls_reduce_rho(self, stream=None):
         self._check(self._lib.ocl_sc_nvls_reduce_rho(self._h, _stream_ptr(stream)), "ocl_sc_nvls_reduce_rho")
+
+    def mailbox_status(self, synchronise=True) -> int:
+        """0: every fused exchange so far completed; 1 / 2 / 3: a momentum / extent / barrier exchange timed out."""
+        st = C.c_int(0)
+        self._check(self._lib.ocl_sc_mailbox_status(self._h, 1 if synchronise else 0, C.byref(st)),
+                    "ocl_sc_mailbox_status")
+        return int(st.value)
 
     def mailbox_exchange(self, which, stream=None):
         self._check(self._lib.ocl_sc_mailbox_exchange(self._h, int(which), _stream_ptr(stream)),

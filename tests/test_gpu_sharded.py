@@ -38,6 +38,9 @@ def test_sharded_wrapper_single_rank_equals_plugin():
     sc.apply(a, 0.1)
     sh.apply(b, 0.1)
     assert _row_err(b.to_host().rparticles, a.to_host().rparticles) < 1e-12
+    sh.check()                                 # failure detection: no fused exchange timed out (none exist at world 1)
+    sh.finalize()
+    assert sh.exchange_status() == 0
 
 
 def _worker(rank, world, port, n, nmesh, out, slab=False, p2p_rho=False, nvls=False, p2p=True, empty_rank=None):
@@ -67,6 +70,7 @@ def _worker(rank, world, port, n, nmesh, out, slab=False, p2p_rho=False, nvls=Fa
             sc.apply(shard, 0.1)
         torch.cuda.synchronize()
         out[rank] = (lo, hi, shard.to_host().rparticles.copy(), sc._engine.nvls is not None)
+        sc.check()                             # no fused exchange gave up waiting for the peer
         sc.finalize()                          # graphs holding NCCL work must go before the communicator
     finally:
         torch.cuda.synchronize()
