@@ -276,3 +276,48 @@ def test_cavity_coefficients_from_the_library_match_the_oracle_map():
         assert (mode == 2) == (E + de_ref <= 0)
         assert np.max(np.abs(y5 - want[5])) <= 1e-13 * max(1e-30, np.max(np.abs(want[5]))), (v, phi, E)
         assert np.max(np.abs(y4 - want[4])) <= 1e-13 * np.max(np.abs(want[4])), (v, phi, E)
+
+
+def test_envelope_recorder_host_logic(monkeypatch):
+    """beam.EnvelopeRecorder without a GPU: a stand-in for the native handle writes the oracle's moments into the slot
+    it is given; the recorder must hand out one slot per record across buffer chunks, keep the caller's s and the
+    bunch's E at recording time, give an empty Twiss-like record for a bunch of fewer than 3 particles
+    (analysis.py:86-88) and post-process every slot exactly like get_envelope (analysis.py:179-220)."""
+    torch = pytest.importorskip("torch")
+    import types
+    from oracle import sc_oracle as orc
+    from ocelot_b200 import beam, native
+
+    class FakeSolver:
+        MOMENT_KEYS = native.Solver.MOMENT_KEYS
+        calls = 0
+
+        def beam_moments_device(self, r, q, out):
+            m = orc.beam_moments(r.numpy())
+            out[:18] = torch.tensor([m[k] for k in self.MOMENT_KEYS])
+            out[18] = float(q.sum())
+            FakeSolver.calls += 1
+
+    monkeypatch.setattr(beam, "_scratch_solver", lambda device: FakeSolver())
+    monkeypatch.setattr(beam.EnvelopeRecorder, "CHUNK", 4)
+    rng = np.random.RandomState(0)
+    rec = beam.EnvelopeRecorder(None)
+    bunches = []
+    for k in range(11):
+        n = 2 if k == 5 else 500
+        p = types.SimpleNamespace(rparticles=torch.from_numpy(rng.randn(6, n) * 1e-4), q_array=torch.full((n,), 1e-12, dtype=torch.float64),
+                                  E=0.1 + 0.01 * k, s=99.0)
+        rec.record(p, s=0.5 * k)
+        bunches.append(p)
+    assert len(rec) == 11 and FakeSolver.calls == 10 and len(rec._chunks) == 3
+    got = rec.collect()
+    for k, (t, p) in enumerate(zip(got, bunches)):
+        assert t.E == p.E
+        if k == 5:
+            assert t.xx == 0.0 and t.s == 0.0
+            continue
+        ref = orc.beam_moments(p.rparticles.numpy())
+        assert t.s == 0.5 * k and abs(t.q - 500e-12) < 1e-24
+        for key in ("x", "xx", "xpx", "pxpx", "tautau", "pp", "xpy"):
+            assert getattr(t, key) == ref[key], (k, key)
+        assert abs(t.emit_x / ref["emit_x"] - 1) < 1e-12 and t.beta_x == t.xx / t.emit_x
