@@ -294,7 +294,7 @@ def test_envelope_recorder_host_logic(monkeypatch):
 
         def beam_moments_device(self, r, q, out):
             m = orc.beam_moments(r.numpy())
-            out[:18] = torch.tensor([m[k] for k in self.MOMENT_KEYS])
+            out[:18] = torch.tensor([m[k] for k in self.MOMENT_KEYS], dtype=torch.float64)
             out[18] = float(q.sum())
             FakeSolver.calls += 1
 
