@@ -180,8 +180,13 @@ class DeviceParticleArray:
         """Copy back into ``p_array`` (in place) or into a new ParticleArray."""
         if p_array is None:
             p_array = ParticleArray(self._n)
-        p_array.rparticles[:] = self.rparticles.cpu().numpy()
-        p_array.q_array[:] = self.q_array.cpu().numpy()
+        r, q = self.rparticles.cpu().numpy(), self.q_array.cpu().numpy()
+        if p_array.rparticles.shape == r.shape:
+            p_array.rparticles[:] = r
+            p_array.q_array[:] = q
+        else:                                   # apertures changed N on the device: new arrays, as the reference's
+            p_array.rparticles = r              # delete_particles does on the host (beam/particle.py:323-333)
+            p_array.q_array = q
         p_array.E = self.E
         p_array.s = self.s
         return p_array

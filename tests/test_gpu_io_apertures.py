@@ -29,6 +29,11 @@ def test_apertures_match_reference_rule_and_kick_still_works():
         assert np.array_equal(dev.to_host().rparticles, host.rparticles)
         assert np.array_equal(dev.q_array.cpu().numpy(), host.q_array)
     assert len(dev.lost_particles) == 60_000 - dev.n
+    # copying back into a host container that still has the original size replaces its arrays (the INTEGRATION.md flow)
+    full = _bunch(60_000, 12)[0]
+    dev.to_host(full)
+    assert full.rparticles.shape == (6, dev.n) and np.array_equal(full.rparticles, host.rparticles)
+    assert np.array_equal(full.q_array, host.q_array)
     # lost-particle recorder: original indices, in the order the reference deletes them (x plane, y plane, ellipse)
     r0 = _bunch(60_000, 12)[0].rparticles
     ids = np.arange(60_000)
