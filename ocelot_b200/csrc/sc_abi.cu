@@ -636,7 +636,8 @@ int ocl_sc_use_device_params(ocl_sc_t* h, int on) {
 
 // Ordered deposit on / off (SURVEY section 8e "Determinism"): every cell's charges are added in ascending particle
 // order, as np.bincount does (sc.py:193), instead of by L2 atomics in arrival order.  For debugging cell-flip /
-// reproducibility questions: about 3x the deposit's time, and the kick runs stage by stage instead of as one graph.
+// reproducibility questions: the whole kick takes 2.5-3x as long (measured, tools/r2_ordered_cost.py) and runs stage by
+// stage instead of as one graph.  Also switches sweep 1 to numpy's pairwise tree over exactly rounded momenta.
 int ocl_sc_set_deterministic(ocl_sc_t* h, int on) {
     if (!h) return 1;
     h->ordered = on != 0;
